@@ -1,0 +1,163 @@
+"""TEST INFRASTRUCTURE — numpy/ctypes front end of the CPU oracle (oracle/ndstats_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs may
+import this module.  It never touches the product library.  Parity pinning: partial — see the
+header of ndstats_oracle.c.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libndstats_oracle.so")
+
+OK, EMPTY_INPUT, INVALID_QUANTILE, NAN_IN_INPUT, UNSUPPORTED = 0, 1, 2, 3, 4
+BAD_ARGUMENT, PANIC = 7, 8
+LOWER, HIGHER, NEAREST, MIDPOINT, LINEAR = range(5)
+INTERP = {"lower": LOWER, "higher": HIGHER, "nearest": NEAREST, "midpoint": MIDPOINT, "linear": LINEAR}
+
+DTYPES = {
+    np.dtype(np.int8): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3,
+    np.dtype(np.uint8): 4, np.dtype(np.uint16): 5, np.dtype(np.uint32): 6, np.dtype(np.uint64): 7,
+    np.dtype(np.float32): 8, np.dtype(np.float64): 9,
+}
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (gcc; seconds)."""
+    if force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+        for f in ("ndstats_oracle.c", "oracle_typed.inc", "Makefile")
+    ):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        L.oracle_quantiles_axis.restype = ctypes.c_int
+        L.oracle_quantiles_axis.argtypes = [
+            ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t),
+            ctypes.POINTER(ctypes.c_ssize_t), ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_size_t,
+            ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_int,
+            ctypes.c_int,
+        ]
+        L.oracle_partition_mut_i64.restype = ctypes.c_size_t
+        L.oracle_partition_mut_i64.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_ssize_t, ctypes.c_size_t]
+        L.oracle_get_many_from_sorted_i64.restype = ctypes.c_size_t
+        L.oracle_get_many_from_sorted_i64.argtypes = [
+            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_ssize_t, ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t,
+            ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p,
+        ]
+        L.oracle_remove_nan_mut_f64.restype = ctypes.c_size_t
+        L.oracle_remove_nan_mut_f64.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_ssize_t]
+        for name in ("oracle_lower_index_pub", "oracle_higher_index_pub"):
+            getattr(L, name).restype = ctypes.c_size_t
+            getattr(L, name).argtypes = [ctypes.c_double, ctypes.c_size_t]
+        L.oracle_index_fraction_pub.restype = ctypes.c_double
+        L.oracle_index_fraction_pub.argtypes = [ctypes.c_double, ctypes.c_size_t]
+        L.oracle_max_threads.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+class OracleError(Exception):
+    def __init__(self, status, bad_q=None):
+        super().__init__(f"oracle status {status} (bad_q={bad_q})")
+        self.status = status
+        self.bad_q = bad_q
+
+
+def _lowest_address_view(a):
+    """Element offset (from the lowest touched address) of a's logical origin."""
+    off = 0
+    for n, s in zip(a.shape, a.strides):
+        if s < 0 and n > 0:
+            off += (n - 1) * (-s)
+    return off
+
+
+def quantiles_axis(a, axis, qs, interp, skipnan=False, select_impl=0, nthreads=1, mutate=False):
+    """Reference semantics of quantiles_axis_mut / quantile_axis_skipnan_mut on a numpy array.
+
+    Returns (status, out, bad_q).  ``out`` is C-order with shape[axis] = len(qs) (None on error).
+    The input is copied unless mutate=True (the reference permutes lanes in place).
+    """
+    a = np.asarray(a)
+    if a.dtype not in DTYPES:
+        return UNSUPPORTED, None, None
+    if isinstance(interp, str):
+        interp = INTERP[interp]
+    work = a if mutate else a.copy(order="K")
+    if not mutate and work.strides != a.strides and a.size:
+        # copy(order="K") may normalise negative strides; rebuild the same logical view
+        work = np.array(a, order="C", copy=True)
+    qs = np.ascontiguousarray(qs, dtype=np.float64).reshape(-1)
+    ndim = work.ndim
+    itemsize = work.dtype.itemsize
+    shape = (ctypes.c_size_t * ndim)(*work.shape)
+    strides = (ctypes.c_ssize_t * ndim)(*[s // itemsize for s in work.strides])
+    out_shape = list(work.shape)
+    out_shape[axis] = qs.size
+    out = np.zeros(out_shape, dtype=work.dtype)
+    bad = ctypes.c_size_t(0)
+    st = lib().oracle_quantiles_axis(
+        DTYPES[work.dtype], ctypes.c_void_p(work.__array_interface__["data"][0]), ndim, shape, strides, axis,
+        qs.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), qs.size, interp, int(bool(skipnan)),
+        ctypes.c_void_p(out.ctypes.data), ctypes.byref(bad), select_impl, nthreads,
+    )
+    if st == INVALID_QUANTILE:
+        return st, None, bad.value
+    if st != OK:
+        return st, None, None
+    return st, out, None
+
+
+def partition_mut_i64(arr, pivot_index):
+    arr = np.asarray(arr)
+    assert arr.dtype == np.int64 and arr.ndim == 1
+    return lib().oracle_partition_mut_i64(
+        ctypes.c_void_p(arr.__array_interface__["data"][0]), arr.size, arr.strides[0] // 8, pivot_index)
+
+
+def get_many_from_sorted_i64(arr, indexes):
+    arr = np.array(arr, dtype=np.int64)
+    idx = np.ascontiguousarray(indexes, dtype=np.uintp)
+    out_idx = (ctypes.c_size_t * max(1, idx.size))()
+    out_val = np.zeros(max(1, idx.size), dtype=np.int64)
+    m = lib().oracle_get_many_from_sorted_i64(
+        ctypes.c_void_p(arr.ctypes.data), arr.size, 1, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_size_t)),
+        idx.size, out_idx, ctypes.c_void_p(out_val.ctypes.data))
+    return list(out_idx[:m]), out_val[:m].copy()
+
+
+def remove_nan_mut_f64(view):
+    """In place on a (possibly strided / reversed) 1-D float64 view; returns the NaN-free prefix view."""
+    assert view.dtype == np.float64 and view.ndim == 1
+    n = lib().oracle_remove_nan_mut_f64(
+        ctypes.c_void_p(view.__array_interface__["data"][0]), view.size, view.strides[0] // 8 if view.size else 1)
+    return view[:n]
+
+
+def lower_index(q, n):
+    return lib().oracle_lower_index_pub(q, n)
+
+
+def higher_index(q, n):
+    return lib().oracle_higher_index_pub(q, n)
+
+
+def index_fraction(q, n):
+    return lib().oracle_index_fraction_pub(q, n)
+
+
+def max_threads():
+    return lib().oracle_max_threads()

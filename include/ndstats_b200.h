@@ -1,0 +1,165 @@
+/*
+ * ndstats_b200 — C ABI of the B200-native bulk quantile path.
+ *
+ * This header is the drop-in boundary for ONE path of rust-ndarray/ndarray-stats v0.7.0: the bulk
+ * quantile path.  The reference has no FFI of its own; the boundary it exposes is a set of sealed
+ * Rust extension traits.  Every entry point below states which reference interface it replaces
+ * (paths relative to the reference checkout).  The Rust shim that binds these symbols and restores
+ * the trait surface is shown in INTEGRATION.md (sources in ndarray-stats_b200/rust/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary;
+ *   - `data` / `out` may be host or device pointers (detected with cudaPointerGetAttributes); host
+ *     buffers are staged through the context's device arena;
+ *   - `shape` and `strides_elems` describe an ndarray-style view: strides are in ELEMENTS, may be
+ *     negative, `data` points at the logical first element (ndarray's `as_ptr()`);
+ *   - `out` is always written C-contiguous with shape[axis] replaced by nq
+ *     (src/quantile/mod.rs:451-452,469); single-q wrappers drop that axis (mod.rs:507);
+ *   - the input is never modified (the reference permutes lanes in place and leaves the order
+ *     unspecified, mod.rs:190-195, so "unchanged" is conformant);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns
+ *     NDS_CUDA_ERROR.
+ */
+#ifndef NDSTATS_B200_H
+#define NDSTATS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDS_MAX_DIMS 12
+#define NDS_ABI_VERSION 1
+
+typedef struct nds_ctx nds_ctx;
+
+typedef enum nds_status {
+    NDS_OK = 0,
+    NDS_EMPTY_INPUT = 1,      /* QuantileError::EmptyInput          src/errors.rs:121-122 */
+    NDS_INVALID_QUANTILE = 2, /* QuantileError::InvalidQuantile(q)  src/errors.rs:123-124; *bad_q_index = first offender */
+    NDS_NAN_IN_INPUT = 3,     /* f32/f64 input held a NaN on a non-skipnan call: N32/N64 cannot represent
+                                 it (src/quantile/mod.rs:213-216), so the shim panics like noisy_float */
+    NDS_UNSUPPORTED = 4,      /* dtype / rank count / layout outside what the device path covers */
+    NDS_CUDA_ERROR = 5,
+    NDS_NCCL_ERROR = 6,
+    NDS_BAD_ARGUMENT = 7,     /* null pointer, ndim out of range, axis out of bounds (the reference panics) */
+    NDS_CAST_OVERFLOW = 8,    /* integer Linear: T::from_f64(..).unwrap() would panic, interpolate.rs:142 */
+    NDS_INDEX_OUT_OF_BOUNDS = 9 /* Sort1dExt: index >= n (the reference panics, src/sort.rs:27,38) */
+} nds_status;
+
+typedef enum nds_dtype {
+    NDS_I8 = 0, NDS_I16 = 1, NDS_I32 = 2, NDS_I64 = 3,
+    NDS_U8 = 4, NDS_U16 = 5, NDS_U32 = 6, NDS_U64 = 7,
+    NDS_F32 = 8, /* N32 on plain calls, raw f32 on skipnan calls */
+    NDS_F64 = 9  /* N64 / f64 */
+} nds_dtype;
+
+/* interpolate::{Lower, Higher, Nearest, Midpoint, Linear} — src/quantile/interpolate.rs:51-62 */
+typedef enum nds_interp {
+    NDS_LOWER = 0, NDS_HIGHER = 1, NDS_NEAREST = 2, NDS_MIDPOINT = 3, NDS_LINEAR = 4
+} nds_interp;
+
+/* ---- library / context ------------------------------------------------------------------ */
+
+int nds_abi_version(void);
+const char *nds_status_string(nds_status s); /* Display strings of src/errors.rs:126-135 for 1 and 2 */
+size_t nds_dtype_size(nds_dtype t);
+
+/* One context per host thread and GPU: stream, device scratch arena, deferred status word.
+ * (The reference is stateless and single-threaded; a ctx is not thread-safe.) */
+nds_status nds_ctx_create(int device, nds_ctx **out);
+void nds_ctx_destroy(nds_ctx *ctx);
+/* Borrow an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx's own. */
+nds_status nds_ctx_set_stream(nds_ctx *ctx, void *cuda_stream);
+void *nds_ctx_get_stream(nds_ctx *ctx);
+/* Wait for everything enqueued on the ctx stream; returns (and clears) the deferred data-dependent
+ * status of *_enqueue calls: NDS_NAN_IN_INPUT, NDS_CAST_OVERFLOW or a CUDA error. */
+nds_status nds_ctx_synchronize(nds_ctx *ctx);
+const char *nds_ctx_last_error(nds_ctx *ctx);
+/* Number of kernels this ctx has launched so far (bench.py's gpu_launches is a difference of these). */
+uint64_t nds_ctx_kernel_launches(nds_ctx *ctx);
+/* Name of the selection path the last call dispatched to ("short_bitslice", "generic_cta", "long_radix", ...). */
+const char *nds_ctx_last_path(nds_ctx *ctx);
+/* Force a selection path for testing (NULL or "auto" = default dispatch). Returns NDS_BAD_ARGUMENT for unknown names. */
+nds_status nds_ctx_force_path(nds_ctx *ctx, const char *name);
+
+/* Host-only argument check with the reference's precedence (src/quantile/mod.rs:440-455): first q outside
+ * [0,1] -> NDS_INVALID_QUANTILE (+ *bad_q_index); shape[axis] == 0 -> NDS_EMPTY_INPUT; bad ndim / axis ->
+ * NDS_BAD_ARGUMENT; otherwise NDS_OK.  *result_elems (optional) receives the size of the result, 0 meaning
+ * "Ok(empty array)".  Needs no GPU and no context; every compute entry point applies the same check. */
+nds_status nds_validate_quantile_args(int ndim, const size_t *shape, int axis, const double *qs, size_t nq,
+                                      nds_interp interp, size_t *bad_q_index, size_t *result_elems);
+
+/* ---- the quantile path --------------------------------------------------------------------- */
+
+/*
+ * QuantileExt::quantiles_axis_mut            src/quantile/mod.rs:417-493   (skipnan = 0, any nq)
+ * QuantileExt::quantile_axis_mut             src/quantile/mod.rs:495-508   (skipnan = 0, nq = 1)
+ * QuantileExt::quantile_axis_skipnan_mut     src/quantile/mod.rs:510-544   (skipnan = 1; the reference
+ *                                            has only the single-q form, any nq is accepted here)
+ * Quantile1dExt::{quantile_mut,quantiles_mut} src/quantile/mod.rs:612-633  (ndim = 1, axis = 0)
+ *
+ * Error precedence as the reference: first q outside [0,1] (NaN included) in qs order ->
+ * NDS_INVALID_QUANTILE with *bad_q_index set (mod.rs:440-444, 522-524); then shape[axis] == 0 ->
+ * NDS_EMPTY_INPUT (mod.rs:446-449, 526-528); then a zero-size result -> NDS_OK, nothing written
+ * (mod.rs:451-455).  skipnan lanes without any non-NaN value yield the canonical quiet NaN
+ * (f32 0x7FC00000, f64 0x7FF8000000000000; src/maybe_nan/mod.rs:126-131); for integer dtypes skipnan
+ * is a no-op.  Synchronous: `out` is complete on return.
+ */
+nds_status nds_quantiles_axis(nds_ctx *ctx, nds_dtype dtype, const void *data, int ndim, const size_t *shape,
+                              const ptrdiff_t *strides_elems, int axis, const double *qs, size_t nq,
+                              nds_interp interp, int skipnan, void *out, size_t *bad_q_index);
+
+/*
+ * Same computation for device-resident `data` and `out`, enqueued on the ctx stream without a host
+ * synchronisation.  Argument errors are returned immediately; data-dependent conditions
+ * (NDS_NAN_IN_INPUT, NDS_CAST_OVERFLOW) are reported by the next nds_ctx_synchronize().
+ */
+nds_status nds_quantiles_axis_enqueue(nds_ctx *ctx, nds_dtype dtype, const void *data, int ndim,
+                                      const size_t *shape, const ptrdiff_t *strides_elems, int axis,
+                                      const double *qs, size_t nq, nds_interp interp, int skipnan, void *out,
+                                      size_t *bad_q_index);
+
+/*
+ * skipnan over Option<T> elements (impl MaybeNan for Option<i32> ..., src/maybe_nan/mod.rs:152-213):
+ * `valid` is a byte mask with the same shape and element strides as `data` (0 = None).  `out_valid`
+ * (C-order, result shape) receives 0 for lanes that held no Some value (the reference returns None).
+ */
+nds_status nds_quantiles_axis_masked(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8_t *valid,
+                                     int ndim, const size_t *shape, const ptrdiff_t *strides_elems, int axis,
+                                     const double *qs, size_t nq, nds_interp interp, void *out,
+                                     uint8_t *out_valid, size_t *bad_q_index);
+
+/*
+ * Sort1dExt::get_many_from_sorted_mut   src/sort.rs:121-131,184-202  (k indexes, any order, duplicates allowed)
+ * Sort1dExt::get_from_sorted_mut        src/sort.rs:99-120           (k = 1)
+ * `out_values[j]` is the element that would sit at `indexes[j]` in the sorted array; the shim sorts and
+ * de-duplicates the pairs to rebuild the reference's IndexMap (ascending keys).  Any index >= n ->
+ * NDS_INDEX_OUT_OF_BOUNDS (the reference panics).  n == 0 with k == 0 -> NDS_OK.
+ */
+nds_status nds_get_many_from_sorted(nds_ctx *ctx, nds_dtype dtype, const void *data, size_t n,
+                                    ptrdiff_t stride_elems, const size_t *indexes, size_t k, void *out_values);
+
+/* ---- one 1-D array sharded over several GPUs (one process per GPU) ------------------------ */
+
+#define NDS_UNIQUE_ID_BYTES 128
+/* Rank 0 creates the id and ships it to the others out of band (torch.distributed store, MPI, file). */
+nds_status nds_comm_get_unique_id(void *id_out /* NDS_UNIQUE_ID_BYTES */);
+nds_status nds_comm_init_rank(nds_ctx *ctx, int nranks, int rank, const void *id);
+nds_status nds_comm_destroy(nds_ctx *ctx);
+/*
+ * Quantile1dExt::quantiles_mut (src/quantile/mod.rs:623-633) over the concatenation of every rank's
+ * shard.  Collective: all ranks call with the same qs / interp / skipnan.  Per selection round each rank
+ * builds digit histograms of its own shard and the histograms are summed with ncclAllReduce on the ctx
+ * stream; element data never leaves its GPU.  Every rank receives the full result in `out` (nq values).
+ */
+nds_status nds_quantiles_1d_sharded(nds_ctx *ctx, nds_dtype dtype, const void *local_shard, size_t n_local,
+                                    const double *qs, size_t nq, nds_interp interp, int skipnan, void *out,
+                                    size_t *bad_q_index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDSTATS_B200_H */

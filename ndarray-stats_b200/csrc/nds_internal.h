@@ -1,0 +1,64 @@
+// Host-side internals shared by the translation units of libndstats_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "nds_common.cuh"
+
+struct nds_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    // grow-only device arena (scratch for staged inputs, key buffers, histograms, rank state)
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    int *d_status = nullptr;       // deferred status bits
+    int *h_status = nullptr;       // pinned mirror
+    uint64_t launches = 0;
+    std::string last_error;
+    const char *last_path = "none";
+    std::string forced_path = "auto";
+    // NCCL (dlopen'd lazily, see nds_nccl.cpp)
+    void *nccl_comm = nullptr;
+    int nranks = 1;
+    int rank = 0;
+};
+
+namespace nds {
+
+// Everything one quantile call needs once pointers are on the device.
+struct DeviceCall {
+    nds_dtype dtype;
+    const void *data;        // device pointer to the logical first element
+    const uint8_t *valid;    // optional validity mask with the same geometry (nullptr = none)
+    LaneGeom geom;
+    QuantArgs q;
+    void *out;               // device, C-order result
+    uint8_t *out_valid;      // optional, C-order result shape
+};
+
+// Arena: returns a device pointer to at least `bytes` (256-byte aligned); contents are scratch.
+cudaError_t arena_reserve(nds_ctx *ctx, size_t bytes);
+
+// --- selection paths (each returns cudaSuccess or the first launch error) -------------------------
+// CTA-per-lane MSB radix select; any dtype / stride / lane length / mask.  The correctness workhorse.
+cudaError_t launch_generic_cta(nds_ctx *ctx, const DeviceCall &c);
+// One (or few) very long lanes: grid-wide multi-pass radix select, histograms in the arena.
+// `scratch` must hold long_scratch_bytes(nq).  When ctx->nccl_comm is set and `sharded` is true the
+// per-pass histograms and element counts are summed over ranks with ncclAllReduce.
+size_t long_scratch_bytes(int nq);
+const void *long_total_count_ptr(const void *scratch, int nq);  // device address of the global element count
+cudaError_t launch_long_radix(nds_ctx *ctx, const DeviceCall &c, void *scratch, bool sharded);
+// Contiguous short lanes (f32/f64/ints up to a few thousand elements): warp-per-lane bit-sliced select
+// fed by TMA bulk copies.  Returns cudaErrorNotSupported when the call does not qualify.
+bool short_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c);
+cudaError_t launch_short_bitslice(nds_ctx *ctx, const DeviceCall &c);
+
+// NCCL shim (nds_nccl.cpp)
+int nccl_allreduce_sum_u64(nds_ctx *ctx, void *buf, size_t count, cudaStream_t stream, std::string *err);
+
+}  // namespace nds

@@ -1,0 +1,239 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Bars: bit-exact for every order statistic and for Lower/Higher/Nearest/Midpoint (-0.0 folded onto +0.0,
+SURVEY.md note Z); Linear <= 1 ulp (and in fact 0 — asserted as such where noted)."""
+import math
+
+import numpy as np
+import pytest
+
+from kat_util import assert_bit_equal, kat_array, kat_expect, load_kats, np_reference, ulp_distance
+
+pytestmark = pytest.mark.gpu
+
+KATS = load_kats()
+INTERPS = ["lower", "higher", "nearest", "midpoint", "linear"]
+ALL_DTYPES = [np.int8, np.int16, np.int32, np.int64, np.uint8, np.uint16, np.uint32, np.uint64, np.float32, np.float64]
+LINEAR_ULP_TOL = 1  # north_star: "Linear must match within 1 ulp"
+
+
+def check(ctx, oracle, a, axis, qs, interp, skipnan=False, select_impl=0):
+    st, want, _ = oracle.quantiles_axis(a, axis, qs, interp, skipnan, select_impl)
+    assert st == oracle.OK, f"oracle status {st}"
+    got = ctx.quantiles_axis(a, axis, qs, interp, skipnan=skipnan)
+    if interp == "linear" and got.dtype.kind == "f":
+        assert ulp_distance(got, want) <= LINEAR_ULP_TOL
+        assert ulp_distance(got, want) == 0  # stronger than required: same operations, same roundings
+    else:
+        assert_bit_equal(got, want, msg=f"{a.dtype} {a.shape} axis={axis} {interp} path={ctx.last_path}")
+    return got
+
+
+# ---- the reference's own known-answer tests, through the CUDA path ------------------------------------
+@pytest.mark.parametrize("case", KATS["quantile"], ids=lambda c: c["id"])
+def test_reference_kats(nds, gpu_ctx, case):
+    data = kat_array(case, none_as="mask")
+    interp = case["interp"]
+    if "error" in case:
+        with pytest.raises(nds.EmptyInput):
+            nds.quantile_axis_mut(data, case["axis"], case["qs"][0], interp, ctx=gpu_ctx)
+        return
+    if isinstance(data, tuple):  # Option<i32> lanes (tests/quantile.rs:216-246,260-268)
+        out, valid = nds.quantile_axis_skipnan_mut(data, case["axis"], case["qs"][0], interp, ctx=gpu_ctx)
+        want = kat_expect(case)
+        assert out.shape == want.shape
+        assert np.array_equal(valid, ~np.isnan(want))
+        assert np.array_equal(out[valid].astype(np.float64), want[valid])
+        return
+    if case["skipnan"]:
+        out = nds.quantile_axis_skipnan_mut(data, case["axis"], case["qs"][0], interp, ctx=gpu_ctx)
+    elif case["single"]:
+        out = nds.quantile_axis_mut(data, case["axis"], case["qs"][0], interp, ctx=gpu_ctx)
+    else:
+        out = nds.quantiles_axis_mut(data, case["axis"], case["qs"], interp, ctx=gpu_ctx)
+    if "expect_shape" in case:
+        assert list(out.shape) == case["expect_shape"]
+        return
+    want = kat_expect(case)
+    assert out.shape == want.shape
+    assert_bit_equal(np.asarray(out, dtype=np.float64), want)
+
+
+def test_quantile1d_and_errors(nds, gpu_ctx):
+    a = np.array([1, 3, 22, 10], dtype=np.int32)
+    assert nds.quantile_mut(a, 1.0, nds.Lower, ctx=gpu_ctx) == 22
+    assert nds.quantile_mut(a, 0.0, nds.Lower(), ctx=gpu_ctx) == 1
+    assert np.array_equal(a, [1, 3, 22, 10])  # input untouched
+    with pytest.raises(nds.EmptyInput):
+        nds.quantile_mut(np.zeros(0, dtype=np.float64), 0.5, nds.Linear, ctx=gpu_ctx)
+    with pytest.raises(nds.InvalidQuantile) as ei:
+        nds.quantiles_mut(a, [0.5, 1.5, -2.0], nds.Linear, ctx=gpu_ctx)
+    assert ei.value.q == 1.5 and "1.5 is not between 0. and 1. (inclusive)." == str(ei.value)
+    with pytest.raises(nds.InvalidQuantile):  # bad q beats empty input (src/quantile/mod.rs:440-449)
+        nds.quantile_mut(np.zeros(0), float("nan"), nds.Linear, ctx=gpu_ctx)
+    with pytest.raises(nds.NanInInput):
+        nds.quantile_mut(np.array([1.0, np.nan]), 0.5, nds.Lower, ctx=gpu_ctx)
+    with pytest.raises(nds.CastOverflow):
+        nds.quantile_mut(np.array([np.iinfo(np.int64).min, np.iinfo(np.int64).max]), 0.75, nds.Linear, ctx=gpu_ctx)
+    with pytest.raises(IndexError):
+        nds.quantile_axis_mut(a, 1, 0.5, nds.Lower, ctx=gpu_ctx)
+    out = nds.quantiles_axis_mut(np.zeros((5, 0)), 0, [0.1, 0.2], nds.Lower, ctx=gpu_ctx)
+    assert out.shape == (2, 0)
+
+
+# ---- dtype x strategy x layout matrix, both selectors of the oracle ------------------------------------
+@pytest.mark.parametrize("dtype", ALL_DTYPES, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("interp", INTERPS)
+def test_matrix(gpu_ctx, oracle, dtype, interp):
+    dtype = np.dtype(dtype)
+    rng = np.random.default_rng(abs(hash((dtype.name, interp))) % 2**32)
+    qs = KATS["quickcheck_qs"]["qs"] + [0.31, 0.001]
+    for shape, axis in [((9, 257), 1), ((257, 9), 0), ((3, 5, 130), 1), ((1000,), 0), ((1, 1), 1), ((4, 3, 2, 5), 3)]:
+        if dtype.kind == "f":
+            a = rng.standard_normal(shape).astype(dtype)
+            a.flat[::5] = 0.0
+            a.flat[1::11] = -0.0
+        else:
+            info = np.iinfo(dtype)
+            a = rng.integers(info.min // 2, info.max // 2, size=shape, dtype=dtype, endpoint=True)
+        check(gpu_ctx, oracle, a, axis, qs, interp)
+        # reversed / strided views: lanes along non-contiguous axes, negative strides (tests/maybe_nan.rs:5-31 spirit)
+        v = a[..., ::-2] if a.shape[-1] > 2 else a
+        check(gpu_ctx, oracle, v, axis, qs, interp, select_impl=1)
+        if a.ndim >= 2:
+            check(gpu_ctx, oracle, np.swapaxes(a, 0, -1), a.ndim - 1 - axis if axis in (0, a.ndim - 1) else axis, qs, interp)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("interp", INTERPS)
+def test_skipnan(gpu_ctx, oracle, dtype, interp):
+    rng = np.random.default_rng(11)
+    a = rng.standard_normal((61, 130)).astype(dtype)
+    a[rng.random(a.shape) < 0.1] = np.nan
+    a[:, 7] = np.nan
+    a[13, :] = np.nan
+    a[2, 2] = -np.nan
+    for axis in (0, 1):
+        for q in (0.0, 0.5, 0.37, 1.0):
+            got = check(gpu_ctx, oracle, a, axis, [q], interp, skipnan=True)
+    # all-NaN lanes give the canonical quiet NaN bit pattern
+    got = gpu_ctx.quantiles_axis(a, 0, [0.5], interp, skipnan=True)
+    canonical = {4: 0x7FC00000, 8: 0x7FF8000000000000}[np.dtype(dtype).itemsize]
+    ut = {4: np.uint32, 8: np.uint64}[np.dtype(dtype).itemsize]
+    assert int(got.view(ut)[0, 7]) == canonical
+
+
+def test_ties_and_extremes(gpu_ctx, oracle):
+    rng = np.random.default_rng(5)
+    for dtype in (np.uint32, np.int64, np.float32, np.float64):
+        a = rng.integers(0, 16, size=(33, 4096)).astype(dtype)           # 16 distinct values (C5-style)
+        for interp in ("lower", "higher", "midpoint"):
+            check(gpu_ctx, oracle, a, 1, [0.1, 0.5, 0.9], interp, select_impl=1)
+        b = np.full((4, 1000), 7, dtype=dtype)                           # all equal
+        check(gpu_ctx, oracle, b, 1, [0.0, 0.5, 1.0], "nearest", select_impl=1)
+    f = np.array([np.inf, -np.inf, 0.0, -0.0, 1e-45, -1e-45, 3.4e38, -3.4e38] * 5, dtype=np.float32)
+    for interp in INTERPS:
+        check(gpu_ctx, oracle, f, 0, [0.0, 0.13, 0.5, 0.77, 1.0], interp)
+    # Nearest exactly at fraction 0.5 goes up (src/quantile/interpolate.rs:92)
+    assert gpu_ctx.quantiles_axis(np.array([10.0, 20.0]), 0, [0.5], "nearest")[0] == 20.0
+    # extremes of the integer ranges with the wrapping Midpoint
+    for dtype in (np.int8, np.int32, np.int64, np.uint64):
+        info = np.iinfo(dtype)
+        e = np.array([info.min, info.max, info.min, info.max, 0], dtype=dtype)
+        for interp in ("lower", "higher", "nearest", "midpoint"):
+            check(gpu_ctx, oracle, e, 0, [0.0, 0.4, 0.5, 0.6, 1.0], interp)
+
+
+def test_bulk_equals_single_property(nds, gpu_ctx):
+    """tests/quantile.rs:281-419 — bulk == per-q for unordered qs with a duplicate, all strategies."""
+    rng = np.random.default_rng(3)
+    qs = KATS["quickcheck_qs"]["qs"]
+    v = rng.integers(-2**62, 2**62, size=300, dtype=np.int64)
+    m = rng.integers(0, 2**63, size=(17, 17), dtype=np.uint64)
+    for interp in (nds.Lower, nds.Higher, nds.Nearest, nds.Midpoint, nds.Linear):
+        bulk = nds.quantiles_mut(v, qs, interp, ctx=gpu_ctx)
+        for t, q in enumerate(qs):
+            assert nds.quantile_mut(v, q, interp, ctx=gpu_ctx) == bulk[t]
+        bulk = nds.quantiles_axis_mut(m, 0, qs, interp, ctx=gpu_ctx)
+        for t, q in enumerate(qs):
+            assert np.array_equal(nds.quantile_axis_mut(m, 0, q, interp, ctx=gpu_ctx), bulk[t])
+
+
+def test_sort1d_ext(nds, gpu_ctx):
+    """tests/sort.rs:35-86 on the device: get_from_sorted == sort; get_many with every index twice == sort."""
+    k = KATS["get_from_sorted"]
+    a = np.array(k["data"], dtype=np.int64)
+    for i, want in k["cases"]:
+        assert nds.get_from_sorted_mut(a, i, ctx=gpu_ctx) == want
+    rng = np.random.default_rng(9)
+    xs = rng.integers(-2**63, 2**63 - 1, size=257, dtype=np.int64)
+    got = nds.get_many_from_sorted_mut(xs, list(range(257)) * 2, ctx=gpu_ctx)
+    assert list(got.keys()) == list(range(257))
+    assert np.array_equal(np.array(list(got.values())), np.sort(xs))
+    with pytest.raises(IndexError):
+        nds.get_from_sorted_mut(a, 4, ctx=gpu_ctx)
+    assert nds.get_many_from_sorted_mut(a, [], ctx=gpu_ctx) == {}
+
+
+@pytest.mark.parametrize("path", ["generic_cta", "long_radix"])
+def test_forced_paths_agree(gpu_ctx, oracle, path):
+    rng = np.random.default_rng(21)
+    try:
+        gpu_ctx.force_path(path)
+        for dtype in (np.float64, np.float32, np.int16, np.uint64):
+            a = (rng.standard_normal((3, 5000)) * 1000).astype(dtype)
+            for interp in INTERPS:
+                check(gpu_ctx, oracle, a, 1, np.arange(1, 100) / 100.0, interp)
+                assert gpu_ctx.last_path == path
+            check(gpu_ctx, oracle, a.astype(np.float64) if dtype in (np.float32, np.float64) else a, 0, [0.5], "lower")
+        b = rng.standard_normal(70001)
+        b[rng.random(b.size) < 0.2] = np.nan
+        check(gpu_ctx, oracle, b, 0, [0.01, 0.5, 0.99], "linear", skipnan=True)
+        check(gpu_ctx, oracle, np.full(100, np.nan), 0, [0.5], "linear", skipnan=True)
+    finally:
+        gpu_ctx.force_path("auto")
+
+
+def test_device_resident_and_enqueue(nds, gpu_ctx, oracle):
+    import torch
+    rng = np.random.default_rng(2)
+    a = rng.random((128, 4096), dtype=np.float32)
+    t = torch.from_numpy(a).cuda()
+    out = nds.quantile_axis_mut(t, 1, 0.5, nds.Midpoint, ctx=gpu_ctx)
+    st, want, _ = oracle.quantiles_axis(a, 1, [0.5], "midpoint")
+    assert_bit_equal(out.cpu().numpy(), want[:, 0])
+    # column lanes of the same tensor (strided), enqueue + deferred status
+    out2 = gpu_ctx.quantiles_axis(t, 0, [0.25, 0.75], "linear", enqueue=True)
+    gpu_ctx.synchronize()
+    st, want2, _ = oracle.quantiles_axis(a, 0, [0.25, 0.75], "linear")
+    assert ulp_distance(out2.cpu().numpy(), want2) == 0
+    t[3, 5] = float("nan")
+    gpu_ctx.quantiles_axis(t, 1, [0.5], "lower", enqueue=True)
+    with pytest.raises(nds.NanInInput):
+        gpu_ctx.synchronize()
+    gpu_ctx.synchronize()  # status was cleared
+
+
+def test_full_size_properties_c2(nds, gpu_ctx):
+    """BASELINE config 2 at full size (65536 x 4096 f32, row medians, Midpoint): size-independent checks —
+    the median splits each row in half (rank property), is invariant under row reversal, and the
+    checksum over rows matches the checksum of per-block results."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(1002)
+    t = torch.rand((65536, 4096), generator=g, device="cuda", dtype=torch.float32)
+    lo = nds.quantile_axis_mut(t, 1, 0.5, nds.Lower, ctx=gpu_ctx)
+    hi = nds.quantile_axis_mut(t, 1, 0.5, nds.Higher, ctx=gpu_ctx)
+    mid = nds.quantile_axis_mut(t, 1, 0.5, nds.Midpoint, ctx=gpu_ctx)
+    # rank property: exactly 2047 elements strictly below-or-tied-before `lo`, i.e. count(< lo) <= 2047 < count(<= lo)
+    lt = (t < lo[:, None]).sum(1)
+    le = (t <= lo[:, None]).sum(1)
+    assert bool(((lt <= 2047) & (le > 2047)).all())
+    lt = (t < hi[:, None]).sum(1)
+    le = (t <= hi[:, None]).sum(1)
+    assert bool(((lt <= 2048) & (le > 2048)).all())
+    want_mid = lo + (hi - lo) / 2
+    assert torch.equal(mid, want_mid)
+    rev = nds.quantile_axis_mut(t.flip(1), 1, 0.5, nds.Midpoint, ctx=gpu_ctx)
+    assert torch.equal(rev, mid)
+    blocks = torch.cat([nds.quantile_axis_mut(t[i:i + 8192], 1, 0.5, nds.Midpoint, ctx=gpu_ctx) for i in range(0, 65536, 8192)])
+    assert torch.equal(blocks, mid)

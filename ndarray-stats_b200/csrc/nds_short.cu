@@ -1,6 +1,487 @@
-// Contiguous short lanes — placeholder until the bit-sliced kernel lands.
+// Contiguous short lanes (up to 4096 elements of a 4- or 8-byte type): warp-per-lane, bit-sliced
+// MSB-first selection, lanes staged through shared memory by 1-D TMA bulk copies.
+//
+// Why not the shared-memory digit histogram: a shared atomic costs ~2 cycles per element per SM
+// (B300_MICROARCH.md "ATOMS"), i.e. <= 0.5 element/cycle/SM, while streaming f32 lanes at the HBM
+// roofline needs ~5.8 elements/cycle/SM.  Here every warp owns one lane:
+//   1. the lane arrives in the warp's shared-memory buffer by cp.async.bulk (TMA) + mbarrier, the
+//      next lane's copy is issued as soon as this one has been consumed, so HBM always has
+//      (warps per SM) x (lane bytes) in flight;
+//   2. each thread transposes 32 elements x 16 key bits into 16 "plane" words (bit b of 32 elements)
+//      with byte-permute / shift-mask butterflies (~4 instructions per element);
+//   3. selection walks the key bits MSB-first: count = popc(candidates & plane) summed over the warp
+//      with one REDUX, keep the side that contains the rank.  One step costs ~20 instructions for
+//      4096 elements instead of 2 per element;
+//   4. as soon as <= 32 candidates remain they are gathered (from L2) and ranked directly.
+// Key bits beyond the first 16 are handled by further rounds that re-read the lane (L2-resident).
+// No key transform is applied: the walk interprets IEEE sign / two's-complement sign on the fly.
+#include <type_traits>
+
 #include "nds_internal.h"
+
 namespace nds {
-bool short_bitslice_supported(const nds_ctx *, const DeviceCall &) { return false; }
-cudaError_t launch_short_bitslice(nds_ctx *, const DeviceCall &) { return cudaErrorNotSupported; }
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "NDS_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra NDS_DONE;\n"
+        "bra NDS_WAIT;\n"
+        "NDS_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk tensor copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 16 words holding 32 16-bit fields (word k: field of slot 2k in the low half, slot 2k+1 in the high half)
+// -> 16 plane words: word b, bit p = bit b of the field of slot 2*(p&15) + (p>>4).
+__device__ __forceinline__ void transpose16(uint32_t (&w)[16]) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        uint32_t a = w[r], b = w[r + 8];
+        w[r] = __byte_perm(a, b, 0x6240);
+        w[r + 8] = __byte_perm(a, b, 0x7351);
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        if (r & 4) continue;
+        uint32_t a = w[r], b = w[r + 4];
+        w[r] = (a & 0x0F0F0F0Fu) | ((b << 4) & 0xF0F0F0F0u);
+        w[r + 4] = ((a >> 4) & 0x0F0F0F0Fu) | (b & 0xF0F0F0F0u);
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        if (r & 2) continue;
+        uint32_t a = w[r], b = w[r + 2];
+        w[r] = (a & 0x33333333u) | ((b << 2) & 0xCCCCCCCCu);
+        w[r + 2] = ((a >> 2) & 0x33333333u) | (b & 0xCCCCCCCCu);
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        if (r & 1) continue;
+        uint32_t a = w[r], b = w[r + 1];
+        w[r] = (a & 0x55555555u) | ((b << 1) & 0xAAAAAAAAu);
+        w[r + 1] = ((a >> 1) & 0x55555555u) | (b & 0xAAAAAAAAu);
+    }
+}
+
+template <typename T> struct RawBits;
+template <> struct RawBits<float> { using U = uint32_t; };
+template <> struct RawBits<double> { using U = uint64_t; };
+template <> struct RawBits<int32_t> { using U = uint32_t; };
+template <> struct RawBits<uint32_t> { using U = uint32_t; };
+template <> struct RawBits<int64_t> { using U = uint64_t; };
+template <> struct RawBits<uint64_t> { using U = uint64_t; };
+
+template <typename T> __device__ __forceinline__ T from_raw(typename RawBits<T>::U r) {
+    T x;
+    memcpy(&x, &r, sizeof x);
+    return x;
+}
+template <typename T> __device__ __forceinline__ typename RawBits<T>::U to_raw(T x) {
+    typename RawBits<T>::U r;
+    memcpy(&r, &x, sizeof x);
+    return r;
+}
+
+template <typename T, int NB>
+__global__ void __launch_bounds__(NB >= 4 ? 384 : 512, 1)
+short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__restrict__ out, unsigned buf_bytes) {
+    using Tr = Traits<T>;
+    using Key = typename Tr::Key;   // order-preserving key (only used to rank the final <= 32 candidates)
+    using Raw = typename RawBits<T>::U;
+    constexpr int ES = (int)sizeof(T);
+    constexpr int VEC = 16 / ES;          // elements per 16-byte chunk
+    constexpr int LD_PER_BLK = 32 / VEC;  // 16-byte loads per thread per 32-element block
+    constexpr int ROUNDS = ES * 8 / 16;   // 16 key bits per round
+    constexpr int KEYBITS = ES * 8;
+    constexpr bool IS_FLOAT = Tr::is_float;
+    constexpr bool TOP_INVERTED = IS_FLOAT || std::is_signed<T>::value;  // sign bit set => smaller
+    constexpr unsigned FULL = 0xffffffffu;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+    unsigned char *buf = smem + (size_t)warp * buf_bytes;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)W * buf_bytes) + warp;
+    unsigned *clist = reinterpret_cast<unsigned *>(smem + (size_t)W * buf_bytes + (size_t)W * 8) + warp * 32;
+
+    const unsigned n = (unsigned)g.axis_len;
+    const unsigned lane_bytes = n * ES;
+    const unsigned n_chunks = lane_bytes / 16;
+
+    // element index of slot s (0..31) of block blk held by this thread
+    auto elem_index = [&](int blk, int s) -> unsigned {
+        if (ES == 4) return (unsigned)(((blk * LD_PER_BLK + (s >> 2)) * 32 + lane) * 4 + (s & 3));
+        return (unsigned)(((blk * LD_PER_BLK + (s >> 1)) * 32 + lane) * 2 + (s & 1));
+    };
+    auto slot_of_pos = [](int p) -> int { return 2 * (p & 15) + (p >> 4); };
+
+    uint32_t valid[NB];
+#pragma unroll
+    for (int blk = 0; blk < NB; ++blk) {
+        uint32_t v = 0;
+        for (int p = 0; p < 32; ++p)
+            if (elem_index(blk, slot_of_pos(p)) < n) v |= 1u << p;
+        valid[blk] = v;
+    }
+
+    if (lane == 0) mbar_init(bar, 1);
+    fence_mbar_init();
+    __syncwarp();
+
+    const unsigned long long nw = (unsigned long long)gridDim.x * W;
+    unsigned long long L = (unsigned long long)blockIdx.x * W + warp;
+    unsigned parity = 0;
+    auto issue = [&](unsigned long long lane_id) {
+        long long io, oo;
+        lane_offsets(g, lane_id, io, oo);
+        if (lane == 0) {
+            mbar_expect_tx(bar, lane_bytes);
+            tma_load_1d(buf, data + io, lane_bytes, bar);
+        }
+    };
+    if (L < g.nlanes) issue(L);
+
+    uint32_t P[NB][16];
+
+    // Build the 16 planes of round `round` (key bits [KEYBITS-16*(round+1), KEYBITS-16*round)) for all blocks.
+    // src: the warp's shared-memory buffer (round 0) or the lane in global memory (later rounds; L2-resident).
+    auto build = [&](auto from_smem_tag, const unsigned char *gsrc, int round) {
+        constexpr bool from_smem = decltype(from_smem_tag)::value;
+#pragma unroll
+        for (int blk = 0; blk < NB; ++blk) {
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < LD_PER_BLK; ++j) {
+                const unsigned chunk = (unsigned)((blk * LD_PER_BLK + j) * 32 + lane);
+                uint4 q = make_uint4(0, 0, 0, 0);
+                if (chunk < n_chunks) {
+                    if constexpr (from_smem) q = *reinterpret_cast<const uint4 *>(buf + (size_t)chunk * 16);
+                    else q = __ldg(reinterpret_cast<const uint4 *>(gsrc + (size_t)chunk * 16));
+                }
+                if constexpr (ES == 4) {
+                    const unsigned sel = (round == 0) ? 0x7632u : 0x5410u;
+                    w[2 * j] = __byte_perm(q.x, q.y, sel);
+                    w[2 * j + 1] = __byte_perm(q.z, q.w, sel);
+                } else {
+                    const unsigned sel = (round & 1) ? 0x5410u : 0x7632u;
+                    const uint32_t w0 = (round < 2) ? q.y : q.x, w1 = (round < 2) ? q.w : q.z;
+                    w[j] = __byte_perm(w0, w1, sel);
+                }
+            }
+            transpose16(w);
+#pragma unroll
+            for (int b = 0; b < 16; ++b) P[blk][b] = w[b];
+        }
+    };
+
+    for (; L < g.nlanes; L += nw) {
+        long long in_off, out_off;
+        lane_offsets(g, L, in_off, out_off);
+        const T *lp = data + in_off;
+
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        build(std::true_type{}, nullptr, 0);
+
+        // ---- NaN handling (floats): elements with an all-ones exponent are inspected individually ----
+        uint32_t init_mask[NB];
+        unsigned n_eff = n;
+#pragma unroll
+        for (int blk = 0; blk < NB; ++blk) init_mask[blk] = valid[blk];
+        if (IS_FLOAT) {
+            uint32_t special_any = 0;
+            uint32_t special[NB];
+#pragma unroll
+            for (int blk = 0; blk < NB; ++blk) {
+                uint32_t e = valid[blk];
+                constexpr int EXP_LO = (ES == 4) ? 7 : 4;  // exponent bits inside the top 16-bit field
+#pragma unroll
+                for (int b = EXP_LO; b <= 14; ++b) e &= P[blk][b];
+                special[blk] = e;
+                special_any |= e;
+            }
+            if (__any_sync(FULL, special_any != 0)) {
+                unsigned my_nan = 0;
+#pragma unroll
+                for (int blk = 0; blk < NB; ++blk) {
+                    uint32_t bits = special[blk];
+                    while (bits) {
+                        int p = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        T x = *reinterpret_cast<const T *>(buf + (size_t)elem_index(blk, slot_of_pos(p)) * ES);
+                        if (x != x) {
+                            init_mask[blk] &= ~(1u << p);
+                            my_nan += 1;
+                        }
+                    }
+                }
+                unsigned nan_total = __reduce_add_sync(FULL, my_nan);
+                if (nan_total) {
+                    if (!qa.skipnan && lane == 0) atomicOr(qa.status, STATUS_BIT_NAN);
+                    n_eff = n - nan_total;  // non-skipnan: result is meaningless (status is raised) but stays in bounds
+                }
+            }
+        }
+        __syncwarp();
+        // the buffer has been consumed: start the next lane's copy now so it overlaps the selection
+        if (L + nw < g.nlanes) {
+            fence_proxy_async();
+            issue(L + nw);
+        }
+
+        if (n_eff == 0) {
+            for (int t = lane; t < qa.nq; t += 32) out[out_off + (long long)t * g.out_axis_stride] = canonical_nan<T>();
+            continue;
+        }
+
+        bool planes_dirty = false;  // P no longer holds round 0
+
+        // ---- select rank r (and r+1 when want_next): returns raw bit patterns --------------------------
+        auto select = [&](unsigned r, bool want_next, Raw &raw_r, Raw &raw_next) {
+            for (int pass = 0; pass < 2; ++pass) {  // pass 1 only when r+1 fell outside r's final bucket
+                const unsigned target = r + (unsigned)pass;
+                if (planes_dirty) {
+                    build(std::false_type{}, reinterpret_cast<const unsigned char *>(lp), 0);
+                    planes_dirty = false;
+                }
+                uint32_t m[NB];
+#pragma unroll
+                for (int blk = 0; blk < NB; ++blk) m[blk] = init_mask[blk];
+                unsigned total = n_eff, rem = target;
+                bool neg = false;
+                Raw prefix = 0;
+                bool small = false;
+                for (int round = 0; round < ROUNDS && !small; ++round) {
+                    if (round > 0) {
+                        build(std::false_type{}, reinterpret_cast<const unsigned char *>(lp), round);
+                        planes_dirty = true;
+                    }
+#pragma unroll
+                    for (int b = 15; b >= 0; --b) {
+                        if (total <= 32) {
+                            small = true;
+                            break;
+                        }
+                        unsigned ones = 0;
+#pragma unroll
+                        for (int blk = 0; blk < NB; ++blk) ones += __popc(m[blk] & P[blk][b]);
+                        ones = __reduce_add_sync(FULL, ones);
+                        const bool ones_small = (round == 0 && b == 15) ? TOP_INVERTED : (IS_FLOAT && neg);
+                        const unsigned small_cnt = ones_small ? ones : total - ones;
+                        const bool take_small = rem < small_cnt;
+                        const bool bit = take_small ? ones_small : !ones_small;
+                        total = take_small ? small_cnt : total - small_cnt;
+                        rem = take_small ? rem : rem - small_cnt;
+#pragma unroll
+                        for (int blk = 0; blk < NB; ++blk) m[blk] &= bit ? P[blk][b] : ~P[blk][b];
+                        prefix |= (Raw)(bit ? 1u : 0u) << (KEYBITS - 1 - (round * 16 + (15 - b)));
+                        if (round == 0 && b == 15 && IS_FLOAT) neg = bit;
+                    }
+                }
+                Raw found, found_next = 0;
+                bool have_next = false;
+                if (!small && total > 32) {
+                    // every key bit decided: all remaining candidates are equal to `prefix`
+                    found = prefix;
+                    if (rem + 1 < total) {
+                        found_next = prefix;
+                        have_next = true;
+                    }
+                } else {
+                    // gather the <= 32 candidates and rank them by full key
+                    unsigned mycnt = 0;
+#pragma unroll
+                    for (int blk = 0; blk < NB; ++blk) mycnt += __popc(m[blk]);
+                    unsigned incl = mycnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        unsigned tt = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= d) incl += tt;
+                    }
+                    unsigned base = incl - mycnt;
+#pragma unroll
+                    for (int blk = 0; blk < NB; ++blk) {
+                        uint32_t bits = m[blk];
+                        while (bits) {
+                            int p = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            clist[base++] = elem_index(blk, slot_of_pos(p));
+                        }
+                    }
+                    __syncwarp();
+                    Raw myraw = 0;
+                    Key mykey = 0;
+                    if ((unsigned)lane < total) {
+                        T x = lp[clist[lane]];
+                        myraw = to_raw<T>(x);
+                        mykey = Tr::to_key(x);
+                    }
+                    __syncwarp();
+                    unsigned less = 0;
+                    for (unsigned j = 0; j < total; ++j) {
+                        Key kj = __shfl_sync(FULL, mykey, (int)j);
+                        less += (kj < mykey || (kj == mykey && j < (unsigned)lane)) ? 1u : 0u;
+                    }
+                    unsigned hit = __ballot_sync(FULL, (unsigned)lane < total && less == rem);
+                    found = __shfl_sync(FULL, myraw, __ffs(hit) - 1);
+                    if (rem + 1 < total) {
+                        unsigned hit2 = __ballot_sync(FULL, (unsigned)lane < total && less == rem + 1);
+                        found_next = __shfl_sync(FULL, myraw, __ffs(hit2) - 1);
+                        have_next = true;
+                    }
+                }
+                if (pass == 0) {
+                    raw_r = found;
+                    if (!want_next) return;
+                    if (have_next) {
+                        raw_next = found_next;
+                        return;
+                    }
+                } else {
+                    raw_next = found;
+                }
+            }
+        };
+
+        // ---- every requested quantile of the lane (src/quantile/mod.rs:475-487) ------------------------
+        unsigned cache_rank[2] = {0xffffffffu, 0xffffffffu};
+        Raw cache_raw[2] = {0, 0};
+        auto remember = [&](unsigned r, Raw v) {
+            cache_rank[1] = cache_rank[0];
+            cache_raw[1] = cache_raw[0];
+            cache_rank[0] = r;
+            cache_raw[0] = v;
+        };
+        auto lookup = [&](unsigned r, Raw &v) -> bool {
+            if (r == cache_rank[0]) { v = cache_raw[0]; return true; }
+            if (r == cache_rank[1]) { v = cache_raw[1]; return true; }
+            return false;
+        };
+        for (int t = 0; t < qa.nq; ++t) {
+            RankMath rm = slot_rank_math(qa, t, n_eff);
+            const bool nl = needs_lower(qa.interp, rm.frac), nh = needs_higher(qa.interp, rm.frac);
+            const unsigned rl = (unsigned)rm.lower, rh = (unsigned)rm.higher;
+            Raw vl = 0, vh = 0;
+            for (;;) {
+                const bool have_l = !nl || lookup(rl, vl);
+                const bool have_h = !nh || lookup(rh, vh);
+                if (have_l && have_h) break;
+                const unsigned r = !have_l ? rl : rh;
+                const bool want_next = !have_l && !have_h && rh == rl + 1;
+                Raw a = 0, b = 0;
+                select(r, want_next, a, b);
+                remember(r, a);
+                if (want_next) remember(r + 1, b);
+            }
+            if (lane == 0) {
+                out[out_off + (long long)t * g.out_axis_stride] =
+                    interpolate<T>(qa.interp, from_raw<T>(vl), from_raw<T>(vh), rm.frac, qa.status);
+            }
+        }
+    }
+}
+
+template <typename T> constexpr bool short_type_ok() {
+    return std::is_same<T, float>::value || std::is_same<T, double>::value || std::is_same<T, int32_t>::value ||
+           std::is_same<T, uint32_t>::value || std::is_same<T, int64_t>::value || std::is_same<T, uint64_t>::value;
+}
+
+struct ShortPlan {
+    bool ok = false;
+    int nb = 0, warps = 0;
+    unsigned buf_bytes = 0;
+    size_t smem = 0;
+};
+
+ShortPlan plan_short(const nds_ctx *ctx, const DeviceCall &c) {
+    ShortPlan p;
+    size_t es = 0;
+    switch (c.dtype) {
+    case NDS_F32: case NDS_I32: case NDS_U32: es = 4; break;
+    case NDS_F64: case NDS_I64: case NDS_U64: es = 8; break;
+    default: return p;
+    }
+    const LaneGeom &g = c.geom;
+    if (c.valid || c.out_valid) return p;
+    if (g.axis_stride != 1 || g.axis_len < 64 || g.axis_len > 4096) return p;
+    if ((g.axis_len * es) % 16 != 0) return p;
+    if (((uintptr_t)c.data) % 16 != 0) return p;
+    for (int d = 0; d < g.n_outer; ++d)
+        if (g.oshape[d] > 1 && ((g.in_ostride[d] * (long long)es) % 16) != 0) return p;
+    if (g.nlanes < 64) return p;  // too few lanes to fill the machine warp-per-lane
+    p.nb = g.axis_len <= 1024 ? 1 : (g.axis_len <= 2048 ? 2 : 4);
+    size_t lane_bytes = g.axis_len * es;
+    p.buf_bytes = (unsigned)((lane_bytes + 127) / 128 * 128);
+    size_t per_warp = p.buf_bytes + 8 + 128;
+    size_t budget = (size_t)ctx->max_smem_optin > 4096 ? (size_t)ctx->max_smem_optin - 1024 : 0;
+    int maxw = p.nb >= 4 ? 12 : 16;
+    p.warps = (int)std::min<size_t>((size_t)maxw, budget / per_warp);
+    if (p.warps < 4) return p;
+    p.smem = (size_t)p.warps * per_warp;
+    p.ok = true;
+    return p;
+}
+
+template <typename T, int NB>
+cudaError_t launch_short_nb(nds_ctx *ctx, const DeviceCall &c, const ShortPlan &p) {
+    auto kernel = short_bitslice_kernel<T, NB>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return e;
+    unsigned long long need = (c.geom.nlanes + p.warps - 1) / p.warps;
+    unsigned grid = (unsigned)std::min<unsigned long long>(need, (unsigned long long)ctx->sm_count);
+    kernel<<<grid, p.warps * 32, p.smem, ctx->stream>>>((const T *)c.data, c.geom, c.q, (T *)c.out, p.buf_bytes);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_short_typed(nds_ctx *ctx, const DeviceCall &c, const ShortPlan &p) {
+    switch (p.nb) {
+    case 1: return launch_short_nb<T, 1>(ctx, c, p);
+    case 2: return launch_short_nb<T, 2>(ctx, c, p);
+    default: return launch_short_nb<T, 4>(ctx, c, p);
+    }
+}
+
+}  // namespace
+
+bool short_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c) { return plan_short(ctx, c).ok; }
+
+cudaError_t launch_short_bitslice(nds_ctx *ctx, const DeviceCall &c) {
+    ShortPlan p = plan_short(ctx, c);
+    if (!p.ok) return cudaErrorNotSupported;
+    ctx->last_path = "short_bitslice";
+    switch (c.dtype) {
+    case NDS_F32: return launch_short_typed<float>(ctx, c, p);
+    case NDS_F64: return launch_short_typed<double>(ctx, c, p);
+    case NDS_I32: return launch_short_typed<int32_t>(ctx, c, p);
+    case NDS_U32: return launch_short_typed<uint32_t>(ctx, c, p);
+    case NDS_I64: return launch_short_typed<int64_t>(ctx, c, p);
+    case NDS_U64: return launch_short_typed<uint64_t>(ctx, c, p);
+    default: return cudaErrorNotSupported;
+    }
+}
+
 }  // namespace nds

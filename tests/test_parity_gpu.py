@@ -237,3 +237,92 @@ def test_full_size_properties_c2(nds, gpu_ctx):
     assert torch.equal(rev, mid)
     blocks = torch.cat([nds.quantile_axis_mut(t[i:i + 8192], 1, 0.5, nds.Midpoint, ctx=gpu_ctx) for i in range(0, 65536, 8192)])
     assert torch.equal(blocks, mid)
+
+
+SHORT_DTYPES = [np.float32, np.float64, np.int32, np.uint32, np.int64, np.uint64]
+
+
+@pytest.mark.parametrize("dtype", SHORT_DTYPES, ids=lambda d: np.dtype(d).name)
+def test_short_bitslice_path(gpu_ctx, oracle, dtype):
+    """The warp-per-lane bit-sliced kernel on every layout class it accepts, incl. data that needs the
+    later 16-bit rounds (clustered / tie-heavy values) and lane lengths that are not multiples of 1024."""
+    dtype = np.dtype(dtype)
+    rng = np.random.default_rng(abs(hash(dtype.name)) % 2**32)
+    qs_sets = {"midpoint": [0.5], "linear": [0.25, 0.5, 0.75], "lower": [0.0, 0.1, 0.5, 0.9, 1.0],
+               "higher": [0.999, 0.001, 0.5, 0.5], "nearest": [0.3, 0.7]}
+    vec = 16 // dtype.itemsize
+    try:
+        gpu_ctx.force_path("short_bitslice")
+        for n in (4096, 2048, 1024, 64, 100, 4096 - vec, 1028, 2052):
+            lanes = 150
+            kinds = ["normal", "uniform", "clustered", "ties", "equal", "extremes"]
+            for kind in kinds:
+                if dtype.kind == "f":
+                    if kind == "normal":
+                        a = rng.standard_normal((lanes, n))
+                    elif kind == "uniform":
+                        a = rng.random((lanes, n))
+                    elif kind == "clustered":
+                        a = 1000.0 + rng.random((lanes, n)) * 1e-4
+                    elif kind == "ties":
+                        a = rng.integers(-8, 8, size=(lanes, n)).astype(np.float64)
+                    elif kind == "equal":
+                        a = np.full((lanes, n), -3.25)
+                    else:
+                        a = rng.standard_normal((lanes, n))
+                        a[:, ::7] = np.inf
+                        a[:, 1::13] = -np.inf
+                        a[:, 2::17] = 0.0
+                        a[:, 3::19] = -0.0
+                        a[:, 5::23] = np.finfo(dtype).tiny / 4   # subnormal
+                    a = a.astype(dtype)
+                else:
+                    info = np.iinfo(dtype)
+                    if kind in ("normal", "uniform"):
+                        a = rng.integers(info.min // 2, info.max // 2, size=(lanes, n), dtype=dtype, endpoint=True)
+                    elif kind == "clustered":
+                        a = (rng.integers(0, 1000, size=(lanes, n)) + 10**6).astype(dtype)
+                    elif kind == "ties":
+                        a = rng.integers(0, 16, size=(lanes, n)).astype(dtype)
+                    elif kind == "equal":
+                        a = np.full((lanes, n), 7, dtype=dtype)
+                    else:
+                        a = rng.choice(np.array([info.min, info.max, 0, 1], dtype=dtype), size=(lanes, n))
+                for interp, qs in qs_sets.items():
+                    if dtype.kind != "f" and interp == "linear" and kind == "extremes":
+                        continue  # from_f64 overflow is covered elsewhere
+                    check(gpu_ctx, oracle, a, 1, qs, interp, select_impl=1 if kind in ("ties", "equal", "extremes") else 0)
+                    assert gpu_ctx.last_path == "short_bitslice"
+        # a 3-d array whose last axis is the lane; and a column-sliced (pitched) 2-d view with aligned pitch
+        a = rng.standard_normal((5, 40, 512)).astype(dtype) if dtype.kind == "f" else rng.integers(0, 1000, size=(5, 40, 512)).astype(dtype)
+        check(gpu_ctx, oracle, a, 2, [0.5, 0.9], "lower")
+        assert gpu_ctx.last_path == "short_bitslice"
+        wide = rng.standard_normal((200, 1024)).astype(dtype) if dtype.kind == "f" else rng.integers(0, 10**6, size=(200, 1024)).astype(dtype)
+        check(gpu_ctx, oracle, wide[:, :512], 1, [0.5], "higher")
+        assert gpu_ctx.last_path == "short_bitslice"
+    finally:
+        gpu_ctx.force_path("auto")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=lambda d: np.dtype(d).name)
+def test_short_bitslice_nan(nds, gpu_ctx, oracle, dtype):
+    rng = np.random.default_rng(77)
+    a = rng.standard_normal((130, 2048)).astype(dtype)
+    a[rng.random(a.shape) < 0.1] = np.nan
+    a[5, :] = np.nan
+    a[6, :-3] = np.nan
+    a[7, 11] = np.inf
+    a[8, 12] = -np.nan
+    try:
+        gpu_ctx.force_path("short_bitslice")
+        for interp in INTERPS:
+            for q in (0.0, 0.5, 0.77, 1.0):
+                check(gpu_ctx, oracle, a, 1, [q], interp, skipnan=True)
+                assert gpu_ctx.last_path == "short_bitslice"
+        with pytest.raises(nds.NanInInput):
+            gpu_ctx.quantiles_axis(a, 1, [0.5], "lower")
+        b = np.where(np.isnan(a), 0, a)
+        b[3, 3] = np.inf
+        check(gpu_ctx, oracle, b, 1, [0.5, 1.0], "linear")
+    finally:
+        gpu_ctx.force_path("auto")

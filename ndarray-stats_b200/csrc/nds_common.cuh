@@ -31,11 +31,17 @@ __host__ __device__ inline void lane_offsets(const LaneGeom &g, unsigned long lo
                                              long long &out_off) {
     in_off = 0;
     out_off = 0;
-    for (int d = g.n_outer - 1; d >= 0; --d) {
-        unsigned long long c = lane % g.oshape[d];
-        lane /= g.oshape[d];
+#pragma unroll 1
+    for (int d = g.n_outer - 1; d >= 1; --d) {  // 64-bit division only for arrays with >= 3 dims
+        const unsigned long long q = lane / g.oshape[d];
+        const unsigned long long c = lane - q * g.oshape[d];
+        lane = q;
         in_off += (long long)c * g.in_ostride[d];
         out_off += (long long)c * g.out_ostride[d];
+    }
+    if (g.n_outer >= 1) {  // lane < nlanes, so what is left is the coordinate of the outermost dim
+        in_off += (long long)lane * g.in_ostride[0];
+        out_off += (long long)lane * g.out_ostride[0];
     }
 }
 

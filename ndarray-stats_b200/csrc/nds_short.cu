@@ -105,8 +105,11 @@ template <typename T> __device__ __forceinline__ typename RawBits<T>::U to_raw(T
     return r;
 }
 
+// Per-warp shared memory: [lane buffer: buf_bytes][planes: 16 x NB x 32 words][vm: NB x 32][im: NB x 32]
+template <int NB> __host__ __device__ constexpr unsigned short_warp_extra_bytes() { return 16u * NB * 128u + 2u * NB * 128u; }
+
 template <typename T, int NB>
-__global__ void __launch_bounds__(NB >= 4 ? 384 : 512, 1)
+__global__ void __launch_bounds__(512, 1)
 short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__restrict__ out, unsigned buf_bytes) {
     using Tr = Traits<T>;
     using Key = typename Tr::Key;   // order-preserving key (only used to rank the final <= 32 candidates)
@@ -118,32 +121,37 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
     constexpr int KEYBITS = ES * 8;
     constexpr bool IS_FLOAT = Tr::is_float;
     constexpr bool TOP_INVERTED = IS_FLOAT || std::is_signed<T>::value;  // sign bit set => smaller
+    constexpr int EXP_LO = (ES == 4) ? 7 : 4;  // exponent bits inside the top 16-bit field: [EXP_LO, 14]
     constexpr unsigned FULL = 0xffffffffu;
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
-    unsigned char *buf = smem + (size_t)warp * buf_bytes;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)W * buf_bytes) + warp;
-    unsigned *clist = reinterpret_cast<unsigned *>(smem + (size_t)W * buf_bytes + (size_t)W * 8) + warp * 32;
+    const size_t per_warp = (size_t)buf_bytes + short_warp_extra_bytes<NB>();
+    unsigned char *buf = smem + (size_t)warp * per_warp;
+    uint32_t *planes = reinterpret_cast<uint32_t *>(buf + buf_bytes) + lane;  // [b][blk][lane]
+    uint32_t *vm = planes + 16 * NB * 32;                                     // valid positions   [blk][lane]
+    uint32_t *im = vm + NB * 32;                                              // valid and not NaN [blk][lane]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)W * per_warp) + warp;
+    unsigned *clist = reinterpret_cast<unsigned *>(smem + (size_t)W * per_warp + (size_t)W * 8) + warp * 32;
 
     const unsigned n = (unsigned)g.axis_len;
     const unsigned lane_bytes = n * ES;
     const unsigned n_chunks = lane_bytes / 16;
 
-    // element index of slot s (0..31) of block blk held by this thread
+    // element index of slot s (0..31) of block blk held by this thread; plane bit p holds slot 2*(p&15)+(p>>4)
     auto elem_index = [&](int blk, int s) -> unsigned {
         if (ES == 4) return (unsigned)(((blk * LD_PER_BLK + (s >> 2)) * 32 + lane) * 4 + (s & 3));
         return (unsigned)(((blk * LD_PER_BLK + (s >> 1)) * 32 + lane) * 2 + (s & 1));
     };
     auto slot_of_pos = [](int p) -> int { return 2 * (p & 15) + (p >> 4); };
 
-    uint32_t valid[NB];
-#pragma unroll
+#pragma unroll 1
     for (int blk = 0; blk < NB; ++blk) {
         uint32_t v = 0;
+#pragma unroll 1
         for (int p = 0; p < 32; ++p)
             if (elem_index(blk, slot_of_pos(p)) < n) v |= 1u << p;
-        valid[blk] = v;
+        vm[blk * 32] = v;
     }
 
     if (lane == 0) mbar_init(bar, 1);
@@ -163,13 +171,13 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
     };
     if (L < g.nlanes) issue(L);
 
-    uint32_t P[NB][16];
-
-    // Build the 16 planes of round `round` (key bits [KEYBITS-16*(round+1), KEYBITS-16*round)) for all blocks.
-    // src: the warp's shared-memory buffer (round 0) or the lane in global memory (later rounds; L2-resident).
-    auto build = [&](auto from_smem_tag, const unsigned char *gsrc, int round) {
+    // Build the 16 planes of round `round` (key bits [KEYBITS-16*(round+1), KEYBITS-16*round)) of all blocks
+    // into shared memory.  Source: the warp's buffer (round 0) or the lane in global memory (L2-resident).
+    // Returns (floats, round 0) the OR of "exponent all ones" masks, i.e. whether an inf/NaN is present.
+    auto build = [&](auto from_smem_tag, const unsigned char *gsrc, int round) -> uint32_t {
         constexpr bool from_smem = decltype(from_smem_tag)::value;
-#pragma unroll
+        uint32_t special_any = 0;
+#pragma unroll 1
         for (int blk = 0; blk < NB; ++blk) {
             uint32_t w[16];
 #pragma unroll
@@ -191,9 +199,16 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
                 }
             }
             transpose16(w);
+            if constexpr (IS_FLOAT && from_smem) {
+                uint32_t e = vm[blk * 32];
 #pragma unroll
-            for (int b = 0; b < 16; ++b) P[blk][b] = w[b];
+                for (int b = EXP_LO; b <= 14; ++b) e &= w[b];
+                special_any |= e;
+            }
+#pragma unroll
+            for (int b = 0; b < 16; ++b) planes[(b * NB + blk) * 32] = w[b];
         }
+        return special_any;
     };
 
     for (; L < g.nlanes; L += nw) {
@@ -203,45 +218,35 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
 
         mbar_wait(bar, parity);
         parity ^= 1;
-        build(std::true_type{}, nullptr, 0);
+        const uint32_t special_any = build(std::true_type{}, nullptr, 0);
 
         // ---- NaN handling (floats): elements with an all-ones exponent are inspected individually ----
-        uint32_t init_mask[NB];
+        const uint32_t *init = vm;
         unsigned n_eff = n;
-#pragma unroll
-        for (int blk = 0; blk < NB; ++blk) init_mask[blk] = valid[blk];
-        if (IS_FLOAT) {
-            uint32_t special_any = 0;
-            uint32_t special[NB];
-#pragma unroll
+        if (IS_FLOAT && __any_sync(FULL, special_any != 0)) {
+            unsigned my_nan = 0;
+#pragma unroll 1
             for (int blk = 0; blk < NB; ++blk) {
-                uint32_t e = valid[blk];
-                constexpr int EXP_LO = (ES == 4) ? 7 : 4;  // exponent bits inside the top 16-bit field
+                uint32_t keep = vm[blk * 32];
+                uint32_t e = keep;
 #pragma unroll
-                for (int b = EXP_LO; b <= 14; ++b) e &= P[blk][b];
-                special[blk] = e;
-                special_any |= e;
-            }
-            if (__any_sync(FULL, special_any != 0)) {
-                unsigned my_nan = 0;
-#pragma unroll
-                for (int blk = 0; blk < NB; ++blk) {
-                    uint32_t bits = special[blk];
-                    while (bits) {
-                        int p = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        T x = *reinterpret_cast<const T *>(buf + (size_t)elem_index(blk, slot_of_pos(p)) * ES);
-                        if (x != x) {
-                            init_mask[blk] &= ~(1u << p);
-                            my_nan += 1;
-                        }
+                for (int b = EXP_LO; b <= 14; ++b) e &= planes[(b * NB + blk) * 32];
+                while (e) {
+                    int p = __ffs(e) - 1;
+                    e &= e - 1;
+                    T x = *reinterpret_cast<const T *>(buf + (size_t)elem_index(blk, slot_of_pos(p)) * ES);
+                    if (x != x) {
+                        keep &= ~(1u << p);
+                        my_nan += 1;
                     }
                 }
-                unsigned nan_total = __reduce_add_sync(FULL, my_nan);
-                if (nan_total) {
-                    if (!qa.skipnan && lane == 0) atomicOr(qa.status, STATUS_BIT_NAN);
-                    n_eff = n - nan_total;  // non-skipnan: result is meaningless (status is raised) but stays in bounds
-                }
+                im[blk * 32] = keep;
+            }
+            const unsigned nan_total = __reduce_add_sync(FULL, my_nan);
+            if (nan_total) {
+                if (!qa.skipnan && lane == 0) atomicOr(qa.status, STATUS_BIT_NAN);
+                n_eff = n - nan_total;  // non-skipnan: the result is meaningless (status is raised) but in bounds
+                init = im;
             }
         }
         __syncwarp();
@@ -256,53 +261,62 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
             continue;
         }
 
-        bool planes_dirty = false;  // P no longer holds round 0
+        bool planes_dirty = false;  // the plane area no longer holds round 0
 
         // ---- select rank r (and r+1 when want_next): returns raw bit patterns --------------------------
         auto select = [&](unsigned r, bool want_next, Raw &raw_r, Raw &raw_next) {
+#pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {  // pass 1 only when r+1 fell outside r's final bucket
-                const unsigned target = r + (unsigned)pass;
                 if (planes_dirty) {
+                    __syncwarp();
                     build(std::false_type{}, reinterpret_cast<const unsigned char *>(lp), 0);
                     planes_dirty = false;
                 }
                 uint32_t m[NB];
 #pragma unroll
-                for (int blk = 0; blk < NB; ++blk) m[blk] = init_mask[blk];
-                unsigned total = n_eff, rem = target;
+                for (int blk = 0; blk < NB; ++blk) m[blk] = init[blk * 32];
+                unsigned total = n_eff, rem = r + (unsigned)pass;
                 bool neg = false;
                 Raw prefix = 0;
-                bool small = false;
+                bool small = total <= 32;
+#pragma unroll 1
                 for (int round = 0; round < ROUNDS && !small; ++round) {
                     if (round > 0) {
+                        __syncwarp();
                         build(std::false_type{}, reinterpret_cast<const unsigned char *>(lp), round);
                         planes_dirty = true;
                     }
-#pragma unroll
-                    for (int b = 15; b >= 0; --b) {
-                        if (total <= 32) {
-                            small = true;
-                            break;
-                        }
+                    const uint32_t *pp = planes + 15 * NB * 32;
+#pragma unroll 1
+                    for (int b = 15; b >= 0; --b, pp -= NB * 32) {
+                        uint32_t x[NB];
                         unsigned ones = 0;
 #pragma unroll
-                        for (int blk = 0; blk < NB; ++blk) ones += __popc(m[blk] & P[blk][b]);
+                        for (int blk = 0; blk < NB; ++blk) {
+                            x[blk] = pp[blk * 32];
+                            ones += __popc(m[blk] & x[blk]);
+                        }
                         ones = __reduce_add_sync(FULL, ones);
                         const bool ones_small = (round == 0 && b == 15) ? TOP_INVERTED : (IS_FLOAT && neg);
                         const unsigned small_cnt = ones_small ? ones : total - ones;
                         const bool take_small = rem < small_cnt;
-                        const bool bit = take_small ? ones_small : !ones_small;
+                        const bool bit = (take_small == ones_small);
                         total = take_small ? small_cnt : total - small_cnt;
                         rem = take_small ? rem : rem - small_cnt;
+                        const uint32_t flip = bit ? 0u : 0xffffffffu;
 #pragma unroll
-                        for (int blk = 0; blk < NB; ++blk) m[blk] &= bit ? P[blk][b] : ~P[blk][b];
-                        prefix |= (Raw)(bit ? 1u : 0u) << (KEYBITS - 1 - (round * 16 + (15 - b)));
+                        for (int blk = 0; blk < NB; ++blk) m[blk] &= x[blk] ^ flip;
+                        prefix |= (Raw)(bit ? 1u : 0u) << (KEYBITS - 16 * (round + 1) + b);
                         if (round == 0 && b == 15 && IS_FLOAT) neg = bit;
+                        if (total <= 32) {
+                            small = true;
+                            break;
+                        }
                     }
                 }
                 Raw found, found_next = 0;
                 bool have_next = false;
-                if (!small && total > 32) {
+                if (total > 32) {
                     // every key bit decided: all remaining candidates are equal to `prefix`
                     found = prefix;
                     if (rem + 1 < total) {
@@ -340,6 +354,7 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
                     }
                     __syncwarp();
                     unsigned less = 0;
+#pragma unroll 1
                     for (unsigned j = 0; j < total; ++j) {
                         Key kj = __shfl_sync(FULL, mykey, (int)j);
                         less += (kj < mykey || (kj == mykey && j < (unsigned)lane)) ? 1u : 0u;
@@ -379,11 +394,13 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
             if (r == cache_rank[1]) { v = cache_raw[1]; return true; }
             return false;
         };
+#pragma unroll 1
         for (int t = 0; t < qa.nq; ++t) {
             RankMath rm = slot_rank_math(qa, t, n_eff);
             const bool nl = needs_lower(qa.interp, rm.frac), nh = needs_higher(qa.interp, rm.frac);
             const unsigned rl = (unsigned)rm.lower, rh = (unsigned)rm.higher;
             Raw vl = 0, vh = 0;
+#pragma unroll 1
             for (;;) {
                 const bool have_l = !nl || lookup(rl, vl);
                 const bool have_h = !nh || lookup(rh, vh);
@@ -400,6 +417,7 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
                     interpolate<T>(qa.interp, from_raw<T>(vl), from_raw<T>(vh), rm.frac, qa.status);
             }
         }
+        __syncwarp();  // the plane area is rewritten by the next lane's build
     }
 }
 
@@ -434,10 +452,10 @@ ShortPlan plan_short(const nds_ctx *ctx, const DeviceCall &c) {
     p.nb = g.axis_len <= 1024 ? 1 : (g.axis_len <= 2048 ? 2 : 4);
     size_t lane_bytes = g.axis_len * es;
     p.buf_bytes = (unsigned)((lane_bytes + 127) / 128 * 128);
-    size_t per_warp = p.buf_bytes + 8 + 128;
+    size_t extra = p.nb == 1 ? short_warp_extra_bytes<1>() : (p.nb == 2 ? short_warp_extra_bytes<2>() : short_warp_extra_bytes<4>());
+    size_t per_warp = p.buf_bytes + extra + 8 + 128;
     size_t budget = (size_t)ctx->max_smem_optin > 4096 ? (size_t)ctx->max_smem_optin - 1024 : 0;
-    int maxw = p.nb >= 4 ? 12 : 16;
-    p.warps = (int)std::min<size_t>((size_t)maxw, budget / per_warp);
+    p.warps = (int)std::min<size_t>((size_t)16, budget / per_warp);
     if (p.warps < 4) return p;
     p.smem = (size_t)p.warps * per_warp;
     p.ok = true;

@@ -54,8 +54,16 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                  : "memory");
 }
 
+// (a & mask) | (b & ~mask) as ONE LOP3 (the compiler otherwise emits two, one per constant)
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t mask) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(mask));
+    return d;
+}
+
 // 16 words holding 32 16-bit fields (word k: field of slot 2k in the low half, slot 2k+1 in the high half)
 // -> 16 plane words: word b, bit p = bit b of the field of slot 2*(p&15) + (p>>4).
+// Butterfly levels 8 (byte permutes), 4, 2, 1 (shift + bit-select): 16 + 3 * 32 = 112 instructions.
 __device__ __forceinline__ void transpose16(uint32_t (&w)[16]) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -67,22 +75,22 @@ __device__ __forceinline__ void transpose16(uint32_t (&w)[16]) {
     for (int r = 0; r < 16; ++r) {
         if (r & 4) continue;
         uint32_t a = w[r], b = w[r + 4];
-        w[r] = (a & 0x0F0F0F0Fu) | ((b << 4) & 0xF0F0F0F0u);
-        w[r + 4] = ((a >> 4) & 0x0F0F0F0Fu) | (b & 0xF0F0F0F0u);
+        w[r] = bitsel(a, b << 4, 0x0F0F0F0Fu);
+        w[r + 4] = bitsel(a >> 4, b, 0x0F0F0F0Fu);
     }
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         if (r & 2) continue;
         uint32_t a = w[r], b = w[r + 2];
-        w[r] = (a & 0x33333333u) | ((b << 2) & 0xCCCCCCCCu);
-        w[r + 2] = ((a >> 2) & 0x33333333u) | (b & 0xCCCCCCCCu);
+        w[r] = bitsel(a, b << 2, 0x33333333u);
+        w[r + 2] = bitsel(a >> 2, b, 0x33333333u);
     }
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         if (r & 1) continue;
         uint32_t a = w[r], b = w[r + 1];
-        w[r] = (a & 0x55555555u) | ((b << 1) & 0xAAAAAAAAu);
-        w[r + 1] = ((a >> 1) & 0x55555555u) | (b & 0xAAAAAAAAu);
+        w[r] = bitsel(a, b << 1, 0x55555555u);
+        w[r + 1] = bitsel(a >> 1, b, 0x55555555u);
     }
 }
 
@@ -133,6 +141,7 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
     uint32_t *im = vm + NB * 32;                                              // valid and not NaN [blk][lane]
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)W * per_warp) + warp;
     unsigned *clist = reinterpret_cast<unsigned *>(smem + (size_t)W * per_warp + (size_t)W * 8) + warp * 32;
+    Key *ckeys = reinterpret_cast<Key *>(smem + (size_t)W * per_warp + (size_t)W * (8 + 128)) + warp * 32;
 
     const unsigned n = (unsigned)g.axis_len;
     const unsigned lane_bytes = n * ES;
@@ -182,12 +191,12 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
             uint32_t w[16];
 #pragma unroll
             for (int j = 0; j < LD_PER_BLK; ++j) {
-                const unsigned chunk = (unsigned)((blk * LD_PER_BLK + j) * 32 + lane);
-                uint4 q = make_uint4(0, 0, 0, 0);
-                if (chunk < n_chunks) {
-                    if constexpr (from_smem) q = *reinterpret_cast<const uint4 *>(buf + (size_t)chunk * 16);
-                    else q = __ldg(reinterpret_cast<const uint4 *>(gsrc + (size_t)chunk * 16));
-                }
+                // chunks past the end of the lane are clamped onto the last one: their positions are
+                // masked out by vm, so any in-bounds value will do and no predicate is needed
+                const unsigned chunk = min((unsigned)((blk * LD_PER_BLK + j) * 32 + lane), n_chunks - 1);
+                uint4 q;
+                if constexpr (from_smem) q = *reinterpret_cast<const uint4 *>(buf + (size_t)chunk * 16);
+                else q = __ldg(reinterpret_cast<const uint4 *>(gsrc + (size_t)chunk * 16));
                 if constexpr (ES == 4) {
                     const unsigned sel = (round == 0) ? 0x7632u : 0x5410u;
                     w[2 * j] = __byte_perm(q.x, q.y, sel);
@@ -278,6 +287,7 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
                 unsigned total = n_eff, rem = r + (unsigned)pass;
                 bool neg = false;
                 Raw prefix = 0;
+                int bits_done = 0;
                 bool small = total <= 32;
 #pragma unroll 1
                 for (int round = 0; round < ROUNDS && !small; ++round) {
@@ -286,7 +296,11 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
                         build(std::false_type{}, reinterpret_cast<const unsigned char *>(lp), round);
                         planes_dirty = true;
                     }
+                    // Walk the 16 planes MSB-first.  `inv` is all-ones while a set bit means "smaller"
+                    // (the sign bit itself; every later bit of a negative float): x ^ inv is then 1 on the
+                    // LARGER side, so one popc gives the size of the smaller side as total - ones.
                     const uint32_t *pp = planes + 15 * NB * 32;
+                    uint32_t inv = (round == 0) ? (TOP_INVERTED ? 0xffffffffu : 0u) : ((IS_FLOAT && neg) ? 0xffffffffu : 0u);
 #pragma unroll 1
                     for (int b = 15; b >= 0; --b, pp -= NB * 32) {
                         uint32_t x[NB];
@@ -294,26 +308,31 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
 #pragma unroll
                         for (int blk = 0; blk < NB; ++blk) {
                             x[blk] = pp[blk * 32];
-                            ones += __popc(m[blk] & x[blk]);
+                            ones += __popc(m[blk] & (x[blk] ^ inv));
                         }
                         ones = __reduce_add_sync(FULL, ones);
-                        const bool ones_small = (round == 0 && b == 15) ? TOP_INVERTED : (IS_FLOAT && neg);
-                        const unsigned small_cnt = ones_small ? ones : total - ones;
+                        const unsigned small_cnt = total - ones;
                         const bool take_small = rem < small_cnt;
-                        const bool bit = (take_small == ones_small);
-                        total = take_small ? small_cnt : total - small_cnt;
+                        total = take_small ? small_cnt : ones;
                         rem = take_small ? rem : rem - small_cnt;
-                        const uint32_t flip = bit ? 0u : 0xffffffffu;
+                        // smaller side = positions where (x ^ inv) == 0, i.e. x == inv; larger side x == ~inv
+                        const uint32_t keep = take_small ? inv : ~inv;  // value of x on the kept side
+                        prefix = (Raw)(prefix << 1) | (Raw)(keep & 1u);
 #pragma unroll
-                        for (int blk = 0; blk < NB; ++blk) m[blk] &= x[blk] ^ flip;
-                        prefix |= (Raw)(bit ? 1u : 0u) << (KEYBITS - 16 * (round + 1) + b);
-                        if (round == 0 && b == 15 && IS_FLOAT) neg = bit;
+                        for (int blk = 0; blk < NB; ++blk) m[blk] &= ~(x[blk] ^ keep);
+                        if (round == 0 && b == 15) {
+                            neg = IS_FLOAT && (keep & 1u);
+                            inv = neg ? 0xffffffffu : 0u;
+                        }
+                        bits_done += 1;
                         if (total <= 32) {
                             small = true;
                             break;
                         }
                     }
                 }
+                // `prefix` holds the decided leading bits right-aligned; move them to the top of the key
+                if (bits_done < KEYBITS) prefix <<= (KEYBITS - bits_done);
                 Raw found, found_next = 0;
                 bool have_next = false;
                 if (total > 32) {
@@ -346,19 +365,21 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
                     }
                     __syncwarp();
                     Raw myraw = 0;
-                    Key mykey = 0;
+                    Key mykey = (Key) ~(Key)0;  // padding lanes sort last and never count as "less"
                     if ((unsigned)lane < total) {
                         T x = lp[clist[lane]];
                         myraw = to_raw<T>(x);
                         mykey = Tr::to_key(x);
                     }
+                    ckeys[lane] = mykey;
                     __syncwarp();
                     unsigned less = 0;
-#pragma unroll 1
-                    for (unsigned j = 0; j < total; ++j) {
-                        Key kj = __shfl_sync(FULL, mykey, (int)j);
-                        less += (kj < mykey || (kj == mykey && j < (unsigned)lane)) ? 1u : 0u;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {  // broadcast reads: no shuffles, no branches
+                        const Key kj = ckeys[j];
+                        less += (kj < mykey || (kj == mykey && j < lane)) ? 1u : 0u;
                     }
+                    __syncwarp();
                     unsigned hit = __ballot_sync(FULL, (unsigned)lane < total && less == rem);
                     found = __shfl_sync(FULL, myraw, __ffs(hit) - 1);
                     if (rem + 1 < total) {
@@ -453,7 +474,7 @@ ShortPlan plan_short(const nds_ctx *ctx, const DeviceCall &c) {
     size_t lane_bytes = g.axis_len * es;
     p.buf_bytes = (unsigned)((lane_bytes + 127) / 128 * 128);
     size_t extra = p.nb == 1 ? short_warp_extra_bytes<1>() : (p.nb == 2 ? short_warp_extra_bytes<2>() : short_warp_extra_bytes<4>());
-    size_t per_warp = p.buf_bytes + extra + 8 + 128;
+    size_t per_warp = p.buf_bytes + extra + 8 + 128 + 256;
     size_t budget = (size_t)ctx->max_smem_optin > 4096 ? (size_t)ctx->max_smem_optin - 1024 : 0;
     p.warps = (int)std::min<size_t>((size_t)16, budget / per_warp);
     if (p.warps < 4) return p;

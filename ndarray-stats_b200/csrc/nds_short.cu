@@ -15,6 +15,7 @@
 //   4. as soon as <= 32 candidates remain they are gathered (from L2) and ranked directly.
 // Key bits beyond the first 16 are handled by further rounds that re-read the lane (L2-resident).
 // No key transform is applied: the walk interprets IEEE sign / two's-complement sign on the fly.
+#include <cstdlib>
 #include <type_traits>
 
 #include "nds_internal.h"
@@ -113,12 +114,16 @@ template <typename T> __device__ __forceinline__ typename RawBits<T>::U to_raw(T
     return r;
 }
 
-// Per-warp shared memory: [lane buffer: buf_bytes][planes: 16 x NB x 32 words][vm: NB x 32][im: NB x 32]
-template <int NB> __host__ __device__ constexpr unsigned short_warp_extra_bytes() { return 16u * NB * 128u + 2u * NB * 128u; }
+// Per-warp shared memory:
+//   [ring: S stages x (1024 elements)] [planes: 16 x NB x 32 words] [vm: NB x 32] [im: NB x 32]
+// followed (after all warps) by the mbarriers, the candidate index lists and the candidate keys.
+constexpr int SHORT_MAX_STAGES = 4;
+template <int NB> __host__ __device__ constexpr unsigned short_warp_fixed_bytes() { return 16u * NB * 128u + 2u * NB * 128u; }
+constexpr unsigned SHORT_WARP_TAIL_BYTES = SHORT_MAX_STAGES * 8 + 128 + 256;
 
 template <typename T, int NB>
 __global__ void __launch_bounds__(512, 1)
-short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__restrict__ out, unsigned buf_bytes) {
+short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__restrict__ out, int S) {
     using Tr = Traits<T>;
     using Key = typename Tr::Key;   // order-preserving key (only used to rank the final <= 32 candidates)
     using Raw = typename RawBits<T>::U;
@@ -127,6 +132,7 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
     constexpr int LD_PER_BLK = 32 / VEC;  // 16-byte loads per thread per 32-element block
     constexpr int ROUNDS = ES * 8 / 16;   // 16 key bits per round
     constexpr int KEYBITS = ES * 8;
+    constexpr unsigned BLK_BYTES = 1024u * ES;  // one block = 32 elements per thread = 1024 elements per warp
     constexpr bool IS_FLOAT = Tr::is_float;
     constexpr bool TOP_INVERTED = IS_FLOAT || std::is_signed<T>::value;  // sign bit set => smaller
     constexpr int EXP_LO = (ES == 4) ? 7 : 4;  // exponent bits inside the top 16-bit field: [EXP_LO, 14]
@@ -134,18 +140,20 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
-    const size_t per_warp = (size_t)buf_bytes + short_warp_extra_bytes<NB>();
-    unsigned char *buf = smem + (size_t)warp * per_warp;
-    uint32_t *planes = reinterpret_cast<uint32_t *>(buf + buf_bytes) + lane;  // [b][blk][lane]
-    uint32_t *vm = planes + 16 * NB * 32;                                     // valid positions   [blk][lane]
-    uint32_t *im = vm + NB * 32;                                              // valid and not NaN [blk][lane]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)W * per_warp) + warp;
-    unsigned *clist = reinterpret_cast<unsigned *>(smem + (size_t)W * per_warp + (size_t)W * 8) + warp * 32;
-    Key *ckeys = reinterpret_cast<Key *>(smem + (size_t)W * per_warp + (size_t)W * (8 + 128)) + warp * 32;
+    const size_t per_warp = (size_t)S * BLK_BYTES + short_warp_fixed_bytes<NB>();
+    unsigned char *ring = smem + (size_t)warp * per_warp;
+    uint32_t *planes = reinterpret_cast<uint32_t *>(ring + (size_t)S * BLK_BYTES) + lane;  // [b][blk][lane]
+    uint32_t *vm = planes + 16 * NB * 32;                                                  // valid positions
+    uint32_t *im = vm + NB * 32;                                                           // valid and not NaN
+    unsigned char *tail = smem + (size_t)W * per_warp + (size_t)warp * SHORT_WARP_TAIL_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tail);
+    unsigned *clist = reinterpret_cast<unsigned *>(tail + SHORT_MAX_STAGES * 8);
+    Key *ckeys = reinterpret_cast<Key *>(tail + SHORT_MAX_STAGES * 8 + 128);
 
     const unsigned n = (unsigned)g.axis_len;
     const unsigned lane_bytes = n * ES;
     const unsigned n_chunks = lane_bytes / 16;
+    const int nbn = (int)((n + 1023u) / 1024u);  // blocks actually present in a lane (<= NB)
 
     // element index of slot s (0..31) of block blk held by this thread; plane bit p holds slot 2*(p&15)+(p>>4)
     auto elem_index = [&](int blk, int s) -> unsigned {
@@ -163,61 +171,109 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
         vm[blk * 32] = v;
     }
 
-    if (lane == 0) mbar_init(bar, 1);
+    if (lane == 0)
+        for (int st = 0; st < S; ++st) mbar_init(bars + st, 1);
     fence_mbar_init();
     __syncwarp();
 
     const unsigned long long nw = (unsigned long long)gridDim.x * W;
     unsigned long long L = (unsigned long long)blockIdx.x * W + warp;
-    unsigned parity = 0;
-    auto issue = [&](unsigned long long lane_id) {
-        long long io, oo;
-        lane_offsets(g, lane_id, io, oo);
+
+    // ---- TMA producer side of the per-warp block ring (warp-uniform state, lane 0 issues) ------------
+    unsigned long long p_lane = L;  // lane whose block is loaded next
+    int p_blk = 0, p_stage = 0;
+    long long p_in_off = 0;
+    auto produce = [&]() {
+        if (p_lane >= g.nlanes) return;
+        if (p_blk == 0) {
+            long long oo;
+            lane_offsets(g, p_lane, p_in_off, oo);
+        }
+        const unsigned off = (unsigned)p_blk * BLK_BYTES;
+        const unsigned bytes = min(BLK_BYTES, lane_bytes - off);
         if (lane == 0) {
-            mbar_expect_tx(bar, lane_bytes);
-            tma_load_1d(buf, data + io, lane_bytes, bar);
+            fence_proxy_async();  // earlier generic-proxy reads of this stage precede the async-proxy write
+            mbar_expect_tx(bars + p_stage, bytes);
+            tma_load_1d(ring + (size_t)p_stage * BLK_BYTES,
+                        reinterpret_cast<const unsigned char *>(data + p_in_off) + off, bytes, bars + p_stage);
+        }
+        if (++p_blk == nbn) {
+            p_blk = 0;
+            p_lane += nw;
+        }
+        p_stage = (p_stage + 1 == S) ? 0 : p_stage + 1;
+    };
+    for (int st = 0; st < S; ++st) produce();
+
+    int c_stage = 0;          // consumer side
+    unsigned c_parity = 0;    // bit s: parity to wait for on stage s
+
+    // Transpose the 32 16-bit fields in w[] and store the 16 plane words of block blk.
+    auto finish_block = [&](uint32_t (&w)[16], int blk, bool want_special) -> uint32_t {
+        transpose16(w);
+        uint32_t e = 0;
+        if (IS_FLOAT && want_special) {
+            e = vm[blk * 32];
+#pragma unroll
+            for (int b = EXP_LO; b <= 14; ++b) e &= w[b];
+        }
+#pragma unroll
+        for (int b = 0; b < 16; ++b) planes[(b * NB + blk) * 32] = w[b];
+        return e;
+    };
+    auto pack = [&](const uint4 &q, uint32_t (&w)[16], int j, int round) {
+        if constexpr (ES == 4) {
+            const unsigned sel = (round == 0) ? 0x7632u : 0x5410u;
+            w[2 * j] = __byte_perm(q.x, q.y, sel);
+            w[2 * j + 1] = __byte_perm(q.z, q.w, sel);
+        } else {
+            const unsigned sel = (round & 1) ? 0x5410u : 0x7632u;
+            const uint32_t w0 = (round < 2) ? q.y : q.x, w1 = (round < 2) ? q.w : q.z;
+            w[j] = __byte_perm(w0, w1, sel);
         }
     };
-    if (L < g.nlanes) issue(L);
 
-    // Build the 16 planes of round `round` (key bits [KEYBITS-16*(round+1), KEYBITS-16*round)) of all blocks
-    // into shared memory.  Source: the warp's buffer (round 0) or the lane in global memory (L2-resident).
-    // Returns (floats, round 0) the OR of "exponent all ones" masks, i.e. whether an inf/NaN is present.
-    auto build = [&](auto from_smem_tag, const unsigned char *gsrc, int round) -> uint32_t {
-        constexpr bool from_smem = decltype(from_smem_tag)::value;
+    // Round 0 of a fresh lane: consume its blocks from the ring (refilling each stage as soon as it has
+    // been read).  Returns (floats) the OR of the "exponent all ones" masks: is an inf/NaN present?
+    auto build_from_ring = [&]() -> uint32_t {
         uint32_t special_any = 0;
 #pragma unroll 1
-        for (int blk = 0; blk < NB; ++blk) {
-            uint32_t w[16];
+        for (int blk = 0; blk < nbn; ++blk) {
+            const unsigned nchunks_blk = min(BLK_BYTES, lane_bytes - (unsigned)blk * BLK_BYTES) / 16;
+            const unsigned char *src = ring + (size_t)c_stage * BLK_BYTES;
+            mbar_wait(bars + c_stage, (c_parity >> c_stage) & 1u);
+            c_parity ^= 1u << c_stage;
+            c_stage = (c_stage + 1 == S) ? 0 : c_stage + 1;
+            uint4 q[LD_PER_BLK];
 #pragma unroll
             for (int j = 0; j < LD_PER_BLK; ++j) {
                 // chunks past the end of the lane are clamped onto the last one: their positions are
                 // masked out by vm, so any in-bounds value will do and no predicate is needed
-                const unsigned chunk = min((unsigned)((blk * LD_PER_BLK + j) * 32 + lane), n_chunks - 1);
-                uint4 q;
-                if constexpr (from_smem) q = *reinterpret_cast<const uint4 *>(buf + (size_t)chunk * 16);
-                else q = __ldg(reinterpret_cast<const uint4 *>(gsrc + (size_t)chunk * 16));
-                if constexpr (ES == 4) {
-                    const unsigned sel = (round == 0) ? 0x7632u : 0x5410u;
-                    w[2 * j] = __byte_perm(q.x, q.y, sel);
-                    w[2 * j + 1] = __byte_perm(q.z, q.w, sel);
-                } else {
-                    const unsigned sel = (round & 1) ? 0x5410u : 0x7632u;
-                    const uint32_t w0 = (round < 2) ? q.y : q.x, w1 = (round < 2) ? q.w : q.z;
-                    w[j] = __byte_perm(w0, w1, sel);
-                }
+                const unsigned chunk = min((unsigned)(j * 32 + lane), nchunks_blk - 1);
+                q[j] = *reinterpret_cast<const uint4 *>(src + (size_t)chunk * 16);
             }
-            transpose16(w);
-            if constexpr (IS_FLOAT && from_smem) {
-                uint32_t e = vm[blk * 32];
+            __syncwarp();
+            produce();  // this stage is free again: fetch the block S positions ahead
+            uint32_t w[16];
 #pragma unroll
-                for (int b = EXP_LO; b <= 14; ++b) e &= w[b];
-                special_any |= e;
-            }
-#pragma unroll
-            for (int b = 0; b < 16; ++b) planes[(b * NB + blk) * 32] = w[b];
+            for (int j = 0; j < LD_PER_BLK; ++j) pack(q[j], w, j, 0);
+            special_any |= finish_block(w, blk, true);
         }
         return special_any;
+    };
+    // Any round, from the lane in global memory (L2-resident: it was streamed in moments ago).
+    auto build_from_global = [&](const unsigned char *gsrc, int round) {
+#pragma unroll 1
+        for (int blk = 0; blk < nbn; ++blk) {
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < LD_PER_BLK; ++j) {
+                const unsigned chunk = min((unsigned)((blk * LD_PER_BLK + j) * 32 + lane), n_chunks - 1);
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(gsrc + (size_t)chunk * 16));
+                pack(q, w, j, round);
+            }
+            finish_block(w, blk, false);
+        }
     };
 
     for (; L < g.nlanes; L += nw) {
@@ -225,9 +281,7 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
         lane_offsets(g, L, in_off, out_off);
         const T *lp = data + in_off;
 
-        mbar_wait(bar, parity);
-        parity ^= 1;
-        const uint32_t special_any = build(std::true_type{}, nullptr, 0);
+        const uint32_t special_any = build_from_ring();
 
         // ---- NaN handling (floats): elements with an all-ones exponent are inspected individually ----
         const uint32_t *init = vm;
@@ -235,7 +289,7 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
         if (IS_FLOAT && __any_sync(FULL, special_any != 0)) {
             unsigned my_nan = 0;
 #pragma unroll 1
-            for (int blk = 0; blk < NB; ++blk) {
+            for (int blk = 0; blk < nbn; ++blk) {
                 uint32_t keep = vm[blk * 32];
                 uint32_t e = keep;
 #pragma unroll
@@ -243,7 +297,7 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
                 while (e) {
                     int p = __ffs(e) - 1;
                     e &= e - 1;
-                    T x = *reinterpret_cast<const T *>(buf + (size_t)elem_index(blk, slot_of_pos(p)) * ES);
+                    T x = lp[elem_index(blk, slot_of_pos(p))];
                     if (x != x) {
                         keep &= ~(1u << p);
                         my_nan += 1;
@@ -259,11 +313,6 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
             }
         }
         __syncwarp();
-        // the buffer has been consumed: start the next lane's copy now so it overlaps the selection
-        if (L + nw < g.nlanes) {
-            fence_proxy_async();
-            issue(L + nw);
-        }
 
         if (n_eff == 0) {
             for (int t = lane; t < qa.nq; t += 32) out[out_off + (long long)t * g.out_axis_stride] = canonical_nan<T>();
@@ -278,12 +327,13 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
             for (int pass = 0; pass < 2; ++pass) {  // pass 1 only when r+1 fell outside r's final bucket
                 if (planes_dirty) {
                     __syncwarp();
-                    build(std::false_type{}, reinterpret_cast<const unsigned char *>(lp), 0);
+                    build_from_global(reinterpret_cast<const unsigned char *>(lp), 0);
+                    __syncwarp();
                     planes_dirty = false;
                 }
                 uint32_t m[NB];
 #pragma unroll
-                for (int blk = 0; blk < NB; ++blk) m[blk] = init[blk * 32];
+                for (int blk = 0; blk < NB; ++blk) m[blk] = (blk < nbn) ? init[blk * 32] : 0u;
                 unsigned total = n_eff, rem = r + (unsigned)pass;
                 bool neg = false;
                 Raw prefix = 0;
@@ -293,7 +343,8 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
                 for (int round = 0; round < ROUNDS && !small; ++round) {
                     if (round > 0) {
                         __syncwarp();
-                        build(std::false_type{}, reinterpret_cast<const unsigned char *>(lp), round);
+                        build_from_global(reinterpret_cast<const unsigned char *>(lp), round);
+                        __syncwarp();
                         planes_dirty = true;
                     }
                     // Walk the 16 planes MSB-first.  `inv` is all-ones while a set bit means "smaller"
@@ -449,8 +500,7 @@ template <typename T> constexpr bool short_type_ok() {
 
 struct ShortPlan {
     bool ok = false;
-    int nb = 0, warps = 0;
-    unsigned buf_bytes = 0;
+    int nb = 0, warps = 0, stages = 0;
     size_t smem = 0;
 };
 
@@ -465,20 +515,30 @@ ShortPlan plan_short(const nds_ctx *ctx, const DeviceCall &c) {
     const LaneGeom &g = c.geom;
     if (c.valid || c.out_valid) return p;
     if (g.axis_stride != 1 || g.axis_len < 64 || g.axis_len > 4096) return p;
-    if ((g.axis_len * es) % 16 != 0) return p;
+    if ((g.axis_len * es) % 16 != 0) return p;  // TMA bulk copies move multiples of 16 bytes from 16-byte aligned addresses
     if (((uintptr_t)c.data) % 16 != 0) return p;
     for (int d = 0; d < g.n_outer; ++d)
         if (g.oshape[d] > 1 && ((g.in_ostride[d] * (long long)es) % 16) != 0) return p;
     if (g.nlanes < 64) return p;  // too few lanes to fill the machine warp-per-lane
     p.nb = g.axis_len <= 1024 ? 1 : (g.axis_len <= 2048 ? 2 : 4);
-    size_t lane_bytes = g.axis_len * es;
-    p.buf_bytes = (unsigned)((lane_bytes + 127) / 128 * 128);
-    size_t extra = p.nb == 1 ? short_warp_extra_bytes<1>() : (p.nb == 2 ? short_warp_extra_bytes<2>() : short_warp_extra_bytes<4>());
-    size_t per_warp = p.buf_bytes + extra + 8 + 128 + 256;
-    size_t budget = (size_t)ctx->max_smem_optin > 4096 ? (size_t)ctx->max_smem_optin - 1024 : 0;
-    p.warps = (int)std::min<size_t>((size_t)16, budget / per_warp);
-    if (p.warps < 4) return p;
-    p.smem = (size_t)p.warps * per_warp;
+    const size_t fixed = (p.nb == 1 ? short_warp_fixed_bytes<1>() : (p.nb == 2 ? short_warp_fixed_bytes<2>() : short_warp_fixed_bytes<4>())) +
+                         SHORT_WARP_TAIL_BYTES;
+    const size_t blk_bytes = 1024 * es;
+    const size_t budget = (size_t)ctx->max_smem_optin > 4096 ? (size_t)ctx->max_smem_optin - 1024 : 0;
+    // Warps hide the latency of the serial bit walk; ring stages keep HBM requests in flight.  Measured on
+    // B200 (C2 workload, tools/sweep_short.sh): 16 warps x 1 stage 67 %, 12 x 2 62 %, 8 x 3 48 % of the HBM
+    // roofline -- so take as many warps as fit first, then as many stages as still fit.
+    p.stages = 1;
+    p.warps = (int)std::min<size_t>(16, budget / (p.stages * blk_bytes + fixed));
+    while (p.stages < 2 && budget / ((p.stages + 1) * blk_bytes + fixed) >= (size_t)p.warps) p.stages++;
+    if (const char *e = getenv("NDS_SHORT_STAGES")) {  // tuning knobs
+        p.stages = std::min(SHORT_MAX_STAGES, std::max(1, atoi(e)));
+        p.warps = (int)std::min<size_t>(16, budget / (p.stages * blk_bytes + fixed));
+    }
+    p.warps = p.warps / 4 * 4 > 0 ? p.warps / 4 * 4 : p.warps;  // whole warps per scheduler
+    if (const char *e = getenv("NDS_SHORT_WARPS")) p.warps = std::min(p.warps, std::max(1, atoi(e)));
+    if (p.warps < 1) return p;
+    p.smem = (size_t)p.warps * (p.stages * blk_bytes + fixed);
     p.ok = true;
     return p;
 }
@@ -490,7 +550,7 @@ cudaError_t launch_short_nb(nds_ctx *ctx, const DeviceCall &c, const ShortPlan &
     if (e != cudaSuccess) return e;
     unsigned long long need = (c.geom.nlanes + p.warps - 1) / p.warps;
     unsigned grid = (unsigned)std::min<unsigned long long>(need, (unsigned long long)ctx->sm_count);
-    kernel<<<grid, p.warps * 32, p.smem, ctx->stream>>>((const T *)c.data, c.geom, c.q, (T *)c.out, p.buf_bytes);
+    kernel<<<grid, p.warps * 32, p.smem, ctx->stream>>>((const T *)c.data, c.geom, c.q, (T *)c.out, p.stages);
     ctx->launches += 1;
     return cudaGetLastError();
 }

@@ -41,7 +41,8 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(_HERE, "libndstats_b200.so")
+    # NDS_LIB_PATH: A/B-test an alternative build of the same ABI (tuning only)
+    return os.environ.get("NDS_LIB_PATH") or os.path.join(_HERE, "libndstats_b200.so")
 
 
 def load():

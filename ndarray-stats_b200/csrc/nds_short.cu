@@ -426,8 +426,8 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
                     __syncwarp();
                     unsigned less = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {  // broadcast reads: no shuffles, no branches
-                        const Key kj = ckeys[j];
+                    for (int j = 0; j < 32; ++j) {  // broadcast reads, fully unrolled: no shuffles, no branches,
+                        const Key kj = ckeys[j];    // all loads in flight at once (a loop bounded by `total` was slower)
                         less += (kj < mykey || (kj == mykey && j < lane)) ? 1u : 0u;
                     }
                     __syncwarp();
@@ -468,7 +468,7 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
         };
 #pragma unroll 1
         for (int t = 0; t < qa.nq; ++t) {
-            RankMath rm = slot_rank_math(qa, t, n_eff);
+            const RankMath rm = slot_rank_math(qa, t, n_eff);
             const bool nl = needs_lower(qa.interp, rm.frac), nh = needs_higher(qa.interp, rm.frac);
             const unsigned rl = (unsigned)rm.lower, rh = (unsigned)rm.higher;
             Raw vl = 0, vh = 0;

@@ -188,12 +188,17 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
     // ---- dispatch ----------------------------------------------------------------------------------
     cudaError_t e;
     const bool want_short = ctx->forced_path == "auto" || ctx->forced_path == "short_bitslice";
+    const bool want_cols = ctx->forced_path == "auto" || ctx->forced_path == "cols_bitslice";
     if (ctx->forced_path == "short_bitslice" && !short_bitslice_supported(ctx, c))
         return fail(ctx, NDS_UNSUPPORTED, "forced path short_bitslice does not support this call");
+    if (ctx->forced_path == "cols_bitslice" && !cols_bitslice_supported(ctx, c))
+        return fail(ctx, NDS_UNSUPPORTED, "forced path cols_bitslice does not support this call");
     if (long_path) {
         e = launch_long_radix(ctx, c, arena + o_long, sharded);
     } else if (want_short && short_bitslice_supported(ctx, c)) {
         e = launch_short_bitslice(ctx, c);
+    } else if (want_cols && cols_bitslice_supported(ctx, c)) {
+        e = launch_cols_bitslice(ctx, c);
     } else {
         e = launch_generic_cta(ctx, c);
     }
@@ -352,7 +357,7 @@ const char *nds_ctx_last_path(nds_ctx *ctx) { return ctx ? ctx->last_path : "non
 nds_status nds_ctx_force_path(nds_ctx *ctx, const char *name) {
     if (!ctx) return NDS_BAD_ARGUMENT;
     std::string n = name ? name : "auto";
-    if (n != "auto" && n != "generic_cta" && n != "long_radix" && n != "short_bitslice")
+    if (n != "auto" && n != "generic_cta" && n != "long_radix" && n != "short_bitslice" && n != "cols_bitslice")
         return fail(ctx, NDS_BAD_ARGUMENT, "unknown path name");
     ctx->forced_path = n;
     return NDS_OK;

@@ -1,0 +1,398 @@
+// Lanes along a strided axis whose neighbours are contiguous ("column lanes", e.g. Axis(0) of a C-order
+// matrix — BASELINE config 3): one CTA per strip of CW adjacent lanes.
+//
+// Reading one such lane alone touches one 4-byte element per 32-byte sector.  Here the coalescing is
+// ACROSS lanes: a warp load covers 4 rows x (8 lanes x 4 B = one full sector), every thread collects 32
+// consecutive rows of ONE lane in registers, transposes them into 16 bit-planes (nds_bitslice.cuh) and
+// stores the plane words in shared memory (16 KiB per lane of 8192 elements, 8 lanes per CTA).  After the
+// strip has been streamed once, warp w walks the key bits of lane w MSB-first exactly like the short-lane
+// kernel (popc over the lane's plane words, one REDUX per bit), finishing on <= 32 candidates that are
+// fetched again from L2.  Input is read from HBM once; skipnan masks come out of the exponent planes.
+#include <cstdlib>
+#include <type_traits>
+
+#include "nds_bitslice.cuh"
+#include "nds_internal.h"
+
+namespace nds {
+namespace {
+
+constexpr int COLS_CW = 8;           // lanes per strip: 8 x 4 B = one 32-byte sector per row (f32)
+constexpr int COLS_THREADS = 256;    // 8 lanes x 32 row groups
+constexpr int COLS_KMAX = 8;         // plane words per thread in the walk: 8 x 32 x 32 = 8192 elements
+constexpr unsigned FULLMASK = 0xffffffffu;
+
+template <typename T>
+__global__ void __launch_bounds__(COLS_THREADS, 1)
+cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__restrict__ out,
+                     unsigned long long n_strips, unsigned strips_per_group) {
+    using Tr = Traits<T>;
+    using Key = typename Tr::Key;
+    using Raw = typename RawBits<T>::U;
+    constexpr int ES = (int)sizeof(T);
+    constexpr int ROUNDS = ES * 8 / 16;
+    constexpr int KEYBITS = ES * 8;
+    constexpr bool IS_FLOAT = Tr::is_float;
+    constexpr bool TOP_INVERTED = IS_FLOAT || std::is_signed<T>::value;
+    constexpr int EXP_LO = (ES == 4) ? 7 : 4;  // exponent bits of the top 16-bit field are [EXP_LO, 14]
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *planes = reinterpret_cast<uint32_t *>(smem_raw);
+
+    const unsigned n = (unsigned)g.axis_len;
+    const long long pitch = g.axis_stride;
+    const unsigned nrb = (n + 31u) / 32u;             // 32-row blocks per lane
+    const unsigned nrbp = (nrb + 31u) / 32u * 32u;    // padded to a multiple of 32 (<= 256)
+    const unsigned kw = nrbp / 32u;                   // plane words per thread in the walk
+    const unsigned col_pitch = 16u * nrbp + 4u;       // +4: the 8 lanes of a strip hit different banks
+    unsigned *clist = reinterpret_cast<unsigned *>(planes + COLS_CW * col_pitch);  // [warp][32]
+    Key *ckeys = reinterpret_cast<Key *>(clist + COLS_CW * 32);                    // [warp][32]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bc = tid % COLS_CW, brg = tid / COLS_CW;  // build role: lane (column) and row group
+    const int last_outer = g.n_outer - 1;
+    const unsigned long long ncols = g.oshape[last_outer];
+    const long long out_col_stride = g.out_ostride[last_outer];
+    auto slot_of_pos = [](int p) -> int { return 2 * (p & 15) + (p >> 4); };
+
+    for (unsigned long long strip = blockIdx.x; strip < n_strips; strip += gridDim.x) {
+        const unsigned long long grp = strip / strips_per_group;
+        const unsigned long long col0 = (strip - grp * strips_per_group) * COLS_CW;
+        long long in_off, out_off;
+        lane_offsets(g, grp * ncols + col0, in_off, out_off);
+        const T *sp = data + in_off;  // element (row 0, first lane of the strip)
+        const int cols_here = (int)min((unsigned long long)COLS_CW, ncols - col0);
+
+        // ---- stream the strip once: 1024 rows per step, 32 rows x 1 lane per thread ---------------------
+        {
+            const int c = min(bc, cols_here - 1);
+            uint32_t *pdst = planes + (size_t)bc * col_pitch;
+#pragma unroll 1
+            for (unsigned row0 = 0; row0 < nrb * 32u; row0 += 1024u) {
+                const unsigned rb = row0 / 32u + (unsigned)brg;
+                if (rb >= nrb) break;  // blocks past the end of the lane are masked out in the walk
+                Raw x[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const unsigned row = min(rb * 32u + (unsigned)i, n - 1u);  // clamped rows are masked later
+                    x[i] = to_raw<T>(__ldg(sp + (long long)row * pitch + c));
+                }
+                uint32_t w[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if constexpr (ES == 4) w[k] = __byte_perm((uint32_t)x[2 * k], (uint32_t)x[2 * k + 1], 0x7632);
+                    else w[k] = __byte_perm((uint32_t)(x[2 * k] >> 32), (uint32_t)(x[2 * k + 1] >> 32), 0x7632);
+                }
+                transpose16(w);
+#pragma unroll
+                for (int b = 0; b < 16; ++b) pdst[b * nrbp + rb] = w[b];
+            }
+        }
+        __syncthreads();
+
+        // ---- warp w selects the quantiles of lane w -----------------------------------------------------
+        if (warp < cols_here) {
+            const T *lp = sp + warp;  // element (row, this lane) = lp[row * pitch]
+            uint32_t *pl = planes + (size_t)warp * col_pitch + lane;  // word k of plane b: pl[b * nrbp + 32 * k]
+            unsigned *mylist = clist + warp * 32;
+            Key *mykeys = ckeys + warp * 32;
+
+            // valid rows and (floats) NaN positions, from the planes of round 0
+            uint32_t init[COLS_KMAX];
+            unsigned my_nan = 0;
+#pragma unroll
+            for (int k = 0; k < COLS_KMAX; ++k) {
+                uint32_t v = 0;
+                if ((unsigned)k < kw) {
+                    const unsigned rb = (unsigned)lane + 32u * k;
+                    const unsigned base = rb * 32u;
+                    if (base + 32u <= n) v = 0xffffffffu;
+                    else if (base < n)
+                        for (int p = 0; p < 32; ++p)
+                            if (base + (unsigned)slot_of_pos(p) < n) v |= 1u << p;
+                    if (IS_FLOAT && v) {
+                        uint32_t e = v, mhi = 0;
+#pragma unroll
+                        for (int b = EXP_LO; b <= 14; ++b) e &= pl[b * nrbp + 32 * k];
+                        if (e) {
+#pragma unroll
+                            for (int b = 0; b < EXP_LO; ++b) mhi |= pl[b * nrbp + 32 * k];
+                            uint32_t nanm = e & mhi;        // all-ones exponent and a high mantissa bit: NaN
+                            uint32_t amb = e & ~mhi;        // inf, or a NaN whose payload sits in the low bits
+                            while (amb) {
+                                int p = __ffs(amb) - 1;
+                                amb &= amb - 1;
+                                T xv = lp[(long long)(base + slot_of_pos(p)) * pitch];
+                                if (xv != xv) nanm |= 1u << p;
+                            }
+                            v &= ~nanm;
+                            my_nan += __popc(nanm);
+                        }
+                    }
+                }
+                init[k] = v;
+            }
+            unsigned n_eff = n;
+            if (IS_FLOAT) {
+                const unsigned nan_total = __reduce_add_sync(FULLMASK, my_nan);
+                if (nan_total) {
+                    if (!qa.skipnan && lane == 0) atomicOr(qa.status, STATUS_BIT_NAN);
+                    n_eff = n - nan_total;
+                }
+            }
+            const long long my_out = out_off + (long long)warp * out_col_stride;
+
+            if (n_eff == 0) {
+                for (int t = lane; t < qa.nq; t += 32) out[my_out + (long long)t * g.out_axis_stride] = canonical_nan<T>();
+            } else {
+                bool planes_dirty = false;
+                // rebuild this lane's planes for `round` from global memory (L2-resident), warp-local
+                auto rebuild = [&](int round) {
+#pragma unroll 1
+                    for (unsigned k = 0; k < kw; ++k) {
+                        const unsigned rb = (unsigned)lane + 32u * k;
+                        uint32_t w[16];
+#pragma unroll
+                        for (int kk = 0; kk < 16; ++kk) {
+                            const unsigned r0 = min(rb * 32u + 2u * kk, n - 1u), r1 = min(rb * 32u + 2u * kk + 1u, n - 1u);
+                            const Raw a = to_raw<T>(__ldg(lp + (long long)r0 * pitch));
+                            const Raw b = to_raw<T>(__ldg(lp + (long long)r1 * pitch));
+                            const int sh = KEYBITS - 16 * (round + 1);
+                            w[kk] = (uint32_t)((a >> sh) & 0xffffu) | ((uint32_t)((b >> sh) & 0xffffu) << 16);
+                        }
+                        transpose16(w);
+#pragma unroll
+                        for (int b = 0; b < 16; ++b) pl[b * nrbp + 32 * k] = w[b];
+                    }
+                    __syncwarp();
+                };
+
+                auto select = [&](unsigned r, bool want_next, Raw &raw_r, Raw &raw_next) {
+#pragma unroll 1
+                    for (int pass = 0; pass < 2; ++pass) {
+                        if (planes_dirty) {
+                            rebuild(0);
+                            planes_dirty = false;
+                        }
+                        uint32_t m[COLS_KMAX];
+#pragma unroll
+                        for (int k = 0; k < COLS_KMAX; ++k) m[k] = init[k];
+                        unsigned total = n_eff, rem = r + (unsigned)pass;
+                        bool neg = false;
+                        Raw prefix = 0;
+                        int bits_done = 0;
+                        bool small = total <= 32;
+#pragma unroll 1
+                        for (int round = 0; round < ROUNDS && !small; ++round) {
+                            if (round > 0) {
+                                rebuild(round);
+                                planes_dirty = true;
+                            }
+                            uint32_t inv = (round == 0) ? (TOP_INVERTED ? 0xffffffffu : 0u)
+                                                        : ((IS_FLOAT && neg) ? 0xffffffffu : 0u);
+                            const uint32_t *pp = pl + 15 * nrbp;
+#pragma unroll 1
+                            for (int b = 15; b >= 0; --b, pp -= nrbp) {
+                                uint32_t x[COLS_KMAX];
+                                unsigned ones = 0;
+#pragma unroll
+                                for (int k = 0; k < COLS_KMAX; ++k) {
+                                    x[k] = ((unsigned)k < kw) ? pp[32 * k] : 0u;
+                                    ones += __popc(m[k] & (x[k] ^ inv));
+                                }
+                                ones = __reduce_add_sync(FULLMASK, ones);
+                                const unsigned small_cnt = total - ones;
+                                const bool take_small = rem < small_cnt;
+                                total = take_small ? small_cnt : ones;
+                                rem = take_small ? rem : rem - small_cnt;
+                                const uint32_t keep = take_small ? inv : ~inv;
+                                prefix = (Raw)(prefix << 1) | (Raw)(keep & 1u);
+#pragma unroll
+                                for (int k = 0; k < COLS_KMAX; ++k) m[k] &= ~(x[k] ^ keep);
+                                if (round == 0 && b == 15) {
+                                    neg = IS_FLOAT && (keep & 1u);
+                                    inv = neg ? 0xffffffffu : 0u;
+                                }
+                                bits_done += 1;
+                                if (total <= 32) {
+                                    small = true;
+                                    break;
+                                }
+                            }
+                        }
+                        if (bits_done < KEYBITS) prefix <<= (KEYBITS - bits_done);
+                        Raw found, found_next = 0;
+                        bool have_next = false;
+                        if (total > 32) {
+                            found = prefix;
+                            if (rem + 1 < total) {
+                                found_next = prefix;
+                                have_next = true;
+                            }
+                        } else {
+                            unsigned mycnt = 0;
+#pragma unroll
+                            for (int k = 0; k < COLS_KMAX; ++k) mycnt += __popc(m[k]);
+                            unsigned incl = mycnt;
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                unsigned tt = __shfl_up_sync(FULLMASK, incl, d);
+                                if (lane >= d) incl += tt;
+                            }
+                            unsigned base = incl - mycnt;
+#pragma unroll
+                            for (int k = 0; k < COLS_KMAX; ++k) {
+                                uint32_t bits = m[k];
+                                while (bits) {
+                                    int p = __ffs(bits) - 1;
+                                    bits &= bits - 1;
+                                    mylist[base++] = ((unsigned)lane + 32u * k) * 32u + (unsigned)slot_of_pos(p);
+                                }
+                            }
+                            __syncwarp();
+                            Raw myraw = 0;
+                            Key mykey = (Key) ~(Key)0;
+                            if ((unsigned)lane < total) {
+                                T xv = lp[(long long)mylist[lane] * pitch];
+                                myraw = to_raw<T>(xv);
+                                mykey = Tr::to_key(xv);
+                            }
+                            mykeys[lane] = mykey;
+                            __syncwarp();
+                            unsigned less = 0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const Key kj = mykeys[j];
+                                less += (kj < mykey || (kj == mykey && j < lane)) ? 1u : 0u;
+                            }
+                            __syncwarp();
+                            unsigned hit = __ballot_sync(FULLMASK, (unsigned)lane < total && less == rem);
+                            found = __shfl_sync(FULLMASK, myraw, __ffs(hit) - 1);
+                            if (rem + 1 < total) {
+                                unsigned hit2 = __ballot_sync(FULLMASK, (unsigned)lane < total && less == rem + 1);
+                                found_next = __shfl_sync(FULLMASK, myraw, __ffs(hit2) - 1);
+                                have_next = true;
+                            }
+                        }
+                        if (pass == 0) {
+                            raw_r = found;
+                            if (!want_next) return;
+                            if (have_next) {
+                                raw_next = found_next;
+                                return;
+                            }
+                        } else {
+                            raw_next = found;
+                        }
+                    }
+                };
+
+                unsigned cache_rank[2] = {0xffffffffu, 0xffffffffu};
+                Raw cache_raw[2] = {0, 0};
+                auto remember = [&](unsigned r, Raw v) {
+                    cache_rank[1] = cache_rank[0];
+                    cache_raw[1] = cache_raw[0];
+                    cache_rank[0] = r;
+                    cache_raw[0] = v;
+                };
+                auto lookup = [&](unsigned r, Raw &v) -> bool {
+                    if (r == cache_rank[0]) { v = cache_raw[0]; return true; }
+                    if (r == cache_rank[1]) { v = cache_raw[1]; return true; }
+                    return false;
+                };
+#pragma unroll 1
+                for (int t = 0; t < qa.nq; ++t) {
+                    const RankMath rm = slot_rank_math(qa, t, n_eff);
+                    const bool nl = needs_lower(qa.interp, rm.frac), nh = needs_higher(qa.interp, rm.frac);
+                    const unsigned rl = (unsigned)rm.lower, rh = (unsigned)rm.higher;
+                    Raw vl = 0, vh = 0;
+#pragma unroll 1
+                    for (;;) {
+                        const bool have_l = !nl || lookup(rl, vl);
+                        const bool have_h = !nh || lookup(rh, vh);
+                        if (have_l && have_h) break;
+                        const unsigned r = !have_l ? rl : rh;
+                        const bool want_next = !have_l && !have_h && rh == rl + 1;
+                        Raw a = 0, b = 0;
+                        select(r, want_next, a, b);
+                        remember(r, a);
+                        if (want_next) remember(r + 1, b);
+                    }
+                    if (lane == 0)
+                        out[my_out + (long long)t * g.out_axis_stride] =
+                            interpolate<T>(qa.interp, from_raw<T>(vl), from_raw<T>(vh), rm.frac, qa.status);
+                }
+            }
+        }
+        __syncthreads();  // the planes are rewritten by the next strip
+    }
+}
+
+struct ColsPlan {
+    bool ok = false;
+    unsigned long long n_strips = 0;
+    unsigned strips_per_group = 0;
+    size_t smem = 0;
+};
+
+ColsPlan plan_cols(const nds_ctx *ctx, const DeviceCall &c) {
+    ColsPlan p;
+    size_t es = 0;
+    switch (c.dtype) {
+    case NDS_F32: case NDS_I32: case NDS_U32: es = 4; break;
+    case NDS_F64: case NDS_I64: case NDS_U64: es = 8; break;
+    default: return p;
+    }
+    const LaneGeom &g = c.geom;
+    if (c.valid || c.out_valid) return p;
+    if (g.n_outer < 1) return p;
+    const int last = g.n_outer - 1;
+    if (g.in_ostride[last] != 1 || g.oshape[last] < 32) return p;  // neighbouring lanes must be contiguous
+    if (g.axis_len < 64 || g.axis_len > 8192) return p;             // 8 lanes x 16 planes x n/32 words of smem
+    if (g.axis_stride < (long long)g.oshape[last]) return p;        // rows must not overlap
+    const unsigned long long spg = (g.oshape[last] + COLS_CW - 1) / COLS_CW;
+    if (spg > 0xffffffffull) return p;
+    p.strips_per_group = (unsigned)spg;
+    p.n_strips = (g.nlanes / g.oshape[last]) * spg;
+    const unsigned nrb = (unsigned)((g.axis_len + 31) / 32), nrbp = (nrb + 31) / 32 * 32;
+    p.smem = (size_t)COLS_CW * (16 * nrbp + 4) * 4 + COLS_CW * 32 * 4 + COLS_CW * 32 * 8 + 64;
+    if (p.smem > (size_t)ctx->max_smem_optin) return p;
+    (void)es;
+    p.ok = true;
+    return p;
+}
+
+template <typename T> cudaError_t launch_cols_typed(nds_ctx *ctx, const DeviceCall &c, const ColsPlan &p) {
+    auto kernel = cols_bitslice_kernel<T>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, COLS_THREADS, p.smem);
+    if (occ < 1) occ = 1;
+    unsigned grid = (unsigned)std::min<unsigned long long>(p.n_strips, (unsigned long long)ctx->sm_count * occ);
+    kernel<<<grid, COLS_THREADS, p.smem, ctx->stream>>>((const T *)c.data, c.geom, c.q, (T *)c.out, p.n_strips,
+                                                         p.strips_per_group);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool cols_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c) { return plan_cols(ctx, c).ok; }
+
+cudaError_t launch_cols_bitslice(nds_ctx *ctx, const DeviceCall &c) {
+    ColsPlan p = plan_cols(ctx, c);
+    if (!p.ok) return cudaErrorNotSupported;
+    ctx->last_path = "cols_bitslice";
+    switch (c.dtype) {
+    case NDS_F32: return launch_cols_typed<float>(ctx, c, p);
+    case NDS_F64: return launch_cols_typed<double>(ctx, c, p);
+    case NDS_I32: return launch_cols_typed<int32_t>(ctx, c, p);
+    case NDS_U32: return launch_cols_typed<uint32_t>(ctx, c, p);
+    case NDS_I64: return launch_cols_typed<int64_t>(ctx, c, p);
+    case NDS_U64: return launch_cols_typed<uint64_t>(ctx, c, p);
+    default: return cudaErrorNotSupported;
+    }
+}
+
+}  // namespace nds

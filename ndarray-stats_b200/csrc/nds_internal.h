@@ -58,6 +58,10 @@ cudaError_t launch_long_radix(nds_ctx *ctx, const DeviceCall &c, void *scratch, 
 bool short_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c);
 cudaError_t launch_short_bitslice(nds_ctx *ctx, const DeviceCall &c);
 
+// Strided lanes whose neighbours are contiguous (column lanes): CTA per strip of 8 lanes, bit-sliced.
+bool cols_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c);
+cudaError_t launch_cols_bitslice(nds_ctx *ctx, const DeviceCall &c);
+
 // NCCL shim (nds_nccl.cpp)
 int nccl_allreduce_sum_u64(nds_ctx *ctx, void *buf, size_t count, cudaStream_t stream, std::string *err);
 

@@ -326,3 +326,59 @@ def test_short_bitslice_nan(nds, gpu_ctx, oracle, dtype):
         check(gpu_ctx, oracle, b, 1, [0.5, 1.0], "linear")
     finally:
         gpu_ctx.force_path("auto")
+
+
+@pytest.mark.parametrize("dtype", SHORT_DTYPES, ids=lambda d: np.dtype(d).name)
+def test_cols_bitslice_path(nds, gpu_ctx, oracle, dtype):
+    """Column lanes (strided axis, contiguous neighbours): the CTA-per-strip kernel, incl. ragged strip
+    widths, lane lengths that are not multiples of 32/1024, tie-heavy data (later rounds) and 3-d arrays."""
+    dtype = np.dtype(dtype)
+    rng = np.random.default_rng(abs(hash(("cols", dtype.name))) % 2**32)
+    try:
+        gpu_ctx.force_path("cols_bitslice")
+        for n, cols in ((8192, 64), (4096, 37), (1000, 100), (64, 33), (2049, 40)):
+            for kind in ("normal", "ties", "clustered"):
+                if dtype.kind == "f":
+                    a = {"normal": lambda: rng.standard_normal((n, cols)),
+                         "ties": lambda: rng.integers(-4, 4, size=(n, cols)).astype(np.float64),
+                         "clustered": lambda: 1000.0 + rng.random((n, cols)) * 1e-4}[kind]().astype(dtype)
+                else:
+                    info = np.iinfo(dtype)
+                    a = {"normal": lambda: rng.integers(info.min // 2, info.max // 2, size=(n, cols), dtype=dtype),
+                         "ties": lambda: rng.integers(0, 16, size=(n, cols)).astype(dtype),
+                         "clustered": lambda: (rng.integers(0, 1000, size=(n, cols)) + 10**6).astype(dtype)}[kind]()
+                for interp, qs in (("nearest", [0.5]), ("midpoint", [0.5, 0.25]), ("linear", [0.1, 0.9, 0.5]),
+                                   ("lower", [0.0, 1.0]), ("higher", [0.33])):
+                    check(gpu_ctx, oracle, a, 0, qs, interp, select_impl=1 if kind == "ties" else 0)
+                    assert gpu_ctx.last_path == "cols_bitslice"
+        b = (rng.standard_normal((3, 500, 40)) * 100).astype(dtype)
+        check(gpu_ctx, oracle, b, 1, [0.5, 0.75], "lower")
+        assert gpu_ctx.last_path == "cols_bitslice"
+    finally:
+        gpu_ctx.force_path("auto")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=lambda d: np.dtype(d).name)
+def test_cols_bitslice_skipnan(nds, gpu_ctx, oracle, dtype):
+    """BASELINE config 3 in miniature: skipnan down the strided axis with 10 % NaN, all strategies."""
+    rng = np.random.default_rng(303)
+    a = rng.random((2000, 72)).astype(dtype)
+    a[rng.random(a.shape) < 0.1] = np.nan
+    a[:, 5] = np.nan
+    a[:-2, 6] = np.nan
+    a[7, 8] = np.inf
+    a[9, 8] = -np.inf
+    # a NaN whose payload lives only in the low mantissa bits (not visible in the top 16 bits)
+    low_nan = np.array([0x7F800001], dtype=np.uint32).view(np.float32)[0] if dtype == np.float32 else \
+        np.array([0x7FF0000000000001], dtype=np.uint64).view(np.float64)[0]
+    a[11, 9] = low_nan
+    try:
+        gpu_ctx.force_path("cols_bitslice")
+        for interp in INTERPS:
+            for q in (0.0, 0.5, 0.61, 1.0):
+                check(gpu_ctx, oracle, a, 0, [q], interp, skipnan=True)
+                assert gpu_ctx.last_path == "cols_bitslice"
+        with pytest.raises(nds.NanInInput):
+            gpu_ctx.quantiles_axis(a, 0, [0.5], "lower")
+    finally:
+        gpu_ctx.force_path("auto")

@@ -21,6 +21,7 @@ constexpr int COLS_CW = 8;           // lanes per strip: 8 x 4 B = one 32-byte s
 constexpr int COLS_THREADS = 256;    // 8 lanes x 32 row groups
 constexpr int COLS_KMAX = 8;         // plane words per thread in the walk: 8 x 32 x 32 = 8192 elements
 constexpr unsigned FULLMASK = 0xffffffffu;
+constexpr int COLS_CAND = 128;       // candidates ranked directly once the walk has narrowed a lane down to this many
 
 template <typename T>
 __global__ void __launch_bounds__(COLS_THREADS, 1)
@@ -45,8 +46,8 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
     const unsigned nrbp = (nrb + 31u) / 32u * 32u;    // padded to a multiple of 32 (<= 256)
     const unsigned kw = nrbp / 32u;                   // plane words per thread in the walk
     const unsigned col_pitch = 16u * nrbp + 4u;       // +4: the 8 lanes of a strip hit different banks
-    unsigned *clist = reinterpret_cast<unsigned *>(planes + COLS_CW * col_pitch);  // [warp][32]
-    Key *ckeys = reinterpret_cast<Key *>(clist + COLS_CW * 32);                    // [warp][32]
+    unsigned *clist = reinterpret_cast<unsigned *>(planes + COLS_CW * col_pitch);  // [warp][COLS_CAND]
+    Key *ckeys = reinterpret_cast<Key *>(clist + COLS_CW * COLS_CAND);             // [warp][COLS_CAND]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bc = tid % COLS_CW, brg = tid / COLS_CW;  // build role: lane (column) and row group
@@ -94,8 +95,8 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
         if (warp < cols_here) {
             const T *lp = sp + warp;  // element (row, this lane) = lp[row * pitch]
             uint32_t *pl = planes + (size_t)warp * col_pitch + lane;  // word k of plane b: pl[b * nrbp + 32 * k]
-            unsigned *mylist = clist + warp * 32;
-            Key *mykeys = ckeys + warp * 32;
+            unsigned *mylist = clist + warp * COLS_CAND;
+            Key *mykeys = ckeys + warp * COLS_CAND;
 
             // valid rows and (floats) NaN positions, from the planes of round 0
             uint32_t init[COLS_KMAX];
@@ -181,7 +182,7 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                         bool neg = false;
                         Raw prefix = 0;
                         int bits_done = 0;
-                        bool small = total <= 32;
+                        bool small = total <= COLS_CAND;
 #pragma unroll 1
                         for (int round = 0; round < ROUNDS && !small; ++round) {
                             if (round > 0) {
@@ -214,7 +215,7 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                                     inv = neg ? 0xffffffffu : 0u;
                                 }
                                 bits_done += 1;
-                                if (total <= 32) {
+                                if (total <= COLS_CAND) {
                                     small = true;
                                     break;
                                 }
@@ -223,7 +224,7 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                         if (bits_done < KEYBITS) prefix <<= (KEYBITS - bits_done);
                         Raw found, found_next = 0;
                         bool have_next = false;
-                        if (total > 32) {
+                        if (total > COLS_CAND) {
                             found = prefix;
                             if (rem + 1 < total) {
                                 found_next = prefix;
@@ -250,27 +251,60 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                                 }
                             }
                             __syncwarp();
-                            Raw myraw = 0;
-                            Key mykey = (Key) ~(Key)0;
-                            if ((unsigned)lane < total) {
-                                T xv = lp[(long long)mylist[lane] * pitch];
-                                myraw = to_raw<T>(xv);
-                                mykey = Tr::to_key(xv);
-                            }
-                            mykeys[lane] = mykey;
-                            __syncwarp();
-                            unsigned less = 0;
+                            // up to 4 candidates per thread: fetch (L2), publish keys, rank each against all
+                            constexpr int CPT = COLS_CAND / 32;
+                            Raw myraw[CPT];
+                            Key mykey[CPT];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const Key kj = mykeys[j];
-                                less += (kj < mykey || (kj == mykey && j < lane)) ? 1u : 0u;
+                            for (int c = 0; c < CPT; ++c) {
+                                const unsigned idx = (unsigned)lane + 32u * c;
+                                myraw[c] = 0;
+                                mykey[c] = (Key) ~(Key)0;
+                                if (idx < total) {
+                                    T xv = lp[(long long)mylist[idx] * pitch];
+                                    myraw[c] = to_raw<T>(xv);
+                                    mykey[c] = Tr::to_key(xv);
+                                }
+                                mykeys[idx] = mykey[c];
                             }
                             __syncwarp();
-                            unsigned hit = __ballot_sync(FULLMASK, (unsigned)lane < total && less == rem);
-                            found = __shfl_sync(FULLMASK, myraw, __ffs(hit) - 1);
+                            unsigned less[CPT];
+#pragma unroll
+                            for (int c = 0; c < CPT; ++c) less[c] = 0;
+                            const unsigned jmax = (total + 31u) & ~31u;
+#pragma unroll 1
+                            for (unsigned j0 = 0; j0 < jmax; j0 += 32) {
+#pragma unroll
+                                for (unsigned jj = 0; jj < 32; ++jj) {
+                                    const unsigned j = j0 + jj;
+                                    const Key kj = mykeys[j];
+#pragma unroll
+                                    for (int c = 0; c < CPT; ++c) {
+                                        if (32u * c >= jmax) continue;
+                                        const unsigned idx = (unsigned)lane + 32u * c;
+                                        less[c] += (kj < mykey[c] || (kj == mykey[c] && j < idx)) ? 1u : 0u;
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                            // the candidate of rank `want` lives in exactly one (thread, slot)
+                            auto fetch_rank = [&](unsigned want) -> Raw {
+                                Raw v = 0;
+                                int src = -1;
+#pragma unroll
+                                for (int c = 0; c < CPT; ++c) {
+                                    const unsigned idx = (unsigned)lane + 32u * c;
+                                    if (idx < total && less[c] == want) {
+                                        v = myraw[c];
+                                        src = lane;
+                                    }
+                                }
+                                const unsigned hit = __ballot_sync(FULLMASK, src >= 0);
+                                return __shfl_sync(FULLMASK, v, __ffs(hit) - 1);
+                            };
+                            found = fetch_rank(rem);
                             if (rem + 1 < total) {
-                                unsigned hit2 = __ballot_sync(FULLMASK, (unsigned)lane < total && less == rem + 1);
-                                found_next = __shfl_sync(FULLMASK, myraw, __ffs(hit2) - 1);
+                                found_next = fetch_rank(rem + 1);
                                 have_next = true;
                             }
                         }
@@ -355,7 +389,7 @@ ColsPlan plan_cols(const nds_ctx *ctx, const DeviceCall &c) {
     p.strips_per_group = (unsigned)spg;
     p.n_strips = (g.nlanes / g.oshape[last]) * spg;
     const unsigned nrb = (unsigned)((g.axis_len + 31) / 32), nrbp = (nrb + 31) / 32 * 32;
-    p.smem = (size_t)COLS_CW * (16 * nrbp + 4) * 4 + COLS_CW * 32 * 4 + COLS_CW * 32 * 8 + 64;
+    p.smem = (size_t)COLS_CW * (16 * nrbp + 4) * 4 + COLS_CW * COLS_CAND * 4 + COLS_CW * COLS_CAND * 8 + 64;
     if (p.smem > (size_t)ctx->max_smem_optin) return p;
     (void)es;
     p.ok = true;

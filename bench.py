@@ -119,11 +119,26 @@ def make_device_input(torch, name, rank, shape_override=None):
     return t
 
 
-def parity_sample(nds, oracle, name, t, out, nlanes_check=128):
+def parity_sample(nds, oracle, name, t, out, nlanes_check=128, nds_ctx_call=None):
     """Compare a bounded sample of the timed run's result with the oracle on the same device-generated data."""
     desc, dtype, shape, axis, qs, interp, skipnan = WORKLOADS[name]
     if t.dim() == 1:
-        return None  # checked in tests at smaller sizes (the oracle needs the full array)
+        # size-independent rank property on the full lane (the oracle cannot hold it): for a few requested
+        # quantiles the Lower order statistic v satisfies count(x < v) <= rank < count(x <= v)
+        import torch
+        n = t.numel()
+        picks = [qs[0], qs[len(qs) // 2], qs[-1]]
+        low = nds_ctx_call(t, picks)
+        ok = True
+        if t.dtype not in (torch.float32, torch.float64, torch.int32, torch.int64):
+            t = t.to(torch.int64)  # torch has no ordered compare for the unsigned types
+        for q, v in zip(picks, low.tolist()):
+            rank = int(np.floor(q * (n - 1)))
+            vv = torch.tensor(v, dtype=t.dtype, device=t.device) if t.dtype.is_floating_point else int(v)
+            lt = int((t < vv).sum().item())
+            le = int((t <= vv).sum().item())
+            ok = ok and (lt <= rank < le)
+        return {"ranks_checked": len(picks), "ok": bool(ok)}
     lanes = t.shape[1 - axis]
     pick = np.linspace(0, lanes - 1, num=min(nlanes_check, lanes)).astype(np.int64)
     import torch
@@ -321,9 +336,10 @@ def main():
 
     # parity of the timed result on a bounded sample of lanes (checker only)
     parity = None
-    if rank == 0 and not one_d:
+    if rank == 0 and not sharded_1d:
         from oracle import oracle
-        parity = parity_sample(nds, oracle, name, t, out)
+        parity = parity_sample(nds, oracle, name, t, out,
+                               nds_ctx_call=lambda arr, picks: ctx.quantiles_axis(arr, 0, picks, "lower", skipnan=skipnan))
 
     # ---- e2e: the public host-array API, pinned host buffers, copies inside the timed region ---------
     e2e = None

@@ -1,5 +1,6 @@
 // C ABI of libndstats_b200.so (include/ndstats_b200.h): argument validation with the reference's
 // error precedence, host<->device staging, dispatch to the selection paths.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -107,6 +108,7 @@ nds_status parse_call(nds_ctx *ctx, int dtype, int ndim, const size_t *shape, co
 }
 
 nds_status status_from_bits(nds_ctx *ctx, int bits) {
+    // STATUS_BIT_FALLBACK is consumed by nds_ctx_synchronize before this is called
     if (bits & STATUS_BIT_NAN) return fail(ctx, NDS_NAN_IN_INPUT, "NaN in a non-skipnan float input (N32/N64 cannot hold NaN)");
     if (bits & STATUS_BIT_CAST_OVERFLOW)
         return fail(ctx, NDS_CAST_OVERFLOW, "integer Linear interpolation: T::from_f64 out of range (the reference panics)");
@@ -154,6 +156,31 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
     const size_t o_out = out_on_device ? 0 : carve(p.out_elems * esize);
     const size_t o_outv = (out_valid && !out_on_device) ? carve(p.out_elems) : 0;
     const size_t o_long = long_path ? carve(long_scratch_bytes((int)nq)) : 0;
+    // bracket select (one streaming pass) is tried first on long lanes it supports
+    DeviceCall probe;
+    probe.dtype = dtype;
+    probe.valid = valid;
+    probe.out_valid = out_valid;
+    probe.geom = p.geom;
+    probe.q.nq = (int)nq;
+    {
+        double w = 0.0;
+        const double c = brk_csigma();
+        const double nm1 = p.geom.axis_len > 1 ? (double)(p.geom.axis_len - 1) : 1.0;
+        for (size_t t = 0; t < nq; ++t) {
+            double q = ranks ? (double)ranks[t] / nm1 : qs[t];
+            q = q < 0. ? 0. : (q > 1. ? 1. : q);
+            w += 2.0 * c * std::sqrt(q * (1.0 - q)) + 1e-3;
+        }
+        probe.brk_wsum = w;
+    }
+    const bool want_bracket = ctx->forced_path == "auto" || ctx->forced_path == "bracket";
+    const bool use_bracket = (long_path || ctx->forced_path == "bracket") && want_bracket &&
+                             bracket_supported(ctx, probe, sharded, ctx->forced_path == "bracket");
+    if (ctx->forced_path == "bracket" && !use_bracket)
+        return fail(ctx, NDS_UNSUPPORTED, "forced path bracket does not support this call");
+    const size_t o_brk = use_bracket ? carve(bracket_scratch_bytes(probe)) : 0;
+    const size_t o_long_fb = (use_bracket && !long_path) ? carve(long_scratch_bytes((int)nq)) : o_long;
     const size_t o_ntotal = sharded ? carve(sizeof(unsigned long long)) : 0;
     CUDA_TRY(arena_reserve(ctx, off));
     char *arena = (char *)ctx->arena;
@@ -161,6 +188,7 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
     DeviceCall c;
     c.dtype = dtype;
     c.geom = p.geom;
+    c.brk_wsum = probe.brk_wsum;
     c.q.qs = ranks ? nullptr : (const double *)(arena + o_qs);
     c.q.ranks = ranks ? (const unsigned long long *)(arena + o_qs) : nullptr;
     c.q.nq = (int)nq;
@@ -193,7 +221,24 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
         return fail(ctx, NDS_UNSUPPORTED, "forced path short_bitslice does not support this call");
     if (ctx->forced_path == "cols_bitslice" && !cols_bitslice_supported(ctx, c))
         return fail(ctx, NDS_UNSUPPORTED, "forced path cols_bitslice does not support this call");
-    if (long_path) {
+    if (use_bracket) {
+        int failed = 0;
+        e = launch_bracket(ctx, c, arena + o_brk, sharded, synchronous, &failed);
+        if (e == cudaSuccess && synchronous && failed) {
+            // a rank escaped its sampled bracket (or scratch ran out): the exact multi-pass radix select takes over
+            CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+            e = launch_long_radix(ctx, c, arena + o_long_fb, sharded);
+            ctx->last_path = "bracket->long_radix";
+        } else if (e == cudaSuccess && !synchronous) {
+            if (!ctx->pending) ctx->pending = new std::vector<PendingCall>();
+            PendingCall pc;
+            pc.call = c;
+            pc.is_ranks = ranks != nullptr;
+            pc.words.resize(nq);
+            std::memcpy(pc.words.data(), ranks ? (const void *)ranks : (const void *)qs, nq * 8);
+            ctx->pending->push_back(std::move(pc));
+        }
+    } else if (long_path) {
         e = launch_long_radix(ctx, c, arena + o_long, sharded);
     } else if (want_short && short_bitslice_supported(ctx, c)) {
         e = launch_short_bitslice(ctx, c);
@@ -325,6 +370,7 @@ void nds_ctx_destroy(nds_ctx *ctx) {
     if (ctx->nccl_comm) nds_comm_destroy(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->arena) cudaFree(ctx->arena);
+    delete ctx->pending;
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -347,6 +393,32 @@ nds_status nds_ctx_synchronize(nds_ctx *ctx) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     int bits = *ctx->h_status;
     *ctx->h_status = 0;
+    if (ctx->pending && !ctx->pending->empty()) {
+        std::vector<PendingCall> todo;
+        todo.swap(*ctx->pending);
+        if (bits & STATUS_BIT_FALLBACK) {
+            // some enqueued bracket-select call gave up; which one is not recorded, so every pending long-lane
+            // call is re-run on the exact radix passes (rare: a 5-sigma event per bracket, or scratch exhaustion)
+            for (PendingCall &pc : todo) {
+                const size_t nq = pc.words.size();
+                const size_t qbytes = (nq * 8 + 255) / 256 * 256;
+                CUDA_TRY(arena_reserve(ctx, qbytes + long_scratch_bytes((int)nq)));
+                char *arena = (char *)ctx->arena;
+                CUDA_TRY(cudaMemcpyAsync(arena, pc.words.data(), nq * 8, cudaMemcpyHostToDevice, ctx->stream));
+                pc.call.q.qs = pc.is_ranks ? nullptr : (const double *)arena;
+                pc.call.q.ranks = pc.is_ranks ? (const unsigned long long *)arena : nullptr;
+                cudaError_t e = launch_long_radix(ctx, pc.call, arena + qbytes, false);
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "long_radix fallback");
+                ctx->last_path = "bracket->long_radix";
+                CUDA_TRY(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                bits |= *ctx->h_status;
+                *ctx->h_status = 0;
+            }
+        }
+    }
+    bits &= ~STATUS_BIT_FALLBACK;
     return status_from_bits(ctx, bits);
 }
 
@@ -357,7 +429,8 @@ const char *nds_ctx_last_path(nds_ctx *ctx) { return ctx ? ctx->last_path : "non
 nds_status nds_ctx_force_path(nds_ctx *ctx, const char *name) {
     if (!ctx) return NDS_BAD_ARGUMENT;
     std::string n = name ? name : "auto";
-    if (n != "auto" && n != "generic_cta" && n != "long_radix" && n != "short_bitslice" && n != "cols_bitslice")
+    if (n != "auto" && n != "generic_cta" && n != "long_radix" && n != "short_bitslice" && n != "cols_bitslice" &&
+        n != "bracket")
         return fail(ctx, NDS_BAD_ARGUMENT, "unknown path name");
     ctx->forced_path = n;
     return NDS_OK;

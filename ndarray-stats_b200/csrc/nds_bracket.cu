@@ -1,0 +1,1685 @@
+// One (or a few) very long contiguous lanes — BASELINE configs 4 and 5: "bracket select".
+//
+// An MSB radix select re-reads the whole lane once per digit; on a 16 GiB lane that caps the path at
+// 1/8 of the HBM roofline, and uniform [0,1) doubles put half of the keys into ONE top-digit bucket, so
+// the early digits filter nothing.  This path reads the lane ONCE:
+//
+//   1. sample      S1 = n/256 keys at hashed positions; S0 = 8192 of those, sorted by one CTA
+//   2. bucket      count S1 against the sorted S0 (binary search): exact sample ranks of every S0 key
+//   3. plan        per requested quantile pick a value bracket [lo, hi] of S0 keys whose sample-rank span
+//                  is the expected position +- 5 sigma; merge overlapping brackets; build a two-level
+//                  key -> class lookup table (4096 top cells, the cells that hold a bracket edge
+//                  subdivided again) so that one element costs two shared-memory reads to classify
+//   4. stream      THE pass over the lane: every element is classified (class = number of bracket lower
+//                  edges <= key), counted in per-thread private 16-bit shared-memory counters (a plain
+//                  LDS/ADD/STS on a conflict-free layout: shared atomics would cap the pass at 0.5
+//                  element/cycle/SM), and the ~10 % of elements that fall inside a bracket are staged in
+//                  shared memory and appended to that bracket's candidate segment
+//   5. resolve     exact counts below / inside every bracket (summed over ranks with ncclAllReduce when the
+//                  lane is sharded) turn each requested rank into (bracket, rank inside the bracket); a rank
+//                  that escaped its bracket raises FAIL and the caller falls back to the radix passes
+//   6. refine      candidates only: 8-bit digits of (key - lo) with the same private counters, compaction of
+//                  the chosen digit, until a segment holds <= 4096 keys, which one CTA sorts
+//   7. output      Interpolate on device with the reference's formulas (nds_common.cuh)
+//
+// Every decision between the passes is taken on the device; the host only enqueues.
+// Nothing here restates the reference's quickselect (src/sort.rs:133-283): order statistics are determined
+// by the multiset, so the selected values are bit-identical.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+
+#include "nds_bitslice.cuh"
+#include "nds_internal.h"
+
+namespace nds {
+namespace {
+
+constexpr int BRK_MAXB = 120;             // brackets per call
+constexpr int BRK_NCLS = 128;             // counter classes of the streaming pass (127 = invalid: NaN)
+constexpr int BRK_INVALID_CLS = 127;
+constexpr int BRK_THREADS = 256;
+constexpr int BRK_EPT = 16;               // elements per thread per tile
+constexpr int BRK_TILE = BRK_THREADS * BRK_EPT;
+constexpr int BRK_STAGE_CAP = 2 * BRK_TILE;
+constexpr int BRK_NC1 = 4096;             // top-level cells
+constexpr int BRK_L2_PURE = 260;          // 2 * 128 pure (class, inside) combinations + 2 special entries
+constexpr int BRK_L2_SUB = 16384;         // sub-cell entries
+constexpr int BRK_L2N = BRK_L2_PURE + BRK_L2_SUB;
+constexpr int BRK_S0 = 8192;
+constexpr int BRK_MAXQ = 128;             // quantiles per call on this path
+constexpr int BRK_MAXTASK = 2 * BRK_MAXQ; // unique ranks
+constexpr int BRK_MAXSEG = 2 * BRK_MAXQ;
+constexpr int BRK_FINAL_CAP = 4096;       // a segment this small is sorted by one CTA
+constexpr int BRK_RCHUNK = 4096;          // refine passes: elements per chunk
+
+constexpr unsigned ENT_COMPACT = 0x100u, ENT_MIXED = 0x200u, ENT_SPECIAL = 0x400u;
+
+enum : int {
+    H_NTOTAL = 0, H_NINVALID, H_NEFF, H_FAIL, H_B, H_NSEG, H_NTASK, H_NACTIVE, H_S1VALID, H_EMPTY, H_NCHUNK_COUNT,
+    H_NCHUNK_COMPACT, H_NCLS_USED, H_NTIE, H_CUR, H_NEXT_NCHUNK, H_NEXT_NSEG, H_OLD_NSEG, H_WORDS = 20
+};
+enum : int { FAIL_ESCAPED = 1, FAIL_CAPACITY = 2, FAIL_TOO_MANY = 4, FAIL_INCONSISTENT = 8 };
+enum : int { TASK_ACTIVE = 0, TASK_DONE = 1 };
+enum : int { SEG_TIE = 1, SEG_FINAL = 2, SEG_USED = 4, SEG_DONE = 8 };
+
+template <typename Key> struct BrkSeg {
+    Key lo, hi;
+    int shift, flags;
+    unsigned long long off, cnt_local, cnt_global, cursor;
+};
+struct BrkTask {
+    unsigned long long r;      // rank inside its segment (over all ranks when sharded)
+    unsigned long long value;  // the key, once known
+    int seg, state;
+};
+template <typename Key> struct BrkLutConst {
+    Key kmin;
+    int shift1, subshift;
+    unsigned submask;
+    int B, ncls_used;
+};
+
+template <typename Key> struct BrkBuf {
+    unsigned long long *hdr;         // [H_WORDS]
+    unsigned long long *red_n;       // [2]  local element count -> total            (allreduce 0)
+    unsigned long long *s0hist;      // [2 (S0 + 2)] bucket counts of S1 against S0, then #{== S0[i]}        (allreduce 1)
+    unsigned long long *red_stream;  // [NCLS + MAXB] class counts, bracket in-counts  (allreduce 2)
+    unsigned long long *cur_local;   // [MAXB] local fill of the bracket segments
+    unsigned long long *red_refine;  // [MAXSEG * 256]                               (allreduce per refine round)
+    unsigned long long *loc_refine;  // [MAXSEG * 256] local copy (== red_refine on one GPU)
+    Key *s1, *s0, *blo, *bhi;
+    unsigned long long *boff, *bcap;
+    unsigned char *btie;             // tie class of a bracket (lo == hi: counted, never compacted) or 0xff
+    unsigned *lut1;                  // [NC1]
+    unsigned short *lut2;            // [L2N]
+    BrkLutConst<Key> *lutc;
+    BrkSeg<Key> *seg[2];
+    BrkTask *task;
+    int *slot_task;                  // [2 * nq]
+    unsigned long long *slot_rank;   // [2 * nq]
+    short *newid;                    // [MAXSEG * 256]
+    unsigned long long *cprefix_count, *cprefix_compact;  // [MAXSEG + 1] chunk prefix sums
+    Key *cand[2];
+    unsigned long long cand_cap[2];
+    unsigned s1cap;
+};
+
+__device__ __forceinline__ unsigned long long ld_now(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+__device__ __forceinline__ void raise_fail(unsigned long long *hdr, int bits) {
+    atomicOr(&hdr[H_FAIL], (unsigned long long)bits);
+}
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+template <typename Key> __device__ __forceinline__ int key_bits_used(Key x) {
+    if (sizeof(Key) == 8) return x ? 64 - __clzll((long long)x) : 0;
+    return x ? 32 - __clz((int)x) : 0;
+}
+// conflict-free slot of a thread inside one class row of the private 16-bit counters: the 32 lanes of a
+// warp land in 32 different banks, two warps share a 128-byte row (low / high half-word)
+__device__ __forceinline__ unsigned counter_slot() {
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    return (warp >> 1) * 64 + lane * 2 + (warp & 1);
+}
+template <typename T> struct KeyOf { using Key = typename Traits<T>::Key; };
+
+// floats: keys of NaNs lie outside [key(-inf), key(+inf)]
+template <typename T> __device__ __forceinline__ bool key_is_nan(typename Traits<T>::Key k) {
+    using Key = typename Traits<T>::Key;
+    if (!Traits<T>::is_float) return false;
+    if (sizeof(Key) == 8) return k > (Key)0xFFF0000000000000ull || k < (Key)0x000FFFFFFFFFFFFFull;
+    return k > (Key)0xFF800000u || k < (Key)0x007FFFFFu;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1. sample
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void brk_sample_kernel(const T *__restrict__ data, unsigned long long n, unsigned s1,
+                                  BrkBuf<typename Traits<T>::Key> buf) {
+    using Tr = Traits<T>;
+    using Key = typename Tr::Key;
+    unsigned valid = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += gridDim.x * blockDim.x) {
+        // stratum i = [i n / s1, (i + 1) n / s1): one element at a hashed offset (s1 <= n < 2^40, i < 2^24)
+        const unsigned long long p0 = (unsigned long long)i * n / s1, p1 = (unsigned long long)(i + 1) * n / s1;
+        unsigned long long pos = p0 + (p1 - p0 > 1 ? (unsigned long long)mix32(i) % (p1 - p0) : 0ull);
+        if (pos >= n) pos = n - 1;
+        Key k = Tr::to_key(data[pos]);
+        const bool inv = key_is_nan<T>(k);
+        buf.s1[i] = inv ? (Key) ~(Key)0 : k;  // NaN samples sort last and are not counted
+        valid += inv ? 0u : 1u;
+    }
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&buf.hdr[H_S1VALID], (unsigned long long)valid);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&buf.red_n[0], n);
+}
+
+// 2a. S0 = every (s1 / S0)-th sample, sorted by one CTA (bitonic network in shared memory)
+template <typename Key>
+__global__ void __launch_bounds__(1024) brk_sort_s0_kernel(BrkBuf<Key> buf, unsigned s1) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Key *s = reinterpret_cast<Key *>(smem_raw);
+    for (unsigned i = threadIdx.x; i < BRK_S0; i += blockDim.x) {
+        unsigned long long pos = (unsigned long long)i * s1 / BRK_S0;
+        s[i] = buf.s1[pos];
+    }
+    __syncthreads();
+    for (unsigned k = 2; k <= BRK_S0; k <<= 1) {
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = threadIdx.x; i < BRK_S0; i += blockDim.x) {
+                unsigned ixj = i ^ j;
+                if (ixj > i) {
+                    Key a = s[i], b = s[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s[i] = b; s[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (unsigned i = threadIdx.x; i < BRK_S0; i += blockDim.x) buf.s0[i] = s[i];
+}
+
+// 2b. exact sample ranks of the S0 keys: hist[i] = #{ s1 keys k : S0[i-1] < k <= S0[i] }
+template <typename Key, bool IS_FLOAT>
+__global__ void __launch_bounds__(256) brk_bucket_kernel(BrkBuf<Key> buf, unsigned s1) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Key *s = reinterpret_cast<Key *>(smem_raw);
+    for (unsigned i = threadIdx.x; i < BRK_S0; i += blockDim.x) s[i] = buf.s0[i];
+    __syncthreads();
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += gridDim.x * blockDim.x) {
+        const Key k = buf.s1[i];
+        if (IS_FLOAT && k == (Key) ~(Key)0) continue;
+        unsigned lo = 0, hi = BRK_S0;  // lower_bound: #{ S0 < k }
+        while (lo < hi) {
+            unsigned mid = (lo + hi) >> 1;
+            if (s[mid] < k) lo = mid + 1;
+            else hi = mid;
+        }
+        atomicAdd(&buf.s0hist[lo], 1ull);
+        if (lo < BRK_S0 && s[lo] == k) atomicAdd(&buf.s0hist[BRK_S0 + 2 + lo], 1ull);  // #{ s1 == S0[lo] }, first of its run
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. plan: brackets + lookup tables
+// ------------------------------------------------------------------------------------------------
+template <typename Key> struct PointClass { int j; bool in; };
+template <typename Key>
+__device__ __forceinline__ PointClass<Key> classify_point(const Key *blo, const Key *bhi, int B, Key k) {
+    int lo = 0, hi = B;  // j = #{ blo <= k }
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (blo[mid] <= k) lo = mid + 1;
+        else hi = mid;
+    }
+    PointClass<Key> p;
+    p.j = lo;
+    p.in = lo > 0 && k <= bhi[lo - 1];
+    return p;
+}
+__device__ __forceinline__ unsigned pure_entry(int j, bool in, const unsigned char *btie) {
+    if (in) {
+        const unsigned char t = btie[j - 1];
+        if (t != 0xff) return (unsigned)t;     // tie bracket: own class, not compacted
+        return (unsigned)j | ENT_COMPACT;
+    }
+    return (unsigned)j;
+}
+
+template <typename Key, bool IS_FLOAT>
+__global__ void __launch_bounds__(1024)
+brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long n_local, int sharded) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned *cum = reinterpret_cast<unsigned *>(smem_raw);            // [S0 + 1] inclusive: #{ s1 <= S0[i] }
+    __shared__ Key qlo[BRK_MAXQ], qhi[BRK_MAXQ], slo[BRK_MAXQ], shi[BRK_MAXQ];
+    __shared__ Key blo[BRK_MAXB], bhi[BRK_MAXB];
+    __shared__ unsigned char btie[BRK_MAXB];
+    __shared__ unsigned char qheavy[BRK_MAXQ];
+    __shared__ Key hv[2 * BRK_MAXQ];
+    __shared__ unsigned warp_tot[32];
+    __shared__ int sB, sM, sShift1, sNmixed, sFail;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const Key KMAX = (Key) ~(Key)0;
+    const int nq = qa.nq;
+
+    // ---- inclusive scan of the bucket counts (S0 + 1 entries, 1024 threads x 9) ----------------------
+    {
+        constexpr int PER = (BRK_S0 + 1 + 1023) / 1024;
+        unsigned v[PER], sum = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int idx = tid * PER + i;
+            v[i] = idx <= BRK_S0 ? (unsigned)buf.s0hist[idx] : 0u;
+            sum += v[i];
+        }
+        unsigned incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((tid & 31) >= d) incl += t;
+        }
+        if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            unsigned w = warp_tot[tid], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned t = __shfl_up_sync(0xffffffffu, wi, d);
+                if (tid >= d) wi += t;
+            }
+            warp_tot[tid] = wi - w;
+        }
+        __syncthreads();
+        unsigned run = warp_tot[tid >> 5] + incl - sum;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int idx = tid * PER + i;
+            run += v[i];
+            if (idx <= BRK_S0) cum[idx] = run;
+        }
+        if (tid == 0) sFail = 0;
+        __syncthreads();
+    }
+    const unsigned s1v = cum[BRK_S0];  // valid samples (over all ranks when sharded)
+    const unsigned long long n_total = buf.red_n[0];
+    if (tid == 0) {
+        buf.hdr[H_NTOTAL] = n_total;
+    }
+    if (s1v == 0 || n_total == 0) {  // nothing but NaNs in the sample (or nothing at all): no brackets
+        if (tid == 0) {
+            buf.hdr[H_B] = 0;
+            buf.lutc->B = 0;
+            buf.lutc->kmin = 0;
+            buf.lutc->shift1 = 0;
+            buf.lutc->subshift = 0;
+            buf.lutc->submask = 0;
+            buf.lutc->ncls_used = 1;
+        }
+        for (int c = tid; c < BRK_NC1; c += nthreads)
+            buf.lut1[c] = IS_FLOAT && (c == 0 || c == BRK_NC1 - 1) ? (unsigned)(256 + (c ? 1 : 0)) : 0u;
+        for (int i = tid; i < BRK_L2_PURE; i += nthreads)
+            buf.lut2[i] = i == 256 ? (unsigned short)(ENT_MIXED | ENT_SPECIAL | 0u)
+                                   : (i == 257 ? (unsigned short)(ENT_MIXED | ENT_SPECIAL | 0u) : (unsigned short)0);
+        return;
+    }
+
+    // ---- one bracket per requested quantile ----------------------------------------------------------
+    for (int t = tid; t < nq; t += nthreads) {
+        double p;
+        if (qa.ranks) p = n_total > 1 ? (double)qa.ranks[t] / (double)(n_total - 1) : 0.0;
+        else p = qa.qs[t];
+        p = fmin(fmax(p, 0.0), 1.0);
+        const double P = p * (double)(s1v - 1);
+        const double sd = sqrt(fmax(p * (1.0 - p) * (double)s1v, 1.0));
+        const double Plo = floor(P - csigma * sd - 2.0), Phi = ceil(P + csigma * sd + 2.0) + 1.0;
+        Key lo = 0, hi = KMAX;
+        if (Plo > 0.0) {  // largest i with #{ s1 < S0[i] } <= Plo   (strict: ties must not widen the bracket)
+            const unsigned target = (unsigned)fmin(Plo, 4294967295.0);
+            int a = 0, b = BRK_S0;  // first index with cum_lt > target
+            while (a < b) {
+                const int mid = (a + b) >> 1;
+                const Key v = buf.s0[mid];
+                int f0 = 0, f1 = mid;  // first index of the run of keys equal to S0[mid]
+                while (f0 < f1) {
+                    const int m2 = (f0 + f1) >> 1;
+                    if (buf.s0[m2] < v) f0 = m2 + 1;
+                    else f1 = m2;
+                }
+                const unsigned cum_lt = cum[f0] - (unsigned)buf.s0hist[BRK_S0 + 2 + f0];
+                if (cum_lt <= target) a = mid + 1;
+                else b = mid;
+            }
+            if (a > 0) lo = buf.s0[a - 1];
+        }
+        if (Phi + 1.0 <= (double)cum[BRK_S0 - 1]) {  // smallest i with cum[i] >= Phi + 1
+            const unsigned target = (unsigned)(Phi + 1.0);
+            int a = 0, b = BRK_S0;
+            while (a < b) {
+                int mid = (a + b) >> 1;
+                if (cum[mid] < target) a = mid + 1;
+                else b = mid;
+            }
+            if (a < BRK_S0) hi = buf.s0[a];
+        }
+        if (IS_FLOAT) {  // numbers live in [key(-inf), key(+inf)]; the keys outside are NaNs
+            const Key ninf = sizeof(Key) == 8 ? (Key)0x000FFFFFFFFFFFFFull : (Key)0x007FFFFFu;
+            const Key pinf = sizeof(Key) == 8 ? (Key)0xFFF0000000000000ull : (Key)0xFF800000u;
+            if (lo < ninf) lo = ninf;
+            if (hi > pinf) hi = pinf;
+        }
+        if (hi < lo) hi = lo;
+        qlo[t] = lo;
+        qhi[t] = hi;
+        // an edge key that repeats in the sample is a heavy tie: it becomes a bracket of its own (counted, never
+        // compacted) so that the candidates exclude it
+        auto sample_multiplicity = [&](Key v) -> unsigned {
+            int f0 = 0, f1 = BRK_S0;
+            while (f0 < f1) {
+                const int m2 = (f0 + f1) >> 1;
+                if (buf.s0[m2] < v) f0 = m2 + 1;
+                else f1 = m2;
+            }
+            return (f0 < BRK_S0 && buf.s0[f0] == v) ? (unsigned)buf.s0hist[BRK_S0 + 2 + f0] : 0u;
+        };
+        qheavy[t] = (unsigned char)((sample_multiplicity(lo) >= 4 ? 1 : 0) | (sample_multiplicity(hi) >= 4 ? 2 : 0));
+    }
+    __syncthreads();
+    // sort by (lo, hi) with a rank sort (nq <= 128), then merge overlapping brackets sequentially
+    for (int t = tid; t < nq; t += nthreads) {
+        int rank = 0;
+        const Key l = qlo[t], h = qhi[t];
+        for (int u = 0; u < nq; ++u) {
+            const Key lu = qlo[u], hu = qhi[u];
+            if (lu < l || (lu == l && (hu < h || (hu == h && u < t)))) ++rank;
+        }
+        slo[rank] = l;
+        shi[rank] = h;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // heavy edge keys, sorted and unique
+        int nh = 0;
+        for (int t = 0; t < nq; ++t) {
+            for (int side = 0; side < 2; ++side) {
+                if (!(qheavy[t] & (1 << side))) continue;
+                const Key v = side ? qhi[t] : qlo[t];
+                int pos = nh;
+                bool dup = false;
+                for (int i = 0; i < nh; ++i) {
+                    if (hv[i] == v) { dup = true; break; }
+                    if (hv[i] > v) { pos = i; break; }
+                }
+                if (dup) continue;
+                for (int i = nh; i > pos; --i) hv[i] = hv[i - 1];
+                hv[pos] = v;
+                ++nh;
+            }
+        }
+        // merge overlapping / adjacent raw intervals into spans, then cut every span at the heavy keys inside it
+        int B = 0, ih = 0;
+        auto emit = [&](Key l, Key h) {
+            if (B < BRK_MAXB) { blo[B] = l; bhi[B] = h; }
+            ++B;
+        };
+        auto emit_span = [&](Key l, Key h) {
+            while (ih < nh && hv[ih] < l) ++ih;
+            Key cur = l;
+            bool open = true;  // [cur, h] still to emit
+            while (open && ih < nh && hv[ih] <= h) {
+                const Key v = hv[ih++];
+                if (v > cur) emit(cur, v - 1);
+                emit(v, v);
+                if (v == h) open = false;
+                else cur = v + 1;
+            }
+            if (open) emit(cur, h);
+        };
+        Key cl = slo[0], ch = shi[0];
+        for (int t = 1; t < nq; ++t) {
+            if (slo[t] <= ch || (ch != KMAX && slo[t] == ch + 1)) {
+                if (shi[t] > ch) ch = shi[t];
+            } else {
+                emit_span(cl, ch);
+                cl = slo[t];
+                ch = shi[t];
+            }
+        }
+        emit_span(cl, ch);
+        int fail = 0;
+        if (B > BRK_MAXB) { fail |= FAIL_TOO_MANY; B = BRK_MAXB; }
+        // tie brackets (a single key) get their own counter class while classes last
+        int ntie = 0;
+        for (int b = 0; b < B; ++b) {
+            btie[b] = 0xff;
+            if (blo[b] == bhi[b] && B + 1 + ntie < BRK_INVALID_CLS) btie[b] = (unsigned char)(B + 1 + ntie++);
+        }
+        if (B + 1 + ntie > BRK_INVALID_CLS) fail |= FAIL_TOO_MANY;
+        sB = B;
+        // candidate segments: predicted size from the sample, with head room
+        const double scale = (double)n_total / (double)s1v;
+        unsigned long long off = 0;
+        for (int b = 0; b < B; ++b) {
+            unsigned long long cap = 0;
+            if (btie[b] == 0xff) {
+                // upper bound of #{ s1 in [lo, hi] } from the S0 ranks
+                int a = 0, e = BRK_S0;  // upper_bound(hi)
+                while (a < e) { int mid = (a + e) >> 1; if (buf.s0[mid] <= bhi[b]) a = mid + 1; else e = mid; }
+                unsigned all_hi;
+                if (a > 0 && buf.s0[a - 1] == bhi[b]) all_hi = cum[a - 1];   // hi is an S0 key: exact
+                else all_hi = cum[a] - (a < BRK_S0 ? (unsigned)buf.s0hist[BRK_S0 + 2 + a] : 0u);  // #{ s1 < next S0 key } (a starts a run), or everything
+                a = 0; e = BRK_S0;      // lower_bound(lo)
+                while (a < e) { int mid = (a + e) >> 1; if (buf.s0[mid] < blo[b]) a = mid + 1; else e = mid; }
+                const unsigned lt_lo = a > 0 ? cum[a - 1] : 0u;
+                const double cnt = (double)(all_hi > lt_lo ? all_hi - lt_lo : 0u) + 1.0;
+                double want = (cnt + 6.0 * sqrt(cnt) + 16.0) * scale * 1.05 + 2048.0;
+                if (want > (double)n_local) want = (double)n_local;
+                cap = (unsigned long long)want;
+                cap = (cap + 1) & ~1ull;
+            }
+            buf.boff[b] = off;
+            buf.bcap[b] = cap;
+            off += cap;
+        }
+        if (off > buf.cand_cap[0]) fail |= FAIL_CAPACITY;
+        // top-level cell width
+        const Key range = bhi[B - 1] - blo[0];
+        int shift1 = key_bits_used(range) - 12;
+        if (shift1 < 0) shift1 = 0;
+        while ((range >> shift1) > (Key)(BRK_NC1 - 3)) ++shift1;
+        sShift1 = shift1;
+        sNmixed = 0;
+        sFail = fail;
+        buf.hdr[H_B] = (unsigned long long)B;
+        buf.hdr[H_NTIE] = (unsigned long long)ntie;
+        buf.hdr[H_NCLS_USED] = (unsigned long long)(B + 1 + ntie);
+        if (fail) raise_fail(buf.hdr, fail);
+    }
+    __syncthreads();
+    const int B = sB, shift1 = sShift1;
+    const Key kmin = blo[0];
+    for (int b = tid; b < B; b += nthreads) {
+        buf.blo[b] = blo[b];
+        buf.bhi[b] = bhi[b];
+        buf.btie[b] = btie[b];
+    }
+    // pure entries + the two special ones (floats: below / above the bracket range may hold NaN keys)
+    for (int i = tid; i < BRK_L2_PURE; i += nthreads) {
+        unsigned short e = 0;
+        if (i < 256) {
+            const int j = i >> 1;
+            const bool in = i & 1;
+            if (j <= B && (!in || j > 0)) e = (unsigned short)pure_entry(j, in, btie);
+        } else if (i == 256) {
+            e = (unsigned short)(ENT_MIXED | ENT_SPECIAL | 0u);          // scan starts at bracket 0
+        } else if (i == 257) {
+            e = (unsigned short)(ENT_MIXED | ENT_SPECIAL | (unsigned)B);  // above every lower edge
+        } else if (i == 258) {
+            e = (unsigned short)BRK_INVALID_CLS;                           // a range of NaN keys only
+        }
+        buf.lut2[i] = e;
+    }
+    // ---- level 1: which cells hold a bracket edge -----------------------------------------------------
+    const Key width1 = ((Key)1 << shift1) - 1;
+    auto cell_ends = [&](int c, Key &a, Key &e) {  // cells 1 .. NC1-2
+        a = kmin + ((Key)(c - 1) << shift1);
+        e = (a > KMAX - width1) ? KMAX : a + width1;
+    };
+    // Kind of the key range [a, e]: 0 = one class throughout (pa), 1 = holds a bracket edge, 2 = NaN keys only,
+    // 3 = holds the border between numbers and NaN keys (floats: keys outside [key(-inf), key(+inf)] are NaNs)
+    const Key NINF = sizeof(Key) == 8 ? (Key)0x000FFFFFFFFFFFFFull : (Key)0x007FFFFFu;
+    const Key PINF = sizeof(Key) == 8 ? (Key)0xFFF0000000000000ull : (Key)0xFF800000u;
+    auto range_kind = [&](Key a, Key e, PointClass<Key> &pa) -> int {
+        if (IS_FLOAT) {
+            if (a > PINF || e < NINF) return 2;
+            if (e > PINF || a < NINF) {
+                pa = classify_point(blo, bhi, B, a);
+                return 3;
+            }
+        }
+        pa = classify_point(blo, bhi, B, a);
+        const PointClass<Key> pe = classify_point(blo, bhi, B, e);
+        return (pa.j == pe.j && pa.in == pe.in) ? 0 : 1;
+    };
+    // cells past the end of the key space (kmin + (c-1) << shift1 overflows) can never be hit
+    const Key max_cell = (KMAX - kmin) >> shift1;  // largest (c - 1) that exists
+    int my_mixed = 0;
+    for (int c = tid; c < BRK_NC1; c += nthreads) {
+        if (c == 0 || c == BRK_NC1 - 1) continue;
+        if ((Key)(c - 1) > max_cell) continue;
+        Key a, e;
+        cell_ends(c, a, e);
+        PointClass<Key> pa;
+        const int kind = range_kind(a, e, pa);
+        if (kind == 1 || kind == 3) ++my_mixed;
+    }
+    atomicAdd(&sNmixed, my_mixed);
+    __syncthreads();
+    if (tid == 0) {
+        int M = 0;
+        const int nm = sNmixed > 0 ? sNmixed : 1;
+        while (M < shift1 && M < 14 && ((nm << (M + 1)) <= BRK_L2_SUB)) ++M;
+        sM = M;
+        sNmixed = 0;  // reused as the allocation cursor
+        buf.lutc->kmin = kmin;
+        buf.lutc->shift1 = shift1;
+        buf.lutc->subshift = shift1 - M;
+        buf.lutc->submask = (1u << M) - 1u;
+        buf.lutc->B = B;
+        buf.lutc->ncls_used = (int)buf.hdr[H_NCLS_USED];
+    }
+    __syncthreads();
+    const int M = sM, subshift = shift1 - M;
+    const Key width2 = ((Key)1 << subshift) - 1;
+    for (int c = tid; c < BRK_NC1; c += nthreads) {
+        unsigned e1;
+        if (c == 0) {
+            e1 = IS_FLOAT ? 256u : 0u;  // below kmin: class 0, not inside (floats: maybe a negative NaN)
+        } else if (c == BRK_NC1 - 1) {
+            e1 = IS_FLOAT ? 257u : (unsigned)(2 * B);
+        } else if ((Key)(c - 1) > max_cell) {
+            e1 = (unsigned)(2 * B);
+        } else {
+            Key a, e;
+            cell_ends(c, a, e);
+            PointClass<Key> pa;
+            const int kind = range_kind(a, e, pa);
+            if (kind == 0) {
+                e1 = (unsigned)(2 * pa.j + (pa.in ? 1 : 0));
+            } else if (kind == 2) {
+                e1 = 258u;
+            } else {
+                const int slot = atomicAdd(&sNmixed, 1);
+                const unsigned base = BRK_L2_PURE + ((unsigned)slot << M);
+                e1 = 0x80000000u | base;
+                for (unsigned s = 0; s < (1u << M); ++s) {
+                    const Key a2 = a + ((Key)s << subshift);
+                    Key e2 = (a2 > KMAX - width2) ? KMAX : a2 + width2;
+                    if (e2 > e) e2 = e;
+                    PointClass<Key> p2;
+                    const int k2 = range_kind(a2, e2, p2);
+                    unsigned short ent;
+                    if (k2 == 0) ent = (unsigned short)pure_entry(p2.j, p2.in, btie);
+                    else if (k2 == 2) ent = (unsigned short)BRK_INVALID_CLS;
+                    else ent = (unsigned short)(ENT_MIXED | (k2 == 3 ? ENT_SPECIAL : 0u) | (unsigned)p2.j);
+                    buf.lut2[base + s] = ent;
+                }
+            }
+        }
+        buf.lut1[c] = e1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4. the streaming pass
+// ------------------------------------------------------------------------------------------------
+template <typename Key> __host__ __device__ constexpr size_t stream_smem_bytes() {
+    return (size_t)BRK_NCLS * BRK_THREADS * 2 + (size_t)BRK_NC1 * 4 + (((size_t)BRK_L2N * 2 + 15) & ~(size_t)15) +
+           2 * (size_t)BRK_MAXB * sizeof(Key) + 128 + (size_t)BRK_STAGE_CAP * sizeof(Key) + BRK_STAGE_CAP +
+           4 * (size_t)BRK_MAXB * 4 + 64;
+}
+
+// slow path of the classification: a (sub-)cell that holds a bracket edge, or (floats) the region below /
+// above all brackets where NaN keys live
+template <typename Key, bool IS_FLOAT>
+__device__ __noinline__ unsigned brk_resolve_entry(Key k, unsigned ent, const Key *blo, const Key *bhi,
+                                                   const unsigned char *btie, int B) {
+    if (IS_FLOAT && (ent & ENT_SPECIAL)) {
+        const bool nan = sizeof(Key) == 8 ? (k > (Key)0xFFF0000000000000ull || k < (Key)0x000FFFFFFFFFFFFFull)
+                                          : (k > (Key)0xFF800000u || k < (Key)0x007FFFFFu);
+        if (nan) return BRK_INVALID_CLS;
+    }
+    int j = (int)(ent & 0xffu);
+    while (j < B && blo[j] <= k) ++j;
+    const bool in = j > 0 && k <= bhi[j - 1];
+    return pure_entry(j, in, btie);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BRK_THREADS, 1)
+brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typename Traits<T>::Key> buf) {
+    using Tr = Traits<T>;
+    using Key = typename Tr::Key;
+    constexpr bool IS_FLOAT = Tr::is_float;
+    constexpr int ES = (int)sizeof(T);
+    constexpr int VEC = 16 / ES;             // elements per 16-byte load
+    constexpr int NLD = BRK_EPT / VEC;       // 16-byte loads per thread per tile
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // ---- carve shared memory -----------------------------------------------------------------------
+    unsigned char *p = smem_raw;
+    unsigned short *counters = reinterpret_cast<unsigned short *>(p); p += (size_t)BRK_NCLS * BRK_THREADS * 2;
+    unsigned *lut1 = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_NC1 * 4;
+    unsigned short *lut2 = reinterpret_cast<unsigned short *>(p); p += ((size_t)BRK_L2N * 2 + 15) & ~(size_t)15;
+    Key *blo = reinterpret_cast<Key *>(p); p += (size_t)BRK_MAXB * sizeof(Key);
+    Key *bhi = reinterpret_cast<Key *>(p); p += (size_t)BRK_MAXB * sizeof(Key);
+    unsigned char *btie = p; p += 128;
+    Key *skey = reinterpret_cast<Key *>(p); p += (size_t)BRK_STAGE_CAP * sizeof(Key);
+    unsigned char *sbrk = p; p += BRK_STAGE_CAP;
+    unsigned long long *fbase = reinterpret_cast<unsigned long long *>(p); p += (size_t)BRK_MAXB * 8;
+    unsigned *fcnt = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;
+    unsigned *fpos = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;
+    unsigned *s_cursor = reinterpret_cast<unsigned *>(p);
+
+    if (buf.hdr[H_FAIL]) return;  // the plan already gave up: the caller falls back
+    const int tid = threadIdx.x, lane = tid & 31;
+    const BrkLutConst<Key> lc = *buf.lutc;
+    const int B = lc.B;
+    const Key kmin = lc.kmin;
+    const int shift1 = lc.shift1, subshift = lc.subshift;
+    const unsigned submask = lc.submask;
+    const int ncls_used = lc.ncls_used;
+
+    for (int i = tid; i < BRK_NC1; i += BRK_THREADS) lut1[i] = buf.lut1[i];
+    for (int i = tid; i < BRK_L2N; i += BRK_THREADS) lut2[i] = buf.lut2[i];
+    for (int i = tid; i < BRK_MAXB; i += BRK_THREADS) {
+        blo[i] = i < B ? buf.blo[i] : (Key)0;
+        bhi[i] = i < B ? buf.bhi[i] : (Key)0;
+        btie[i] = i < B ? buf.btie[i] : (unsigned char)0xff;
+        fcnt[i] = 0;
+    }
+    for (int i = tid; i < BRK_NCLS * BRK_THREADS / 2; i += BRK_THREADS) reinterpret_cast<unsigned *>(counters)[i] = 0;
+    if (tid == 0) *s_cursor = 0;
+    __syncthreads();
+
+    unsigned short *myctr = counters + counter_slot();
+
+    // classify one key, count it, return its entry (class | ENT_COMPACT)
+    auto classify = [&](Key k) -> unsigned {
+        const Key d = k - kmin;
+        const Key cc = d >> shift1;
+        unsigned cell = 1u + (unsigned)(cc < (Key)(BRK_NC1 - 2) ? cc : (Key)(BRK_NC1 - 2));
+        if (k < kmin) cell = 0;
+        const unsigned e1 = lut1[cell];
+        const unsigned sub = (unsigned)(d >> subshift) & submask & (unsigned)((int)e1 >> 31);
+        unsigned ent = lut2[(e1 & 0x7fffffffu) + sub];
+        if (ent & (ENT_MIXED | ENT_SPECIAL)) ent = brk_resolve_entry<Key, IS_FLOAT>(k, ent, blo, bhi, btie, B);
+        myctr[(ent & 0xffu) * BRK_THREADS] += 1;
+        return ent;
+    };
+
+    // flush the staged candidates to their brackets' segments (whole CTA)
+    auto flush = [&]() {
+        __syncthreads();
+        const unsigned nst = *s_cursor;
+        for (unsigned i = tid; i < nst; i += BRK_THREADS) atomicAdd(&fcnt[sbrk[i]], 1u);
+        __syncthreads();
+        for (int b = tid; b < B; b += BRK_THREADS) {
+            const unsigned c = fcnt[b];
+            if (c) {
+                fbase[b] = atomicAdd(&buf.cur_local[b], (unsigned long long)c);
+                fpos[b] = 0;
+                fcnt[b] = 0;
+            }
+        }
+        __syncthreads();
+        for (unsigned i = tid; i < nst; i += BRK_THREADS) {
+            const unsigned b = sbrk[i];
+            const unsigned long long pos = fbase[b] + atomicAdd(&fpos[b], 1u);
+            // positions beyond the planned capacity are dropped; resolve sees fill > cap and raises FAIL_CAPACITY
+            if (pos < buf.bcap[b]) buf.cand[0][buf.boff[b] + pos] = skey[i];
+        }
+        __syncthreads();
+        if (tid == 0) *s_cursor = 0;
+        __syncthreads();
+    };
+
+    // stage the compact-flagged keys of this thread (mask over its EPT keys)
+    auto stage = [&](const Key (&k)[BRK_EPT], const unsigned char (&brk)[BRK_EPT], unsigned cmask) {
+        const unsigned cnt = __popc(cmask);
+        unsigned incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) return;
+        unsigned base = 0;
+        if (lane == 31) base = atomicAdd(s_cursor, total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        unsigned pos = base + incl - cnt;
+#pragma unroll
+        for (int e = 0; e < BRK_EPT; ++e) {
+            if (cmask & (1u << e)) {
+                skey[pos] = k[e];
+                sbrk[pos] = brk[e];
+                ++pos;
+            }
+        }
+    };
+
+    // ---- full, 16-byte aligned tiles ------------------------------------------------------------------
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(data);
+    unsigned long long head = ((16 - (addr & 15)) & 15) / ES;  // elements before the first aligned one
+    if (head > n) head = n;
+    const unsigned long long n_tiles = (n - head) / BRK_TILE;
+    const uint4 *vdata = reinterpret_cast<const uint4 *>(data + head);
+
+    auto load_tile = [&](unsigned long long tile, uint4 (&q)[NLD]) {
+        const uint4 *src = vdata + tile * (BRK_TILE / VEC);
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) q[j] = __ldg(src + j * BRK_THREADS + tid);
+    };
+    auto process_tile = [&](const uint4 (&q)[NLD]) {
+        Key k[BRK_EPT];
+        unsigned char brk[BRK_EPT];
+        unsigned cmask = 0;
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) {
+            if constexpr (ES == 4) {
+                const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) k[j * 4 + u] = Tr::to_key(from_raw<T>(w[u]));
+            } else {
+                const uint64_t w0 = (uint64_t)q[j].x | ((uint64_t)q[j].y << 32);
+                const uint64_t w1 = (uint64_t)q[j].z | ((uint64_t)q[j].w << 32);
+                k[j * 2] = Tr::to_key(from_raw<T>(w0));
+                k[j * 2 + 1] = Tr::to_key(from_raw<T>(w1));
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < BRK_EPT; ++e) {
+            const unsigned ent = classify(k[e]);
+            brk[e] = (unsigned char)((ent & 0xffu) - 1u);
+            cmask |= ((ent >> 8) & 1u) << e;
+        }
+        stage(k, brk, cmask);
+    };
+
+    unsigned tiles_since_reduce = 0;
+    auto reduce_counters = [&]() {
+        __syncthreads();
+        const int warp = tid >> 5;
+        for (int c = warp; c < BRK_NCLS; c += BRK_THREADS / 32) {
+            if (c >= ncls_used && c != BRK_INVALID_CLS) continue;
+            unsigned sum = 0;
+            for (int i = lane; i < BRK_THREADS; i += 32) {
+                sum += counters[c * BRK_THREADS + i];
+                counters[c * BRK_THREADS + i] = 0;
+            }
+            sum = __reduce_add_sync(0xffffffffu, sum);
+            if (lane == 0 && sum) atomicAdd(&buf.red_stream[c], (unsigned long long)sum);
+        }
+        __syncthreads();
+    };
+
+    {
+        uint4 qa[NLD], qb[NLD];
+        unsigned long long tile = blockIdx.x;
+        if (tile < n_tiles) load_tile(tile, qa);
+        while (tile < n_tiles) {
+            const unsigned long long next = tile + gridDim.x;
+            if (next < n_tiles) load_tile(next, qb);
+            process_tile(qa);
+            __syncthreads();
+            if (*s_cursor > BRK_STAGE_CAP - BRK_TILE) flush();
+            if (++tiles_since_reduce >= 4000) {  // 16-bit private counters: 4000 * 16 < 65536
+                reduce_counters();
+                tiles_since_reduce = 0;
+            }
+            tile = next;
+            if (tile >= n_tiles) break;
+            const unsigned long long next2 = tile + gridDim.x;
+            if (next2 < n_tiles) load_tile(next2, qa);
+            process_tile(qb);
+            __syncthreads();
+            if (*s_cursor > BRK_STAGE_CAP - BRK_TILE) flush();
+            if (++tiles_since_reduce >= 4000) {
+                reduce_counters();
+                tiles_since_reduce = 0;
+            }
+            tile = next2;
+        }
+    }
+    // ---- ragged head and tail: the last CTA, element by element ---------------------------------------
+    if (blockIdx.x == gridDim.x - 1) {
+        const unsigned long long tail0 = head + n_tiles * BRK_TILE;
+        const unsigned long long n_ragged = head + (n - tail0);
+        for (unsigned long long i0 = 0; i0 < n_ragged; i0 += BRK_THREADS) {
+            const unsigned long long i = i0 + tid;
+            unsigned ent = 0;
+            Key k = 0;
+            bool have = i < n_ragged;
+            if (have) {
+                const unsigned long long idx = i < head ? i : tail0 + (i - head);
+                k = Tr::to_key(data[idx]);
+                ent = classify(k);
+            }
+            const bool cflag = have && (ent & ENT_COMPACT);
+            const unsigned m = __ballot_sync(0xffffffffu, cflag);
+            if (m) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(s_cursor, (unsigned)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (cflag) {
+                    const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
+                    skey[pos] = k;
+                    sbrk[pos] = (unsigned char)((ent & 0xffu) - 1u);
+                }
+            }
+            __syncthreads();
+            if (*s_cursor > BRK_STAGE_CAP - BRK_TILE) flush();
+        }
+    }
+    flush();
+    reduce_counters();
+}
+
+// in-counts of the non-tie brackets are their segment fills
+template <typename Key> __global__ void brk_publish_fill_kernel(BrkBuf<Key> buf) {
+    const int B = (int)buf.hdr[H_B];
+    for (int b = threadIdx.x; b < B; b += blockDim.x) buf.red_stream[BRK_NCLS + b] = buf.cur_local[b];
+}
+
+// ------------------------------------------------------------------------------------------------
+// 5. resolve: ranks -> (bracket, rank inside)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked_or_skip) {
+    using Tr = Traits<T>;
+    using Key = typename Tr::Key;
+    __shared__ unsigned long long below[BRK_MAXB], incnt[BRK_MAXB];
+    __shared__ int seg_used[BRK_MAXB];
+    const int tid = threadIdx.x;
+    if (buf.hdr[H_FAIL]) return;
+    const int B = (int)buf.hdr[H_B];
+    const int R = 2 * qa.nq;
+    const unsigned long long n_total = buf.hdr[H_NTOTAL];
+    const unsigned long long n_invalid = buf.red_stream[BRK_INVALID_CLS];
+    const bool drop = masked_or_skip != 0;
+    const unsigned long long n_eff = drop ? n_total - n_invalid : n_total;
+    if (tid == 0) {
+        if (!drop && Tr::is_float && n_invalid) atomicOr(qa.status, STATUS_BIT_NAN);
+        buf.hdr[H_NINVALID] = n_invalid;
+        buf.hdr[H_NEFF] = n_eff;
+        buf.hdr[H_EMPTY] = n_eff == 0;
+        buf.hdr[H_NSEG] = (unsigned long long)B;
+    }
+    for (int b = tid; b < BRK_MAXB; b += blockDim.x) seg_used[b] = 0;
+    if (n_eff == 0) {
+        if (tid == 0) {
+            buf.hdr[H_NTASK] = 0;
+            buf.hdr[H_NACTIVE] = 0;
+            buf.hdr[H_NCHUNK_COUNT] = 0;
+            buf.hdr[H_NCHUNK_COMPACT] = 0;
+            buf.cprefix_count[0] = 0;
+        }
+        return;
+    }
+    if (tid == 0) {  // exact counts below / inside each bracket
+        unsigned long long run = 0, check = 0;
+        for (int b = 0; b < B; ++b) {
+            const unsigned char t = buf.btie[b];
+            const unsigned long long in_b = t != 0xff ? buf.red_stream[t] : buf.red_stream[BRK_NCLS + b];
+            // class j counts the gap before bracket j plus (non-tie) the inside of bracket j-1
+            unsigned long long gap = buf.red_stream[b];
+            if (b > 0 && buf.btie[b - 1] == 0xff) gap -= incnt[b - 1];
+            run += gap;
+            below[b] = run;
+            incnt[b] = in_b;
+            run += in_b;
+        }
+        unsigned long long gap = buf.red_stream[B];
+        if (B > 0 && buf.btie[B - 1] == 0xff) gap -= incnt[B - 1];
+        check = run + gap;
+        if (check != n_total - n_invalid) raise_fail(buf.hdr, FAIL_INCONSISTENT);  // every non-NaN element is in one class
+    }
+    // ---- requested ranks (as long_decide does): slots -> unique ranks -> tasks -------------------------
+    for (int t = tid; t < qa.nq; t += blockDim.x) {
+        RankMath rm = slot_rank_math(qa, t, n_eff);
+        const bool nl = needs_lower(qa.interp, rm.frac), nh = needs_higher(qa.interp, rm.frac);
+        buf.slot_rank[2 * t] = nl ? rm.lower : rm.higher;
+        buf.slot_rank[2 * t + 1] = nh ? rm.higher : rm.lower;
+    }
+    __syncthreads();
+    if (ld_now(&buf.hdr[H_FAIL])) return;
+    for (int i = tid; i < R; i += blockDim.x) {  // first occurrence of each rank, numbered in slot order
+        const unsigned long long ri = buf.slot_rank[i];
+        int first = i;
+        for (int k = 0; k < i; ++k)
+            if (buf.slot_rank[k] == ri) { first = k; break; }
+        buf.slot_task[i] = first == i ? -1 - i : first;  // negative: "I am a first occurrence"
+    }
+    __syncthreads();
+    for (int i = tid; i < R; i += blockDim.x) {
+        if (buf.slot_task[i] < 0) {
+            int id = 0;
+            for (int k = 0; k < i; ++k) id += buf.slot_task[k] < 0 ? 1 : 0;
+            // (ids are dense in slot order)
+            const unsigned long long r = buf.slot_rank[i];
+            BrkTask tk;
+            tk.r = 0;
+            tk.value = 0;
+            tk.seg = -1;
+            tk.state = TASK_ACTIVE;
+            // bracket holding rank r
+            int lo = 0, hi = B;  // first b with below[b] + incnt[b] > r
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (below[mid] + incnt[mid] <= r) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo >= B || below[lo] > r) {
+                raise_fail(buf.hdr, FAIL_ESCAPED);
+            } else {
+                tk.seg = lo;
+                tk.r = r - below[lo];
+                if (buf.btie[lo] != 0xff || buf.blo[lo] == buf.bhi[lo]) {
+                    tk.state = TASK_DONE;
+                    tk.value = (unsigned long long)buf.blo[lo];
+                } else {
+                    seg_used[lo] = 1;
+                }
+            }
+            buf.task[id] = tk;
+        }
+    }
+    __syncthreads();
+    // slot -> task id (second pass: first occurrences know their id by counting)
+    for (int i = tid; i < R; i += blockDim.x) {
+        int f = buf.slot_task[i] < 0 ? i : buf.slot_task[i];
+        int id = 0;
+        for (int k = 0; k < f; ++k) id += buf.slot_task[k] < 0 ? 1 : 0;
+        buf.slot_rank[i] = (unsigned long long)id;  // reuse: slot -> task id
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nt = 0;
+        for (int i = 0; i < R; ++i) nt += buf.slot_task[i] < 0 ? 1 : 0;
+        buf.hdr[H_NTASK] = (unsigned long long)nt;
+    }
+    // ---- round-0 segments are the brackets -------------------------------------------------------------
+    for (int b = tid; b < B; b += blockDim.x) {
+        BrkSeg<Key> s;
+        s.lo = buf.blo[b];
+        s.hi = buf.bhi[b];
+        const int bits = key_bits_used<Key>((Key)(s.hi - s.lo));
+        s.shift = bits > 8 ? bits - 8 : 0;
+        s.flags = 0;
+        if (buf.btie[b] != 0xff) s.flags |= SEG_TIE;
+        if (seg_used[b]) s.flags |= SEG_USED;
+        s.off = buf.boff[b];
+        unsigned long long fill = buf.cur_local[b];
+        if (fill > buf.bcap[b]) {
+            raise_fail(buf.hdr, FAIL_CAPACITY);
+            fill = buf.bcap[b];
+        }
+        s.cnt_local = (s.flags & SEG_TIE) ? 0 : fill;
+        s.cnt_global = incnt[b];
+        s.cursor = 0;
+        if ((s.flags & SEG_USED) && s.cnt_global <= BRK_FINAL_CAP) s.flags |= SEG_FINAL;
+        buf.seg[0][b] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {  // chunk prefix of the segments the first count pass has to read
+        unsigned long long run = 0;
+        int active = 0;
+        for (int b = 0; b < B; ++b) {
+            buf.cprefix_count[b] = run;
+            const BrkSeg<Key> &s = buf.seg[0][b];
+            if ((s.flags & SEG_USED) && !(s.flags & (SEG_FINAL | SEG_TIE))) {
+                run += (s.cnt_local + BRK_RCHUNK - 1) / BRK_RCHUNK;
+                ++active;
+            }
+        }
+        buf.cprefix_count[B] = run;
+        buf.hdr[H_NCHUNK_COUNT] = run;
+        buf.hdr[H_NACTIVE] = (unsigned long long)active;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 6. refine rounds over the candidate segments
+// ------------------------------------------------------------------------------------------------
+// linear chunk id -> segment (binary search over the chunk prefix)
+__device__ __forceinline__ int seg_of_chunk(const unsigned long long *prefix, int nseg, unsigned long long chunk) {
+    int lo = 0, hi = nseg;  // last s with prefix[s] <= chunk
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= chunk) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <typename Key>
+__global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_count_kernel(BrkBuf<Key> buf) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned short *counters = reinterpret_cast<unsigned short *>(smem_raw);  // [256][THREADS]
+    __shared__ unsigned long long sprefix[BRK_MAXSEG + 1];
+    if (buf.hdr[H_FAIL]) return;
+    const unsigned long long nchunks = buf.hdr[H_NCHUNK_COUNT];
+    if (nchunks == 0) return;
+    const int cur = (int)buf.hdr[H_CUR];
+    const int nseg = (int)buf.hdr[H_NSEG];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i <= nseg; i += BRK_THREADS) sprefix[i] = buf.cprefix_count[i];
+    for (int i = tid; i < 256 * BRK_THREADS / 2; i += BRK_THREADS) reinterpret_cast<unsigned *>(counters)[i] = 0;
+    __syncthreads();
+    // contiguous range of chunks per CTA: a CTA stays inside one segment for as long as possible
+    const unsigned long long per = (nchunks + gridDim.x - 1) / gridDim.x;
+    const unsigned long long c0 = (unsigned long long)blockIdx.x * per;
+    const unsigned long long c1 = c0 + per < nchunks ? c0 + per : nchunks;
+    if (c0 >= c1) return;
+    unsigned short *myctr = counters + counter_slot();
+    const Key *src = buf.cand[cur];
+    const BrkSeg<Key> *segs = buf.seg[cur];
+    int cur_seg = -1;
+    unsigned pending = 0;  // chunks counted since the last spill
+    auto spill = [&](int s) {
+        __syncthreads();
+        for (int c = warp; c < 256; c += BRK_THREADS / 32) {
+            unsigned sum = 0;
+            for (int i = lane; i < BRK_THREADS; i += 32) {
+                sum += counters[c * BRK_THREADS + i];
+                counters[c * BRK_THREADS + i] = 0;
+            }
+            sum = __reduce_add_sync(0xffffffffu, sum);
+            if (lane == 0 && sum) atomicAdd(&buf.loc_refine[(size_t)s * 256 + c], (unsigned long long)sum);
+        }
+        __syncthreads();
+    };
+    for (unsigned long long ch = c0; ch < c1; ++ch) {
+        const int s = seg_of_chunk(sprefix, nseg, ch);
+        if (s != cur_seg || pending >= 4000) {
+            if (cur_seg >= 0 && pending) spill(cur_seg);
+            cur_seg = s;
+            pending = 0;
+        }
+        const BrkSeg<Key> sg = segs[s];
+        const unsigned long long e0 = (ch - sprefix[s]) * BRK_RCHUNK;
+        const unsigned long long e1 = e0 + BRK_RCHUNK < sg.cnt_local ? e0 + BRK_RCHUNK : sg.cnt_local;
+        const Key *sp = src + sg.off;
+#pragma unroll 4
+        for (unsigned long long i = e0 + tid; i < e1; i += BRK_THREADS) {
+            const Key k = sp[i];
+            const unsigned c = (unsigned)((Key)(k - sg.lo) >> sg.shift) & 0xffu;
+            myctr[c * BRK_THREADS] += 1;
+        }
+        ++pending;
+    }
+    if (cur_seg >= 0 && pending) spill(cur_seg);
+}
+
+// One CTA: every active task picks its digit; the chosen (segment, digit) pairs become the next segments.
+template <typename Key>
+__global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf) {
+    __shared__ int want[BRK_MAXTASK];                 // seg * 256 + digit of the task, or -1
+    __shared__ int newseg_of[BRK_MAXTASK];            // id of the segment the task moves to
+    __shared__ unsigned long long pad_cnt[BRK_MAXTASK];
+    __shared__ unsigned char first[BRK_MAXTASK];
+    __shared__ unsigned char seg_any[BRK_MAXSEG];
+    __shared__ unsigned long long new_cnt_local[BRK_MAXSEG];
+    __shared__ unsigned char new_final[BRK_MAXSEG];
+    __shared__ int s_nid;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (buf.hdr[H_FAIL]) return;
+    if (buf.hdr[H_NCHUNK_COUNT] == 0) {
+        if (tid == 0) buf.hdr[H_NCHUNK_COMPACT] = 0;
+        return;
+    }
+    const int cur = (int)buf.hdr[H_CUR];
+    const int nseg = (int)buf.hdr[H_NSEG], ntask = (int)buf.hdr[H_NTASK];
+    const BrkSeg<Key> *segs = buf.seg[cur];
+    BrkSeg<Key> *nsegs = buf.seg[cur ^ 1];
+    for (int i = tid; i < nseg * 256; i += blockDim.x) buf.newid[i] = -1;
+    for (int i = tid; i < BRK_MAXTASK; i += blockDim.x) { want[i] = -1; newseg_of[i] = -1; pad_cnt[i] = 0; first[i] = 0; }
+    for (int i = tid; i < BRK_MAXSEG; i += blockDim.x) seg_any[i] = 0;
+    __syncthreads();
+    // ---- digit of every active task --------------------------------------------------------------------
+    for (int t = warp; t < ntask; t += nwarps) {
+        BrkTask tk = buf.task[t];
+        if (tk.state != TASK_ACTIVE) continue;
+        const BrkSeg<Key> sg = segs[tk.seg];
+        if (sg.flags & (SEG_FINAL | SEG_TIE)) continue;  // resolved by the final kernel
+        const unsigned long long *row = buf.red_refine + (size_t)tk.seg * 256;
+        unsigned long long c[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c[j] = row[lane * 8 + j];
+            sum += c[j];
+        }
+        unsigned long long incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        unsigned long long run = incl - sum;
+        int digit = -1;
+        unsigned long long rem = 0;
+        if (tk.r >= run && tk.r < incl) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (tk.r >= run && tk.r < run + c[j]) {
+                    digit = lane * 8 + j;
+                    rem = tk.r - run;
+                }
+                run += c[j];
+            }
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, digit >= 0);
+        if (hit == 0) {  // the rank is not inside this segment: the counts are inconsistent
+            if (lane == 0) raise_fail(buf.hdr, FAIL_INCONSISTENT);
+            continue;
+        }
+        const int srcl = __ffs(hit) - 1;
+        digit = __shfl_sync(0xffffffffu, digit, srcl);
+        rem = __shfl_sync(0xffffffffu, rem, srcl);
+        if (lane == 0) {
+            if (sg.shift == 0) {  // the digit is the rest of the key
+                tk.state = TASK_DONE;
+                tk.value = (unsigned long long)(Key)(sg.lo + (Key)digit);
+            } else {
+                want[t] = tk.seg * 256 + digit;
+                pad_cnt[t] = (buf.loc_refine[(size_t)tk.seg * 256 + digit] + 1) & ~1ull;
+                tk.r = rem;
+            }
+            buf.task[t] = tk;
+        }
+    }
+    __syncthreads();
+    // ---- new segments: one per distinct wanted (segment, digit), numbered in (segment, digit) order ------
+    for (int t = tid; t < ntask; t += blockDim.x) {
+        const int w = want[t];
+        if (w < 0) continue;
+        bool f = true;
+        for (int u = 0; u < t; ++u)
+            if (want[u] == w) { f = false; break; }
+        first[t] = f ? 1 : 0;
+    }
+    if (tid == 0) s_nid = 0;
+    __syncthreads();
+    for (int t = tid; t < ntask; t += blockDim.x) {
+        const int w = want[t];
+        if (w < 0) continue;
+        int id = 0;
+        unsigned long long off = 0;
+        for (int u = 0; u < ntask; ++u) {
+            if (first[u] && want[u] >= 0 && want[u] < w) {
+                ++id;
+                off += pad_cnt[u];
+            }
+        }
+        newseg_of[t] = id;
+        if (first[t]) {
+            const int s = w >> 8, d = w & 255;
+            const BrkSeg<Key> sg = segs[s];
+            BrkSeg<Key> ns;
+            ns.lo = sg.lo + ((Key)d << sg.shift);
+            ns.hi = ns.lo + (((Key)1 << sg.shift) - 1);
+            ns.shift = sg.shift > 8 ? sg.shift - 8 : 0;
+            ns.flags = SEG_USED;
+            ns.off = off;
+            ns.cnt_local = buf.loc_refine[(size_t)w];
+            ns.cnt_global = buf.red_refine[(size_t)w];
+            ns.cursor = 0;
+            if (ns.cnt_global <= BRK_FINAL_CAP) ns.flags |= SEG_FINAL;
+            if (off + pad_cnt[t] > buf.cand_cap[cur ^ 1]) raise_fail(buf.hdr, FAIL_CAPACITY);
+            nsegs[id] = ns;
+            new_cnt_local[id] = ns.cnt_local;
+            new_final[id] = (ns.flags & SEG_FINAL) ? 1 : 0;
+            buf.newid[w] = (short)id;
+            seg_any[s] = 1;
+            atomicAdd(&s_nid, 1);
+        }
+    }
+    __syncthreads();
+    // ---- re-point the tasks; chunk tables of the compaction pass (old segments) and the next count pass ----
+    for (int t = tid; t < ntask; t += blockDim.x) {
+        if (want[t] < 0) continue;
+        BrkTask tk = buf.task[t];
+        tk.seg = newseg_of[t];
+        buf.task[t] = tk;
+    }
+    if (tid == 0) {
+        const int nid = s_nid;
+        unsigned long long chunks_compact = 0, chunks_count = 0;
+        for (int s = 0; s < nseg; ++s) {
+            buf.cprefix_compact[s] = chunks_compact;
+            if (seg_any[s]) chunks_compact += (segs[s].cnt_local + BRK_RCHUNK - 1) / BRK_RCHUNK;
+        }
+        for (int s = nseg; s <= BRK_MAXSEG; ++s) buf.cprefix_compact[s] = chunks_compact;
+        int active = 0;
+        for (int s = 0; s < nid; ++s) {
+            buf.cprefix_count[s] = chunks_count;
+            if (!new_final[s]) {
+                chunks_count += (new_cnt_local[s] + BRK_RCHUNK - 1) / BRK_RCHUNK;
+                ++active;
+            }
+        }
+        for (int s = nid; s <= BRK_MAXSEG; ++s) buf.cprefix_count[s] = chunks_count;
+        buf.hdr[H_NCHUNK_COMPACT] = chunks_compact;
+        // the next count pass must see the new table only after the compaction of this round has read the
+        // old one: brk_refine_advance_kernel publishes these
+        buf.hdr[H_NEXT_NCHUNK] = chunks_count;
+        buf.hdr[H_NEXT_NSEG] = (unsigned long long)nid;
+        buf.hdr[H_OLD_NSEG] = (unsigned long long)nseg;
+        buf.hdr[H_NACTIVE] = (unsigned long long)active;
+    }
+    // the counts of this round are consumed: clear them for the next one
+    __syncthreads();
+    for (int i = tid; i < nseg * 256; i += blockDim.x) {
+        buf.loc_refine[i] = 0;
+        if (buf.red_refine != buf.loc_refine) buf.red_refine[i] = 0;
+    }
+}
+
+template <typename Key>
+__global__ void __launch_bounds__(BRK_THREADS) brk_refine_compact_kernel(BrkBuf<Key> buf) {
+    __shared__ unsigned long long sprefix[BRK_MAXSEG + 1];
+    __shared__ short sid[256];
+    if (buf.hdr[H_FAIL]) return;
+    const unsigned long long nchunks = buf.hdr[H_NCHUNK_COMPACT];
+    if (nchunks == 0) return;
+    const int nseg = (int)buf.hdr[H_OLD_NSEG];
+    const int cur = (int)buf.hdr[H_CUR];
+    const int tid = threadIdx.x;
+    for (int i = tid; i <= nseg; i += BRK_THREADS) sprefix[i] = buf.cprefix_compact[i];
+    __syncthreads();
+    const unsigned long long per = (nchunks + gridDim.x - 1) / gridDim.x;
+    const unsigned long long c0 = (unsigned long long)blockIdx.x * per;
+    const unsigned long long c1 = c0 + per < nchunks ? c0 + per : nchunks;
+    const Key *src = buf.cand[cur];
+    Key *dst = buf.cand[cur ^ 1];
+    const BrkSeg<Key> *segs = buf.seg[cur];
+    BrkSeg<Key> *nsegs = buf.seg[cur ^ 1];
+    int cur_seg = -1;
+    for (unsigned long long ch = c0; ch < c1; ++ch) {
+        // segments without a wanted digit have equal prefix entries: take the LAST s with prefix[s] <= ch
+        // among those that own chunks
+        int s = seg_of_chunk(sprefix, nseg, ch);
+        if (s != cur_seg) {
+            __syncthreads();
+            sid[tid] = buf.newid[s * 256 + tid];
+            __syncthreads();
+            cur_seg = s;
+        }
+        const BrkSeg<Key> sg = segs[s];
+        const unsigned long long e0 = (ch - sprefix[s]) * BRK_RCHUNK;
+        const unsigned long long e1 = e0 + BRK_RCHUNK < sg.cnt_local ? e0 + BRK_RCHUNK : sg.cnt_local;
+        const Key *sp = src + sg.off;
+        for (unsigned long long i = e0 + tid; i < e1; i += BRK_THREADS) {
+            const Key k = sp[i];
+            const unsigned c = (unsigned)((Key)(k - sg.lo) >> sg.shift) & 0xffu;
+            const int id = sid[c];
+            if (id >= 0) {
+                const unsigned long long pos = atomicAdd(&nsegs[id].cursor, 1ull);
+                if (pos < nsegs[id].cnt_local) dst[nsegs[id].off + pos] = k;
+            }
+        }
+    }
+}
+
+// publish the next round's segment table sizes (after the compaction has read the old ones)
+template <typename Key> __global__ void brk_refine_advance_kernel(BrkBuf<Key> buf) {
+    if (threadIdx.x == 0 && !buf.hdr[H_FAIL] && buf.hdr[H_NCHUNK_COUNT] != 0) {
+        buf.hdr[H_NCHUNK_COUNT] = buf.hdr[H_NEXT_NCHUNK];
+        buf.hdr[H_NSEG] = buf.hdr[H_NEXT_NSEG];
+        buf.hdr[H_CUR] = buf.hdr[H_CUR] ^ 1ull;
+    }
+}
+
+// segments of at most FINAL_CAP keys: one CTA sorts the keys and serves every task that points at it
+template <typename Key>
+__global__ void __launch_bounds__(256) brk_final_kernel(BrkBuf<Key> buf) {
+    __shared__ Key s[BRK_FINAL_CAP];
+    if (buf.hdr[H_FAIL] || buf.hdr[H_EMPTY]) return;
+    const int nseg = (int)buf.hdr[H_NSEG], ntask = (int)buf.hdr[H_NTASK];
+    const int cur = (int)buf.hdr[H_CUR];
+    const int tid = threadIdx.x;
+    for (int sidx = blockIdx.x; sidx < nseg; sidx += gridDim.x) {
+        const BrkSeg<Key> sg = buf.seg[cur][sidx];
+        if (!(sg.flags & SEG_FINAL) || (sg.flags & (SEG_TIE | SEG_DONE))) continue;
+        bool wanted = false;
+        for (int t = 0; t < ntask; ++t)
+            if (buf.task[t].state == TASK_ACTIVE && buf.task[t].seg == sidx) { wanted = true; break; }
+        if (!wanted) continue;
+        const unsigned cnt = (unsigned)sg.cnt_local;
+        unsigned np2 = 1;
+        while (np2 < cnt) np2 <<= 1;
+        const Key *src = buf.cand[cur] + sg.off;
+        for (unsigned i = tid; i < np2; i += blockDim.x) s[i] = i < cnt ? src[i] : (Key) ~(Key)0;
+        __syncthreads();
+        for (unsigned k = 2; k <= np2; k <<= 1) {
+            for (unsigned j = k >> 1; j > 0; j >>= 1) {
+                for (unsigned i = tid; i < np2; i += blockDim.x) {
+                    unsigned ixj = i ^ j;
+                    if (ixj > i) {
+                        Key a = s[i], b = s[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) { s[i] = b; s[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int t = tid; t < ntask; t += blockDim.x) {
+            BrkTask tk = buf.task[t];
+            if (tk.state == TASK_ACTIVE && tk.seg == sidx) {
+                if (tk.r < cnt) {
+                    tk.value = (unsigned long long)s[tk.r];
+                    tk.state = TASK_DONE;
+                    buf.task[t] = tk;
+                } else {
+                    raise_fail(buf.hdr, FAIL_INCONSISTENT);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// 7. Interpolate (src/quantile/interpolate.rs:64-144) and write the result
+template <typename T>
+__global__ void brk_output_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, T *out, uint8_t *out_valid,
+                                  long long out_axis_stride, int last) {
+    using Tr = Traits<T>;
+    using Key = typename Tr::Key;
+    if (buf.hdr[H_FAIL]) {  // the caller re-runs this lane on the radix passes (immediately, or at the next synchronize)
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(qa.status, STATUS_BIT_FALLBACK);
+        return;
+    }
+    const unsigned long long n_eff = buf.hdr[H_NEFF];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < qa.nq; t += gridDim.x * blockDim.x) {
+        if (buf.hdr[H_EMPTY]) {
+            out[(long long)t * out_axis_stride] = canonical_nan<T>();
+            if (out_valid) out_valid[(long long)t * out_axis_stride] = 0;
+            continue;
+        }
+        const BrkTask tl = buf.task[(int)buf.slot_rank[2 * t]], th = buf.task[(int)buf.slot_rank[2 * t + 1]];
+        if (tl.state != TASK_DONE || th.state != TASK_DONE) {
+            if (last) {
+                raise_fail(buf.hdr, FAIL_INCONSISTENT);
+                atomicOr(qa.status, STATUS_BIT_FALLBACK);
+            }
+            continue;
+        }
+        RankMath rm = slot_rank_math(qa, t, n_eff);
+        out[(long long)t * out_axis_stride] =
+            interpolate<T>(qa.interp, Tr::from_key((Key)tl.value), Tr::from_key((Key)th.value), rm.frac, qa.status);
+        if (out_valid) out_valid[(long long)t * out_axis_stride] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct BrkSizes {
+    unsigned s1;
+    unsigned long long cap0, cap1;
+    size_t total;
+};
+
+// Sample size: large enough that the brackets of all requested quantiles together hold ~12 % of the lane.
+// wsum = sum over quantiles of 2 c sqrt(p (1 - p)) (the +-c sigma widths in units of sqrt(sample size)).
+unsigned pick_s1(unsigned long long n, double wsum) {
+    const double f_target = 0.12;
+    double need = (wsum / f_target) * (wsum / f_target);
+    if (const char *e = getenv("NDS_BRK_SAMPLE")) {
+        const double v = atof(e);
+        if (v >= 1.0) need = v;
+    }
+    unsigned long long hi = n / 8;
+    if (hi < (1ull << 16)) hi = 1ull << 16;
+    if (hi > (1ull << 24)) hi = 1ull << 24;
+    unsigned long long s1 = need < 65536.0 ? 65536ull : (need > (double)hi ? hi : (unsigned long long)need);
+    if (s1 > n) s1 = n;
+    return (unsigned)s1;
+}
+double predicted_fraction(unsigned long long n, int nq, double wsum) {
+    const unsigned s1 = pick_s1(n, wsum);
+    return s1 ? wsum / std::sqrt((double)s1) + (double)nq / 4096.0 : 1.0;
+}
+
+template <typename Key> BrkSizes brk_sizes(unsigned long long n, int nq, double wsum) {
+    BrkSizes z;
+    z.s1 = pick_s1(n, wsum);
+    z.cap0 = n / 3 + (1ull << 16);
+    if (z.cap0 > n + 1024) z.cap0 = n + 1024;
+    z.cap1 = z.cap0 / 4 + (1ull << 16);
+    size_t t = 0;
+    t += align256(H_WORDS * 8) + align256(2 * 8) + align256(2 * (BRK_S0 + 2) * 8) + align256((BRK_NCLS + BRK_MAXB) * 8) +
+         align256(BRK_MAXB * 8) + 2 * align256((size_t)BRK_MAXSEG * 256 * 8);
+    t += align256((size_t)z.s1 * sizeof(Key)) + align256(BRK_S0 * sizeof(Key)) + 2 * align256(BRK_MAXB * sizeof(Key));
+    t += 2 * align256(BRK_MAXB * 8) + align256(BRK_MAXB) + align256(BRK_NC1 * 4) + align256(BRK_L2N * 2) +
+         align256(sizeof(BrkLutConst<Key>));
+    t += 2 * align256(BRK_MAXSEG * sizeof(BrkSeg<Key>)) + align256(BRK_MAXTASK * sizeof(BrkTask)) +
+         align256(2 * (size_t)nq * 4) + align256(2 * (size_t)nq * 8) + align256((size_t)BRK_MAXSEG * 256 * 2) +
+         2 * align256((BRK_MAXSEG + 1) * 8);
+    t += align256(z.cap0 * sizeof(Key)) + align256(z.cap1 * sizeof(Key));
+    z.total = t;
+    return z;
+}
+
+template <typename Key> BrkBuf<Key> brk_carve(void *scratch, const BrkSizes &z, int nq, size_t *zero_bytes) {
+    BrkBuf<Key> b;
+    char *p = (char *)scratch;
+    auto take = [&](size_t bytes) {
+        char *r = p;
+        p += align256(bytes);
+        return r;
+    };
+    // --- zeroed before every call (one memset) ---
+    b.hdr = (unsigned long long *)take(H_WORDS * 8);
+    b.red_n = (unsigned long long *)take(2 * 8);
+    b.s0hist = (unsigned long long *)take(2 * (BRK_S0 + 2) * 8);
+    b.red_stream = (unsigned long long *)take((BRK_NCLS + BRK_MAXB) * 8);
+    b.cur_local = (unsigned long long *)take(BRK_MAXB * 8);
+    b.red_refine = (unsigned long long *)take((size_t)BRK_MAXSEG * 256 * 8);
+    b.loc_refine = (unsigned long long *)take((size_t)BRK_MAXSEG * 256 * 8);
+    *zero_bytes = (size_t)(p - (char *)scratch);
+    // --- the rest is written before it is read ---
+    b.s1 = (Key *)take((size_t)z.s1 * sizeof(Key));
+    b.s0 = (Key *)take(BRK_S0 * sizeof(Key));
+    b.blo = (Key *)take(BRK_MAXB * sizeof(Key));
+    b.bhi = (Key *)take(BRK_MAXB * sizeof(Key));
+    b.boff = (unsigned long long *)take(BRK_MAXB * 8);
+    b.bcap = (unsigned long long *)take(BRK_MAXB * 8);
+    b.btie = (unsigned char *)take(BRK_MAXB);
+    b.lut1 = (unsigned *)take(BRK_NC1 * 4);
+    b.lut2 = (unsigned short *)take(BRK_L2N * 2);
+    b.lutc = (BrkLutConst<Key> *)take(sizeof(BrkLutConst<Key>));
+    b.seg[0] = (BrkSeg<Key> *)take(BRK_MAXSEG * sizeof(BrkSeg<Key>));
+    b.seg[1] = (BrkSeg<Key> *)take(BRK_MAXSEG * sizeof(BrkSeg<Key>));
+    b.task = (BrkTask *)take(BRK_MAXTASK * sizeof(BrkTask));
+    b.slot_task = (int *)take(2 * (size_t)nq * 4);
+    b.slot_rank = (unsigned long long *)take(2 * (size_t)nq * 8);
+    b.newid = (short *)take((size_t)BRK_MAXSEG * 256 * 2);
+    b.cprefix_count = (unsigned long long *)take((BRK_MAXSEG + 1) * 8);
+    b.cprefix_compact = (unsigned long long *)take((BRK_MAXSEG + 1) * 8);
+    b.cand[0] = (Key *)take(z.cap0 * sizeof(Key));
+    b.cand[1] = (Key *)take(z.cap1 * sizeof(Key));
+    b.cand_cap[0] = z.cap0;
+    b.cand_cap[1] = z.cap1;
+    b.s1cap = z.s1;
+    return b;
+}
+
+}  // namespace
+double brk_csigma() {
+    if (const char *e = getenv("NDS_BRK_SIGMA")) {
+        const double v = atof(e);
+        if (v > 0.5 && v < 20.0) return v;
+    }
+    return 5.0;
+}
+namespace {
+
+template <typename T> constexpr bool brk_type_ok() { return sizeof(T) == 4 || sizeof(T) == 8; }
+
+template <typename T>
+cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long n, const QuantArgs &qa, T *out,
+                                uint8_t *out_valid, long long out_axis_stride, void *scratch, bool sharded,
+                                bool synchronous, double wsum, int *failed) {
+    using Key = typename Traits<T>::Key;
+    constexpr bool IS_FLOAT = Traits<T>::is_float;
+    cudaStream_t st = ctx->stream;
+    const BrkSizes z = brk_sizes<Key>(n, qa.nq, wsum);
+    size_t zero_bytes = 0;
+    BrkBuf<Key> buf = brk_carve<Key>(scratch, z, qa.nq, &zero_bytes);
+    if (!sharded) buf.red_refine = buf.loc_refine;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, zero_bytes, st);
+    if (e != cudaSuccess) return e;
+    const int sm = ctx->sm_count;
+    auto count = [&]() { ctx->launches += 1; return cudaGetLastError(); };
+    auto allreduce = [&](unsigned long long *p, size_t words) -> cudaError_t {
+        if (!(sharded && ctx->nccl_comm)) return cudaSuccess;
+        std::string err;
+        if (nccl_allreduce_sum_u64(ctx, p, words, st, &err) != 0) {
+            ctx->last_error = err;
+            return cudaErrorUnknown;
+        }
+        return cudaSuccess;
+    };
+
+    // 1-2. sample, sort S0, bucket S1
+    if (n) {
+        brk_sample_kernel<T><<<std::min<unsigned>((z.s1 + 255) / 256, sm * 8), 256, 0, st>>>(lane, n, z.s1, buf);
+        if ((e = count()) != cudaSuccess) return e;
+    }
+    // (sharded: S0 is sorted from the local sample only; the bucket counts below are summed over ranks, so the
+    //  ranks of the S0 keys stay exact for the union of the samples as long as every rank plans with the SAME S0:
+    //  rank 0's S0 is broadcast by an allreduce of a buffer that is zero everywhere else.)
+    {
+        auto k = brk_sort_s0_kernel<Key>;
+        const size_t smem = BRK_S0 * sizeof(Key);
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if (z.s1) {
+            k<<<1, 1024, smem, st>>>(buf, z.s1);
+            if ((e = count()) != cudaSuccess) return e;
+        }
+    }
+    {
+        auto k = brk_bucket_kernel<Key, IS_FLOAT>;
+        const size_t smem = BRK_S0 * sizeof(Key);
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if (z.s1) {
+            k<<<std::min<unsigned>((z.s1 + 255) / 256, sm * 4), 256, smem, st>>>(buf, z.s1);
+            if ((e = count()) != cudaSuccess) return e;
+        }
+    }
+    if ((e = allreduce(buf.red_n, 2)) != cudaSuccess) return e;
+    if ((e = allreduce(buf.s0hist, 2 * (BRK_S0 + 2))) != cudaSuccess) return e;
+    // 3. plan
+    {
+        auto k = brk_plan_kernel<Key, IS_FLOAT>;
+        const size_t smem = (BRK_S0 + 1) * 4;
+        k<<<1, 1024, smem, st>>>(buf, qa, brk_csigma(), n, sharded ? 1 : 0);
+        if ((e = count()) != cudaSuccess) return e;
+    }
+    // 4. stream
+    {
+        auto k = brk_stream_kernel<T>;
+        const size_t smem = stream_smem_bytes<Key>();
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        unsigned long long tiles = n / BRK_TILE + 1;
+        unsigned grid = (unsigned)std::min<unsigned long long>(tiles, (unsigned long long)sm);
+        k<<<grid, BRK_THREADS, smem, st>>>(lane, n, buf);
+        if ((e = count()) != cudaSuccess) return e;
+        brk_publish_fill_kernel<Key><<<1, 128, 0, st>>>(buf);
+        if ((e = count()) != cudaSuccess) return e;
+    }
+    if ((e = allreduce(buf.red_stream, BRK_NCLS + BRK_MAXB)) != cudaSuccess) return e;
+    // 5. resolve
+    brk_resolve_kernel<T><<<1, 256, 0, st>>>(buf, qa, qa.skipnan);
+    if ((e = count()) != cudaSuccess) return e;
+    // 6. refine
+    {
+        auto kc = brk_refine_count_kernel<Key>;
+        const size_t smem = (size_t)256 * BRK_THREADS * 2;
+        if ((e = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        const int max_rounds = (int)sizeof(Key) + 1;
+        brk_final_kernel<Key><<<sm, 256, 0, st>>>(buf);
+        if ((e = count()) != cudaSuccess) return e;
+        for (int round = 0; round < max_rounds; ++round) {
+            kc<<<sm, BRK_THREADS, smem, st>>>(buf);
+            if ((e = count()) != cudaSuccess) return e;
+            if (sharded && ctx->nccl_comm) {
+                // red_refine = sum over ranks of loc_refine
+                if ((e = cudaMemcpyAsync(buf.red_refine, buf.loc_refine, (size_t)BRK_MAXSEG * 256 * 8,
+                                         cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
+                if ((e = allreduce(buf.red_refine, (size_t)BRK_MAXSEG * 256)) != cudaSuccess) return e;
+            }
+            brk_refine_decide_kernel<Key><<<1, 256, 0, st>>>(buf);
+            if ((e = count()) != cudaSuccess) return e;
+            brk_refine_compact_kernel<Key><<<sm * 2, BRK_THREADS, 0, st>>>(buf);
+            if ((e = count()) != cudaSuccess) return e;
+            brk_refine_advance_kernel<Key><<<1, 32, 0, st>>>(buf);
+            if ((e = count()) != cudaSuccess) return e;
+            brk_final_kernel<Key><<<sm, 256, 0, st>>>(buf);
+            if ((e = count()) != cudaSuccess) return e;
+            if (synchronous && round >= 1) {
+                unsigned long long h[H_WORDS];
+                if ((e = cudaMemcpyAsync(h, buf.hdr, sizeof h, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+                if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+                if (h[H_FAIL] || h[H_NACTIVE] == 0 || h[H_NCHUNK_COUNT] == 0) break;
+            }
+        }
+    }
+    // 7. output
+    brk_output_kernel<T><<<(qa.nq + 127) / 128, 128, 0, st>>>(buf, qa, out, out_valid, out_axis_stride, 1);
+    if ((e = count()) != cudaSuccess) return e;
+    if (synchronous) {
+        unsigned long long h[H_WORDS];
+        if ((e = cudaMemcpyAsync(h, buf.hdr, sizeof h, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        *failed = (int)h[H_FAIL];
+        if (getenv("NDS_BRK_DEBUG"))
+            fprintf(stderr, "[bracket] n=%llu s1=%u fail=%llu B=%llu ties=%llu tasks=%llu n_eff=%llu invalid=%llu active=%llu\n", n,
+                    z.s1, h[H_FAIL], h[H_B], h[H_NTIE], h[H_NTASK], h[H_NEFF], h[H_NINVALID], h[H_NACTIVE]);
+    } else {
+        // asynchronous call: the FAIL word is folded into the ctx status at the next synchronize
+        *failed = 0;
+    }
+    return cudaSuccess;
+}
+
+template <typename T>
+cudaError_t launch_bracket_typed(nds_ctx *ctx, const DeviceCall &c, void *scratch, bool sharded, bool synchronous,
+                                 int *failed) {
+    *failed = 0;
+    for (unsigned long long lane = 0; lane < c.geom.nlanes; ++lane) {
+        long long in_off, out_off;
+        lane_offsets(c.geom, lane, in_off, out_off);
+        int f = 0;
+        cudaError_t e = launch_bracket_lane<T>(ctx, (const T *)c.data + in_off, c.geom.axis_len, c.q, (T *)c.out + out_off,
+                                               c.out_valid ? c.out_valid + out_off : nullptr, c.geom.out_axis_stride,
+                                               scratch, sharded, synchronous, c.brk_wsum, &f);
+        if (e != cudaSuccess) return e;
+        *failed |= f;
+        if (f) break;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace
+
+bool bracket_supported(const nds_ctx *ctx, const DeviceCall &c, bool sharded, bool forced) {
+    (void)ctx;
+    switch (c.dtype) {
+    case NDS_F32: case NDS_I32: case NDS_U32: case NDS_F64: case NDS_I64: case NDS_U64: break;
+    default: return false;
+    }
+    if (c.valid || c.out_valid) return false;
+    if (c.geom.axis_stride != 1 && c.geom.axis_len > 1) return false;
+    if (c.q.nq < 1 || c.q.nq > BRK_MAXQ) return false;
+    if (!sharded && c.geom.axis_len < (1ull << 16)) return false;
+    if (c.geom.axis_len >= (1ull << 40)) return false;
+    // not worth trying when the brackets would hold more than the candidate scratch (n / 3): many quantiles of
+    // a lane that is too short for a large enough sample go straight to the radix passes
+    if (!forced && predicted_fraction(c.geom.axis_len, c.q.nq, c.brk_wsum) > 0.28) return false;
+    return true;
+}
+
+size_t bracket_scratch_bytes(const DeviceCall &c) {
+    const size_t es = nds_dtype_size(c.dtype);
+    if (es == 8) return brk_sizes<uint64_t>(c.geom.axis_len, c.q.nq, c.brk_wsum).total;
+    return brk_sizes<uint32_t>(c.geom.axis_len, c.q.nq, c.brk_wsum).total;
+}
+
+cudaError_t launch_bracket(nds_ctx *ctx, const DeviceCall &c, void *scratch, bool sharded, bool synchronous,
+                           int *failed) {
+    ctx->last_path = sharded ? "bracket_sharded" : "bracket";
+    switch (c.dtype) {
+    case NDS_F32: return launch_bracket_typed<float>(ctx, c, scratch, sharded, synchronous, failed);
+    case NDS_F64: return launch_bracket_typed<double>(ctx, c, scratch, sharded, synchronous, failed);
+    case NDS_I32: return launch_bracket_typed<int32_t>(ctx, c, scratch, sharded, synchronous, failed);
+    case NDS_U32: return launch_bracket_typed<uint32_t>(ctx, c, scratch, sharded, synchronous, failed);
+    case NDS_I64: return launch_bracket_typed<int64_t>(ctx, c, scratch, sharded, synchronous, failed);
+    case NDS_U64: return launch_bracket_typed<uint64_t>(ctx, c, scratch, sharded, synchronous, failed);
+    default: return cudaErrorNotSupported;
+    }
+}
+
+}  // namespace nds

@@ -4,8 +4,11 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "nds_common.cuh"
+
+namespace nds { struct PendingCall; }
 
 struct nds_ctx {
     int device = 0;
@@ -22,6 +25,9 @@ struct nds_ctx {
     std::string last_error;
     const char *last_path = "none";
     std::string forced_path = "auto";
+    // enqueued bracket-select calls whose rare fallback (a rank escaped its bracket) is decided at the next
+    // nds_ctx_synchronize (see STATUS_BIT_FALLBACK)
+    std::vector<nds::PendingCall> *pending = nullptr;
     // NCCL (dlopen'd lazily, see nds_nccl.cpp)
     void *nccl_comm = nullptr;
     int nranks = 1;
@@ -39,6 +45,14 @@ struct DeviceCall {
     QuantArgs q;
     void *out;               // device, C-order result
     uint8_t *out_valid;      // optional, C-order result shape
+    double brk_wsum = 0.0;   // bracket select: sum over quantiles of 2 c sqrt(p (1 - p)), see nds_bracket.cu
+};
+
+// An enqueued long-lane call that may still need the radix fallback (decided at nds_ctx_synchronize)
+struct PendingCall {
+    DeviceCall call;                         // call.q.qs / call.q.ranks are re-uploaded from `words`
+    std::vector<unsigned long long> words;   // the nq quantiles (as raw doubles) or ranks
+    bool is_ranks;
 };
 
 // Arena: returns a device pointer to at least `bytes` (256-byte aligned); contents are scratch.
@@ -53,6 +67,15 @@ cudaError_t launch_generic_cta(nds_ctx *ctx, const DeviceCall &c);
 size_t long_scratch_bytes(int nq);
 const void *long_total_count_ptr(const void *scratch, int nq);  // device address of the global element count
 cudaError_t launch_long_radix(nds_ctx *ctx, const DeviceCall &c, void *scratch, bool sharded);
+// One long contiguous lane in ONE streaming pass: sampled value brackets, private-counter classification,
+// candidate compaction (nds_bracket.cu).  `*failed` != 0 (synchronous calls) means a rank escaped its bracket
+// or scratch ran out: the caller re-runs the call with launch_long_radix.  Asynchronous calls raise
+// STATUS_BIT_FALLBACK in the ctx status word instead.
+bool bracket_supported(const nds_ctx *ctx, const DeviceCall &c, bool sharded, bool forced);
+double brk_csigma();
+size_t bracket_scratch_bytes(const DeviceCall &c);
+cudaError_t launch_bracket(nds_ctx *ctx, const DeviceCall &c, void *scratch, bool sharded, bool synchronous,
+                           int *failed);
 // Contiguous short lanes (f32/f64/ints up to a few thousand elements): warp-per-lane bit-sliced select
 // fed by TMA bulk copies.  Returns cudaErrorNotSupported when the call does not qualify.
 bool short_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c);

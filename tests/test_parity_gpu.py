@@ -382,3 +382,145 @@ def test_cols_bitslice_skipnan(nds, gpu_ctx, oracle, dtype):
             gpu_ctx.quantiles_axis(a, 0, [0.5], "lower")
     finally:
         gpu_ctx.force_path("auto")
+
+
+# ---- long contiguous lanes: bracket select (one streaming pass), BASELINE configs 4 and 5 in miniature ----
+def _long_data(rng, kind, n, dtype):
+    dtype = np.dtype(dtype)
+    if dtype.kind == "f":
+        a = {"uniform": lambda: rng.random(n),
+             "normal": lambda: rng.standard_normal(n),
+             "clustered": lambda: 1000.0 + rng.random(n) * 1e-4,
+             "lognormal": lambda: np.exp(3.0 * rng.standard_normal(n)),
+             "ties": lambda: rng.integers(-8, 8, size=n).astype(np.float64),
+             "equal": lambda: np.full(n, -3.25),
+             "sorted": lambda: np.sort(rng.standard_normal(n)),
+             "reversed": lambda: np.sort(rng.standard_normal(n))[::-1].copy(),
+             "rounded": lambda: np.round(rng.standard_normal(n), 2),
+             "extremes": lambda: rng.choice(np.array([np.inf, -np.inf, 0.0, -0.0, 1e300, -1e300, 5e-324]), size=n)}[kind]()
+        with np.errstate(over="ignore"):
+            return a.astype(dtype)
+    info = np.iinfo(dtype)
+    return {"uniform": lambda: rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True),
+            "normal": lambda: (rng.standard_normal(n) * 1e6).astype(np.int64).astype(dtype),
+            "clustered": lambda: (rng.integers(0, 1000, size=n) + 10**6).astype(dtype),
+            "lognormal": lambda: np.minimum(np.exp(3.0 * rng.standard_normal(n)) * 100, 2e9).astype(np.int64).astype(dtype),
+            "ties": lambda: (rng.integers(0, 16, size=n).astype(np.uint64) * 0x11111111).astype(dtype),
+            "equal": lambda: np.full(n, 7, dtype=dtype),
+            "sorted": lambda: np.sort(rng.integers(info.min // 2, info.max // 2, size=n, dtype=dtype)),
+            "reversed": lambda: np.sort(rng.integers(info.min // 2, info.max // 2, size=n, dtype=dtype))[::-1].copy(),
+            "rounded": lambda: (rng.integers(0, 300, size=n) * 1000).astype(dtype),
+            "extremes": lambda: rng.choice(np.array([info.min, info.max, 0, 1], dtype=dtype), size=n)}[kind]()
+
+
+LONG_KINDS = ["uniform", "normal", "clustered", "lognormal", "ties", "equal", "sorted", "reversed", "rounded", "extremes"]
+
+
+@pytest.mark.parametrize("dtype", SHORT_DTYPES, ids=lambda d: np.dtype(d).name)
+def test_bracket_path(gpu_ctx, oracle, dtype):
+    """One long lane in one streaming pass: every distribution class, 99 percentiles (C4) and the tie-heavy
+    quantiles of C5, lengths around the tile / alignment edges, explicit extremes q = 0 and q = 1."""
+    dtype = np.dtype(dtype)
+    rng = np.random.default_rng(abs(hash(("bracket", dtype.name))) % 2**32)
+    dec = np.arange(1, 10) / 10.0  # 99 percentiles need a lane of tens of millions: test_bracket_c4_shape
+    fallbacks = []
+    try:
+        gpu_ctx.force_path("bracket")
+        for n in (65536, 70001, 300007, (1 << 20) + 5):
+            for kind in LONG_KINDS:
+                a = _long_data(rng, kind, n, dtype)
+                for interp, qs in (("linear", dec), ("lower", [0.1, 0.5, 0.9]), ("higher", [0.0, 1.0, 0.5]),
+                                   ("midpoint", [0.5]), ("nearest", [0.25, 0.75, 0.999, 0.001])):
+                    if dtype.kind != "f" and interp == "linear" and kind in ("extremes", "uniform"):
+                        continue  # T::from_f64 overflow panics in the reference: covered by test_quantile1d_and_errors
+                    if n > 300007 and interp not in ("linear", "lower"):
+                        continue
+                    check(gpu_ctx, oracle, a, 0, qs, interp, select_impl=1)
+                    assert gpu_ctx.last_path in ("bracket", "bracket->long_radix")
+                    if gpu_ctx.last_path != "bracket":
+                        fallbacks.append((n, kind, interp))
+        # a view that starts off the 16-byte grid, and two long lanes in one call
+        a = _long_data(rng, "normal", 200001, dtype)
+        check(gpu_ctx, oracle, a[1:], 0, [0.5, 0.9], "lower", select_impl=1)
+        b = _long_data(rng, "uniform", 2 * 131072, dtype).reshape(2, 131072)
+        check(gpu_ctx, oracle, b, 1, [0.25, 0.5], "higher", select_impl=1)
+        assert gpu_ctx.last_path == "bracket"
+    finally:
+        gpu_ctx.force_path("auto")
+    # well-behaved inputs must stay on the one-pass path; the fallback is for 5-sigma events only
+    assert not fallbacks, f"bracket select fell back to radix passes for {fallbacks}"
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=lambda d: np.dtype(d).name)
+def test_bracket_path_nan(nds, gpu_ctx, oracle, dtype):
+    rng = np.random.default_rng(4242)
+    try:
+        gpu_ctx.force_path("bracket")
+        for n in (65536, 250001):
+            a = rng.standard_normal(n).astype(dtype)
+            a[rng.random(n) < 0.2] = np.nan
+            a[5] = -np.nan
+            a[7] = np.inf
+            a[9] = -np.inf
+            for interp in INTERPS:
+                check(gpu_ctx, oracle, a, 0, [0.0, 0.01, 0.5, 0.61, 1.0], interp, skipnan=True, select_impl=1)
+                assert gpu_ctx.last_path == "bracket"
+            with pytest.raises(nds.NanInInput):
+                gpu_ctx.quantiles_axis(a, 0, [0.5], "lower")
+            check(gpu_ctx, oracle, np.full(n, np.nan, dtype=dtype), 0, [0.5], "linear", skipnan=True)
+            mostly = np.full(n, np.nan, dtype=dtype)
+            mostly[::1000] = rng.standard_normal(mostly[::1000].size)
+            check(gpu_ctx, oracle, mostly, 0, [0.1, 0.5, 0.9], "linear", skipnan=True, select_impl=1)
+    finally:
+        gpu_ctx.force_path("auto")
+
+
+def test_bracket_sort1d_and_enqueue(nds, gpu_ctx, oracle):
+    """Sort1dExt on a long lane (explicit ranks) and the asynchronous entry point with its deferred fallback."""
+    import torch
+    rng = np.random.default_rng(99)
+    a = rng.standard_normal(400000)
+    idx = [0, 1, 399999, 200000, 200001, 12345, 200000]
+    got = nds.get_many_from_sorted_mut(a, idx, ctx=gpu_ctx)
+    srt = np.sort(a)
+    assert list(got.keys()) == sorted(set(idx))
+    assert all(got[i] == srt[i] for i in got)
+    t = torch.from_numpy(a).cuda()
+    dec = np.arange(1, 10) / 10.0
+    out = gpu_ctx.quantiles_axis(t, 0, dec, "linear", enqueue=True)
+    gpu_ctx.synchronize()
+    st, want, _ = oracle.quantiles_axis(a, 0, dec, "linear", select_impl=1)
+    assert ulp_distance(out.cpu().numpy(), want) == 0
+    assert gpu_ctx.last_path == "bracket"
+    # 99 percentiles of a lane this short cannot be bracketed: automatic dispatch goes straight to the radix
+    # passes; forced, the enqueued call gives up on the device and is re-run at synchronize()
+    pct = np.arange(1, 100) / 100.0
+    st, want, _ = oracle.quantiles_axis(a, 0, pct, "linear", select_impl=1)
+    out = gpu_ctx.quantiles_axis(t, 0, pct, "linear", enqueue=True)
+    gpu_ctx.synchronize()
+    assert gpu_ctx.last_path == "long_radix" and ulp_distance(out.cpu().numpy(), want) == 0
+    try:
+        gpu_ctx.force_path("bracket")
+        out = gpu_ctx.quantiles_axis(t, 0, pct, "linear", enqueue=True)
+        out2 = gpu_ctx.quantiles_axis(t, 0, dec, "lower", enqueue=True)
+        gpu_ctx.synchronize()
+        assert gpu_ctx.last_path == "bracket->long_radix"
+        assert ulp_distance(out.cpu().numpy(), want) == 0
+        st, want2, _ = oracle.quantiles_axis(a, 0, dec, "lower", select_impl=1)
+        assert_bit_equal(out2.cpu().numpy(), want2)
+    finally:
+        gpu_ctx.force_path("auto")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=lambda d: np.dtype(d).name)
+def test_bracket_c4_shape(nds, gpu_ctx, oracle, dtype):
+    """BASELINE config 4 scaled to 2^25 elements: 99 percentiles, Linear, automatic dispatch must pick the
+    one-pass path and stay on it; bit-exact against the sort-and-index oracle."""
+    rng = np.random.default_rng(1004)
+    a = rng.random(1 << 25).astype(dtype)
+    qs = np.arange(1, 100) / 100.0
+    check(gpu_ctx, oracle, a, 0, qs, "linear", select_impl=1)
+    assert gpu_ctx.last_path == "bracket"
+    b = (rng.standard_normal(1 << 25) * 3.0).astype(dtype)
+    check(gpu_ctx, oracle, b, 0, qs, "linear", select_impl=1)
+    assert gpu_ctx.last_path == "bracket"

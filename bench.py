@@ -256,7 +256,8 @@ def main():
     esize = np.dtype(dtype).itemsize
 
     ctx = nds.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real stream: the CUDA events below must sit on the launching stream
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     sharded_1d = one_d and distributed

@@ -71,7 +71,8 @@ size_t nds_dtype_size(nds_dtype t);
  * (The reference is stateless and single-threaded; a ctx is not thread-safe.) */
 nds_status nds_ctx_create(int device, nds_ctx **out);
 void nds_ctx_destroy(nds_ctx *ctx);
-/* Borrow an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx's own. */
+/* Borrow an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx's own.
+ * To run on the legacy default stream pass cudaStreamLegacy ((cudaStream_t)0x1), not NULL. */
 nds_status nds_ctx_set_stream(nds_ctx *ctx, void *cuda_stream);
 void *nds_ctx_get_stream(nds_ctx *ctx);
 /* Wait for everything enqueued on the ctx stream; returns (and clears) the deferred data-dependent

@@ -212,7 +212,9 @@ class Context:
             if not a.is_cuda:
                 raise TypeError("torch inputs must be CUDA tensors (pass numpy arrays for host data)")
             import torch
-            self.set_stream(torch.cuda.current_stream(a.device).cuda_stream)
+            # torch's default stream has handle 0 = the legacy default stream: name it explicitly (cudaStreamLegacy),
+            # NULL would mean "the ctx's own stream" and lose the ordering with the kernels that produced `a`
+            self.set_stream(torch.cuda.current_stream(a.device).cuda_stream or 1)
             return _torch_dtype_code(a), a.data_ptr(), tuple(a.shape), tuple(a.stride()), a, True
         a = np.asarray(a)
         if a.dtype not in _NP_DTYPES:

@@ -379,8 +379,10 @@ void nds_ctx_destroy(nds_ctx *ctx) {
 
 nds_status nds_ctx_set_stream(nds_ctx *ctx, void *cuda_stream) {
     if (!ctx) return NDS_BAD_ARGUMENT;
-    cudaStreamSynchronize(ctx->stream);
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    if (next == ctx->stream) return NDS_OK;
+    cudaStreamSynchronize(ctx->stream);  // the arena is stream-ordered: drain the old stream before switching
+    ctx->stream = next;
     return NDS_OK;
 }
 void *nds_ctx_get_stream(nds_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }

@@ -30,6 +30,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
+#include <vector>
 
 #include "nds_bitslice.cuh"
 #include "nds_internal.h"
@@ -239,6 +240,9 @@ __global__ void __launch_bounds__(1024)
 brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long n_local, int sharded) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned *cum = reinterpret_cast<unsigned *>(smem_raw);            // [S0 + 1] inclusive: #{ s1 <= S0[i] }
+    Key *s0 = reinterpret_cast<Key *>(smem_raw + ((BRK_S0 + 1) * 4 + 15) / 16 * 16);  // [S0] the sorted sample
+    unsigned short *mixcell = reinterpret_cast<unsigned short *>(s0 + BRK_S0);          // [NC1] cells that hold an edge
+    __shared__ unsigned long long scap[BRK_MAXB];
     __shared__ Key qlo[BRK_MAXQ], qhi[BRK_MAXQ], slo[BRK_MAXQ], shi[BRK_MAXQ];
     __shared__ Key blo[BRK_MAXB], bhi[BRK_MAXB];
     __shared__ unsigned char btie[BRK_MAXB];
@@ -286,6 +290,7 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             if (idx <= BRK_S0) cum[idx] = run;
         }
         if (tid == 0) sFail = 0;
+        for (int i = tid; i < BRK_S0; i += nthreads) s0[i] = buf.s0[i];
         __syncthreads();
     }
     const unsigned s1v = cum[BRK_S0];  // valid samples (over all ranks when sharded)
@@ -303,11 +308,10 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             buf.lutc->submask = 0;
             buf.lutc->ncls_used = 1;
         }
-        for (int c = tid; c < BRK_NC1; c += nthreads)
-            buf.lut1[c] = IS_FLOAT && (c == 0 || c == BRK_NC1 - 1) ? (unsigned)(256 + (c ? 1 : 0)) : 0u;
+        for (int c = tid; c < BRK_NC1; c += nthreads) buf.lut1[c] = 256u;  // everything is "outside": class 0 or NaN
         for (int i = tid; i < BRK_L2_PURE; i += nthreads)
-            buf.lut2[i] = i == 256 ? (unsigned short)(ENT_MIXED | ENT_SPECIAL | 0u)
-                                   : (i == 257 ? (unsigned short)(ENT_MIXED | ENT_SPECIAL | 0u) : (unsigned short)0);
+            buf.lut2[i] = i == 256 ? (unsigned short)(ENT_MIXED | ENT_SPECIAL | 0xffu)
+                                   : (i == 258 ? (unsigned short)BRK_INVALID_CLS : (unsigned short)0);
         return;
     }
 
@@ -326,18 +330,18 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             int a = 0, b = BRK_S0;  // first index with cum_lt > target
             while (a < b) {
                 const int mid = (a + b) >> 1;
-                const Key v = buf.s0[mid];
+                const Key v = s0[mid];
                 int f0 = 0, f1 = mid;  // first index of the run of keys equal to S0[mid]
                 while (f0 < f1) {
                     const int m2 = (f0 + f1) >> 1;
-                    if (buf.s0[m2] < v) f0 = m2 + 1;
+                    if (s0[m2] < v) f0 = m2 + 1;
                     else f1 = m2;
                 }
                 const unsigned cum_lt = cum[f0] - (unsigned)buf.s0hist[BRK_S0 + 2 + f0];
                 if (cum_lt <= target) a = mid + 1;
                 else b = mid;
             }
-            if (a > 0) lo = buf.s0[a - 1];
+            if (a > 0) lo = s0[a - 1];
         }
         if (Phi + 1.0 <= (double)cum[BRK_S0 - 1]) {  // smallest i with cum[i] >= Phi + 1
             const unsigned target = (unsigned)(Phi + 1.0);
@@ -347,7 +351,7 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
                 if (cum[mid] < target) a = mid + 1;
                 else b = mid;
             }
-            if (a < BRK_S0) hi = buf.s0[a];
+            if (a < BRK_S0) hi = s0[a];
         }
         if (IS_FLOAT) {  // numbers live in [key(-inf), key(+inf)]; the keys outside are NaNs
             const Key ninf = sizeof(Key) == 8 ? (Key)0x000FFFFFFFFFFFFFull : (Key)0x007FFFFFu;
@@ -364,10 +368,10 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             int f0 = 0, f1 = BRK_S0;
             while (f0 < f1) {
                 const int m2 = (f0 + f1) >> 1;
-                if (buf.s0[m2] < v) f0 = m2 + 1;
+                if (s0[m2] < v) f0 = m2 + 1;
                 else f1 = m2;
             }
-            return (f0 < BRK_S0 && buf.s0[f0] == v) ? (unsigned)buf.s0hist[BRK_S0 + 2 + f0] : 0u;
+            return (f0 < BRK_S0 && s0[f0] == v) ? (unsigned)buf.s0hist[BRK_S0 + 2 + f0] : 0u;
         };
         qheavy[t] = (unsigned char)((sample_multiplicity(lo) >= 4 ? 1 : 0) | (sample_multiplicity(hi) >= 4 ? 2 : 0));
     }
@@ -443,37 +447,11 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
         }
         if (B + 1 + ntie > BRK_INVALID_CLS) fail |= FAIL_TOO_MANY;
         sB = B;
-        // candidate segments: predicted size from the sample, with head room
-        const double scale = (double)n_total / (double)s1v;
-        unsigned long long off = 0;
-        for (int b = 0; b < B; ++b) {
-            unsigned long long cap = 0;
-            if (btie[b] == 0xff) {
-                // upper bound of #{ s1 in [lo, hi] } from the S0 ranks
-                int a = 0, e = BRK_S0;  // upper_bound(hi)
-                while (a < e) { int mid = (a + e) >> 1; if (buf.s0[mid] <= bhi[b]) a = mid + 1; else e = mid; }
-                unsigned all_hi;
-                if (a > 0 && buf.s0[a - 1] == bhi[b]) all_hi = cum[a - 1];   // hi is an S0 key: exact
-                else all_hi = cum[a] - (a < BRK_S0 ? (unsigned)buf.s0hist[BRK_S0 + 2 + a] : 0u);  // #{ s1 < next S0 key } (a starts a run), or everything
-                a = 0; e = BRK_S0;      // lower_bound(lo)
-                while (a < e) { int mid = (a + e) >> 1; if (buf.s0[mid] < blo[b]) a = mid + 1; else e = mid; }
-                const unsigned lt_lo = a > 0 ? cum[a - 1] : 0u;
-                const double cnt = (double)(all_hi > lt_lo ? all_hi - lt_lo : 0u) + 1.0;
-                double want = (cnt + 6.0 * sqrt(cnt) + 16.0) * scale * 1.05 + 2048.0;
-                if (want > (double)n_local) want = (double)n_local;
-                cap = (unsigned long long)want;
-                cap = (cap + 1) & ~1ull;
-            }
-            buf.boff[b] = off;
-            buf.bcap[b] = cap;
-            off += cap;
-        }
-        if (off > buf.cand_cap[0]) fail |= FAIL_CAPACITY;
         // top-level cell width
         const Key range = bhi[B - 1] - blo[0];
         int shift1 = key_bits_used(range) - 12;
         if (shift1 < 0) shift1 = 0;
-        while ((range >> shift1) > (Key)(BRK_NC1 - 3)) ++shift1;
+        while ((range >> shift1) > (Key)(BRK_NC1 - 2)) ++shift1;
         sShift1 = shift1;
         sNmixed = 0;
         sFail = fail;
@@ -484,6 +462,40 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
     }
     __syncthreads();
     const int B = sB, shift1 = sShift1;
+    // candidate segments: predicted size from the sample, with head room (one bracket per thread)
+    {
+        const double scale = (double)n_total / (double)s1v;
+        for (int b = tid; b < B; b += nthreads) {
+            unsigned long long cap = 0;
+            if (btie[b] == 0xff) {
+                // upper bound of #{ s1 in [lo, hi] } from the S0 ranks
+                int a = 0, e = BRK_S0;  // upper_bound(hi)
+                while (a < e) { int mid = (a + e) >> 1; if (s0[mid] <= bhi[b]) a = mid + 1; else e = mid; }
+                unsigned all_hi;
+                if (a > 0 && s0[a - 1] == bhi[b]) all_hi = cum[a - 1];   // hi is an S0 key: exact
+                else all_hi = cum[a] - (a < BRK_S0 ? (unsigned)buf.s0hist[BRK_S0 + 2 + a] : 0u);  // #{ s1 < next S0 key }, or everything
+                a = 0; e = BRK_S0;      // lower_bound(lo)
+                while (a < e) { int mid = (a + e) >> 1; if (s0[mid] < blo[b]) a = mid + 1; else e = mid; }
+                const unsigned lt_lo = a > 0 ? cum[a - 1] : 0u;
+                const double cnt = (double)(all_hi > lt_lo ? all_hi - lt_lo : 0u) + 1.0;
+                double want = (cnt + 6.0 * sqrt(cnt) + 16.0) * scale * 1.05 + 2048.0;
+                if (want > (double)n_local) want = (double)n_local;
+                cap = (unsigned long long)want;
+                cap = (cap + 3) & ~3ull;
+            }
+            scap[b] = cap;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long off = 0;
+            for (int b = 0; b < B; ++b) {
+                buf.boff[b] = off;
+                buf.bcap[b] = scap[b];
+                off += scap[b];
+            }
+            if (off > buf.cand_cap[0]) raise_fail(buf.hdr, FAIL_CAPACITY);
+        }
+    }
     const Key kmin = blo[0];
     for (int b = tid; b < B; b += nthreads) {
         buf.blo[b] = blo[b];
@@ -498,25 +510,29 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             const bool in = i & 1;
             if (j <= B && (!in || j > 0)) e = (unsigned short)pure_entry(j, in, btie);
         } else if (i == 256) {
-            e = (unsigned short)(ENT_MIXED | ENT_SPECIAL | 0u);          // scan starts at bracket 0
-        } else if (i == 257) {
-            e = (unsigned short)(ENT_MIXED | ENT_SPECIAL | (unsigned)B);  // above every lower edge
+            e = (unsigned short)(ENT_MIXED | ENT_SPECIAL | 0xffu);       // outside [kmin, kmax]: below, above or NaN
         } else if (i == 258) {
             e = (unsigned short)BRK_INVALID_CLS;                           // a range of NaN keys only
         }
         buf.lut2[i] = e;
     }
     // ---- level 1: which cells hold a bracket edge -----------------------------------------------------
+    // cell c (0 .. NC1-2) covers keys [kmin + (c << shift1), +2^shift1); cell NC1-1 is everything outside
+    // [kmin, kmax] (k - kmin wraps around below kmin)
     const Key width1 = ((Key)1 << shift1) - 1;
-    auto cell_ends = [&](int c, Key &a, Key &e) {  // cells 1 .. NC1-2
-        a = kmin + ((Key)(c - 1) << shift1);
+    auto cell_ends = [&](int c, Key &a, Key &e) {
+        a = kmin + ((Key)c << shift1);
         e = (a > KMAX - width1) ? KMAX : a + width1;
     };
     // Kind of the key range [a, e]: 0 = one class throughout (pa), 1 = holds a bracket edge, 2 = NaN keys only,
     // 3 = holds the border between numbers and NaN keys (floats: keys outside [key(-inf), key(+inf)] are NaNs)
     const Key NINF = sizeof(Key) == 8 ? (Key)0x000FFFFFFFFFFFFFull : (Key)0x007FFFFFu;
     const Key PINF = sizeof(Key) == 8 ? (Key)0xFFF0000000000000ull : (Key)0xFF800000u;
+    const Key kmax = bhi[B - 1];
     auto range_kind = [&](Key a, Key e, PointClass<Key> &pa) -> int {
+        // past the last bracket: keys BELOW kmin alias into these cells (k - kmin wraps around), so they resolve
+        // like the outside cell
+        if (a > kmax) return 4;
         if (IS_FLOAT) {
             if (a > PINF || e < NINF) return 2;
             if (e > PINF || a < NINF) {
@@ -528,26 +544,39 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
         const PointClass<Key> pe = classify_point(blo, bhi, B, e);
         return (pa.j == pe.j && pa.in == pe.in) ? 0 : 1;
     };
-    // cells past the end of the key space (kmin + (c-1) << shift1 overflows) can never be hit
-    const Key max_cell = (KMAX - kmin) >> shift1;  // largest (c - 1) that exists
-    int my_mixed = 0;
+    const Key max_cell = (KMAX - kmin) >> shift1;  // cells past the end of the key space can never be hit
     for (int c = tid; c < BRK_NC1; c += nthreads) {
-        if (c == 0 || c == BRK_NC1 - 1) continue;
-        if ((Key)(c - 1) > max_cell) continue;
-        Key a, e;
-        cell_ends(c, a, e);
-        PointClass<Key> pa;
-        const int kind = range_kind(a, e, pa);
-        if (kind == 1 || kind == 3) ++my_mixed;
+        unsigned e1;
+        if (c == BRK_NC1 - 1) {
+            e1 = 256u;
+        } else if ((Key)c > max_cell) {
+            e1 = 256u;
+        } else {
+            Key a, e;
+            cell_ends(c, a, e);
+            PointClass<Key> pa;
+            int kind = range_kind(a, e, pa);
+            // the cell that runs past the end of the key space also receives the keys below kmin (k - kmin wraps
+            // around): it must not be "pure"
+            if (a > KMAX - width1 && kmin > 0 && (kind == 0 || kind == 2)) kind = 1;
+            if (kind == 0) e1 = (unsigned)(2 * pa.j + (pa.in ? 1 : 0));
+            else if (kind == 2) e1 = 258u;
+            else if (kind == 4) e1 = 256u;
+            else {
+                const int slot = atomicAdd(&sNmixed, 1);
+                mixcell[slot] = (unsigned short)c;
+                e1 = 0x80000000u | (unsigned)slot;  // the table base is filled in once M is known
+            }
+        }
+        buf.lut1[c] = e1;
     }
-    atomicAdd(&sNmixed, my_mixed);
     __syncthreads();
+    const int nmixed = sNmixed;
     if (tid == 0) {
         int M = 0;
-        const int nm = sNmixed > 0 ? sNmixed : 1;
+        const int nm = nmixed > 0 ? nmixed : 1;
         while (M < shift1 && M < 14 && ((nm << (M + 1)) <= BRK_L2_SUB)) ++M;
         sM = M;
-        sNmixed = 0;  // reused as the allocation cursor
         buf.lutc->kmin = kmin;
         buf.lutc->shift1 = shift1;
         buf.lutc->subshift = shift1 - M;
@@ -558,42 +587,27 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
     __syncthreads();
     const int M = sM, subshift = shift1 - M;
     const Key width2 = ((Key)1 << subshift) - 1;
-    for (int c = tid; c < BRK_NC1; c += nthreads) {
-        unsigned e1;
-        if (c == 0) {
-            e1 = IS_FLOAT ? 256u : 0u;  // below kmin: class 0, not inside (floats: maybe a negative NaN)
-        } else if (c == BRK_NC1 - 1) {
-            e1 = IS_FLOAT ? 257u : (unsigned)(2 * B);
-        } else if ((Key)(c - 1) > max_cell) {
-            e1 = (unsigned)(2 * B);
-        } else {
-            Key a, e;
-            cell_ends(c, a, e);
-            PointClass<Key> pa;
-            const int kind = range_kind(a, e, pa);
-            if (kind == 0) {
-                e1 = (unsigned)(2 * pa.j + (pa.in ? 1 : 0));
-            } else if (kind == 2) {
-                e1 = 258u;
-            } else {
-                const int slot = atomicAdd(&sNmixed, 1);
-                const unsigned base = BRK_L2_PURE + ((unsigned)slot << M);
-                e1 = 0x80000000u | base;
-                for (unsigned s = 0; s < (1u << M); ++s) {
-                    const Key a2 = a + ((Key)s << subshift);
-                    Key e2 = (a2 > KMAX - width2) ? KMAX : a2 + width2;
-                    if (e2 > e) e2 = e;
-                    PointClass<Key> p2;
-                    const int k2 = range_kind(a2, e2, p2);
-                    unsigned short ent;
-                    if (k2 == 0) ent = (unsigned short)pure_entry(p2.j, p2.in, btie);
-                    else if (k2 == 2) ent = (unsigned short)BRK_INVALID_CLS;
-                    else ent = (unsigned short)(ENT_MIXED | (k2 == 3 ? ENT_SPECIAL : 0u) | (unsigned)p2.j);
-                    buf.lut2[base + s] = ent;
-                }
-            }
-        }
-        buf.lut1[c] = e1;
+    for (int slot = tid; slot < nmixed; slot += nthreads)
+        buf.lut1[mixcell[slot]] = 0x80000000u | (BRK_L2_PURE + ((unsigned)slot << M));
+    // ---- level 2: the sub-cells of those cells, all threads ---------------------------------------------
+    for (unsigned g = tid; g < ((unsigned)nmixed << M); g += nthreads) {
+        const unsigned slot = g >> M, sidx = g & ((1u << M) - 1u);
+        Key a, e;
+        cell_ends((int)mixcell[slot], a, e);
+        const Key a2 = a + ((Key)sidx << subshift);
+        Key e2 = (a2 > KMAX - width2) ? KMAX : a2 + width2;
+        if (e2 > e) e2 = e;
+        PointClass<Key> p2;
+        const int k2 = range_kind(a2, e2, p2);
+        unsigned short ent;
+        const bool straddles_wrap = a2 >= a && a2 > KMAX - width2 && kmin > 0;  // same aliasing, at sub-cell level
+        if (straddles_wrap && (k2 == 0 || k2 == 2))
+            ent = (unsigned short)(ENT_MIXED | (IS_FLOAT ? ENT_SPECIAL : 0u) | (unsigned)classify_point(blo, bhi, B, a2).j);
+        else if (k2 == 0) ent = (unsigned short)pure_entry(p2.j, p2.in, btie);
+        else if (k2 == 2) ent = (unsigned short)BRK_INVALID_CLS;
+        else if (k2 == 4) ent = (unsigned short)(ENT_MIXED | ENT_SPECIAL | 0xffu);
+        else ent = (unsigned short)(ENT_MIXED | (k2 == 3 ? ENT_SPECIAL : 0u) | (unsigned)p2.j);
+        buf.lut2[BRK_L2_PURE + g] = ent;
     }
 }
 
@@ -606,16 +620,18 @@ template <typename Key> __host__ __device__ constexpr size_t stream_smem_bytes()
            4 * (size_t)BRK_MAXB * 4 + 64;
 }
 
-// slow path of the classification: a (sub-)cell that holds a bracket edge, or (floats) the region below /
-// above all brackets where NaN keys live
+// slow path of the classification: a (sub-)cell that holds a bracket edge, the region outside [kmin, kmax], or
+// (floats) a cell on the border to the NaN keys
 template <typename Key, bool IS_FLOAT>
-__device__ __noinline__ unsigned brk_resolve_entry(Key k, unsigned ent, const Key *blo, const Key *bhi,
+__device__ __noinline__ unsigned brk_resolve_entry(Key k, unsigned ent, Key kmin, const Key *blo, const Key *bhi,
                                                    const unsigned char *btie, int B) {
     if (IS_FLOAT && (ent & ENT_SPECIAL)) {
         const bool nan = sizeof(Key) == 8 ? (k > (Key)0xFFF0000000000000ull || k < (Key)0x000FFFFFFFFFFFFFull)
                                           : (k > (Key)0xFF800000u || k < (Key)0x007FFFFFu);
         if (nan) return BRK_INVALID_CLS;
     }
+    if (k < kmin) return 0u;  // below every bracket (k - kmin wrapped around into a cell at or past the last bracket)
+    if ((ent & 0xffu) == 0xffu) return (unsigned)B;  // above every bracket
     int j = (int)(ent & 0xffu);
     while (j < B && blo[j] <= k) ++j;
     const bool in = j > 0 && k <= bhi[j - 1];
@@ -670,16 +686,19 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
 
     unsigned short *myctr = counters + counter_slot();
 
-    // classify one key, count it, return its entry (class | ENT_COMPACT)
-    auto classify = [&](Key k) -> unsigned {
+    // two table reads per key, no side effects (k - kmin wraps to a huge value below kmin: the "outside" cell)
+    auto lookup = [&](Key k) -> unsigned {
         const Key d = k - kmin;
         const Key cc = d >> shift1;
-        unsigned cell = 1u + (unsigned)(cc < (Key)(BRK_NC1 - 2) ? cc : (Key)(BRK_NC1 - 2));
-        if (k < kmin) cell = 0;
+        const unsigned cell = (unsigned)(cc < (Key)(BRK_NC1 - 1) ? cc : (Key)(BRK_NC1 - 1));
         const unsigned e1 = lut1[cell];
         const unsigned sub = (unsigned)(d >> subshift) & submask & (unsigned)((int)e1 >> 31);
-        unsigned ent = lut2[(e1 & 0x7fffffffu) + sub];
-        if (ent & (ENT_MIXED | ENT_SPECIAL)) ent = brk_resolve_entry<Key, IS_FLOAT>(k, ent, blo, bhi, btie, B);
+        return lut2[(e1 & 0x7fffffffu) + sub];
+    };
+    // one key at a time (ragged head / tail)
+    auto classify = [&](Key k) -> unsigned {
+        unsigned ent = lookup(k);
+        if (ent & (ENT_MIXED | ENT_SPECIAL)) ent = brk_resolve_entry<Key, IS_FLOAT>(k, ent, kmin, blo, bhi, btie, B);
         myctr[(ent & 0xffu) * BRK_THREADS] += 1;
         return ent;
     };
@@ -764,15 +783,52 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
                 k[j * 2 + 1] = Tr::to_key(from_raw<T>(w1));
             }
         }
+        // phase 1: all table reads of the tile are independent of each other
+        unsigned ent[BRK_EPT];
+        unsigned slow = 0;
 #pragma unroll
         for (int e = 0; e < BRK_EPT; ++e) {
-            const unsigned ent = classify(k[e]);
-            brk[e] = (unsigned char)((ent & 0xffu) - 1u);
-            cmask |= ((ent >> 8) & 1u) << e;
+            ent[e] = lookup(k[e]);
+            slow |= ent[e];
+        }
+        // phase 2: the few keys next to a bracket edge (or outside all brackets)
+        if (slow & (ENT_MIXED | ENT_SPECIAL)) {
+#pragma unroll
+            for (int e = 0; e < BRK_EPT; ++e)
+                if (ent[e] & (ENT_MIXED | ENT_SPECIAL))
+                    ent[e] = brk_resolve_entry<Key, IS_FLOAT>(k[e], ent[e], kmin, blo, bhi, btie, B);
+        }
+        // phase 3: private counters, four keys at a time: the four loads go out together, equal classes inside a
+        // group are merged (each stores old + multiplicity), so no read-after-write chain inside the group
+#pragma unroll
+        for (int g = 0; g < BRK_EPT; g += 4) {
+            const unsigned c0 = ent[g] & 0xffu, c1 = ent[g + 1] & 0xffu, c2 = ent[g + 2] & 0xffu, c3 = ent[g + 3] & 0xffu;
+            unsigned short *p0 = myctr + c0 * BRK_THREADS, *p1 = myctr + c1 * BRK_THREADS, *p2 = myctr + c2 * BRK_THREADS,
+                           *p3 = myctr + c3 * BRK_THREADS;
+            const unsigned x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
+            const unsigned m0 = 1u + (c1 == c0) + (c2 == c0) + (c3 == c0), m1 = 1u + (c0 == c1) + (c2 == c1) + (c3 == c1);
+            const unsigned m2 = 1u + (c0 == c2) + (c1 == c2) + (c3 == c2), m3 = 1u + (c0 == c3) + (c1 == c3) + (c2 == c3);
+            *p0 = (unsigned short)(x0 + m0);
+            *p1 = (unsigned short)(x1 + m1);
+            *p2 = (unsigned short)(x2 + m2);
+            *p3 = (unsigned short)(x3 + m3);
+        }
+#pragma unroll
+        for (int e = 0; e < BRK_EPT; ++e) {
+            brk[e] = (unsigned char)((ent[e] & 0xffu) - 1u);
+            cmask |= ((ent[e] >> 8) & 1u) << e;
         }
         stage(k, brk, cmask);
     };
 
+    // CTA-uniform decision; the second barrier keeps a fast warp from staging the next tile (moving the cursor)
+    // before a slow one has read it
+    auto flush_needed = [&]() -> bool {
+        __syncthreads();
+        const bool need = *s_cursor > BRK_STAGE_CAP - BRK_TILE;
+        __syncthreads();
+        return need;
+    };
     unsigned tiles_since_reduce = 0;
     auto reduce_counters = [&]() {
         __syncthreads();
@@ -798,8 +854,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             const unsigned long long next = tile + gridDim.x;
             if (next < n_tiles) load_tile(next, qb);
             process_tile(qa);
-            __syncthreads();
-            if (*s_cursor > BRK_STAGE_CAP - BRK_TILE) flush();
+            if (flush_needed()) flush();
             if (++tiles_since_reduce >= 4000) {  // 16-bit private counters: 4000 * 16 < 65536
                 reduce_counters();
                 tiles_since_reduce = 0;
@@ -809,8 +864,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             const unsigned long long next2 = tile + gridDim.x;
             if (next2 < n_tiles) load_tile(next2, qa);
             process_tile(qb);
-            __syncthreads();
-            if (*s_cursor > BRK_STAGE_CAP - BRK_TILE) flush();
+            if (flush_needed()) flush();
             if (++tiles_since_reduce >= 4000) {
                 reduce_counters();
                 tiles_since_reduce = 0;
@@ -844,8 +898,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
                     sbrk[pos] = (unsigned char)((ent & 0xffu) - 1u);
                 }
             }
-            __syncthreads();
-            if (*s_cursor > BRK_STAGE_CAP - BRK_TILE) flush();
+            if (flush_needed()) flush();
         }
     }
     flush();
@@ -1019,6 +1072,23 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
 // ------------------------------------------------------------------------------------------------
 // 6. refine rounds over the candidate segments
 // ------------------------------------------------------------------------------------------------
+// 16 keys per thread of one full, 16-byte aligned chunk of BRK_RCHUNK keys
+template <typename Key>
+__device__ __forceinline__ void load_chunk_keys(const Key *chunk, int tid, Key (&k)[BRK_RCHUNK / BRK_THREADS]) {
+    constexpr int VEC = 16 / (int)sizeof(Key), NLD = (BRK_RCHUNK / BRK_THREADS) / VEC;
+    const uint4 *v = reinterpret_cast<const uint4 *>(chunk);
+#pragma unroll
+    for (int j = 0; j < NLD; ++j) {
+        const uint4 q = __ldg(v + j * BRK_THREADS + tid);
+        if constexpr (sizeof(Key) == 4) {
+            k[j * 4] = q.x; k[j * 4 + 1] = q.y; k[j * 4 + 2] = q.z; k[j * 4 + 3] = q.w;
+        } else {
+            k[j * 2] = (Key)q.x | ((Key)q.y << 32);
+            k[j * 2 + 1] = (Key)q.z | ((Key)q.w << 32);
+        }
+    }
+}
+
 // linear chunk id -> segment (binary search over the chunk prefix)
 __device__ __forceinline__ int seg_of_chunk(const unsigned long long *prefix, int nseg, unsigned long long chunk) {
     int lo = 0, hi = nseg;  // last s with prefix[s] <= chunk
@@ -1078,11 +1148,31 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_count_kernel(BrkBuf
         const unsigned long long e0 = (ch - sprefix[s]) * BRK_RCHUNK;
         const unsigned long long e1 = e0 + BRK_RCHUNK < sg.cnt_local ? e0 + BRK_RCHUNK : sg.cnt_local;
         const Key *sp = src + sg.off;
-#pragma unroll 4
-        for (unsigned long long i = e0 + tid; i < e1; i += BRK_THREADS) {
-            const Key k = sp[i];
-            const unsigned c = (unsigned)((Key)(k - sg.lo) >> sg.shift) & 0xffu;
-            myctr[c * BRK_THREADS] += 1;
+        if (e1 - e0 == BRK_RCHUNK) {
+            Key k[BRK_RCHUNK / BRK_THREADS];
+            load_chunk_keys<Key>(sp + e0, tid, k);
+#pragma unroll
+            for (int g = 0; g < BRK_RCHUNK / BRK_THREADS; g += 4) {  // as in the streaming pass: 4 loads, merged, 4 stores
+                const unsigned c0 = (unsigned)((Key)(k[g] - sg.lo) >> sg.shift) & 0xffu;
+                const unsigned c1 = (unsigned)((Key)(k[g + 1] - sg.lo) >> sg.shift) & 0xffu;
+                const unsigned c2 = (unsigned)((Key)(k[g + 2] - sg.lo) >> sg.shift) & 0xffu;
+                const unsigned c3 = (unsigned)((Key)(k[g + 3] - sg.lo) >> sg.shift) & 0xffu;
+                unsigned short *p0 = myctr + c0 * BRK_THREADS, *p1 = myctr + c1 * BRK_THREADS,
+                               *p2 = myctr + c2 * BRK_THREADS, *p3 = myctr + c3 * BRK_THREADS;
+                const unsigned x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
+                const unsigned m0 = 1u + (c1 == c0) + (c2 == c0) + (c3 == c0), m1 = 1u + (c0 == c1) + (c2 == c1) + (c3 == c1);
+                const unsigned m2 = 1u + (c0 == c2) + (c1 == c2) + (c3 == c2), m3 = 1u + (c0 == c3) + (c1 == c3) + (c2 == c3);
+                *p0 = (unsigned short)(x0 + m0);
+                *p1 = (unsigned short)(x1 + m1);
+                *p2 = (unsigned short)(x2 + m2);
+                *p3 = (unsigned short)(x3 + m3);
+            }
+        } else {
+            for (unsigned long long i = e0 + tid; i < e1; i += BRK_THREADS) {
+                const Key k = sp[i];
+                const unsigned c = (unsigned)((Key)(k - sg.lo) >> sg.shift) & 0xffu;
+                myctr[c * BRK_THREADS] += 1;
+            }
         }
         ++pending;
     }
@@ -1160,7 +1250,7 @@ __global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf)
                 tk.value = (unsigned long long)(Key)(sg.lo + (Key)digit);
             } else {
                 want[t] = tk.seg * 256 + digit;
-                pad_cnt[t] = (buf.loc_refine[(size_t)tk.seg * 256 + digit] + 1) & ~1ull;
+                pad_cnt[t] = (buf.loc_refine[(size_t)tk.seg * 256 + digit] + 3) & ~3ull;
                 tk.r = rem;
             }
             buf.task[t] = tk;
@@ -1287,14 +1377,21 @@ __global__ void __launch_bounds__(BRK_THREADS) brk_refine_compact_kernel(BrkBuf<
         const unsigned long long e0 = (ch - sprefix[s]) * BRK_RCHUNK;
         const unsigned long long e1 = e0 + BRK_RCHUNK < sg.cnt_local ? e0 + BRK_RCHUNK : sg.cnt_local;
         const Key *sp = src + sg.off;
-        for (unsigned long long i = e0 + tid; i < e1; i += BRK_THREADS) {
-            const Key k = sp[i];
+        auto keep = [&](Key k) {
             const unsigned c = (unsigned)((Key)(k - sg.lo) >> sg.shift) & 0xffu;
             const int id = sid[c];
             if (id >= 0) {
                 const unsigned long long pos = atomicAdd(&nsegs[id].cursor, 1ull);
                 if (pos < nsegs[id].cnt_local) dst[nsegs[id].off + pos] = k;
             }
+        };
+        if (e1 - e0 == BRK_RCHUNK) {
+            Key k[BRK_RCHUNK / BRK_THREADS];
+            load_chunk_keys<Key>(sp + e0, tid, k);
+#pragma unroll
+            for (int e = 0; e < BRK_RCHUNK / BRK_THREADS; ++e) keep(k[e]);
+        } else {
+            for (unsigned long long i = e0 + tid; i < e1; i += BRK_THREADS) keep(sp[i]);
         }
     }
 }
@@ -1312,16 +1409,31 @@ template <typename Key> __global__ void brk_refine_advance_kernel(BrkBuf<Key> bu
 template <typename Key>
 __global__ void __launch_bounds__(256) brk_final_kernel(BrkBuf<Key> buf) {
     __shared__ Key s[BRK_FINAL_CAP];
+    __shared__ int tseg[BRK_MAXTASK];  // segment of every still active task, -1 otherwise
+    __shared__ int s_any;
     if (buf.hdr[H_FAIL] || buf.hdr[H_EMPTY]) return;
     const int nseg = (int)buf.hdr[H_NSEG], ntask = (int)buf.hdr[H_NTASK];
     const int cur = (int)buf.hdr[H_CUR];
     const int tid = threadIdx.x;
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    for (int t = tid; t < BRK_MAXTASK; t += blockDim.x) {
+        int sg = -1;
+        if (t < ntask) {
+            const BrkTask tk = buf.task[t];
+            if (tk.state == TASK_ACTIVE) sg = tk.seg;
+        }
+        tseg[t] = sg;
+        if (sg >= 0) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) return;
     for (int sidx = blockIdx.x; sidx < nseg; sidx += gridDim.x) {
         const BrkSeg<Key> sg = buf.seg[cur][sidx];
         if (!(sg.flags & SEG_FINAL) || (sg.flags & (SEG_TIE | SEG_DONE))) continue;
         bool wanted = false;
         for (int t = 0; t < ntask; ++t)
-            if (buf.task[t].state == TASK_ACTIVE && buf.task[t].seg == sidx) { wanted = true; break; }
+            if (tseg[t] == sidx) { wanted = true; break; }
         if (!wanted) continue;
         const unsigned cnt = (unsigned)sg.cnt_local;
         unsigned np2 = 1;
@@ -1554,7 +1666,8 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     // 3. plan
     {
         auto k = brk_plan_kernel<Key, IS_FLOAT>;
-        const size_t smem = (BRK_S0 + 1) * 4;
+        const size_t smem = ((BRK_S0 + 1) * 4 + 15) / 16 * 16 + BRK_S0 * sizeof(Key) + BRK_NC1 * 2;
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<1, 1024, smem, st>>>(buf, qa, brk_csigma(), n, sharded ? 1 : 0);
         if ((e = count()) != cudaSuccess) return e;
     }
@@ -1615,6 +1728,26 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         if ((e = cudaMemcpyAsync(h, buf.hdr, sizeof h, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
         *failed = (int)h[H_FAIL];
+        if (const char *dbg = getenv("NDS_BRK_DEBUG")) {
+            if (atoi(dbg) >= 2) {  // brackets and exact class counts, for tools/dbg_bracket.py
+                const int B = (int)h[H_B];
+                std::vector<Key> lo(BRK_MAXB), hi(BRK_MAXB);
+                std::vector<unsigned long long> red(BRK_NCLS + BRK_MAXB);
+                std::vector<unsigned char> tie(BRK_MAXB);
+                cudaMemcpy(lo.data(), buf.blo, BRK_MAXB * sizeof(Key), cudaMemcpyDeviceToHost);
+                cudaMemcpy(hi.data(), buf.bhi, BRK_MAXB * sizeof(Key), cudaMemcpyDeviceToHost);
+                cudaMemcpy(tie.data(), buf.btie, BRK_MAXB, cudaMemcpyDeviceToHost);
+                cudaMemcpy(red.data(), buf.red_stream, red.size() * 8, cudaMemcpyDeviceToHost);
+                BrkLutConst<Key> lc;
+                cudaMemcpy(&lc, buf.lutc, sizeof lc, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[bracket-lut] kmin=%llu shift1=%d subshift=%d submask=%u\n", (unsigned long long)lc.kmin,
+                        lc.shift1, lc.subshift, lc.submask);
+                for (int b = 0; b < B; ++b)
+                    fprintf(stderr, "[bracket-b] %d lo=%llu hi=%llu tie=%d cls_count=%llu in=%llu\n", b,
+                            (unsigned long long)lo[b], (unsigned long long)hi[b], (int)tie[b], red[b], red[BRK_NCLS + b]);
+                fprintf(stderr, "[bracket-b] %d (above) cls_count=%llu\n", B, red[B]);
+            }
+        }
         if (getenv("NDS_BRK_DEBUG"))
             fprintf(stderr, "[bracket] n=%llu s1=%u fail=%llu B=%llu ties=%llu tasks=%llu n_eff=%llu invalid=%llu active=%llu\n", n,
                     z.s1, h[H_FAIL], h[H_B], h[H_NTIE], h[H_NTASK], h[H_NEFF], h[H_NINVALID], h[H_NACTIVE]);

@@ -614,14 +614,20 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
 // ------------------------------------------------------------------------------------------------
 // 4. the streaming pass
 // ------------------------------------------------------------------------------------------------
+constexpr int STR_THREADS = 512;          // 16 warps per SM: the table-lookup chains are latency bound
+constexpr int STR_EPT = 8;                // keys per thread per tile
+constexpr int STR_TILE = STR_THREADS * STR_EPT;
+constexpr int STR_STAGE_CAP = 2 * STR_TILE;
+constexpr int STR_SPILL_TILES = 31;       // 8-bit private counters: 31 * 8 < 256
+
 template <typename Key> __host__ __device__ constexpr size_t stream_smem_bytes() {
-    return (size_t)BRK_NCLS * BRK_THREADS * 2 + (size_t)BRK_NC1 * 4 + (((size_t)BRK_L2N * 2 + 15) & ~(size_t)15) +
-           2 * (size_t)BRK_MAXB * sizeof(Key) + 128 + (size_t)BRK_STAGE_CAP * sizeof(Key) + BRK_STAGE_CAP +
-           4 * (size_t)BRK_MAXB * 4 + 64;
+    return (size_t)BRK_NCLS * STR_THREADS + (size_t)BRK_NC1 * 4 + (((size_t)BRK_L2N * 2 + 15) & ~(size_t)15) +
+           2 * (size_t)BRK_MAXB * sizeof(Key) + 128 + (size_t)STR_STAGE_CAP * sizeof(Key) + STR_STAGE_CAP +
+           4 * (size_t)BRK_MAXB * 4 + (size_t)BRK_NCLS * 4 + 64;
 }
 
-// slow path of the classification: a (sub-)cell that holds a bracket edge, the region outside [kmin, kmax], or
-// (floats) a cell on the border to the NaN keys
+// slow path of the classification: a (sub-)cell that holds a bracket edge, or (floats) a cell on the border to
+// the NaN keys.  (Keys outside [kmin, kmax] are handled inline by the caller.)
 template <typename Key, bool IS_FLOAT>
 __device__ __noinline__ unsigned brk_resolve_entry(Key k, unsigned ent, Key kmin, const Key *blo, const Key *bhi,
                                                    const unsigned char *btie, int B) {
@@ -639,32 +645,33 @@ __device__ __noinline__ unsigned brk_resolve_entry(Key k, unsigned ent, Key kmin
 }
 
 template <typename T>
-__global__ void __launch_bounds__(BRK_THREADS, 1)
+__global__ void __launch_bounds__(STR_THREADS, 1)
 brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typename Traits<T>::Key> buf) {
     using Tr = Traits<T>;
     using Key = typename Tr::Key;
     constexpr bool IS_FLOAT = Tr::is_float;
     constexpr int ES = (int)sizeof(T);
     constexpr int VEC = 16 / ES;             // elements per 16-byte load
-    constexpr int NLD = BRK_EPT / VEC;       // 16-byte loads per thread per tile
+    constexpr int NLD = STR_EPT / VEC;       // 16-byte loads per thread per tile
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // ---- carve shared memory -----------------------------------------------------------------------
     unsigned char *p = smem_raw;
-    unsigned short *counters = reinterpret_cast<unsigned short *>(p); p += (size_t)BRK_NCLS * BRK_THREADS * 2;
+    unsigned char *counters = p; p += (size_t)BRK_NCLS * STR_THREADS;                 // [class][thread] 8-bit
     unsigned *lut1 = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_NC1 * 4;
     unsigned short *lut2 = reinterpret_cast<unsigned short *>(p); p += ((size_t)BRK_L2N * 2 + 15) & ~(size_t)15;
     Key *blo = reinterpret_cast<Key *>(p); p += (size_t)BRK_MAXB * sizeof(Key);
     Key *bhi = reinterpret_cast<Key *>(p); p += (size_t)BRK_MAXB * sizeof(Key);
     unsigned char *btie = p; p += 128;
-    Key *skey = reinterpret_cast<Key *>(p); p += (size_t)BRK_STAGE_CAP * sizeof(Key);
-    unsigned char *sbrk = p; p += BRK_STAGE_CAP;
+    Key *skey = reinterpret_cast<Key *>(p); p += (size_t)STR_STAGE_CAP * sizeof(Key);
+    unsigned char *sbrk = p; p += STR_STAGE_CAP;
     unsigned long long *fbase = reinterpret_cast<unsigned long long *>(p); p += (size_t)BRK_MAXB * 8;
     unsigned *fcnt = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;
     unsigned *fpos = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;
+    unsigned *cta_cnt = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_NCLS * 4;   // spilled private counters
     unsigned *s_cursor = reinterpret_cast<unsigned *>(p);
 
     if (buf.hdr[H_FAIL]) return;  // the plan already gave up: the caller falls back
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const BrkLutConst<Key> lc = *buf.lutc;
     const int B = lc.B;
     const Key kmin = lc.kmin;
@@ -672,19 +679,22 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     const unsigned submask = lc.submask;
     const int ncls_used = lc.ncls_used;
 
-    for (int i = tid; i < BRK_NC1; i += BRK_THREADS) lut1[i] = buf.lut1[i];
-    for (int i = tid; i < BRK_L2N; i += BRK_THREADS) lut2[i] = buf.lut2[i];
-    for (int i = tid; i < BRK_MAXB; i += BRK_THREADS) {
+    for (int i = tid; i < BRK_NC1; i += STR_THREADS) lut1[i] = buf.lut1[i];
+    for (int i = tid; i < BRK_L2N; i += STR_THREADS) lut2[i] = buf.lut2[i];
+    for (int i = tid; i < BRK_MAXB; i += STR_THREADS) {
         blo[i] = i < B ? buf.blo[i] : (Key)0;
         bhi[i] = i < B ? buf.bhi[i] : (Key)0;
         btie[i] = i < B ? buf.btie[i] : (unsigned char)0xff;
         fcnt[i] = 0;
     }
-    for (int i = tid; i < BRK_NCLS * BRK_THREADS / 2; i += BRK_THREADS) reinterpret_cast<unsigned *>(counters)[i] = 0;
+    for (int i = tid; i < BRK_NCLS; i += STR_THREADS) cta_cnt[i] = 0;
+    for (int i = tid; i < BRK_NCLS * STR_THREADS / 4; i += STR_THREADS) reinterpret_cast<unsigned *>(counters)[i] = 0;
     if (tid == 0) *s_cursor = 0;
     __syncthreads();
 
-    unsigned short *myctr = counters + counter_slot();
+    // conflict-free private counter of this thread in a class row of 512 bytes: the 32 lanes of a warp hit 32
+    // different banks, four warps share a 128-byte line (byte 0..3 of each word)
+    unsigned char *myctr = counters + (warp >> 2) * 128 + lane * 4 + (warp & 3);
 
     // two table reads per key, no side effects (k - kmin wraps to a huge value below kmin: the "outside" cell)
     auto lookup = [&](Key k) -> unsigned {
@@ -695,11 +705,23 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         const unsigned sub = (unsigned)(d >> subshift) & submask & (unsigned)((int)e1 >> 31);
         return lut2[(e1 & 0x7fffffffu) + sub];
     };
+    // entries that need a second look: outside [kmin, kmax] is decided inline (no NaN: class 0 below, B above),
+    // everything else (a sub-cell with a bracket edge, the border to the NaN keys) by the out-of-line scan
+    auto settle = [&](Key k, unsigned ent) -> unsigned {
+        if ((ent & 0xffu) == 0xffu) {
+            bool nan = false;
+            if (IS_FLOAT)
+                nan = sizeof(Key) == 8 ? (k > (Key)0xFFF0000000000000ull || k < (Key)0x000FFFFFFFFFFFFFull)
+                                       : (k > (Key)0xFF800000u || k < (Key)0x007FFFFFu);
+            return nan ? (unsigned)BRK_INVALID_CLS : (k < kmin ? 0u : (unsigned)B);
+        }
+        return brk_resolve_entry<Key, IS_FLOAT>(k, ent, kmin, blo, bhi, btie, B);
+    };
     // one key at a time (ragged head / tail)
     auto classify = [&](Key k) -> unsigned {
         unsigned ent = lookup(k);
-        if (ent & (ENT_MIXED | ENT_SPECIAL)) ent = brk_resolve_entry<Key, IS_FLOAT>(k, ent, kmin, blo, bhi, btie, B);
-        myctr[(ent & 0xffu) * BRK_THREADS] += 1;
+        if (ent & (ENT_MIXED | ENT_SPECIAL)) ent = settle(k, ent);
+        myctr[(ent & 0xffu) * STR_THREADS] += 1;
         return ent;
     };
 
@@ -707,9 +729,9 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     auto flush = [&]() {
         __syncthreads();
         const unsigned nst = *s_cursor;
-        for (unsigned i = tid; i < nst; i += BRK_THREADS) atomicAdd(&fcnt[sbrk[i]], 1u);
+        for (unsigned i = tid; i < nst; i += STR_THREADS) atomicAdd(&fcnt[sbrk[i]], 1u);
         __syncthreads();
-        for (int b = tid; b < B; b += BRK_THREADS) {
+        for (int b = tid; b < B; b += STR_THREADS) {
             const unsigned c = fcnt[b];
             if (c) {
                 fbase[b] = atomicAdd(&buf.cur_local[b], (unsigned long long)c);
@@ -718,7 +740,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             }
         }
         __syncthreads();
-        for (unsigned i = tid; i < nst; i += BRK_THREADS) {
+        for (unsigned i = tid; i < nst; i += STR_THREADS) {
             const unsigned b = sbrk[i];
             const unsigned long long pos = fbase[b] + atomicAdd(&fpos[b], 1u);
             // positions beyond the planned capacity are dropped; resolve sees fill > cap and raises FAIL_CAPACITY
@@ -728,9 +750,35 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         if (tid == 0) *s_cursor = 0;
         __syncthreads();
     };
+    // CTA-uniform decision; the second barrier keeps a fast warp from staging the next tile (moving the cursor)
+    // before a slow one has read it
+    auto flush_needed = [&]() -> bool {
+        __syncthreads();
+        const bool need = *s_cursor > STR_STAGE_CAP - STR_TILE;
+        __syncthreads();
+        return need;
+    };
+    // private 8-bit counters -> 32-bit CTA counters (every STR_SPILL_TILES tiles)
+    auto spill_counters = [&]() {
+        __syncthreads();
+        for (int c = warp; c < BRK_NCLS; c += STR_THREADS / 32) {
+            if (c >= ncls_used && c != BRK_INVALID_CLS) continue;
+            unsigned *row = reinterpret_cast<unsigned *>(counters + (size_t)c * STR_THREADS);
+            unsigned sum = 0;
+#pragma unroll
+            for (int i = 0; i < STR_THREADS / 4 / 32; ++i) {
+                const unsigned w = row[i * 32 + lane];
+                sum = __dp4a(w, 0x01010101u, sum);
+                row[i * 32 + lane] = 0;
+            }
+            sum = __reduce_add_sync(0xffffffffu, sum);
+            if (lane == 0 && sum) cta_cnt[c] += sum;
+        }
+        __syncthreads();
+    };
 
     // stage the compact-flagged keys of this thread (mask over its EPT keys)
-    auto stage = [&](const Key (&k)[BRK_EPT], const unsigned char (&brk)[BRK_EPT], unsigned cmask) {
+    auto stage = [&](const Key (&k)[STR_EPT], const unsigned (&ent)[STR_EPT], unsigned cmask) {
         const unsigned cnt = __popc(cmask);
         unsigned incl = cnt;
 #pragma unroll
@@ -745,10 +793,10 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         base = __shfl_sync(0xffffffffu, base, 31);
         unsigned pos = base + incl - cnt;
 #pragma unroll
-        for (int e = 0; e < BRK_EPT; ++e) {
+        for (int e = 0; e < STR_EPT; ++e) {
             if (cmask & (1u << e)) {
                 skey[pos] = k[e];
-                sbrk[pos] = brk[e];
+                sbrk[pos] = (unsigned char)((ent[e] & 0xffu) - 1u);
                 ++pos;
             }
         }
@@ -758,18 +806,16 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     const uintptr_t addr = reinterpret_cast<uintptr_t>(data);
     unsigned long long head = ((16 - (addr & 15)) & 15) / ES;  // elements before the first aligned one
     if (head > n) head = n;
-    const unsigned long long n_tiles = (n - head) / BRK_TILE;
+    const unsigned long long n_tiles = (n - head) / STR_TILE;
     const uint4 *vdata = reinterpret_cast<const uint4 *>(data + head);
 
     auto load_tile = [&](unsigned long long tile, uint4 (&q)[NLD]) {
-        const uint4 *src = vdata + tile * (BRK_TILE / VEC);
+        const uint4 *src = vdata + tile * (STR_TILE / VEC);
 #pragma unroll
-        for (int j = 0; j < NLD; ++j) q[j] = __ldg(src + j * BRK_THREADS + tid);
+        for (int j = 0; j < NLD; ++j) q[j] = __ldg(src + j * STR_THREADS + tid);
     };
     auto process_tile = [&](const uint4 (&q)[NLD]) {
-        Key k[BRK_EPT];
-        unsigned char brk[BRK_EPT];
-        unsigned cmask = 0;
+        Key k[STR_EPT];
 #pragma unroll
         for (int j = 0; j < NLD; ++j) {
             if constexpr (ES == 4) {
@@ -784,68 +830,30 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             }
         }
         // phase 1: all table reads of the tile are independent of each other
-        unsigned ent[BRK_EPT];
+        unsigned ent[STR_EPT];
         unsigned slow = 0;
 #pragma unroll
-        for (int e = 0; e < BRK_EPT; ++e) {
+        for (int e = 0; e < STR_EPT; ++e) {
             ent[e] = lookup(k[e]);
             slow |= ent[e];
         }
-        // phase 2: the few keys next to a bracket edge (or outside all brackets)
+        // phase 2: the few keys next to a bracket edge or outside all brackets
         if (slow & (ENT_MIXED | ENT_SPECIAL)) {
 #pragma unroll
-            for (int e = 0; e < BRK_EPT; ++e)
-                if (ent[e] & (ENT_MIXED | ENT_SPECIAL))
-                    ent[e] = brk_resolve_entry<Key, IS_FLOAT>(k[e], ent[e], kmin, blo, bhi, btie, B);
+            for (int e = 0; e < STR_EPT; ++e)
+                if (ent[e] & (ENT_MIXED | ENT_SPECIAL)) ent[e] = settle(k[e], ent[e]);
         }
-        // phase 3: private counters, four keys at a time: the four loads go out together, equal classes inside a
-        // group are merged (each stores old + multiplicity), so no read-after-write chain inside the group
+        // phase 3: private counters (plain read-modify-write of this thread's own bytes), candidate mask
+        unsigned cmask = 0;
 #pragma unroll
-        for (int g = 0; g < BRK_EPT; g += 4) {
-            const unsigned c0 = ent[g] & 0xffu, c1 = ent[g + 1] & 0xffu, c2 = ent[g + 2] & 0xffu, c3 = ent[g + 3] & 0xffu;
-            unsigned short *p0 = myctr + c0 * BRK_THREADS, *p1 = myctr + c1 * BRK_THREADS, *p2 = myctr + c2 * BRK_THREADS,
-                           *p3 = myctr + c3 * BRK_THREADS;
-            const unsigned x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
-            const unsigned m0 = 1u + (c1 == c0) + (c2 == c0) + (c3 == c0), m1 = 1u + (c0 == c1) + (c2 == c1) + (c3 == c1);
-            const unsigned m2 = 1u + (c0 == c2) + (c1 == c2) + (c3 == c2), m3 = 1u + (c0 == c3) + (c1 == c3) + (c2 == c3);
-            *p0 = (unsigned short)(x0 + m0);
-            *p1 = (unsigned short)(x1 + m1);
-            *p2 = (unsigned short)(x2 + m2);
-            *p3 = (unsigned short)(x3 + m3);
-        }
-#pragma unroll
-        for (int e = 0; e < BRK_EPT; ++e) {
-            brk[e] = (unsigned char)((ent[e] & 0xffu) - 1u);
+        for (int e = 0; e < STR_EPT; ++e) {
+            myctr[(ent[e] & 0xffu) * STR_THREADS] += 1;
             cmask |= ((ent[e] >> 8) & 1u) << e;
         }
-        stage(k, brk, cmask);
+        stage(k, ent, cmask);
     };
 
-    // CTA-uniform decision; the second barrier keeps a fast warp from staging the next tile (moving the cursor)
-    // before a slow one has read it
-    auto flush_needed = [&]() -> bool {
-        __syncthreads();
-        const bool need = *s_cursor > BRK_STAGE_CAP - BRK_TILE;
-        __syncthreads();
-        return need;
-    };
-    unsigned tiles_since_reduce = 0;
-    auto reduce_counters = [&]() {
-        __syncthreads();
-        const int warp = tid >> 5;
-        for (int c = warp; c < BRK_NCLS; c += BRK_THREADS / 32) {
-            if (c >= ncls_used && c != BRK_INVALID_CLS) continue;
-            unsigned sum = 0;
-            for (int i = lane; i < BRK_THREADS; i += 32) {
-                sum += counters[c * BRK_THREADS + i];
-                counters[c * BRK_THREADS + i] = 0;
-            }
-            sum = __reduce_add_sync(0xffffffffu, sum);
-            if (lane == 0 && sum) atomicAdd(&buf.red_stream[c], (unsigned long long)sum);
-        }
-        __syncthreads();
-    };
-
+    unsigned tiles_since_spill = 0;
     {
         uint4 qa[NLD], qb[NLD];
         unsigned long long tile = blockIdx.x;
@@ -855,9 +863,9 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             if (next < n_tiles) load_tile(next, qb);
             process_tile(qa);
             if (flush_needed()) flush();
-            if (++tiles_since_reduce >= 4000) {  // 16-bit private counters: 4000 * 16 < 65536
-                reduce_counters();
-                tiles_since_reduce = 0;
+            if (++tiles_since_spill >= STR_SPILL_TILES) {
+                spill_counters();
+                tiles_since_spill = 0;
             }
             tile = next;
             if (tile >= n_tiles) break;
@@ -865,18 +873,20 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             if (next2 < n_tiles) load_tile(next2, qa);
             process_tile(qb);
             if (flush_needed()) flush();
-            if (++tiles_since_reduce >= 4000) {
-                reduce_counters();
-                tiles_since_reduce = 0;
+            if (++tiles_since_spill >= STR_SPILL_TILES) {
+                spill_counters();
+                tiles_since_spill = 0;
             }
             tile = next2;
         }
     }
+    spill_counters();
     // ---- ragged head and tail: the last CTA, element by element ---------------------------------------
     if (blockIdx.x == gridDim.x - 1) {
-        const unsigned long long tail0 = head + n_tiles * BRK_TILE;
+        const unsigned long long tail0 = head + n_tiles * STR_TILE;
         const unsigned long long n_ragged = head + (n - tail0);
-        for (unsigned long long i0 = 0; i0 < n_ragged; i0 += BRK_THREADS) {
+        unsigned rounds = 0;
+        for (unsigned long long i0 = 0; i0 < n_ragged; i0 += STR_THREADS) {
             const unsigned long long i = i0 + tid;
             unsigned ent = 0;
             Key k = 0;
@@ -899,10 +909,17 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
                 }
             }
             if (flush_needed()) flush();
+            if (++rounds >= 200) {
+                spill_counters();
+                rounds = 0;
+            }
         }
+        spill_counters();
     }
     flush();
-    reduce_counters();
+    __syncthreads();
+    for (int c = tid; c < BRK_NCLS; c += STR_THREADS)
+        if (cta_cnt[c]) atomicAdd(&buf.red_stream[c], (unsigned long long)cta_cnt[c]);
 }
 
 // in-counts of the non-tie brackets are their segment fills
@@ -1676,9 +1693,9 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         auto k = brk_stream_kernel<T>;
         const size_t smem = stream_smem_bytes<Key>();
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        unsigned long long tiles = n / BRK_TILE + 1;
+        unsigned long long tiles = n / STR_TILE + 1;
         unsigned grid = (unsigned)std::min<unsigned long long>(tiles, (unsigned long long)sm);
-        k<<<grid, BRK_THREADS, smem, st>>>(lane, n, buf);
+        k<<<grid, STR_THREADS, smem, st>>>(lane, n, buf);
         if ((e = count()) != cudaSuccess) return e;
         brk_publish_fill_kernel<Key><<<1, 128, 0, st>>>(buf);
         if ((e = count()) != cudaSuccess) return e;

@@ -55,12 +55,15 @@ constexpr int BRK_MAXTASK = 2 * BRK_MAXQ; // unique ranks
 constexpr int BRK_MAXSEG = 2 * BRK_MAXQ;
 constexpr int BRK_FINAL_CAP = 4096;       // a segment this small is sorted by one CTA
 constexpr int BRK_RCHUNK = 4096;          // refine passes: elements per chunk
+constexpr int STR_THREADS = 512;          // streaming pass: 16 warps per SM, the table-lookup chains are latency bound
+constexpr int STR_WARPS = STR_THREADS / 32;
+constexpr int STR_TILE = STR_THREADS * 8;
 
 constexpr unsigned ENT_COMPACT = 0x100u, ENT_MIXED = 0x200u, ENT_SPECIAL = 0x400u;
 
 enum : int {
     H_NTOTAL = 0, H_NINVALID, H_NEFF, H_FAIL, H_B, H_NSEG, H_NTASK, H_NACTIVE, H_S1VALID, H_EMPTY, H_NCHUNK_COUNT,
-    H_NCHUNK_COMPACT, H_NCLS_USED, H_NTIE, H_CUR, H_NEXT_NCHUNK, H_NEXT_NSEG, H_OLD_NSEG, H_WORDS = 20
+    H_NCHUNK_COMPACT, H_NCLS_USED, H_NTIE, H_CUR, H_NEXT_NCHUNK, H_NEXT_NSEG, H_OLD_NSEG, H_NW, H_ROUND, H_DID, H_WORDS = 26
 };
 enum : int { FAIL_ESCAPED = 1, FAIL_CAPACITY = 2, FAIL_TOO_MANY = 4, FAIL_INCONSISTENT = 8 };
 enum : int { TASK_ACTIVE = 0, TASK_DONE = 1 };
@@ -70,6 +73,7 @@ template <typename Key> struct BrkSeg {
     Key lo, hi;
     int shift, flags;
     unsigned long long off, cnt_local, cnt_global, cursor;
+    unsigned long long piece_cap;  // round 0: the segment is H_NW pieces of this capacity (one per streaming CTA), fills in buf.fill
 };
 struct BrkTask {
     unsigned long long r;      // rank inside its segment (over all ranks when sharded)
@@ -77,10 +81,12 @@ struct BrkTask {
     int seg, state;
 };
 template <typename Key> struct BrkLutConst {
-    Key kmin;
+    Key kmin;          // origin of the lookup cells (64-bit keys in hi32 mode: a multiple of 2^32)
+    Key kmin_true;     // lower edge of the first bracket
     int shift1, subshift;
     unsigned submask;
     int B, ncls_used;
+    int hi32;          // 64-bit keys: the tables are indexed with the high word only (shift1, subshift >= 32)
 };
 
 template <typename Key> struct BrkBuf {
@@ -88,7 +94,8 @@ template <typename Key> struct BrkBuf {
     unsigned long long *red_n;       // [2]  local element count -> total            (allreduce 0)
     unsigned long long *s0hist;      // [2 (S0 + 2)] bucket counts of S1 against S0, then #{== S0[i]}        (allreduce 1)
     unsigned long long *red_stream;  // [NCLS + MAXB] class counts, bracket in-counts  (allreduce 2)
-    unsigned long long *cur_local;   // [MAXB] local fill of the bracket segments
+    unsigned long long *cur_local;   // [MAXB] local fill of the bracket segments (sum of the pieces)
+    unsigned *fill;                  // [MAXB * nw_cap] fill of every (bracket, streaming CTA) piece
     unsigned long long *red_refine;  // [MAXSEG * 256]                               (allreduce per refine round)
     unsigned long long *loc_refine;  // [MAXSEG * 256] local copy (== red_refine on one GPU)
     Key *s1, *s0, *blo, *bhi;
@@ -105,7 +112,7 @@ template <typename Key> struct BrkBuf {
     unsigned long long *cprefix_count, *cprefix_compact;  // [MAXSEG + 1] chunk prefix sums
     Key *cand[2];
     unsigned long long cand_cap[2];
-    unsigned s1cap;
+    unsigned s1cap, nw_cap;
 };
 
 __device__ __forceinline__ unsigned long long ld_now(const unsigned long long *p) {
@@ -237,7 +244,7 @@ __device__ __forceinline__ unsigned pure_entry(int j, bool in, const unsigned ch
 
 template <typename Key, bool IS_FLOAT>
 __global__ void __launch_bounds__(1024)
-brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long n_local, int sharded) {
+brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long n_local, int sharded, unsigned nw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned *cum = reinterpret_cast<unsigned *>(smem_raw);            // [S0 + 1] inclusive: #{ s1 <= S0[i] }
     Key *s0 = reinterpret_cast<Key *>(smem_raw + ((BRK_S0 + 1) * 4 + 15) / 16 * 16);  // [S0] the sorted sample
@@ -249,7 +256,8 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
     __shared__ unsigned char qheavy[BRK_MAXQ];
     __shared__ Key hv[2 * BRK_MAXQ];
     __shared__ unsigned warp_tot[32];
-    __shared__ int sB, sM, sShift1, sNmixed, sFail;
+    __shared__ int sB, sM, sShift1, sNmixed, sFail, sHi32;
+    __shared__ Key sKminLut;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const Key KMAX = (Key) ~(Key)0;
     const int nq = qa.nq;
@@ -303,6 +311,9 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             buf.hdr[H_B] = 0;
             buf.lutc->B = 0;
             buf.lutc->kmin = 0;
+            buf.lutc->kmin_true = 0;
+            buf.lutc->hi32 = 0;
+            buf.hdr[H_NW] = nw;
             buf.lutc->shift1 = 0;
             buf.lutc->subshift = 0;
             buf.lutc->submask = 0;
@@ -447,12 +458,24 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
         }
         if (B + 1 + ntie > BRK_INVALID_CLS) fail |= FAIL_TOO_MANY;
         sB = B;
-        // top-level cell width
-        const Key range = bhi[B - 1] - blo[0];
+        // top-level cell width.  64-bit keys whose brackets span many high words are indexed by the high word only
+        // (half the integer work per key); the cell origin is then rounded down to a multiple of 2^32 so that
+        // (k - kmin) >> 32 is exactly hi(k) - hi(kmin).
+        Key kmin_lut = blo[0];
+        int hi32 = 0;
+        if (sizeof(Key) == 8 && key_bits_used((Key)(bhi[B - 1] - blo[0])) >= 44) {
+            hi32 = 1;
+            kmin_lut = (Key)((unsigned long long)blo[0] & 0xFFFFFFFF00000000ull);
+        }
+        const Key range = bhi[B - 1] - kmin_lut;
         int shift1 = key_bits_used(range) - 12;
         if (shift1 < 0) shift1 = 0;
+        if (hi32 && shift1 < 32) shift1 = 32;
         while ((range >> shift1) > (Key)(BRK_NC1 - 2)) ++shift1;
         sShift1 = shift1;
+        sHi32 = hi32;
+        sKminLut = kmin_lut;
+        buf.hdr[H_NW] = nw;
         sNmixed = 0;
         sFail = fail;
         buf.hdr[H_B] = (unsigned long long)B;
@@ -480,7 +503,14 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
                 const double cnt = (double)(all_hi > lt_lo ? all_hi - lt_lo : 0u) + 1.0;
                 double want = (cnt + 6.0 * sqrt(cnt) + 16.0) * scale * 1.05 + 2048.0;
                 if (want > (double)n_local) want = (double)n_local;
-                cap = (unsigned long long)want;
+                // every streaming CTA owns one piece of the segment: its share, 6 sigma of head room
+                const double share = want / (double)nw;
+                const double stat_cap = share + 6.0 * sqrt(share) + 24.0;
+                // sorted input: the bracket is one contiguous run of tiles, dealt round-robin to the CTAs; a warp
+                // takes 256 keys of every tile of its CTA
+                const double grid = (double)nw;
+                const double run_cap = (double)STR_TILE * (ceil((want / (double)STR_TILE + 2.0) / grid) + 1.0);
+                cap = (unsigned long long)fmax(stat_cap, fmin(run_cap, want + 24.0));
                 cap = (cap + 3) & ~3ull;
             }
             scap[b] = cap;
@@ -490,13 +520,13 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             unsigned long long off = 0;
             for (int b = 0; b < B; ++b) {
                 buf.boff[b] = off;
-                buf.bcap[b] = scap[b];
-                off += scap[b];
+                buf.bcap[b] = scap[b];          // capacity of ONE piece
+                off += scap[b] * (unsigned long long)nw;
             }
             if (off > buf.cand_cap[0]) raise_fail(buf.hdr, FAIL_CAPACITY);
         }
     }
-    const Key kmin = blo[0];
+    const Key kmin = sKminLut;  // origin of the cells
     for (int b = tid; b < B; b += nthreads) {
         buf.blo[b] = blo[b];
         buf.bhi[b] = bhi[b];
@@ -575,9 +605,12 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
     if (tid == 0) {
         int M = 0;
         const int nm = nmixed > 0 ? nmixed : 1;
-        while (M < shift1 && M < 14 && ((nm << (M + 1)) <= BRK_L2_SUB)) ++M;
+        const int m_max = sHi32 ? shift1 - 32 : shift1;
+        while (M < m_max && M < 14 && ((nm << (M + 1)) <= BRK_L2_SUB)) ++M;
         sM = M;
         buf.lutc->kmin = kmin;
+        buf.lutc->kmin_true = blo[0];
+        buf.lutc->hi32 = sHi32;
         buf.lutc->shift1 = shift1;
         buf.lutc->subshift = shift1 - M;
         buf.lutc->submask = (1u << M) - 1u;
@@ -614,16 +647,14 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
 // ------------------------------------------------------------------------------------------------
 // 4. the streaming pass
 // ------------------------------------------------------------------------------------------------
-constexpr int STR_THREADS = 512;          // 16 warps per SM: the table-lookup chains are latency bound
 constexpr int STR_EPT = 8;                // keys per thread per tile
-constexpr int STR_TILE = STR_THREADS * STR_EPT;
-constexpr int STR_STAGE_CAP = 2 * STR_TILE;
+static_assert(STR_TILE == STR_THREADS * STR_EPT, "tile size");
 constexpr int STR_SPILL_TILES = 31;       // 8-bit private counters: 31 * 8 < 256
 
 template <typename Key> __host__ __device__ constexpr size_t stream_smem_bytes() {
     return (size_t)BRK_NCLS * STR_THREADS + (size_t)BRK_NC1 * 4 + (((size_t)BRK_L2N * 2 + 15) & ~(size_t)15) +
-           2 * (size_t)BRK_MAXB * sizeof(Key) + 128 + (size_t)STR_STAGE_CAP * sizeof(Key) + STR_STAGE_CAP +
-           4 * (size_t)BRK_MAXB * 4 + (size_t)BRK_NCLS * 4 + 64;
+           2 * (size_t)BRK_MAXB * sizeof(Key) + 128 + (size_t)BRK_MAXB * 8 + (size_t)BRK_MAXB * 4 +
+           (size_t)BRK_MAXB * 4 + (size_t)BRK_NCLS * 4 + (size_t)STR_WARPS * 256 * (sizeof(Key) + 1) + 64;
 }
 
 // slow path of the classification: a (sub-)cell that holds a bracket edge, or (floats) a cell on the border to
@@ -636,7 +667,7 @@ __device__ __noinline__ unsigned brk_resolve_entry(Key k, unsigned ent, Key kmin
                                           : (k > (Key)0xFF800000u || k < (Key)0x007FFFFFu);
         if (nan) return BRK_INVALID_CLS;
     }
-    if (k < kmin) return 0u;  // below every bracket (k - kmin wrapped around into a cell at or past the last bracket)
+    if (k < kmin) return 0u;  // below every bracket (k - origin wrapped around into a cell at or past the last bracket)
     if ((ent & 0xffu) == 0xffu) return (unsigned)B;  // above every bracket
     int j = (int)(ent & 0xffu);
     while (j < B && blo[j] <= k) ++j;
@@ -644,7 +675,8 @@ __device__ __noinline__ unsigned brk_resolve_entry(Key k, unsigned ent, Key kmin
     return pure_entry(j, in, btie);
 }
 
-template <typename T>
+// HI32: 64-bit keys, tables indexed with the high word (see brk_plan_kernel); the kernel of the other mode returns
+template <typename T, bool HI32>
 __global__ void __launch_bounds__(STR_THREADS, 1)
 brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typename Traits<T>::Key> buf) {
     using Tr = Traits<T>;
@@ -656,54 +688,66 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // ---- carve shared memory -----------------------------------------------------------------------
     unsigned char *p = smem_raw;
-    unsigned char *counters = p; p += (size_t)BRK_NCLS * STR_THREADS;                 // [class][thread] 8-bit
-    unsigned *lut1 = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_NC1 * 4;
-    unsigned short *lut2 = reinterpret_cast<unsigned short *>(p); p += ((size_t)BRK_L2N * 2 + 15) & ~(size_t)15;
+    unsigned char *__restrict__ counters = p; p += (size_t)BRK_NCLS * STR_THREADS;                 // [class][thread] 8-bit
+    const unsigned *__restrict__ lut1 = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_NC1 * 4;
+    const unsigned short *__restrict__ lut2 = reinterpret_cast<unsigned short *>(p); p += ((size_t)BRK_L2N * 2 + 15) & ~(size_t)15;
     Key *blo = reinterpret_cast<Key *>(p); p += (size_t)BRK_MAXB * sizeof(Key);
     Key *bhi = reinterpret_cast<Key *>(p); p += (size_t)BRK_MAXB * sizeof(Key);
     unsigned char *btie = p; p += 128;
-    Key *skey = reinterpret_cast<Key *>(p); p += (size_t)STR_STAGE_CAP * sizeof(Key);
-    unsigned char *sbrk = p; p += STR_STAGE_CAP;
-    unsigned long long *fbase = reinterpret_cast<unsigned long long *>(p); p += (size_t)BRK_MAXB * 8;
-    unsigned *fcnt = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;
-    unsigned *fpos = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;
-    unsigned *cta_cnt = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_NCLS * 4;   // spilled private counters
-    unsigned *s_cursor = reinterpret_cast<unsigned *>(p);
+    unsigned long long *pbase = reinterpret_cast<unsigned long long *>(p); p += (size_t)BRK_MAXB * 8;  // first piece of a bracket
+    unsigned *pcap = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;                         // capacity of one piece
+    unsigned *pfill = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;                        // fill of this CTA's pieces
+    unsigned *cta_cnt = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_NCLS * 4;                      // spilled private counters
+    Key *__restrict__ wkey = reinterpret_cast<Key *>(p); p += (size_t)STR_WARPS * 256 * sizeof(Key);                  // per-warp candidate staging
+    unsigned char *wbrk = p;
 
     if (buf.hdr[H_FAIL]) return;  // the plan already gave up: the caller falls back
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const BrkLutConst<Key> lc = *buf.lutc;
+    if ((lc.hi32 != 0) != HI32) return;
     const int B = lc.B;
-    const Key kmin = lc.kmin;
+    const Key kmin = lc.kmin, kmin_true = lc.kmin_true;
     const int shift1 = lc.shift1, subshift = lc.subshift;
     const unsigned submask = lc.submask;
     const int ncls_used = lc.ncls_used;
+    const unsigned nw = (unsigned)buf.hdr[H_NW];        // pieces per bracket segment = streaming CTAs
 
-    for (int i = tid; i < BRK_NC1; i += STR_THREADS) lut1[i] = buf.lut1[i];
-    for (int i = tid; i < BRK_L2N; i += STR_THREADS) lut2[i] = buf.lut2[i];
+    for (int i = tid; i < BRK_NC1; i += STR_THREADS) const_cast<unsigned *>(lut1)[i] = buf.lut1[i];
+    for (int i = tid; i < BRK_L2N; i += STR_THREADS) const_cast<unsigned short *>(lut2)[i] = buf.lut2[i];
     for (int i = tid; i < BRK_MAXB; i += STR_THREADS) {
         blo[i] = i < B ? buf.blo[i] : (Key)0;
         bhi[i] = i < B ? buf.bhi[i] : (Key)0;
         btie[i] = i < B ? buf.btie[i] : (unsigned char)0xff;
-        fcnt[i] = 0;
+        pbase[i] = i < B ? buf.boff[i] : 0ull;
+        pcap[i] = i < B ? (unsigned)buf.bcap[i] : 0u;
     }
+    for (int i = tid; i < BRK_MAXB; i += STR_THREADS) pfill[i] = 0;
     for (int i = tid; i < BRK_NCLS; i += STR_THREADS) cta_cnt[i] = 0;
     for (int i = tid; i < BRK_NCLS * STR_THREADS / 4; i += STR_THREADS) reinterpret_cast<unsigned *>(counters)[i] = 0;
-    if (tid == 0) *s_cursor = 0;
     __syncthreads();
 
     // conflict-free private counter of this thread in a class row of 512 bytes: the 32 lanes of a warp hit 32
     // different banks, four warps share a 128-byte line (byte 0..3 of each word)
-    unsigned char *myctr = counters + (warp >> 2) * 128 + lane * 4 + (warp & 3);
+    unsigned char *__restrict__ myctr = counters + (warp >> 2) * 128 + lane * 4 + (warp & 3);
+    Key *cand = buf.cand[0];
 
-    // two table reads per key, no side effects (k - kmin wraps to a huge value below kmin: the "outside" cell)
+    // two table reads per key, no side effects (k - origin wraps to a huge value below it: the "outside" cell)
     auto lookup = [&](Key k) -> unsigned {
-        const Key d = k - kmin;
-        const Key cc = d >> shift1;
-        const unsigned cell = (unsigned)(cc < (Key)(BRK_NC1 - 1) ? cc : (Key)(BRK_NC1 - 1));
-        const unsigned e1 = lut1[cell];
-        const unsigned sub = (unsigned)(d >> subshift) & submask & (unsigned)((int)e1 >> 31);
-        return lut2[(e1 & 0x7fffffffu) + sub];
+        if constexpr (HI32) {
+            const unsigned d = (unsigned)(k >> 32) - (unsigned)(kmin >> 32);
+            const unsigned cc = d >> (shift1 - 32);
+            const unsigned cell = cc < (unsigned)(BRK_NC1 - 1) ? cc : (unsigned)(BRK_NC1 - 1);
+            const unsigned e1 = lut1[cell];
+            const unsigned sub = (d >> (subshift - 32)) & submask & (unsigned)((int)e1 >> 31);
+            return lut2[(e1 & 0x7fffffffu) + sub];
+        } else {
+            const Key d = k - kmin;
+            const Key cc = d >> shift1;
+            const unsigned cell = (unsigned)(cc < (Key)(BRK_NC1 - 1) ? cc : (Key)(BRK_NC1 - 1));
+            const unsigned e1 = lut1[cell];
+            const unsigned sub = (unsigned)(d >> subshift) & submask & (unsigned)((int)e1 >> 31);
+            return lut2[(e1 & 0x7fffffffu) + sub];
+        }
     };
     // entries that need a second look: outside [kmin, kmax] is decided inline (no NaN: class 0 below, B above),
     // everything else (a sub-cell with a bracket edge, the border to the NaN keys) by the out-of-line scan
@@ -713,55 +757,30 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             if (IS_FLOAT)
                 nan = sizeof(Key) == 8 ? (k > (Key)0xFFF0000000000000ull || k < (Key)0x000FFFFFFFFFFFFFull)
                                        : (k > (Key)0xFF800000u || k < (Key)0x007FFFFFu);
-            return nan ? (unsigned)BRK_INVALID_CLS : (k < kmin ? 0u : (unsigned)B);
+            return nan ? (unsigned)BRK_INVALID_CLS : (k < kmin_true ? 0u : (unsigned)B);
         }
-        return brk_resolve_entry<Key, IS_FLOAT>(k, ent, kmin, blo, bhi, btie, B);
+        return brk_resolve_entry<Key, IS_FLOAT>(k, ent, kmin_true, blo, bhi, btie, B);
     };
-    // one key at a time (ragged head / tail)
-    auto classify = [&](Key k) -> unsigned {
-        unsigned ent = lookup(k);
-        if (ent & (ENT_MIXED | ENT_SPECIAL)) ent = settle(k, ent);
-        myctr[(ent & 0xffu) * STR_THREADS] += 1;
-        return ent;
-    };
-
-    // flush the staged candidates to their brackets' segments (whole CTA)
-    auto flush = [&]() {
-        __syncthreads();
-        const unsigned nst = *s_cursor;
-        for (unsigned i = tid; i < nst; i += STR_THREADS) atomicAdd(&fcnt[sbrk[i]], 1u);
-        __syncthreads();
-        for (int b = tid; b < B; b += STR_THREADS) {
-            const unsigned c = fcnt[b];
-            if (c) {
-                fbase[b] = atomicAdd(&buf.cur_local[b], (unsigned long long)c);
-                fpos[b] = 0;
-                fcnt[b] = 0;
-            }
-        }
-        __syncthreads();
-        for (unsigned i = tid; i < nst; i += STR_THREADS) {
-            const unsigned b = sbrk[i];
-            const unsigned long long pos = fbase[b] + atomicAdd(&fpos[b], 1u);
-            // positions beyond the planned capacity are dropped; resolve sees fill > cap and raises FAIL_CAPACITY
-            if (pos < buf.bcap[b]) buf.cand[0][buf.boff[b] + pos] = skey[i];
-        }
-        __syncthreads();
-        if (tid == 0) *s_cursor = 0;
-        __syncthreads();
-    };
-    // CTA-uniform decision; the second barrier keeps a fast warp from staging the next tile (moving the cursor)
-    // before a slow one has read it
-    auto flush_needed = [&]() -> bool {
-        __syncthreads();
-        const bool need = *s_cursor > STR_STAGE_CAP - STR_TILE;
-        __syncthreads();
-        return need;
+    // Append this lane's candidate `k` of bracket `b` (if `has`) to this CTA's piece of the bracket's segment.
+    // Lanes with the same bracket are grouped with match.any and the group leader reserves the positions with ONE
+    // shared-memory atomic on the CTA's fill of that bracket.  Called by all 32 lanes; no CTA barrier anywhere.
+    auto append = [&](bool has, Key k, unsigned b) {
+        const unsigned hasmask = __ballot_sync(0xffffffffu, has);
+        if (!has) return;
+        const unsigned peers = __match_any_sync(hasmask, b);
+        const int leader = __ffs(peers) - 1;
+        const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(&pfill[b], (unsigned)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const unsigned pos = base + rank;
+        if (pos < pcap[b]) cand[pbase[b] + (unsigned long long)blockIdx.x * pcap[b] + pos] = k;
+        else raise_fail(buf.hdr, FAIL_CAPACITY);
     };
     // private 8-bit counters -> 32-bit CTA counters (every STR_SPILL_TILES tiles)
     auto spill_counters = [&]() {
         __syncthreads();
-        for (int c = warp; c < BRK_NCLS; c += STR_THREADS / 32) {
+        for (int c = warp; c < BRK_NCLS; c += STR_WARPS) {
             if (c >= ncls_used && c != BRK_INVALID_CLS) continue;
             unsigned *row = reinterpret_cast<unsigned *>(counters + (size_t)c * STR_THREADS);
             unsigned sum = 0;
@@ -777,37 +796,13 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         __syncthreads();
     };
 
-    // stage the compact-flagged keys of this thread (mask over its EPT keys)
-    auto stage = [&](const Key (&k)[STR_EPT], const unsigned (&ent)[STR_EPT], unsigned cmask) {
-        const unsigned cnt = __popc(cmask);
-        unsigned incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) return;
-        unsigned base = 0;
-        if (lane == 31) base = atomicAdd(s_cursor, total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        unsigned pos = base + incl - cnt;
-#pragma unroll
-        for (int e = 0; e < STR_EPT; ++e) {
-            if (cmask & (1u << e)) {
-                skey[pos] = k[e];
-                sbrk[pos] = (unsigned char)((ent[e] & 0xffu) - 1u);
-                ++pos;
-            }
-        }
-    };
-
     // ---- full, 16-byte aligned tiles ------------------------------------------------------------------
     const uintptr_t addr = reinterpret_cast<uintptr_t>(data);
     unsigned long long head = ((16 - (addr & 15)) & 15) / ES;  // elements before the first aligned one
     if (head > n) head = n;
     const unsigned long long n_tiles = (n - head) / STR_TILE;
-    const uint4 *vdata = reinterpret_cast<const uint4 *>(data + head);
+    const T *adata = data + head;
+    const uint4 *vdata = reinterpret_cast<const uint4 *>(adata);
 
     auto load_tile = [&](unsigned long long tile, uint4 (&q)[NLD]) {
         const uint4 *src = vdata + tile * (STR_TILE / VEC);
@@ -846,11 +841,43 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         // phase 3: private counters (plain read-modify-write of this thread's own bytes), candidate mask
         unsigned cmask = 0;
 #pragma unroll
-        for (int e = 0; e < STR_EPT; ++e) {
-            myctr[(ent[e] & 0xffu) * STR_THREADS] += 1;
-            cmask |= ((ent[e] >> 8) & 1u) << e;
+        for (int e = 0; e < STR_EPT; e += 2) {  // pairs: both loads go out together; equal classes store old + 2 twice
+            const unsigned c0 = ent[e] & 0xffu, c1 = ent[e + 1] & 0xffu;
+            unsigned char *p0 = myctr + c0 * STR_THREADS, *p1 = myctr + c1 * STR_THREADS;
+            const unsigned x0 = *p0, x1 = *p1, same = c0 == c1 ? 1u : 0u;
+            *p0 = (unsigned char)(x0 + 1u + same);
+            *p1 = (unsigned char)(x1 + 1u + same);
+            cmask |= (((ent[e] >> 8) & 1u) << e) | (((ent[e + 1] >> 8) & 1u) << (e + 1));
         }
-        stage(k, ent, cmask);
+        // phase 4: the ~10 % of keys inside a bracket are packed into the warp's staging area (warp prefix sum),
+        // then appended 32 at a time
+        const unsigned cnt = __popc(cmask);
+        unsigned incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) return;
+        Key *mykey = wkey + warp * 256;
+        unsigned char *mybrk = wbrk + warp * 256;
+        unsigned pos = incl - cnt;
+#pragma unroll
+        for (int e = 0; e < STR_EPT; ++e) {
+            if (cmask & (1u << e)) {
+                mykey[pos] = k[e];
+                mybrk[pos] = (unsigned char)((ent[e] & 0xffu) - 1u);
+                ++pos;
+            }
+        }
+        __syncwarp();
+        for (unsigned i0 = 0; i0 < total; i0 += 32) {
+            const unsigned i = i0 + lane;
+            const bool has = i < total;
+            append(has, has ? mykey[i] : (Key)0, has ? (unsigned)mybrk[i] : 0u);
+        }
+        __syncwarp();
     };
 
     unsigned tiles_since_spill = 0;
@@ -862,7 +889,6 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             const unsigned long long next = tile + gridDim.x;
             if (next < n_tiles) load_tile(next, qb);
             process_tile(qa);
-            if (flush_needed()) flush();
             if (++tiles_since_spill >= STR_SPILL_TILES) {
                 spill_counters();
                 tiles_since_spill = 0;
@@ -872,7 +898,6 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             const unsigned long long next2 = tile + gridDim.x;
             if (next2 < n_tiles) load_tile(next2, qa);
             process_tile(qb);
-            if (flush_needed()) flush();
             if (++tiles_since_spill >= STR_SPILL_TILES) {
                 spill_counters();
                 tiles_since_spill = 0;
@@ -890,25 +915,15 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             const unsigned long long i = i0 + tid;
             unsigned ent = 0;
             Key k = 0;
-            bool have = i < n_ragged;
+            const bool have = i < n_ragged;
             if (have) {
                 const unsigned long long idx = i < head ? i : tail0 + (i - head);
                 k = Tr::to_key(data[idx]);
-                ent = classify(k);
+                ent = lookup(k);
+                if (ent & (ENT_MIXED | ENT_SPECIAL)) ent = settle(k, ent);
+                myctr[(ent & 0xffu) * STR_THREADS] += 1;
             }
-            const bool cflag = have && (ent & ENT_COMPACT);
-            const unsigned m = __ballot_sync(0xffffffffu, cflag);
-            if (m) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(s_cursor, (unsigned)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (cflag) {
-                    const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
-                    skey[pos] = k;
-                    sbrk[pos] = (unsigned char)((ent & 0xffu) - 1u);
-                }
-            }
-            if (flush_needed()) flush();
+            append(have && (ent & ENT_COMPACT), k, ((ent & 0xffu) - 1u) & 0xffu);
             if (++rounds >= 200) {
                 spill_counters();
                 rounds = 0;
@@ -916,10 +931,15 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         }
         spill_counters();
     }
-    flush();
     __syncthreads();
     for (int c = tid; c < BRK_NCLS; c += STR_THREADS)
         if (cta_cnt[c]) atomicAdd(&buf.red_stream[c], (unsigned long long)cta_cnt[c]);
+    // fills of this CTA's pieces; their sums are the brackets' in-counts
+    for (int b = tid; b < B; b += STR_THREADS) {
+        const unsigned f = pfill[b];
+        buf.fill[(size_t)b * nw + blockIdx.x] = f;
+        if (f) atomicAdd(&buf.cur_local[b], (unsigned long long)f);
+    }
 }
 
 // in-counts of the non-tie brackets are their segment fills
@@ -1057,32 +1077,23 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
         if (buf.btie[b] != 0xff) s.flags |= SEG_TIE;
         if (seg_used[b]) s.flags |= SEG_USED;
         s.off = buf.boff[b];
-        unsigned long long fill = buf.cur_local[b];
-        if (fill > buf.bcap[b]) {
-            raise_fail(buf.hdr, FAIL_CAPACITY);
-            fill = buf.bcap[b];
-        }
-        s.cnt_local = (s.flags & SEG_TIE) ? 0 : fill;
+        s.piece_cap = buf.bcap[b];
+        s.cnt_local = (s.flags & SEG_TIE) ? 0 : buf.cur_local[b];  // sum over this GPU's pieces
         s.cnt_global = incnt[b];
         s.cursor = 0;
         if ((s.flags & SEG_USED) && s.cnt_global <= BRK_FINAL_CAP) s.flags |= SEG_FINAL;
         buf.seg[0][b] = s;
     }
     __syncthreads();
-    if (tid == 0) {  // chunk prefix of the segments the first count pass has to read
-        unsigned long long run = 0;
+    if (tid == 0) {
         int active = 0;
         for (int b = 0; b < B; ++b) {
-            buf.cprefix_count[b] = run;
             const BrkSeg<Key> &s = buf.seg[0][b];
-            if ((s.flags & SEG_USED) && !(s.flags & (SEG_FINAL | SEG_TIE))) {
-                run += (s.cnt_local + BRK_RCHUNK - 1) / BRK_RCHUNK;
-                ++active;
-            }
+            if ((s.flags & SEG_USED) && !(s.flags & (SEG_FINAL | SEG_TIE))) ++active;
         }
-        buf.cprefix_count[B] = run;
-        buf.hdr[H_NCHUNK_COUNT] = run;
+        buf.hdr[H_NCHUNK_COUNT] = 0;   // round 0 walks the pieces (brk_refine_count0_kernel), not a chunk table
         buf.hdr[H_NACTIVE] = (unsigned long long)active;
+        buf.hdr[H_ROUND] = 0;
     }
 }
 
@@ -1122,7 +1133,7 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_count_kernel(BrkBuf
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned short *counters = reinterpret_cast<unsigned short *>(smem_raw);  // [256][THREADS]
     __shared__ unsigned long long sprefix[BRK_MAXSEG + 1];
-    if (buf.hdr[H_FAIL]) return;
+    if (buf.hdr[H_FAIL] || buf.hdr[H_ROUND] == 0 || buf.hdr[H_NACTIVE] == 0) return;
     const unsigned long long nchunks = buf.hdr[H_NCHUNK_COUNT];
     if (nchunks == 0) return;
     const int cur = (int)buf.hdr[H_CUR];
@@ -1196,6 +1207,148 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_count_kernel(BrkBuf
     if (cur_seg >= 0 && pending) spill(cur_seg);
 }
 
+// Round 0 of the refinement reads the brackets' segments as the streaming pass wrote them: one piece per streaming
+// CTA (fills in buf.fill).  A group of `cpb` CTAs shares one bracket and walks its pieces, so a CTA never mixes
+// brackets in its private counters.  `COMPACT` = second pass: keep the keys whose digit was chosen.
+template <typename Key, bool COMPACT>
+__global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_round0_kernel(BrkBuf<Key> buf) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned short *counters = reinterpret_cast<unsigned short *>(smem_raw);  // [256][THREADS]  (count pass only)
+    __shared__ short sid[256];
+    __shared__ int wanted[256];   // the digits of this bracket that some rank chose (usually one or two)
+    __shared__ int n_wanted;
+    if (buf.hdr[H_FAIL] || buf.hdr[H_ROUND] != 0 || buf.hdr[H_NACTIVE] == 0) return;
+    if (COMPACT && !buf.hdr[H_DID]) return;
+    const int B = (int)(COMPACT ? buf.hdr[H_OLD_NSEG] : buf.hdr[H_NSEG]);
+    const unsigned nw = (unsigned)buf.hdr[H_NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int WARPS = BRK_THREADS / 32;
+    constexpr int KPT = BRK_RCHUNK / BRK_THREADS;
+    const int groups = (int)gridDim.x / B > 0 ? B : (int)gridDim.x;      // brackets in flight at once
+    const int cpb = (int)gridDim.x / groups;                             // CTAs per bracket
+    if ((int)blockIdx.x >= groups * cpb) return;
+    const int part = blockIdx.x % cpb;
+    unsigned short *myctr = counters + counter_slot();
+    BrkSeg<Key> *nsegs = buf.seg[1];
+    Key *dst = buf.cand[1];
+    for (int b = blockIdx.x / cpb; b < B; b += groups) {
+        const BrkSeg<Key> sg = buf.seg[0][b];
+        if (!(sg.flags & SEG_USED) || (sg.flags & (SEG_FINAL | SEG_TIE))) continue;  // CTA-uniform
+        if (COMPACT) {
+            __syncthreads();
+            if (tid == 0) n_wanted = 0;
+            __syncthreads();
+            const short id = buf.newid[b * 256 + tid];
+            sid[tid] = id;
+            if (id >= 0) wanted[atomicAdd(&n_wanted, 1)] = tid;
+            __syncthreads();
+            if (n_wanted == 0) continue;
+        } else {
+            __syncthreads();
+            for (int i = tid; i < 256 * BRK_THREADS / 2; i += BRK_THREADS) reinterpret_cast<unsigned *>(counters)[i] = 0;
+            __syncthreads();
+        }
+        const unsigned *fills = buf.fill + (size_t)b * nw;
+        const Key *src = buf.cand[0] + sg.off;
+        auto digit = [&](Key k) -> unsigned { return (unsigned)((Key)(k - sg.lo) >> sg.shift) & 0xffu; };
+        auto keep = [&](Key k) {
+            const int id = sid[digit(k)];
+            if (id >= 0) {
+                const unsigned long long pos = atomicAdd(&nsegs[id].cursor, 1ull);
+                if (pos < nsegs[id].cnt_local) dst[nsegs[id].off + pos] = k;
+            }
+        };
+        unsigned chunks_since_spill = 0;
+        auto spill = [&]() {
+            __syncthreads();
+            for (int c = warp; c < 256; c += WARPS) {
+                unsigned sum = 0;
+                for (int i = lane; i < BRK_THREADS; i += 32) {
+                    sum += counters[c * BRK_THREADS + i];
+                    counters[c * BRK_THREADS + i] = 0;
+                }
+                sum = __reduce_add_sync(0xffffffffu, sum);
+                if (lane == 0 && sum) atomicAdd(&buf.loc_refine[(size_t)b * 256 + c], (unsigned long long)sum);
+            }
+            __syncthreads();
+        };
+        for (unsigned w = (unsigned)part; w < nw; w += (unsigned)cpb) {
+            unsigned f = fills[w];
+            if (f > sg.piece_cap) f = (unsigned)sg.piece_cap;
+            const Key *piece = src + (unsigned long long)w * sg.piece_cap;  // 16-byte aligned (piece_cap % 4 == 0)
+            for (unsigned e0 = 0; e0 < f; e0 += BRK_RCHUNK) {
+                if (f - e0 >= BRK_RCHUNK) {
+                    Key k[KPT];
+                    load_chunk_keys<Key>(piece + e0, tid, k);
+                    if (COMPACT) {
+                        // one global atomic per warp, chunk and wanted digit instead of one per kept key (their
+                        // latency would serialise the warp)
+                        const int nwd = n_wanted;
+                        if (nwd > 4) {
+#pragma unroll
+                            for (int e = 0; e < KPT; ++e) keep(k[e]);
+                        } else {
+                            for (int j = 0; j < nwd; ++j) {
+                                const unsigned wd = (unsigned)wanted[j];
+                                unsigned m = 0;
+#pragma unroll
+                                for (int e = 0; e < KPT; ++e) m |= (digit(k[e]) == wd ? 1u : 0u) << e;
+                                const unsigned cnt = __popc(m);
+                                unsigned incl = cnt;
+#pragma unroll
+                                for (int d = 1; d < 32; d <<= 1) {
+                                    const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+                                    if (lane >= d) incl += t;
+                                }
+                                const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+                                if (total == 0) continue;
+                                const int id = sid[wd];
+                                unsigned long long base = 0;
+                                if (lane == 31) base = atomicAdd(&nsegs[id].cursor, (unsigned long long)total);
+                                base = __shfl_sync(0xffffffffu, base, 31);
+                                unsigned long long pos = base + incl - cnt;
+                                const unsigned long long cap = nsegs[id].cnt_local, off = nsegs[id].off;
+#pragma unroll
+                                for (int e = 0; e < KPT; ++e) {
+                                    if (m & (1u << e)) {
+                                        if (pos < cap) dst[off + pos] = k[e];
+                                        ++pos;
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < KPT; g += 4) {  // 4 loads, equal digits merged, 4 stores (see the count kernel)
+                            const unsigned c0 = digit(k[g]), c1 = digit(k[g + 1]), c2 = digit(k[g + 2]), c3 = digit(k[g + 3]);
+                            unsigned short *p0 = myctr + c0 * BRK_THREADS, *p1 = myctr + c1 * BRK_THREADS,
+                                           *p2 = myctr + c2 * BRK_THREADS, *p3 = myctr + c3 * BRK_THREADS;
+                            const unsigned x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
+                            const unsigned m0 = 1u + (c1 == c0) + (c2 == c0) + (c3 == c0), m1 = 1u + (c0 == c1) + (c2 == c1) + (c3 == c1);
+                            const unsigned m2 = 1u + (c0 == c2) + (c1 == c2) + (c3 == c2), m3 = 1u + (c0 == c3) + (c1 == c3) + (c2 == c3);
+                            *p0 = (unsigned short)(x0 + m0);
+                            *p1 = (unsigned short)(x1 + m1);
+                            *p2 = (unsigned short)(x2 + m2);
+                            *p3 = (unsigned short)(x3 + m3);
+                        }
+                    }
+                } else {
+                    for (unsigned i = e0 + tid; i < f; i += BRK_THREADS) {
+                        const Key k = piece[i];
+                        if (COMPACT) keep(k);
+                        else myctr[digit(k) * BRK_THREADS] += 1;
+                    }
+                }
+                if (!COMPACT && ++chunks_since_spill >= 4000) {  // CTA-uniform: f, e0 are
+                    spill();
+                    chunks_since_spill = 0;
+                }
+            }
+        }
+        if (!COMPACT) spill();
+    }
+}
+
 // One CTA: every active task picks its digit; the chosen (segment, digit) pairs become the next segments.
 template <typename Key>
 __global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf) {
@@ -1209,8 +1362,11 @@ __global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf)
     __shared__ int s_nid;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     if (buf.hdr[H_FAIL]) return;
-    if (buf.hdr[H_NCHUNK_COUNT] == 0) {
-        if (tid == 0) buf.hdr[H_NCHUNK_COMPACT] = 0;
+    if (buf.hdr[H_NACTIVE] == 0) {
+        if (tid == 0) {
+            buf.hdr[H_NCHUNK_COMPACT] = 0;
+            buf.hdr[H_DID] = 0;
+        }
         return;
     }
     const int cur = (int)buf.hdr[H_CUR];
@@ -1309,6 +1465,7 @@ __global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf)
             ns.cnt_local = buf.loc_refine[(size_t)w];
             ns.cnt_global = buf.red_refine[(size_t)w];
             ns.cursor = 0;
+            ns.piece_cap = 0;
             if (ns.cnt_global <= BRK_FINAL_CAP) ns.flags |= SEG_FINAL;
             if (off + pad_cnt[t] > buf.cand_cap[cur ^ 1]) raise_fail(buf.hdr, FAIL_CAPACITY);
             nsegs[id] = ns;
@@ -1350,7 +1507,8 @@ __global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf)
         buf.hdr[H_NEXT_NCHUNK] = chunks_count;
         buf.hdr[H_NEXT_NSEG] = (unsigned long long)nid;
         buf.hdr[H_OLD_NSEG] = (unsigned long long)nseg;
-        buf.hdr[H_NACTIVE] = (unsigned long long)active;
+        buf.hdr[H_WORDS - 1] = (unsigned long long)active;  // becomes H_NACTIVE once the compaction has run
+        buf.hdr[H_DID] = 1;
     }
     // the counts of this round are consumed: clear them for the next one
     __syncthreads();
@@ -1364,7 +1522,7 @@ template <typename Key>
 __global__ void __launch_bounds__(BRK_THREADS) brk_refine_compact_kernel(BrkBuf<Key> buf) {
     __shared__ unsigned long long sprefix[BRK_MAXSEG + 1];
     __shared__ short sid[256];
-    if (buf.hdr[H_FAIL]) return;
+    if (buf.hdr[H_FAIL] || buf.hdr[H_ROUND] == 0 || !buf.hdr[H_DID]) return;
     const unsigned long long nchunks = buf.hdr[H_NCHUNK_COMPACT];
     if (nchunks == 0) return;
     const int nseg = (int)buf.hdr[H_OLD_NSEG];
@@ -1415,10 +1573,13 @@ __global__ void __launch_bounds__(BRK_THREADS) brk_refine_compact_kernel(BrkBuf<
 
 // publish the next round's segment table sizes (after the compaction has read the old ones)
 template <typename Key> __global__ void brk_refine_advance_kernel(BrkBuf<Key> buf) {
-    if (threadIdx.x == 0 && !buf.hdr[H_FAIL] && buf.hdr[H_NCHUNK_COUNT] != 0) {
+    if (threadIdx.x == 0 && !buf.hdr[H_FAIL] && buf.hdr[H_DID]) {
         buf.hdr[H_NCHUNK_COUNT] = buf.hdr[H_NEXT_NCHUNK];
         buf.hdr[H_NSEG] = buf.hdr[H_NEXT_NSEG];
+        buf.hdr[H_NACTIVE] = buf.hdr[H_WORDS - 1];
         buf.hdr[H_CUR] = buf.hdr[H_CUR] ^ 1ull;
+        buf.hdr[H_ROUND] = buf.hdr[H_ROUND] + 1;
+        buf.hdr[H_DID] = 0;
     }
 }
 
@@ -1456,7 +1617,27 @@ __global__ void __launch_bounds__(256) brk_final_kernel(BrkBuf<Key> buf) {
         unsigned np2 = 1;
         while (np2 < cnt) np2 <<= 1;
         const Key *src = buf.cand[cur] + sg.off;
-        for (unsigned i = tid; i < np2; i += blockDim.x) s[i] = i < cnt ? src[i] : (Key) ~(Key)0;
+        if (sg.piece_cap == 0) {
+            for (unsigned i = tid; i < np2; i += blockDim.x) s[i] = i < cnt ? src[i] : (Key) ~(Key)0;
+        } else {  // a round-0 segment: one piece per streaming CTA, gathered by the warps of this CTA
+            const unsigned nw = (unsigned)buf.hdr[H_NW];
+            const unsigned *fills = buf.fill + (size_t)sidx * nw;
+            if (tid == 0) s_any = 0;   // reused as the gather cursor (every thread has read it above)
+            __syncthreads();
+            const int lane = tid & 31;
+            for (unsigned w = tid >> 5; w < nw; w += blockDim.x >> 5) {
+                const unsigned f = fills[w];
+                if (f == 0) continue;
+                unsigned base = 0;
+                if (lane == 0) base = (unsigned)atomicAdd(&s_any, (int)f);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const Key *piece = src + (unsigned long long)w * sg.piece_cap;
+                for (unsigned i = lane; i < f; i += 32)
+                    if (base + i < BRK_FINAL_CAP) s[base + i] = piece[i];
+            }
+            __syncthreads();
+            for (unsigned i = cnt + tid; i < np2; i += blockDim.x) s[i] = (Key) ~(Key)0;
+        }
         __syncthreads();
         for (unsigned k = 2; k <= np2; k <<= 1) {
             for (unsigned j = k >> 1; j > 0; j >>= 1) {
@@ -1554,12 +1735,12 @@ double predicted_fraction(unsigned long long n, int nq, double wsum) {
 template <typename Key> BrkSizes brk_sizes(unsigned long long n, int nq, double wsum) {
     BrkSizes z;
     z.s1 = pick_s1(n, wsum);
-    z.cap0 = n / 3 + (1ull << 16);
-    if (z.cap0 > n + 1024) z.cap0 = n + 1024;
+    // candidates: up to ~0.3 n, plus the head room of the per-warp pieces (<= MAXB * 148 * 16 pieces)
+    z.cap0 = n / 2 + (unsigned long long)BRK_MAXB * 148 * 2 * STR_TILE + (1ull << 16);
     z.cap1 = z.cap0 / 4 + (1ull << 16);
     size_t t = 0;
     t += align256(H_WORDS * 8) + align256(2 * 8) + align256(2 * (BRK_S0 + 2) * 8) + align256((BRK_NCLS + BRK_MAXB) * 8) +
-         align256(BRK_MAXB * 8) + 2 * align256((size_t)BRK_MAXSEG * 256 * 8);
+         align256(BRK_MAXB * 8) + 2 * align256((size_t)BRK_MAXSEG * 256 * 8) + align256((size_t)BRK_MAXB * 148 * STR_WARPS * 4);
     t += align256((size_t)z.s1 * sizeof(Key)) + align256(BRK_S0 * sizeof(Key)) + 2 * align256(BRK_MAXB * sizeof(Key));
     t += 2 * align256(BRK_MAXB * 8) + align256(BRK_MAXB) + align256(BRK_NC1 * 4) + align256(BRK_L2N * 2) +
          align256(sizeof(BrkLutConst<Key>));
@@ -1587,6 +1768,8 @@ template <typename Key> BrkBuf<Key> brk_carve(void *scratch, const BrkSizes &z, 
     b.cur_local = (unsigned long long *)take(BRK_MAXB * 8);
     b.red_refine = (unsigned long long *)take((size_t)BRK_MAXSEG * 256 * 8);
     b.loc_refine = (unsigned long long *)take((size_t)BRK_MAXSEG * 256 * 8);
+    b.fill = (unsigned *)take((size_t)BRK_MAXB * 148 * STR_WARPS * 4);
+    b.nw_cap = 148 * STR_WARPS;
     *zero_bytes = (size_t)(p - (char *)scratch);
     // --- the rest is written before it is read ---
     b.s1 = (Key *)take((size_t)z.s1 * sizeof(Key));
@@ -1681,22 +1864,29 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     if ((e = allreduce(buf.red_n, 2)) != cudaSuccess) return e;
     if ((e = allreduce(buf.s0hist, 2 * (BRK_S0 + 2))) != cudaSuccess) return e;
     // 3. plan
+    const unsigned long long tiles = n / STR_TILE + 1;
+    const unsigned sgrid = (unsigned)std::min<unsigned long long>(tiles, (unsigned long long)std::min(sm, 148));
+    const unsigned nw = sgrid;  // streaming CTAs = pieces per bracket segment
     {
         auto k = brk_plan_kernel<Key, IS_FLOAT>;
         const size_t smem = ((BRK_S0 + 1) * 4 + 15) / 16 * 16 + BRK_S0 * sizeof(Key) + BRK_NC1 * 2;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<1, 1024, smem, st>>>(buf, qa, brk_csigma(), n, sharded ? 1 : 0);
+        k<<<1, 1024, smem, st>>>(buf, qa, brk_csigma(), n, sharded ? 1 : 0, nw);
         if ((e = count()) != cudaSuccess) return e;
     }
-    // 4. stream
+    // 4. stream (the kernel of the table mode the plan did not choose returns at once)
     {
-        auto k = brk_stream_kernel<T>;
         const size_t smem = stream_smem_bytes<Key>();
-        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        unsigned long long tiles = n / STR_TILE + 1;
-        unsigned grid = (unsigned)std::min<unsigned long long>(tiles, (unsigned long long)sm);
-        k<<<grid, STR_THREADS, smem, st>>>(lane, n, buf);
+        auto k0 = brk_stream_kernel<T, false>;
+        if ((e = cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k0<<<sgrid, STR_THREADS, smem, st>>>(lane, n, buf);
         if ((e = count()) != cudaSuccess) return e;
+        if constexpr (sizeof(Key) == 8) {
+            auto k1 = brk_stream_kernel<T, true>;
+            if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            k1<<<sgrid, STR_THREADS, smem, st>>>(lane, n, buf);
+            if ((e = count()) != cudaSuccess) return e;
+        }
         brk_publish_fill_kernel<Key><<<1, 128, 0, st>>>(buf);
         if ((e = count()) != cudaSuccess) return e;
     }
@@ -1707,13 +1897,17 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     // 6. refine
     {
         auto kc = brk_refine_count_kernel<Key>;
+        auto kc0 = brk_refine_round0_kernel<Key, false>;
+        auto kp0 = brk_refine_round0_kernel<Key, true>;
         const size_t smem = (size_t)256 * BRK_THREADS * 2;
         if ((e = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(kc0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         const int max_rounds = (int)sizeof(Key) + 1;
         brk_final_kernel<Key><<<sm, 256, 0, st>>>(buf);
         if ((e = count()) != cudaSuccess) return e;
         for (int round = 0; round < max_rounds; ++round) {
-            kc<<<sm, BRK_THREADS, smem, st>>>(buf);
+            if (round == 0) kc0<<<sm * 2, BRK_THREADS, smem, st>>>(buf);
+            else kc<<<sm, BRK_THREADS, smem, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
             if (sharded && ctx->nccl_comm) {
                 // red_refine = sum over ranks of loc_refine
@@ -1723,7 +1917,8 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
             }
             brk_refine_decide_kernel<Key><<<1, 256, 0, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
-            brk_refine_compact_kernel<Key><<<sm * 2, BRK_THREADS, 0, st>>>(buf);
+            if (round == 0) kp0<<<sm * 2, BRK_THREADS, 0, st>>>(buf);
+            else brk_refine_compact_kernel<Key><<<sm * 2, BRK_THREADS, 0, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
             brk_refine_advance_kernel<Key><<<1, 32, 0, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
@@ -1733,7 +1928,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
                 unsigned long long h[H_WORDS];
                 if ((e = cudaMemcpyAsync(h, buf.hdr, sizeof h, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
                 if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-                if (h[H_FAIL] || h[H_NACTIVE] == 0 || h[H_NCHUNK_COUNT] == 0) break;
+                if (h[H_FAIL] || h[H_NACTIVE] == 0) break;
             }
         }
     }

@@ -493,13 +493,17 @@ def test_bracket_sort1d_and_enqueue(nds, gpu_ctx, oracle):
     st, want, _ = oracle.quantiles_axis(a, 0, dec, "linear", select_impl=1)
     assert ulp_distance(out.cpu().numpy(), want) == 0
     assert gpu_ctx.last_path == "bracket"
-    # 99 percentiles of a lane this short cannot be bracketed: automatic dispatch goes straight to the radix
-    # passes; forced, the enqueued call gives up on the device and is re-run at synchronize()
+    # 99 percentiles of a lane this short: the brackets would hold most of the lane, automatic dispatch goes
+    # straight to the radix passes
     pct = np.arange(1, 100) / 100.0
     st, want, _ = oracle.quantiles_axis(a, 0, pct, "linear", select_impl=1)
     out = gpu_ctx.quantiles_axis(t, 0, pct, "linear", enqueue=True)
     gpu_ctx.synchronize()
     assert gpu_ctx.last_path == "long_radix" and ulp_distance(out.cpu().numpy(), want) == 0
+    # ranks that escape their bracket (forced here with absurdly narrow brackets): an enqueued call gives up on the
+    # device and is re-run on the radix passes at synchronize(); a synchronous call falls back at once
+    import os
+    os.environ["NDS_BRK_SIGMA"] = "0.6"
     try:
         gpu_ctx.force_path("bracket")
         out = gpu_ctx.quantiles_axis(t, 0, pct, "linear", enqueue=True)
@@ -509,7 +513,10 @@ def test_bracket_sort1d_and_enqueue(nds, gpu_ctx, oracle):
         assert ulp_distance(out.cpu().numpy(), want) == 0
         st, want2, _ = oracle.quantiles_axis(a, 0, dec, "lower", select_impl=1)
         assert_bit_equal(out2.cpu().numpy(), want2)
+        got = gpu_ctx.quantiles_axis(a, 0, pct, "linear")
+        assert gpu_ctx.last_path == "bracket->long_radix" and ulp_distance(got, want) == 0
     finally:
+        del os.environ["NDS_BRK_SIGMA"]
         gpu_ctx.force_path("auto")
 
 

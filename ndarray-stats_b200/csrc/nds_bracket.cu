@@ -1992,6 +1992,9 @@ cudaError_t launch_bracket_typed(nds_ctx *ctx, const DeviceCall &c, void *scratc
 
 bool bracket_supported(const nds_ctx *ctx, const DeviceCall &c, bool sharded, bool forced) {
     (void)ctx;
+    // A lane sharded over ranks needs ONE sample for all of them (the brackets must be identical on every rank);
+    // until the sample exchange exists the sharded entry point uses the radix passes with their NCCL allreduce.
+    if (sharded) return false;
     switch (c.dtype) {
     case NDS_F32: case NDS_I32: case NDS_U32: case NDS_F64: case NDS_I64: case NDS_U64: break;
     default: return false;

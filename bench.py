@@ -195,7 +195,12 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     from oracle import oracle
-    threads = oracle.max_threads()
+    # all host threads the process may use: torchrun exports OMP_NUM_THREADS=1, which is not the machine
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    threads = max(threads, oracle.max_threads())
     name = args.workload
     desc = WORKLOADS[name][0]
     # `--steps K --warmup W`: each step is one bounded sample; the whole run stays within a few minutes

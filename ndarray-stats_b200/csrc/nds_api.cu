@@ -179,7 +179,7 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
                              bracket_supported(ctx, probe, sharded, ctx->forced_path == "bracket");
     if (ctx->forced_path == "bracket" && !use_bracket)
         return fail(ctx, NDS_UNSUPPORTED, "forced path bracket does not support this call");
-    const size_t o_brk = use_bracket ? carve(bracket_scratch_bytes(probe)) : 0;
+    const size_t o_brk = use_bracket ? carve(bracket_scratch_bytes(probe, sharded)) : 0;
     const size_t o_long_fb = (use_bracket && !long_path) ? carve(long_scratch_bytes((int)nq)) : o_long;
     const size_t o_ntotal = sharded ? carve(sizeof(unsigned long long)) : 0;
     CUDA_TRY(arena_reserve(ctx, off));
@@ -215,6 +215,8 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
 
     // ---- dispatch ----------------------------------------------------------------------------------
     cudaError_t e;
+    unsigned long long bracket_n_total = 0;
+    bool bracket_done = false;
     const bool want_short = ctx->forced_path == "auto" || ctx->forced_path == "short_bitslice";
     const bool want_cols = ctx->forced_path == "auto" || ctx->forced_path == "cols_bitslice";
     if (ctx->forced_path == "short_bitslice" && !short_bitslice_supported(ctx, c))
@@ -223,7 +225,8 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
         return fail(ctx, NDS_UNSUPPORTED, "forced path cols_bitslice does not support this call");
     if (use_bracket) {
         int failed = 0;
-        e = launch_bracket(ctx, c, arena + o_brk, sharded, synchronous, &failed);
+        e = launch_bracket(ctx, c, arena + o_brk, sharded, synchronous, &failed, &bracket_n_total);
+        bracket_done = e == cudaSuccess && synchronous && !failed;
         if (e == cudaSuccess && synchronous && failed) {
             // a rank escaped its sampled bracket (or scratch ran out): the exact multi-pass radix select takes over
             CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
@@ -255,10 +258,12 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
     }
     if (sharded) {
         // global element count (summed over ranks in the first pass): 0 => QuantileError::EmptyInput
-        unsigned long long n_total = 0;
-        CUDA_TRY(cudaMemcpyAsync(arena + o_ntotal, long_total_count_ptr(arena + o_long, (int)nq),
-                                 sizeof n_total, cudaMemcpyDeviceToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(&n_total, arena + o_ntotal, sizeof n_total, cudaMemcpyDeviceToHost, ctx->stream));
+        unsigned long long n_total = bracket_n_total;
+        if (!bracket_done) {
+            CUDA_TRY(cudaMemcpyAsync(arena + o_ntotal, long_total_count_ptr(arena + o_long_fb, (int)nq),
+                                     sizeof n_total, cudaMemcpyDeviceToDevice, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(&n_total, arena + o_ntotal, sizeof n_total, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         nds_status st = nds_ctx_synchronize(ctx);
         if (n_total == 0) return fail(ctx, NDS_EMPTY_INPUT, "Empty input.");
         return st;

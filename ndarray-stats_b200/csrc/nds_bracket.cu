@@ -63,9 +63,9 @@ constexpr unsigned ENT_COMPACT = 0x100u, ENT_MIXED = 0x200u, ENT_SPECIAL = 0x400
 
 enum : int {
     H_NTOTAL = 0, H_NINVALID, H_NEFF, H_FAIL, H_B, H_NSEG, H_NTASK, H_NACTIVE, H_S1VALID, H_EMPTY, H_NCHUNK_COUNT,
-    H_NCHUNK_COMPACT, H_NCLS_USED, H_NTIE, H_CUR, H_NEXT_NCHUNK, H_NEXT_NSEG, H_OLD_NSEG, H_NW, H_ROUND, H_DID, H_WORDS = 26
+    H_NCHUNK_COMPACT, H_NCLS_USED, H_NTIE, H_CUR, H_NEXT_NCHUNK, H_NEXT_NSEG, H_OLD_NSEG, H_NW, H_ROUND, H_DID, H_FINALCAP, H_SPARE, H_WORDS = 28
 };
-enum : int { FAIL_ESCAPED = 1, FAIL_CAPACITY = 2, FAIL_TOO_MANY = 4, FAIL_INCONSISTENT = 8 };
+enum : int { FAIL_ESCAPED = 1, FAIL_CAPACITY = 2, FAIL_TOO_MANY = 4, FAIL_INCONSISTENT = 8, FAIL_REMOTE = 16 };
 enum : int { TASK_ACTIVE = 0, TASK_DONE = 1 };
 enum : int { SEG_TIE = 1, SEG_FINAL = 2, SEG_USED = 4, SEG_DONE = 8 };
 
@@ -99,6 +99,8 @@ template <typename Key> struct BrkBuf {
     unsigned long long *red_refine;  // [MAXSEG * 256]                               (allreduce per refine round)
     unsigned long long *loc_refine;  // [MAXSEG * 256] local copy (== red_refine on one GPU)
     Key *s1, *s0, *blo, *bhi;
+    Key *s0part, *s0all;             // sharded lanes: this rank's share of S0, the all-gathered S0
+    unsigned long long *red_end;     // [2] final agreement on FAIL over ranks
     unsigned long long *boff, *bcap;
     unsigned char *btie;             // tie class of a bracket (lo == hi: counted, never compacted) or 0xff
     unsigned *lut1;                  // [NC1]
@@ -166,17 +168,46 @@ __global__ void brk_sample_kernel(const T *__restrict__ data, unsigned long long
     }
     valid = __reduce_add_sync(0xffffffffu, valid);
     if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&buf.hdr[H_S1VALID], (unsigned long long)valid);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&buf.red_n[0], n);
 }
 
-// 2a. S0 = every (s1 / S0)-th sample, sorted by one CTA (bitonic network in shared memory)
+// 0. this rank's element count (summed over ranks by the caller when the lane is sharded); final-sort threshold
+template <typename Key> __global__ void brk_begin_kernel(BrkBuf<Key> buf, unsigned long long n_local, unsigned final_cap) {
+    if (threadIdx.x == 0) {
+        buf.red_n[0] = n_local;
+        buf.hdr[H_FINALCAP] = final_cap;
+    }
+}
+// sharded lanes: this rank's share of the S0 keys (all-gathered, then sorted identically on every rank)
+template <typename Key> __global__ void brk_pick_s0_kernel(BrkBuf<Key> buf, unsigned s1, Key *dst, unsigned count) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        dst[i] = s1 ? buf.s1[(unsigned long long)i * s1 / count] : (Key) ~(Key)0;
+}
+// local fail bits travel with the counts of every exchange step, so that all ranks give up together
+template <typename Key> __global__ void brk_merge_fail_kernel(BrkBuf<Key> buf, const unsigned long long *word) {
+    if (threadIdx.x == 0 && *word) raise_fail(buf.hdr, FAIL_REMOTE);
+}
+template <typename Key> __global__ void brk_post_fail_kernel(BrkBuf<Key> buf, unsigned long long *word) {
+    if (threadIdx.x == 0) *word = buf.hdr[H_FAIL] ? 1ull : 0ull;
+}
+template <typename Key> __global__ void brk_copy_counts_kernel(BrkBuf<Key> buf) {  // red_refine = loc_refine (+ fail word)
+    const int nseg = (int)buf.hdr[H_NSEG];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BRK_MAXSEG * 256; i += gridDim.x * blockDim.x)
+        buf.red_refine[i] = i < nseg * 256 ? buf.loc_refine[i] : 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) buf.red_refine[BRK_MAXSEG * 256] = buf.hdr[H_FAIL] ? 1ull : 0ull;
+}
+
+// 2a. S0 = every (s1 / S0)-th sample (or the gathered shares of all ranks), sorted by one CTA (bitonic network)
 template <typename Key>
-__global__ void __launch_bounds__(1024) brk_sort_s0_kernel(BrkBuf<Key> buf, unsigned s1) {
+__global__ void __launch_bounds__(1024) brk_sort_s0_kernel(BrkBuf<Key> buf, unsigned s1, const Key *gathered) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Key *s = reinterpret_cast<Key *>(smem_raw);
     for (unsigned i = threadIdx.x; i < BRK_S0; i += blockDim.x) {
-        unsigned long long pos = (unsigned long long)i * s1 / BRK_S0;
-        s[i] = buf.s1[pos];
+        if (gathered) {
+            s[i] = gathered[i];
+        } else {
+            unsigned long long pos = (unsigned long long)i * s1 / BRK_S0;
+            s[i] = buf.s1[pos];
+        }
     }
     __syncthreads();
     for (unsigned k = 2; k <= BRK_S0; k <<= 1) {
@@ -502,6 +533,7 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
                 const unsigned lt_lo = a > 0 ? cum[a - 1] : 0u;
                 const double cnt = (double)(all_hi > lt_lo ? all_hi - lt_lo : 0u) + 1.0;
                 double want = (cnt + 6.0 * sqrt(cnt) + 16.0) * scale * 1.05 + 2048.0;
+                if (sharded) want = want * ((double)n_local / (double)n_total) * 1.5 + 4096.0;  // this rank's share
                 if (want > (double)n_local) want = (double)n_local;
                 // every streaming CTA owns one piece of the segment: its share, 6 sigma of head room
                 const double share = want / (double)nw;
@@ -946,6 +978,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
 template <typename Key> __global__ void brk_publish_fill_kernel(BrkBuf<Key> buf) {
     const int B = (int)buf.hdr[H_B];
     for (int b = threadIdx.x; b < B; b += blockDim.x) buf.red_stream[BRK_NCLS + b] = buf.cur_local[b];
+    if (threadIdx.x == 0) buf.red_stream[BRK_NCLS + BRK_MAXB] = buf.hdr[H_FAIL] ? 1ull : 0ull;  // summed over ranks
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -959,6 +992,10 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
     __shared__ unsigned long long below[BRK_MAXB], incnt[BRK_MAXB];
     __shared__ int seg_used[BRK_MAXB];
     const int tid = threadIdx.x;
+    if (buf.red_stream[BRK_NCLS + BRK_MAXB]) {  // some rank gave up in the streaming pass: everybody does
+        if (tid == 0) raise_fail(buf.hdr, FAIL_REMOTE);
+        return;
+    }
     if (buf.hdr[H_FAIL]) return;
     const int B = (int)buf.hdr[H_B];
     const int R = 2 * qa.nq;
@@ -1081,7 +1118,7 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
         s.cnt_local = (s.flags & SEG_TIE) ? 0 : buf.cur_local[b];  // sum over this GPU's pieces
         s.cnt_global = incnt[b];
         s.cursor = 0;
-        if ((s.flags & SEG_USED) && s.cnt_global <= BRK_FINAL_CAP) s.flags |= SEG_FINAL;
+        if ((s.flags & SEG_USED) && s.cnt_global <= buf.hdr[H_FINALCAP]) s.flags |= SEG_FINAL;
         buf.seg[0][b] = s;
     }
     __syncthreads();
@@ -1361,6 +1398,10 @@ __global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf)
     __shared__ unsigned char new_final[BRK_MAXSEG];
     __shared__ int s_nid;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (buf.red_refine != buf.loc_refine && buf.red_refine[BRK_MAXSEG * 256]) {
+        if (tid == 0) raise_fail(buf.hdr, FAIL_REMOTE);
+        return;
+    }
     if (buf.hdr[H_FAIL]) return;
     if (buf.hdr[H_NACTIVE] == 0) {
         if (tid == 0) {
@@ -1466,7 +1507,7 @@ __global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf)
             ns.cnt_global = buf.red_refine[(size_t)w];
             ns.cursor = 0;
             ns.piece_cap = 0;
-            if (ns.cnt_global <= BRK_FINAL_CAP) ns.flags |= SEG_FINAL;
+            if (ns.cnt_global <= buf.hdr[H_FINALCAP]) ns.flags |= SEG_FINAL;
             if (off + pad_cnt[t] > buf.cand_cap[cur ^ 1]) raise_fail(buf.hdr, FAIL_CAPACITY);
             nsegs[id] = ns;
             new_cnt_local[id] = ns.cnt_local;
@@ -1732,16 +1773,21 @@ double predicted_fraction(unsigned long long n, int nq, double wsum) {
     return s1 ? wsum / std::sqrt((double)s1) + (double)nq / 4096.0 : 1.0;
 }
 
-template <typename Key> BrkSizes brk_sizes(unsigned long long n, int nq, double wsum) {
+template <typename Key> BrkSizes brk_sizes(unsigned long long n, int nq, double wsum, bool sharded) {
     BrkSizes z;
     z.s1 = pick_s1(n, wsum);
+    if (sharded) {  // the sample size follows the TOTAL length, known only after the first exchange: take the bound
+        unsigned long long cap = n + 65536;
+        if (cap > (1ull << 24)) cap = 1ull << 24;
+        z.s1 = (unsigned)cap;
+    }
     // candidates: up to ~0.3 n, plus the head room of the per-warp pieces (<= MAXB * 148 * 16 pieces)
     z.cap0 = n / 2 + (unsigned long long)BRK_MAXB * 148 * 2 * STR_TILE + (1ull << 16);
     z.cap1 = z.cap0 / 4 + (1ull << 16);
     size_t t = 0;
-    t += align256(H_WORDS * 8) + align256(2 * 8) + align256(2 * (BRK_S0 + 2) * 8) + align256((BRK_NCLS + BRK_MAXB) * 8) +
-         align256(BRK_MAXB * 8) + 2 * align256((size_t)BRK_MAXSEG * 256 * 8) + align256((size_t)BRK_MAXB * 148 * STR_WARPS * 4);
-    t += align256((size_t)z.s1 * sizeof(Key)) + align256(BRK_S0 * sizeof(Key)) + 2 * align256(BRK_MAXB * sizeof(Key));
+    t += align256(H_WORDS * 8) + align256(2 * 8) + align256(2 * (BRK_S0 + 2) * 8) + align256((BRK_NCLS + BRK_MAXB + 2) * 8) +
+         align256(BRK_MAXB * 8) + 2 * align256(((size_t)BRK_MAXSEG * 256 + 2) * 8) + align256(16) + align256((size_t)BRK_MAXB * 148 * STR_WARPS * 4);
+    t += align256((size_t)z.s1 * sizeof(Key)) + 3 * align256(BRK_S0 * sizeof(Key)) + 2 * align256(BRK_MAXB * sizeof(Key));
     t += 2 * align256(BRK_MAXB * 8) + align256(BRK_MAXB) + align256(BRK_NC1 * 4) + align256(BRK_L2N * 2) +
          align256(sizeof(BrkLutConst<Key>));
     t += 2 * align256(BRK_MAXSEG * sizeof(BrkSeg<Key>)) + align256(BRK_MAXTASK * sizeof(BrkTask)) +
@@ -1764,9 +1810,10 @@ template <typename Key> BrkBuf<Key> brk_carve(void *scratch, const BrkSizes &z, 
     b.hdr = (unsigned long long *)take(H_WORDS * 8);
     b.red_n = (unsigned long long *)take(2 * 8);
     b.s0hist = (unsigned long long *)take(2 * (BRK_S0 + 2) * 8);
-    b.red_stream = (unsigned long long *)take((BRK_NCLS + BRK_MAXB) * 8);
+    b.red_stream = (unsigned long long *)take((BRK_NCLS + BRK_MAXB + 2) * 8);
     b.cur_local = (unsigned long long *)take(BRK_MAXB * 8);
-    b.red_refine = (unsigned long long *)take((size_t)BRK_MAXSEG * 256 * 8);
+    b.red_refine = (unsigned long long *)take(((size_t)BRK_MAXSEG * 256 + 2) * 8);
+    b.red_end = (unsigned long long *)take(2 * 8);
     b.loc_refine = (unsigned long long *)take((size_t)BRK_MAXSEG * 256 * 8);
     b.fill = (unsigned *)take((size_t)BRK_MAXB * 148 * STR_WARPS * 4);
     b.nw_cap = 148 * STR_WARPS;
@@ -1774,6 +1821,8 @@ template <typename Key> BrkBuf<Key> brk_carve(void *scratch, const BrkSizes &z, 
     // --- the rest is written before it is read ---
     b.s1 = (Key *)take((size_t)z.s1 * sizeof(Key));
     b.s0 = (Key *)take(BRK_S0 * sizeof(Key));
+    b.s0part = (Key *)take(BRK_S0 * sizeof(Key));
+    b.s0all = (Key *)take(BRK_S0 * sizeof(Key));
     b.blo = (Key *)take(BRK_MAXB * sizeof(Key));
     b.bhi = (Key *)take(BRK_MAXB * sizeof(Key));
     b.boff = (unsigned long long *)take(BRK_MAXB * 8);
@@ -1813,20 +1862,21 @@ template <typename T> constexpr bool brk_type_ok() { return sizeof(T) == 4 || si
 template <typename T>
 cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long n, const QuantArgs &qa, T *out,
                                 uint8_t *out_valid, long long out_axis_stride, void *scratch, bool sharded,
-                                bool synchronous, double wsum, int *failed) {
+                                bool synchronous, double wsum, int *failed, unsigned long long *n_total_out) {
     using Key = typename Traits<T>::Key;
     constexpr bool IS_FLOAT = Traits<T>::is_float;
     cudaStream_t st = ctx->stream;
-    const BrkSizes z = brk_sizes<Key>(n, qa.nq, wsum);
+    const bool multi = sharded && ctx->nccl_comm && ctx->nranks > 1;
+    const BrkSizes z = brk_sizes<Key>(n, qa.nq, wsum, sharded);
     size_t zero_bytes = 0;
     BrkBuf<Key> buf = brk_carve<Key>(scratch, z, qa.nq, &zero_bytes);
-    if (!sharded) buf.red_refine = buf.loc_refine;
+    if (!multi) buf.red_refine = buf.loc_refine;
     cudaError_t e = cudaMemsetAsync(scratch, 0, zero_bytes, st);
     if (e != cudaSuccess) return e;
     const int sm = ctx->sm_count;
     auto count = [&]() { ctx->launches += 1; return cudaGetLastError(); };
     auto allreduce = [&](unsigned long long *p, size_t words) -> cudaError_t {
-        if (!(sharded && ctx->nccl_comm)) return cudaSuccess;
+        if (!multi) return cudaSuccess;
         std::string err;
         if (nccl_allreduce_sum_u64(ctx, p, words, st, &err) != 0) {
             ctx->last_error = err;
@@ -1834,21 +1884,57 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         }
         return cudaSuccess;
     };
+    auto read_hdr = [&](unsigned long long (&h)[H_WORDS]) -> cudaError_t {
+        cudaError_t e2 = cudaMemcpyAsync(h, buf.hdr, sizeof h, cudaMemcpyDeviceToHost, st);
+        if (e2 != cudaSuccess) return e2;
+        return cudaStreamSynchronize(st);
+    };
 
-    // 1-2. sample, sort S0, bucket S1
-    if (n) {
-        brk_sample_kernel<T><<<std::min<unsigned>((z.s1 + 255) / 256, sm * 8), 256, 0, st>>>(lane, n, z.s1, buf);
+    // 0. element count (over all ranks), threshold below which a segment is sorted by one CTA.  A lane sharded over
+    //    ranks never gathers elements: its segments are refined digit by digit down to single keys.
+    unsigned final_cap = multi ? 0u : (unsigned)BRK_FINAL_CAP;
+    if (const char *fc = getenv("NDS_BRK_FINALCAP")) final_cap = std::min<unsigned>((unsigned)atoi(fc), BRK_FINAL_CAP);  // tests
+    brk_begin_kernel<Key><<<1, 32, 0, st>>>(buf, n, final_cap);
+    if ((e = count()) != cudaSuccess) return e;
+    unsigned long long n_total = n;
+    if (multi) {
+        if ((e = allreduce(buf.red_n, 2)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(&n_total, buf.red_n, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    }
+    // 1-2. sample (every rank at the same rate), sort S0, bucket S1
+    unsigned s1 = z.s1;
+    if (multi) {
+        const unsigned s1_total = pick_s1(n_total, wsum);
+        const double share = n_total ? (double)n / (double)n_total : 0.0;
+        unsigned long long want = (unsigned long long)std::ceil(share * (double)s1_total);
+        if (want > n) want = n;
+        if (want > z.s1) want = z.s1;
+        s1 = (unsigned)want;
+    }
+    if (s1) {
+        brk_sample_kernel<T><<<std::min<unsigned>((s1 + 255) / 256, sm * 8), 256, 0, st>>>(lane, n, s1, buf);
         if ((e = count()) != cudaSuccess) return e;
     }
-    // (sharded: S0 is sorted from the local sample only; the bucket counts below are summed over ranks, so the
-    //  ranks of the S0 keys stay exact for the union of the samples as long as every rank plans with the SAME S0:
-    //  rank 0's S0 is broadcast by an allreduce of a buffer that is zero everywhere else.)
     {
+        const Key *gathered = nullptr;
+        if (multi) {
+            // every rank contributes S0 / nranks keys of its sample; the union, sorted, is the same on every rank
+            const unsigned share = BRK_S0 / (unsigned)ctx->nranks;
+            brk_pick_s0_kernel<Key><<<8, 256, 0, st>>>(buf, s1, buf.s0part, share);
+            if ((e = count()) != cudaSuccess) return e;
+            std::string err;
+            if (nccl_allgather_bytes(ctx, buf.s0part, buf.s0all, (size_t)share * sizeof(Key), st, &err) != 0) {
+                ctx->last_error = err;
+                return cudaErrorUnknown;
+            }
+            gathered = buf.s0all;
+        }
         auto k = brk_sort_s0_kernel<Key>;
         const size_t smem = BRK_S0 * sizeof(Key);
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if (z.s1) {
-            k<<<1, 1024, smem, st>>>(buf, z.s1);
+        if (s1 || gathered) {
+            k<<<1, 1024, smem, st>>>(buf, s1, gathered);
             if ((e = count()) != cudaSuccess) return e;
         }
     }
@@ -1856,12 +1942,11 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         auto k = brk_bucket_kernel<Key, IS_FLOAT>;
         const size_t smem = BRK_S0 * sizeof(Key);
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if (z.s1) {
-            k<<<std::min<unsigned>((z.s1 + 255) / 256, sm * 4), 256, smem, st>>>(buf, z.s1);
+        if (s1) {
+            k<<<std::min<unsigned>((s1 + 255) / 256, sm * 4), 256, smem, st>>>(buf, s1);
             if ((e = count()) != cudaSuccess) return e;
         }
     }
-    if ((e = allreduce(buf.red_n, 2)) != cudaSuccess) return e;
     if ((e = allreduce(buf.s0hist, 2 * (BRK_S0 + 2))) != cudaSuccess) return e;
     // 3. plan
     const unsigned long long tiles = n / STR_TILE + 1;
@@ -1871,7 +1956,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         auto k = brk_plan_kernel<Key, IS_FLOAT>;
         const size_t smem = ((BRK_S0 + 1) * 4 + 15) / 16 * 16 + BRK_S0 * sizeof(Key) + BRK_NC1 * 2;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<1, 1024, smem, st>>>(buf, qa, brk_csigma(), n, sharded ? 1 : 0, nw);
+        k<<<1, 1024, smem, st>>>(buf, qa, brk_csigma(), n, multi ? 1 : 0, nw);
         if ((e = count()) != cudaSuccess) return e;
     }
     // 4. stream (the kernel of the table mode the plan did not choose returns at once)
@@ -1890,7 +1975,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         brk_publish_fill_kernel<Key><<<1, 128, 0, st>>>(buf);
         if ((e = count()) != cudaSuccess) return e;
     }
-    if ((e = allreduce(buf.red_stream, BRK_NCLS + BRK_MAXB)) != cudaSuccess) return e;
+    if ((e = allreduce(buf.red_stream, BRK_NCLS + BRK_MAXB + 2)) != cudaSuccess) return e;
     // 5. resolve
     brk_resolve_kernel<T><<<1, 256, 0, st>>>(buf, qa, qa.skipnan);
     if ((e = count()) != cudaSuccess) return e;
@@ -1909,11 +1994,10 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
             if (round == 0) kc0<<<sm * 2, BRK_THREADS, smem, st>>>(buf);
             else kc<<<sm, BRK_THREADS, smem, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
-            if (sharded && ctx->nccl_comm) {
-                // red_refine = sum over ranks of loc_refine
-                if ((e = cudaMemcpyAsync(buf.red_refine, buf.loc_refine, (size_t)BRK_MAXSEG * 256 * 8,
-                                         cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
-                if ((e = allreduce(buf.red_refine, (size_t)BRK_MAXSEG * 256)) != cudaSuccess) return e;
+            if (multi) {  // the exchange step: digit counts of every active segment, summed over ranks
+                brk_copy_counts_kernel<Key><<<64, 256, 0, st>>>(buf);
+                if ((e = count()) != cudaSuccess) return e;
+                if ((e = allreduce(buf.red_refine, (size_t)BRK_MAXSEG * 256 + 2)) != cudaSuccess) return e;
             }
             brk_refine_decide_kernel<Key><<<1, 256, 0, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
@@ -1924,10 +2008,10 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
             if ((e = count()) != cudaSuccess) return e;
             brk_final_kernel<Key><<<sm, 256, 0, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
-            if (synchronous && round >= 1) {
+            // every rank sees the same (reduced) counts and fail words, so all of them leave the loop together
+            if (synchronous && (multi || round >= 1)) {
                 unsigned long long h[H_WORDS];
-                if ((e = cudaMemcpyAsync(h, buf.hdr, sizeof h, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-                if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+                if ((e = read_hdr(h)) != cudaSuccess) return e;
                 if (h[H_FAIL] || h[H_NACTIVE] == 0) break;
             }
         }
@@ -1935,13 +2019,23 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     // 7. output
     brk_output_kernel<T><<<(qa.nq + 127) / 128, 128, 0, st>>>(buf, qa, out, out_valid, out_axis_stride, 1);
     if ((e = count()) != cudaSuccess) return e;
+    if (multi) {  // agree on the outcome: either every rank keeps its result or all of them fall back
+        brk_post_fail_kernel<Key><<<1, 32, 0, st>>>(buf, buf.red_end);
+        if ((e = count()) != cudaSuccess) return e;
+        if ((e = allreduce(buf.red_end, 2)) != cudaSuccess) return e;
+    }
     if (synchronous) {
         unsigned long long h[H_WORDS];
-        if ((e = cudaMemcpyAsync(h, buf.hdr, sizeof h, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        if ((e = read_hdr(h)) != cudaSuccess) return e;
         *failed = (int)h[H_FAIL];
+        if (n_total_out) *n_total_out = n_total;
+        if (multi) {
+            unsigned long long agreed = 0;
+            if ((e = cudaMemcpy(&agreed, buf.red_end, 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+            if (agreed) *failed |= FAIL_REMOTE;
+        }
         if (const char *dbg = getenv("NDS_BRK_DEBUG")) {
-            if (atoi(dbg) >= 2) {  // brackets and exact class counts, for tools/dbg_bracket.py
+            if (atoi(dbg) >= 2) {  // brackets and exact class counts, for tools/dbg_bracket2.py
                 const int B = (int)h[H_B];
                 std::vector<Key> lo(BRK_MAXB), hi(BRK_MAXB);
                 std::vector<unsigned long long> red(BRK_NCLS + BRK_MAXB);
@@ -1952,17 +2046,17 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
                 cudaMemcpy(red.data(), buf.red_stream, red.size() * 8, cudaMemcpyDeviceToHost);
                 BrkLutConst<Key> lc;
                 cudaMemcpy(&lc, buf.lutc, sizeof lc, cudaMemcpyDeviceToHost);
-                fprintf(stderr, "[bracket-lut] kmin=%llu shift1=%d subshift=%d submask=%u\n", (unsigned long long)lc.kmin,
-                        lc.shift1, lc.subshift, lc.submask);
+                fprintf(stderr, "[bracket-lut] kmin=%llu shift1=%d subshift=%d submask=%u hi32=%d\n", (unsigned long long)lc.kmin,
+                        lc.shift1, lc.subshift, lc.submask, lc.hi32);
                 for (int b = 0; b < B; ++b)
                     fprintf(stderr, "[bracket-b] %d lo=%llu hi=%llu tie=%d cls_count=%llu in=%llu\n", b,
                             (unsigned long long)lo[b], (unsigned long long)hi[b], (int)tie[b], red[b], red[BRK_NCLS + b]);
                 fprintf(stderr, "[bracket-b] %d (above) cls_count=%llu\n", B, red[B]);
             }
+            fprintf(stderr, "[bracket] rank=%d n=%llu n_total=%llu s1=%u fail=%llu B=%llu ties=%llu tasks=%llu n_eff=%llu invalid=%llu active=%llu round=%llu\n",
+                    ctx->rank, n, n_total, s1, h[H_FAIL], h[H_B], h[H_NTIE], h[H_NTASK], h[H_NEFF], h[H_NINVALID], h[H_NACTIVE],
+                    h[H_ROUND]);
         }
-        if (getenv("NDS_BRK_DEBUG"))
-            fprintf(stderr, "[bracket] n=%llu s1=%u fail=%llu B=%llu ties=%llu tasks=%llu n_eff=%llu invalid=%llu active=%llu\n", n,
-                    z.s1, h[H_FAIL], h[H_B], h[H_NTIE], h[H_NTASK], h[H_NEFF], h[H_NINVALID], h[H_NACTIVE]);
     } else {
         // asynchronous call: the FAIL word is folded into the ctx status at the next synchronize
         *failed = 0;
@@ -1972,7 +2066,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
 
 template <typename T>
 cudaError_t launch_bracket_typed(nds_ctx *ctx, const DeviceCall &c, void *scratch, bool sharded, bool synchronous,
-                                 int *failed) {
+                                 int *failed, unsigned long long *n_total_out) {
     *failed = 0;
     for (unsigned long long lane = 0; lane < c.geom.nlanes; ++lane) {
         long long in_off, out_off;
@@ -1980,7 +2074,7 @@ cudaError_t launch_bracket_typed(nds_ctx *ctx, const DeviceCall &c, void *scratc
         int f = 0;
         cudaError_t e = launch_bracket_lane<T>(ctx, (const T *)c.data + in_off, c.geom.axis_len, c.q, (T *)c.out + out_off,
                                                c.out_valid ? c.out_valid + out_off : nullptr, c.geom.out_axis_stride,
-                                               scratch, sharded, synchronous, c.brk_wsum, &f);
+                                               scratch, sharded, synchronous, c.brk_wsum, &f, n_total_out);
         if (e != cudaSuccess) return e;
         *failed |= f;
         if (f) break;
@@ -1992,9 +2086,8 @@ cudaError_t launch_bracket_typed(nds_ctx *ctx, const DeviceCall &c, void *scratc
 
 bool bracket_supported(const nds_ctx *ctx, const DeviceCall &c, bool sharded, bool forced) {
     (void)ctx;
-    // A lane sharded over ranks needs ONE sample for all of them (the brackets must be identical on every rank);
-    // until the sample exchange exists the sharded entry point uses the radix passes with their NCCL allreduce.
-    if (sharded) return false;
+    // sharded over ranks: every rank contributes S0 / nranks keys of its sample to the common S0
+    if (sharded && (ctx->nranks < 1 || BRK_S0 % ctx->nranks != 0)) return false;
     switch (c.dtype) {
     case NDS_F32: case NDS_I32: case NDS_U32: case NDS_F64: case NDS_I64: case NDS_U64: break;
     default: return false;
@@ -2002,30 +2095,31 @@ bool bracket_supported(const nds_ctx *ctx, const DeviceCall &c, bool sharded, bo
     if (c.valid || c.out_valid) return false;
     if (c.geom.axis_stride != 1 && c.geom.axis_len > 1) return false;
     if (c.q.nq < 1 || c.q.nq > BRK_MAXQ) return false;
+    // (sharded: the decision must be the same on every rank, so it must not depend on the local shard length)
     if (!sharded && c.geom.axis_len < (1ull << 16)) return false;
     if (c.geom.axis_len >= (1ull << 40)) return false;
     // not worth trying when the brackets would hold more than the candidate scratch (n / 3): many quantiles of
     // a lane that is too short for a large enough sample go straight to the radix passes
-    if (!forced && predicted_fraction(c.geom.axis_len, c.q.nq, c.brk_wsum) > 0.28) return false;
+    if (!forced && !sharded && predicted_fraction(c.geom.axis_len, c.q.nq, c.brk_wsum) > 0.28) return false;
     return true;
 }
 
-size_t bracket_scratch_bytes(const DeviceCall &c) {
+size_t bracket_scratch_bytes(const DeviceCall &c, bool sharded) {
     const size_t es = nds_dtype_size(c.dtype);
-    if (es == 8) return brk_sizes<uint64_t>(c.geom.axis_len, c.q.nq, c.brk_wsum).total;
-    return brk_sizes<uint32_t>(c.geom.axis_len, c.q.nq, c.brk_wsum).total;
+    if (es == 8) return brk_sizes<uint64_t>(c.geom.axis_len, c.q.nq, c.brk_wsum, sharded).total;
+    return brk_sizes<uint32_t>(c.geom.axis_len, c.q.nq, c.brk_wsum, sharded).total;
 }
 
 cudaError_t launch_bracket(nds_ctx *ctx, const DeviceCall &c, void *scratch, bool sharded, bool synchronous,
-                           int *failed) {
+                           int *failed, unsigned long long *n_total_out) {
     ctx->last_path = sharded ? "bracket_sharded" : "bracket";
     switch (c.dtype) {
-    case NDS_F32: return launch_bracket_typed<float>(ctx, c, scratch, sharded, synchronous, failed);
-    case NDS_F64: return launch_bracket_typed<double>(ctx, c, scratch, sharded, synchronous, failed);
-    case NDS_I32: return launch_bracket_typed<int32_t>(ctx, c, scratch, sharded, synchronous, failed);
-    case NDS_U32: return launch_bracket_typed<uint32_t>(ctx, c, scratch, sharded, synchronous, failed);
-    case NDS_I64: return launch_bracket_typed<int64_t>(ctx, c, scratch, sharded, synchronous, failed);
-    case NDS_U64: return launch_bracket_typed<uint64_t>(ctx, c, scratch, sharded, synchronous, failed);
+    case NDS_F32: return launch_bracket_typed<float>(ctx, c, scratch, sharded, synchronous, failed, n_total_out);
+    case NDS_F64: return launch_bracket_typed<double>(ctx, c, scratch, sharded, synchronous, failed, n_total_out);
+    case NDS_I32: return launch_bracket_typed<int32_t>(ctx, c, scratch, sharded, synchronous, failed, n_total_out);
+    case NDS_U32: return launch_bracket_typed<uint32_t>(ctx, c, scratch, sharded, synchronous, failed, n_total_out);
+    case NDS_I64: return launch_bracket_typed<int64_t>(ctx, c, scratch, sharded, synchronous, failed, n_total_out);
+    case NDS_U64: return launch_bracket_typed<uint64_t>(ctx, c, scratch, sharded, synchronous, failed, n_total_out);
     default: return cudaErrorNotSupported;
     }
 }

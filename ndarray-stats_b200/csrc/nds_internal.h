@@ -73,9 +73,9 @@ cudaError_t launch_long_radix(nds_ctx *ctx, const DeviceCall &c, void *scratch, 
 // STATUS_BIT_FALLBACK in the ctx status word instead.
 bool bracket_supported(const nds_ctx *ctx, const DeviceCall &c, bool sharded, bool forced);
 double brk_csigma();
-size_t bracket_scratch_bytes(const DeviceCall &c);
+size_t bracket_scratch_bytes(const DeviceCall &c, bool sharded);
 cudaError_t launch_bracket(nds_ctx *ctx, const DeviceCall &c, void *scratch, bool sharded, bool synchronous,
-                           int *failed);
+                           int *failed, unsigned long long *n_total_out);
 // Contiguous short lanes (f32/f64/ints up to a few thousand elements): warp-per-lane bit-sliced select
 // fed by TMA bulk copies.  Returns cudaErrorNotSupported when the call does not qualify.
 bool short_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c);
@@ -87,5 +87,7 @@ cudaError_t launch_cols_bitslice(nds_ctx *ctx, const DeviceCall &c);
 
 // NCCL shim (nds_nccl.cpp)
 int nccl_allreduce_sum_u64(nds_ctx *ctx, void *buf, size_t count, cudaStream_t stream, std::string *err);
+int nccl_allgather_bytes(nds_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank, cudaStream_t stream,
+                         std::string *err);
 
 }  // namespace nds

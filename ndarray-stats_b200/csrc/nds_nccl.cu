@@ -18,6 +18,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     std::string error;
 };
@@ -39,8 +40,9 @@ NcclApi &api() {
         a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.handle, "ncclCommInitRank");
         a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.handle, "ncclCommDestroy");
         a.AllReduce = (decltype(a.AllReduce))dlsym(a.handle, "ncclAllReduce");
+        a.AllGather = (decltype(a.AllGather))dlsym(a.handle, "ncclAllGather");
         a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.handle, "ncclGetErrorString");
-        if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString)
+        if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.AllGather || !a.GetErrorString)
             a.error = "libnccl is missing a required symbol";
     });
     return a;
@@ -65,6 +67,20 @@ int nccl_allreduce_sum_u64(nds_ctx *ctx, void *buf, size_t count, cudaStream_t s
     ncclResult_t r = a.AllReduce(buf, buf, count, ncclUint64, ncclSum, (ncclComm_t)ctx->nccl_comm, stream);
     if (r != ncclSuccess) {
         if (err) *err = std::string("ncclAllReduce: ") + a.GetErrorString(r);
+        return -1;
+    }
+    return 0;
+}
+int nccl_allgather_bytes(nds_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank, cudaStream_t stream,
+                         std::string *err) {
+    NcclApi &a = api();
+    if (!a.error.empty() || !ctx->nccl_comm) {
+        if (err) *err = a.error.empty() ? "no communicator" : a.error;
+        return -1;
+    }
+    ncclResult_t r = a.AllGather(send, recv, bytes_per_rank, ncclUint8, (ncclComm_t)ctx->nccl_comm, stream);
+    if (r != ncclSuccess) {
+        if (err) *err = std::string("ncclAllGather: ") + a.GetErrorString(r);
         return -1;
     }
     return 0;

@@ -37,11 +37,17 @@ def main():
         (np.uint32, 1 << 18, [0.1, 0.5, 0.9], "lower", False),
         (np.int64, 99999, [0.1, 0.5, 0.9], "higher", False),
         (np.float32, 5, [0.5], "linear", False),
+        (np.float64, 1 << 24, list(np.arange(1, 10) / 10.0), "linear", False),   # the one-pass path, 9 brackets
+        (np.float32, (1 << 23) + 77, [0.001, 0.5, 0.999], "midpoint", True),
+        (np.int64, 1 << 22, [0.25, 0.75], "lower", False),
     ]
+    paths = []
     for dtype, n_total, qs, interp, skipnan in cases:
         rng = np.random.default_rng(1234 + n_total)  # same full array on every rank, each keeps its slice
         if np.dtype(dtype).kind == "f":
             full = rng.standard_normal(n_total).astype(dtype)
+            if n_total == 1 << 24:
+                full.sort()  # sorted and sharded: every rank holds a different value range
             if skipnan:
                 full[rng.random(n_total) < 0.2] = np.nan
         elif dtype == np.uint32:
@@ -61,7 +67,8 @@ def main():
             assert ulp_distance(got, want) == 0
         else:
             assert_bit_equal(got, want, msg=f"rank {rank} {dtype} {n_total} {interp}")
-        assert ctx.last_path == "long_radix_sharded"
+        assert ctx.last_path in ("bracket_sharded", "long_radix_sharded", "bracket->long_radix"), ctx.last_path
+        paths.append(ctx.last_path)
     # error paths are collective too
     try:
         ctx.quantiles_1d_sharded(torch.empty(0, dtype=torch.float64, device="cuda"), [0.5], "linear")
@@ -70,7 +77,7 @@ def main():
         pass
     dist.barrier()
     if rank == 0:
-        print(f"sharded NCCL check ok on {world} GPUs")
+        print(f"sharded NCCL check ok on {world} GPUs; paths: {paths}")
     ctx.comm_destroy()
     dist.destroy_process_group()
 

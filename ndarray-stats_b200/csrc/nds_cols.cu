@@ -21,9 +21,24 @@ constexpr int COLS_CW = 8;           // lanes per strip: 8 x 4 B = one 32-byte s
 constexpr int COLS_THREADS = 256;    // 8 lanes x 32 row groups
 constexpr int COLS_KMAX = 8;         // plane words per thread in the walk: 8 x 32 x 32 = 8192 elements
 constexpr unsigned FULLMASK = 0xffffffffu;
-constexpr int COLS_CAND = 128;       // candidates ranked directly once the walk has narrowed a lane down to this many
+constexpr int COLS_CAND = 64;        // candidates ranked directly once the walk has narrowed a lane down to this many
 
-template <typename T>
+constexpr int COLS_TILE_ROWS = 1024;                    // rows of a strip staged per cp.async group (4-byte types)
+constexpr int COLS_RB_WORDS = 32 * COLS_CW + 8;         // one 32-row block of a staged tile: +8 words of padding
+                                                        // so that the four row groups of a warp read 32 banks
+constexpr int COLS_STAGE_WORDS = 32 * COLS_RB_WORDS;    // 32 row blocks = 1024 rows x 8 lanes
+constexpr int COLS_STAGES = 2;
+
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ASYNC (4-byte types, full aligned strips): the strip is staged through shared memory by cp.async (LDGSTS), two tiles
+// of 1024 rows in flight, the first tiles of the NEXT strip already during the bit walk of this one.
+template <typename T, bool ASYNC>
 __global__ void __launch_bounds__(COLS_THREADS, 1)
 cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__restrict__ out,
                      unsigned long long n_strips, unsigned strips_per_group) {
@@ -48,6 +63,8 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
     const unsigned col_pitch = 16u * nrbp + 4u;       // +4: the 8 lanes of a strip hit different banks
     unsigned *clist = reinterpret_cast<unsigned *>(planes + COLS_CW * col_pitch);  // [warp][COLS_CAND]
     Key *ckeys = reinterpret_cast<Key *>(clist + COLS_CW * COLS_CAND);             // [warp][COLS_CAND]
+    uint32_t *stage_base = reinterpret_cast<uint32_t *>(                             // [COLS_STAGES][COLS_STAGE_WORDS]
+        (reinterpret_cast<uintptr_t>(ckeys + COLS_CW * COLS_CAND) + 15) & ~(uintptr_t)15);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bc = tid % COLS_CW, brg = tid / COLS_CW;  // build role: lane (column) and row group
@@ -56,7 +73,39 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
     const long long out_col_stride = g.out_ostride[last_outer];
     auto slot_of_pos = [](int p) -> int { return 2 * (p & 15) + (p >> 4); };
 
-    for (unsigned long long strip = blockIdx.x; strip < n_strips; strip += gridDim.x) {
+    // ---- cp.async tile stream of this CTA: tile gt = (iteration, tile of the strip) ----------------------------
+    const unsigned tiles = (n + COLS_TILE_ROWS - 1) / COLS_TILE_ROWS;
+    auto issue_tile = [&](unsigned long long gt) {
+        if constexpr (ASYNC) {
+            const unsigned long long it = gt / tiles;
+            const unsigned t = (unsigned)(gt - it * tiles);
+            const unsigned long long strip_i = blockIdx.x + it * gridDim.x;
+            if (strip_i < n_strips) {
+                const unsigned long long grp_i = strip_i / strips_per_group;
+                const unsigned long long col_i = (strip_i - grp_i * strips_per_group) * COLS_CW;
+                long long io, oo;
+                lane_offsets(g, grp_i * ncols + col_i, io, oo);
+                const T *src = data + io;
+                uint32_t *st = stage_base + (size_t)(gt % COLS_STAGES) * COLS_STAGE_WORDS;
+#pragma unroll
+                for (int j = 0; j < COLS_TILE_ROWS * COLS_CW * 4 / 16 / COLS_THREADS; ++j) {  // 8 chunks of 16 bytes per thread
+                    const unsigned q = (unsigned)j * COLS_THREADS + tid;
+                    const unsigned rl = q >> 1, half = q & 1u;          // row inside the tile, first / second four lanes
+                    const unsigned row = t * COLS_TILE_ROWS + rl;
+                    if (row < n)
+                        cp_async16(st + (rl >> 5) * COLS_RB_WORDS + (rl & 31u) * COLS_CW + half * 4,
+                                   src + (long long)row * pitch + half * 4);
+                }
+            }
+            cp_async_commit();  // (an empty group past the end keeps the group count uniform)
+        }
+    };
+    if constexpr (ASYNC) {
+        issue_tile(0);
+        issue_tile(1);
+    }
+    unsigned long long iter = 0;
+    for (unsigned long long strip = blockIdx.x; strip < n_strips; strip += gridDim.x, ++iter) {
         const unsigned long long grp = strip / strips_per_group;
         const unsigned long long col0 = (strip - grp * strips_per_group) * COLS_CW;
         long long in_off, out_off;
@@ -65,7 +114,30 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
         const int cols_here = (int)min((unsigned long long)COLS_CW, ncols - col0);
 
         // ---- stream the strip once: 1024 rows per step, 32 rows x 1 lane per thread ---------------------
-        {
+        if constexpr (ASYNC) {
+            uint32_t *pdst = planes + (size_t)bc * col_pitch;
+#pragma unroll 1
+            for (unsigned t = 0; t < tiles; ++t) {
+                const unsigned long long gt = iter * tiles + t;
+                cp_async_wait<COLS_STAGES - 1>();   // tile gt has landed (for this thread's copies) ...
+                __syncthreads();                    // ... and for everybody's
+                const uint32_t *st = stage_base + (size_t)(gt % COLS_STAGES) * COLS_STAGE_WORDS + brg * COLS_RB_WORDS + bc;
+                const unsigned rb = t * 32u + (unsigned)brg;
+                uint32_t x[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[i] = st[i * COLS_CW];
+                __syncthreads();                    // the stage is free again
+                issue_tile(gt + COLS_STAGES);       // next tile of this strip, or the first tiles of the next one
+                if (rb < nrb) {                     // rows past the end of the lane are masked out in the walk
+                    uint32_t w[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) w[k] = __byte_perm(x[2 * k], x[2 * k + 1], 0x7632);
+                    transpose16(w);
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) pdst[b * nrbp + rb] = w[b];
+                }
+            }
+        } else {
             const int c = min(bc, cols_here - 1);
             uint32_t *pdst = planes + (size_t)bc * col_pitch;
 #pragma unroll 1
@@ -367,6 +439,7 @@ struct ColsPlan {
     unsigned long long n_strips = 0;
     unsigned strips_per_group = 0;
     size_t smem = 0;
+    bool async = false;   // cp.async staged build (4-byte types, whole 16-byte aligned strips)
 };
 
 ColsPlan plan_cols(const nds_ctx *ctx, const DeviceCall &c) {
@@ -391,13 +464,21 @@ ColsPlan plan_cols(const nds_ctx *ctx, const DeviceCall &c) {
     const unsigned nrb = (unsigned)((g.axis_len + 31) / 32), nrbp = (nrb + 31) / 32 * 32;
     p.smem = (size_t)COLS_CW * (16 * nrbp + 4) * 4 + COLS_CW * COLS_CAND * 4 + COLS_CW * COLS_CAND * 8 + 64;
     if (p.smem > (size_t)ctx->max_smem_optin) return p;
-    (void)es;
     p.ok = true;
+    // the staged build wants every row of every strip to be two aligned 16-byte chunks
+    bool aligned = es == 4 && g.oshape[last] % COLS_CW == 0 && ((uintptr_t)c.data % 16) == 0 && (g.axis_stride * 4) % 16 == 0;
+    for (int d = 0; d < last; ++d)
+        if (g.oshape[d] > 1 && (g.in_ostride[d] * 4) % 16 != 0) aligned = false;
+    const size_t smem_async = ((p.smem + 15) & ~(size_t)15) + (size_t)COLS_STAGES * COLS_STAGE_WORDS * 4 + 16;
+    if (aligned && smem_async <= (size_t)ctx->max_smem_optin && !getenv("NDS_COLS_NO_ASYNC")) {
+        p.async = true;
+        p.smem = smem_async;
+    }
     return p;
 }
 
-template <typename T> cudaError_t launch_cols_typed(nds_ctx *ctx, const DeviceCall &c, const ColsPlan &p) {
-    auto kernel = cols_bitslice_kernel<T>;
+template <typename T, bool ASYNC> cudaError_t launch_cols_typed2(nds_ctx *ctx, const DeviceCall &c, const ColsPlan &p) {
+    auto kernel = cols_bitslice_kernel<T, ASYNC>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
     int occ = 1;
@@ -408,6 +489,13 @@ template <typename T> cudaError_t launch_cols_typed(nds_ctx *ctx, const DeviceCa
                                                          p.strips_per_group);
     ctx->launches += 1;
     return cudaGetLastError();
+}
+
+template <typename T> cudaError_t launch_cols_typed(nds_ctx *ctx, const DeviceCall &c, const ColsPlan &p) {
+    if constexpr (sizeof(T) == 4) {
+        if (p.async) return launch_cols_typed2<T, true>(ctx, c, p);
+    }
+    return launch_cols_typed2<T, false>(ctx, c, p);
 }
 
 }  // namespace

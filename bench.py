@@ -331,13 +331,15 @@ def main():
     peak, peak_src = peaks()
     per_gpu_bytes = t.numel() * esize + out.numel() * esize
     achieved = per_gpu_bytes / (ms_per_step * 1e-3) / 1e9
-    traffic = None
+    traffic, dominant = None, path
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one ncu --set full capture
         with open(tpath) as f:
-            traffic = json.load(f).get(f"{name}:{path}")
+            rec = json.load(f).get(name)
+        if rec:
+            traffic, dominant = rec["dram_bytes_per_launch"], rec["kernel"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": path, "peak_source": peak_src,
+                "traffic": traffic, "kernel": dominant, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": per_gpu_bytes}
 
     # parity of the timed result on a bounded sample of lanes (checker only)

@@ -77,8 +77,8 @@ def main():
                         if w.startswith("dram__bytes_write"):
                             wr = float(r[i].replace(",", "")) * UNIT.get(units[i], 1.0)
                 f.write(f"\nDRAM traffic per launch (read + write): {(rd + wr) / 1e9:.4f} GB\n\n")
-                short = kname.split("(")[0].split("::")[-1].split("<")[0].replace("_kernel", "")
-                traffic[f"{wl}:{short}"] = rd + wr
+                short = kname.split("(")[0].split("::")[-1].split("<")[0]
+                traffic[wl] = {"kernel": short, "dram_bytes_per_launch": rd + wr, "round": rnd}
         json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
         print("wrote", out, traffic)
     for name in (f"bench_{wl}.json", f"bench_{wl}_reference.json"):

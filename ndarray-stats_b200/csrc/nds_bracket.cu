@@ -1254,6 +1254,8 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_round0_kernel(BrkBu
     __shared__ short sid[256];
     __shared__ int wanted[256];   // the digits of this bracket that some rank chose (usually one or two)
     __shared__ int n_wanted;
+    __shared__ unsigned sfill[148];                       // fills of this bracket's pieces
+    __shared__ unsigned long long wseg_off[4], wseg_cap[4];  // destination segments of the first wanted digits
     if (buf.hdr[H_FAIL] || buf.hdr[H_ROUND] != 0 || buf.hdr[H_NACTIVE] == 0) return;
     if (COMPACT && !buf.hdr[H_DID]) return;
     const int B = (int)(COMPACT ? buf.hdr[H_OLD_NSEG] : buf.hdr[H_NSEG]);
@@ -1309,77 +1311,141 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_round0_kernel(BrkBu
             }
             __syncthreads();
         };
-        for (unsigned w = (unsigned)part; w < nw; w += (unsigned)cpb) {
+        // ---- the chunks of this CTA's pieces as one stream: the next chunk is loaded while this one is processed ----
+        __syncthreads();
+        for (unsigned w = tid; w < nw; w += BRK_THREADS) {
             unsigned f = fills[w];
-            if (f > sg.piece_cap) f = (unsigned)sg.piece_cap;
-            const Key *piece = src + (unsigned long long)w * sg.piece_cap;  // 16-byte aligned (piece_cap % 4 == 0)
-            for (unsigned e0 = 0; e0 < f; e0 += BRK_RCHUNK) {
-                if (f - e0 >= BRK_RCHUNK) {
-                    Key k[KPT];
-                    load_chunk_keys<Key>(piece + e0, tid, k);
-                    if (COMPACT) {
-                        // one global atomic per warp, chunk and wanted digit instead of one per kept key (their
-                        // latency would serialise the warp)
-                        const int nwd = n_wanted;
-                        if (nwd > 4) {
+            sfill[w] = f > sg.piece_cap ? (unsigned)sg.piece_cap : f;
+        }
+        if (COMPACT)
+            for (int j = tid; j < n_wanted && j < 4; j += BRK_THREADS) {
+                const int id = sid[wanted[j]];
+                wseg_off[j] = nsegs[id].off;
+                wseg_cap[j] = nsegs[id].cnt_local;
+            }
+        __syncthreads();
+        unsigned cw = (unsigned)part, ce0 = 0;   // current chunk: piece cw, first key ce0
+        auto seek = [&](unsigned &w, unsigned &e0) -> bool {  // move (w, e0) to the next non-empty chunk at or after it
+            while (w < nw && e0 >= sfill[w]) {
+                w += (unsigned)cpb;
+                e0 = 0;
+            }
+            return w < nw;
+        };
+        // keys of chunk (w, e0) into k[]; bit e of the result is set when k[e] is a real key
+        auto load = [&](unsigned w, unsigned e0, Key (&k)[KPT]) -> unsigned {
+            constexpr int VEC = 16 / (int)sizeof(Key);
+            const unsigned cnt = sfill[w] - e0 < (unsigned)BRK_RCHUNK ? sfill[w] - e0 : (unsigned)BRK_RCHUNK;
+            const Key *ptr = src + (unsigned long long)w * sg.piece_cap + e0;  // 16-byte aligned
+            unsigned valid = 0;
 #pragma unroll
-                            for (int e = 0; e < KPT; ++e) keep(k[e]);
-                        } else {
-                            for (int j = 0; j < nwd; ++j) {
-                                const unsigned wd = (unsigned)wanted[j];
-                                unsigned m = 0;
-#pragma unroll
-                                for (int e = 0; e < KPT; ++e) m |= (digit(k[e]) == wd ? 1u : 0u) << e;
-                                const unsigned cnt = __popc(m);
-                                unsigned incl = cnt;
-#pragma unroll
-                                for (int d = 1; d < 32; d <<= 1) {
-                                    const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
-                                    if (lane >= d) incl += t;
-                                }
-                                const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-                                if (total == 0) continue;
-                                const int id = sid[wd];
-                                unsigned long long base = 0;
-                                if (lane == 31) base = atomicAdd(&nsegs[id].cursor, (unsigned long long)total);
-                                base = __shfl_sync(0xffffffffu, base, 31);
-                                unsigned long long pos = base + incl - cnt;
-                                const unsigned long long cap = nsegs[id].cnt_local, off = nsegs[id].off;
-#pragma unroll
-                                for (int e = 0; e < KPT; ++e) {
-                                    if (m & (1u << e)) {
-                                        if (pos < cap) dst[off + pos] = k[e];
-                                        ++pos;
-                                    }
-                                }
-                            }
-                        }
+            for (int j = 0; j < KPT / VEC; ++j) {
+                const unsigned idx = ((unsigned)j * BRK_THREADS + tid) * VEC;
+                if (idx + VEC <= cnt) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(ptr + idx));
+                    if constexpr (sizeof(Key) == 4) {
+                        k[j * 4] = q.x; k[j * 4 + 1] = q.y; k[j * 4 + 2] = q.z; k[j * 4 + 3] = q.w;
                     } else {
-#pragma unroll
-                        for (int g = 0; g < KPT; g += 4) {  // 4 loads, equal digits merged, 4 stores (see the count kernel)
-                            const unsigned c0 = digit(k[g]), c1 = digit(k[g + 1]), c2 = digit(k[g + 2]), c3 = digit(k[g + 3]);
-                            unsigned short *p0 = myctr + c0 * BRK_THREADS, *p1 = myctr + c1 * BRK_THREADS,
-                                           *p2 = myctr + c2 * BRK_THREADS, *p3 = myctr + c3 * BRK_THREADS;
-                            const unsigned x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
-                            const unsigned m0 = 1u + (c1 == c0) + (c2 == c0) + (c3 == c0), m1 = 1u + (c0 == c1) + (c2 == c1) + (c3 == c1);
-                            const unsigned m2 = 1u + (c0 == c2) + (c1 == c2) + (c3 == c2), m3 = 1u + (c0 == c3) + (c1 == c3) + (c2 == c3);
-                            *p0 = (unsigned short)(x0 + m0);
-                            *p1 = (unsigned short)(x1 + m1);
-                            *p2 = (unsigned short)(x2 + m2);
-                            *p3 = (unsigned short)(x3 + m3);
-                        }
+                        k[j * 2] = (Key)q.x | ((Key)q.y << 32);
+                        k[j * 2 + 1] = (Key)q.z | ((Key)q.w << 32);
                     }
+                    valid |= ((1u << VEC) - 1u) << (j * VEC);
                 } else {
-                    for (unsigned i = e0 + tid; i < f; i += BRK_THREADS) {
-                        const Key k = piece[i];
-                        if (COMPACT) keep(k);
-                        else myctr[digit(k) * BRK_THREADS] += 1;
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) {
+                        k[j * VEC + u] = 0;
+                        if (idx + u < cnt) {
+                            k[j * VEC + u] = ptr[idx + u];
+                            valid |= 1u << (j * VEC + u);
+                        }
                     }
                 }
-                if (!COMPACT && ++chunks_since_spill >= 4000) {  // CTA-uniform: f, e0 are
+            }
+            return valid;
+        };
+        auto process = [&](const Key (&k)[KPT], unsigned valid) {
+            if (COMPACT) {
+                // one global atomic per warp, chunk and wanted digit instead of one per kept key (their latency would
+                // serialise the warp)
+                const int nwd = n_wanted;
+                if (nwd > 4) {
+#pragma unroll
+                    for (int e = 0; e < KPT; ++e)
+                        if (valid & (1u << e)) keep(k[e]);
+                    return;
+                }
+                for (int j = 0; j < nwd; ++j) {
+                    const unsigned wd = (unsigned)wanted[j];
+                    unsigned m = 0;
+#pragma unroll
+                    for (int e = 0; e < KPT; ++e) m |= (digit(k[e]) == wd ? 1u : 0u) << e;
+                    m &= valid;
+                    const unsigned cnt = __popc(m);
+                    unsigned incl = cnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total == 0) continue;
+                    unsigned long long base = 0;
+                    if (lane == 31) base = atomicAdd(&nsegs[sid[wd]].cursor, (unsigned long long)total);
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    unsigned long long pos = base + incl - cnt;
+                    const unsigned long long cap = wseg_cap[j], off = wseg_off[j];
+#pragma unroll
+                    for (int e = 0; e < KPT; ++e) {
+                        if (m & (1u << e)) {
+                            if (pos < cap) dst[off + pos] = k[e];
+                            ++pos;
+                        }
+                    }
+                }
+            } else if (valid == (KPT == 32 ? 0xffffffffu : (1u << KPT) - 1u)) {
+#pragma unroll
+                for (int g = 0; g < KPT; g += 4) {  // 4 loads, equal digits merged, 4 stores (see the count kernel)
+                    const unsigned c0 = digit(k[g]), c1 = digit(k[g + 1]), c2 = digit(k[g + 2]), c3 = digit(k[g + 3]);
+                    unsigned short *p0 = myctr + c0 * BRK_THREADS, *p1 = myctr + c1 * BRK_THREADS,
+                                   *p2 = myctr + c2 * BRK_THREADS, *p3 = myctr + c3 * BRK_THREADS;
+                    const unsigned x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
+                    const unsigned m0 = 1u + (c1 == c0) + (c2 == c0) + (c3 == c0), m1 = 1u + (c0 == c1) + (c2 == c1) + (c3 == c1);
+                    const unsigned m2 = 1u + (c0 == c2) + (c1 == c2) + (c3 == c2), m3 = 1u + (c0 == c3) + (c1 == c3) + (c2 == c3);
+                    *p0 = (unsigned short)(x0 + m0);
+                    *p1 = (unsigned short)(x1 + m1);
+                    *p2 = (unsigned short)(x2 + m2);
+                    *p3 = (unsigned short)(x3 + m3);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < KPT; ++e)
+                    if (valid & (1u << e)) myctr[digit(k[e]) * BRK_THREADS] += 1;
+            }
+        };
+        if (seek(cw, ce0)) {
+            Key ka[KPT], kb[KPT];
+            unsigned va = load(cw, ce0, ka), vb = 0;
+            for (;;) {
+                unsigned nw_ = cw, ne0 = ce0 + BRK_RCHUNK;
+                bool more = seek(nw_, ne0);
+                if (more) vb = load(nw_, ne0, kb);
+                process(ka, va);
+                if (!COMPACT && ++chunks_since_spill >= 4000) {  // CTA-uniform (the chunk sequence is)
                     spill();
                     chunks_since_spill = 0;
                 }
+                if (!more) break;
+                cw = nw_; ce0 = ne0;
+                nw_ = cw; ne0 = ce0 + BRK_RCHUNK;
+                more = seek(nw_, ne0);
+                if (more) va = load(nw_, ne0, ka);
+                process(kb, vb);
+                if (!COMPACT && ++chunks_since_spill >= 4000) {
+                    spill();
+                    chunks_since_spill = 0;
+                }
+                if (!more) break;
+                cw = nw_; ce0 = ne0;
             }
         }
         if (!COMPACT) spill();

@@ -55,6 +55,8 @@ constexpr int BRK_MAXTASK = 2 * BRK_MAXQ; // unique ranks
 constexpr int BRK_MAXSEG = 2 * BRK_MAXQ;
 constexpr int BRK_FINAL_CAP = 4096;       // a segment this small is sorted by one CTA
 constexpr int BRK_RCHUNK = 4096;          // refine passes: elements per chunk
+constexpr int BRK_GATHER_CAP = 1 << 15;   // sharded lanes: keys of the small segments one rank may contribute per round
+constexpr int BRK_MAX_RANKS = 8;
 constexpr int STR_THREADS = 512;          // streaming pass: 16 warps per SM, the table-lookup chains are latency bound
 constexpr int STR_WARPS = STR_THREADS / 32;
 constexpr int STR_TILE = STR_THREADS * 8;
@@ -101,6 +103,7 @@ template <typename Key> struct BrkBuf {
     Key *s1, *s0, *blo, *bhi;
     Key *s0part, *s0all;             // sharded lanes: this rank's share of S0, the all-gathered S0
     unsigned long long *red_end;     // [2] final agreement on FAIL over ranks
+    unsigned char *gsend, *grecv;    // sharded lanes: packed small segments of this rank / of all ranks (header + keys)
     unsigned long long *boff, *bcap;
     unsigned char *btie;             // tie class of a bracket (lo == hi: counted, never compacted) or 0xff
     unsigned *lut1;                  // [NC1]
@@ -1460,7 +1463,7 @@ __global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf)
     __shared__ unsigned long long pad_cnt[BRK_MAXTASK];
     __shared__ unsigned char first[BRK_MAXTASK];
     __shared__ unsigned char seg_any[BRK_MAXSEG];
-    __shared__ unsigned long long new_cnt_local[BRK_MAXSEG];
+    __shared__ unsigned long long new_cnt_local[BRK_MAXSEG], old_cnt_local[BRK_MAXSEG];
     __shared__ unsigned char new_final[BRK_MAXSEG];
     __shared__ int s_nid;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -1591,12 +1594,14 @@ __global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf)
         tk.seg = newseg_of[t];
         buf.task[t] = tk;
     }
+    for (int s = tid; s < nseg; s += blockDim.x) old_cnt_local[s] = seg_any[s] ? segs[s].cnt_local : 0ull;
+    __syncthreads();
     if (tid == 0) {
         const int nid = s_nid;
         unsigned long long chunks_compact = 0, chunks_count = 0;
         for (int s = 0; s < nseg; ++s) {
             buf.cprefix_compact[s] = chunks_compact;
-            if (seg_any[s]) chunks_compact += (segs[s].cnt_local + BRK_RCHUNK - 1) / BRK_RCHUNK;
+            if (seg_any[s]) chunks_compact += (old_cnt_local[s] + BRK_RCHUNK - 1) / BRK_RCHUNK;
         }
         for (int s = nseg; s <= BRK_MAXSEG; ++s) buf.cprefix_compact[s] = chunks_compact;
         int active = 0;
@@ -1690,16 +1695,79 @@ template <typename Key> __global__ void brk_refine_advance_kernel(BrkBuf<Key> bu
     }
 }
 
-// segments of at most FINAL_CAP keys: one CTA sorts the keys and serves every task that points at it
+// Sharded lanes: the small (FINAL) segments that still have a task are packed into one send buffer per rank --
+// header of BRK_MAXSEG counts, then the keys segment after segment -- and all-gathered, so that every rank can
+// sort the union.  One CTA: the volume is a few thousand keys.
 template <typename Key>
-__global__ void __launch_bounds__(256) brk_final_kernel(BrkBuf<Key> buf) {
-    __shared__ Key s[BRK_FINAL_CAP];
-    __shared__ int tseg[BRK_MAXTASK];  // segment of every still active task, -1 otherwise
-    __shared__ int s_any;
+__global__ void __launch_bounds__(1024) brk_pack_final_kernel(BrkBuf<Key> buf) {
+    __shared__ unsigned cnt[BRK_MAXSEG], off[BRK_MAXSEG];
+    __shared__ unsigned char wanted[BRK_MAXSEG];
+    unsigned *hdr_out = reinterpret_cast<unsigned *>(buf.gsend);
+    Key *keys_out = reinterpret_cast<Key *>(buf.gsend + (size_t)BRK_MAXSEG * 4);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < BRK_MAXSEG; i += blockDim.x) { cnt[i] = 0; off[i] = 0; wanted[i] = 0; hdr_out[i] = 0; }
+    __syncthreads();
     if (buf.hdr[H_FAIL] || buf.hdr[H_EMPTY]) return;
     const int nseg = (int)buf.hdr[H_NSEG], ntask = (int)buf.hdr[H_NTASK];
     const int cur = (int)buf.hdr[H_CUR];
-    const int tid = threadIdx.x;
+    for (int t = tid; t < ntask; t += blockDim.x) {
+        const BrkTask tk = buf.task[t];
+        if (tk.state == TASK_ACTIVE && tk.seg >= 0) wanted[tk.seg] = 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned run = 0;
+        for (int sidx = 0; sidx < nseg; ++sidx) {
+            const BrkSeg<Key> &sg = buf.seg[cur][sidx];
+            if (!wanted[sidx] || !(sg.flags & SEG_FINAL) || (sg.flags & SEG_TIE)) continue;
+            unsigned c = (unsigned)sg.cnt_local;
+            if (run + c > (unsigned)BRK_GATHER_CAP) {  // cannot happen with FINAL_CAP * tasks <= GATHER_CAP; be safe
+                raise_fail(buf.hdr, FAIL_CAPACITY);
+                c = 0;
+            }
+            cnt[sidx] = c;
+            off[sidx] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    const unsigned nw = (unsigned)buf.hdr[H_NW];
+    for (int sidx = 0; sidx < nseg; ++sidx) {
+        const unsigned c = cnt[sidx];
+        if (tid == 0) hdr_out[sidx] = c;
+        if (c == 0) continue;
+        const BrkSeg<Key> sg = buf.seg[cur][sidx];
+        const Key *src = buf.cand[cur] + sg.off;
+        if (sg.piece_cap == 0) {
+            for (unsigned i = tid; i < c; i += blockDim.x) keys_out[off[sidx] + i] = src[i];
+        } else {  // a round-0 segment: pieces (fills in buf.fill); one warp per piece, positions by prefix over the pieces
+            const unsigned *fills = buf.fill + (size_t)sidx * nw;
+            const int lane = tid & 31;
+            for (unsigned w = tid >> 5; w < nw; w += blockDim.x >> 5) {
+                unsigned before = 0;
+                for (unsigned u = lane; u < w; u += 32) before += fills[u];
+                before = __reduce_add_sync(0xffffffffu, before);
+                const unsigned f = fills[w];
+                const Key *piece = src + (unsigned long long)w * sg.piece_cap;
+                for (unsigned i = lane; i < f; i += 32)
+                    if (before + i < c) keys_out[off[sidx] + before + i] = piece[i];
+            }
+        }
+    }
+}
+
+// segments of at most FINAL_CAP keys: one CTA sorts the keys and serves every task that points at it.
+// `nranks` > 0: the keys of a segment are the union of what every rank packed (brk_pack_final_kernel + all-gather).
+template <typename Key>
+__global__ void __launch_bounds__(256) brk_final_kernel(BrkBuf<Key> buf, int nranks) {
+    __shared__ Key s[BRK_FINAL_CAP];
+    __shared__ int tseg[BRK_MAXTASK];  // segment of every still active task, -1 otherwise
+    __shared__ int s_any;
+    __shared__ unsigned roff[BRK_MAX_RANKS], rcnt[BRK_MAX_RANKS];
+    if (buf.hdr[H_FAIL] || buf.hdr[H_EMPTY]) return;
+    const int nseg = (int)buf.hdr[H_NSEG], ntask = (int)buf.hdr[H_NTASK];
+    const int cur = (int)buf.hdr[H_CUR];
+    const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) s_any = 0;
     __syncthreads();
     for (int t = tid; t < BRK_MAXTASK; t += blockDim.x) {
@@ -1720,18 +1788,43 @@ __global__ void __launch_bounds__(256) brk_final_kernel(BrkBuf<Key> buf) {
         for (int t = 0; t < ntask; ++t)
             if (tseg[t] == sidx) { wanted = true; break; }
         if (!wanted) continue;
-        const unsigned cnt = (unsigned)sg.cnt_local;
+        unsigned cnt = (unsigned)sg.cnt_local;
+        if (nranks > 0) cnt = (unsigned)sg.cnt_global;
         unsigned np2 = 1;
         while (np2 < cnt) np2 <<= 1;
         const Key *src = buf.cand[cur] + sg.off;
-        if (sg.piece_cap == 0) {
+        if (nranks > 0) {
+            // every rank packed the same segments in the same order: the part of rank r starts after the counts of
+            // the earlier segments in r's header
+            const size_t stride = (size_t)BRK_MAXSEG * 4 + (size_t)BRK_GATHER_CAP * sizeof(Key);
+            for (int r = tid >> 5; r < nranks; r += blockDim.x >> 5) {
+                const unsigned *h = reinterpret_cast<const unsigned *>(buf.grecv + (size_t)r * stride);
+                unsigned before = 0;
+                for (int u = lane; u < sidx; u += 32) before += h[u];
+                before = __reduce_add_sync(0xffffffffu, before);
+                if (lane == 0) { roff[r] = before; rcnt[r] = h[sidx]; }
+            }
+            __syncthreads();
+            unsigned base = 0, total = 0;
+            for (int r = 0; r < nranks; ++r) total += rcnt[r];
+            if (total != cnt) {
+                if (tid == 0) raise_fail(buf.hdr, FAIL_INCONSISTENT);
+                __syncthreads();
+                continue;
+            }
+            for (int r = 0; r < nranks; ++r) {
+                const Key *part = reinterpret_cast<const Key *>(buf.grecv + (size_t)r * stride + (size_t)BRK_MAXSEG * 4) + roff[r];
+                for (unsigned i = tid; i < rcnt[r]; i += blockDim.x) s[base + i] = part[i];
+                base += rcnt[r];
+            }
+            for (unsigned i = cnt + tid; i < np2; i += blockDim.x) s[i] = (Key) ~(Key)0;
+        } else if (sg.piece_cap == 0) {
             for (unsigned i = tid; i < np2; i += blockDim.x) s[i] = i < cnt ? src[i] : (Key) ~(Key)0;
         } else {  // a round-0 segment: one piece per streaming CTA, gathered by the warps of this CTA
             const unsigned nw = (unsigned)buf.hdr[H_NW];
             const unsigned *fills = buf.fill + (size_t)sidx * nw;
             if (tid == 0) s_any = 0;   // reused as the gather cursor (every thread has read it above)
             __syncthreads();
-            const int lane = tid & 31;
             for (unsigned w = tid >> 5; w < nw; w += blockDim.x >> 5) {
                 const unsigned f = fills[w];
                 if (f == 0) continue;
@@ -1811,6 +1904,7 @@ __global__ void brk_output_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs
 // host side
 // ------------------------------------------------------------------------------------------------
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+template <typename Key> constexpr size_t gather_bytes() { return (size_t)BRK_MAXSEG * 4 + (size_t)BRK_GATHER_CAP * sizeof(Key); }
 
 struct BrkSizes {
     unsigned s1;
@@ -1854,6 +1948,7 @@ template <typename Key> BrkSizes brk_sizes(unsigned long long n, int nq, double 
     t += align256(H_WORDS * 8) + align256(2 * 8) + align256(2 * (BRK_S0 + 2) * 8) + align256((BRK_NCLS + BRK_MAXB + 2) * 8) +
          align256(BRK_MAXB * 8) + 2 * align256(((size_t)BRK_MAXSEG * 256 + 2) * 8) + align256(16) + align256((size_t)BRK_MAXB * 148 * STR_WARPS * 4);
     t += align256((size_t)z.s1 * sizeof(Key)) + 3 * align256(BRK_S0 * sizeof(Key)) + 2 * align256(BRK_MAXB * sizeof(Key));
+    t += align256(gather_bytes<Key>()) + align256(gather_bytes<Key>() * BRK_MAX_RANKS);
     t += 2 * align256(BRK_MAXB * 8) + align256(BRK_MAXB) + align256(BRK_NC1 * 4) + align256(BRK_L2N * 2) +
          align256(sizeof(BrkLutConst<Key>));
     t += 2 * align256(BRK_MAXSEG * sizeof(BrkSeg<Key>)) + align256(BRK_MAXTASK * sizeof(BrkTask)) +
@@ -1889,6 +1984,8 @@ template <typename Key> BrkBuf<Key> brk_carve(void *scratch, const BrkSizes &z, 
     b.s0 = (Key *)take(BRK_S0 * sizeof(Key));
     b.s0part = (Key *)take(BRK_S0 * sizeof(Key));
     b.s0all = (Key *)take(BRK_S0 * sizeof(Key));
+    b.gsend = (unsigned char *)take(gather_bytes<Key>());
+    b.grecv = (unsigned char *)take(gather_bytes<Key>() * BRK_MAX_RANKS);
     b.blo = (Key *)take(BRK_MAXB * sizeof(Key));
     b.bhi = (Key *)take(BRK_MAXB * sizeof(Key));
     b.boff = (unsigned long long *)take(BRK_MAXB * 8);
@@ -1956,9 +2053,24 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         return cudaStreamSynchronize(st);
     };
 
-    // 0. element count (over all ranks), threshold below which a segment is sorted by one CTA.  A lane sharded over
-    //    ranks never gathers elements: its segments are refined digit by digit down to single keys.
-    unsigned final_cap = multi ? 0u : (unsigned)BRK_FINAL_CAP;
+    // small segments: sorted by one CTA; over ranks: packed, all-gathered, sorted by every rank
+    auto finish_small = [&]() -> cudaError_t {
+        cudaError_t e2;
+        if (multi) {
+            brk_pack_final_kernel<Key><<<1, 1024, 0, st>>>(buf);
+            if ((e2 = count()) != cudaSuccess) return e2;
+            std::string err;
+            if (nccl_allgather_bytes(ctx, buf.gsend, buf.grecv, gather_bytes<Key>(), st, &err) != 0) {
+                ctx->last_error = err;
+                return cudaErrorUnknown;
+            }
+        }
+        brk_final_kernel<Key><<<sm, 256, 0, st>>>(buf, multi ? ctx->nranks : 0);
+        return count();
+    };
+    // 0. element count (over all ranks), threshold below which a segment is sorted by one CTA (sharded: small enough
+    //    that all tasks' segments fit one rank's send buffer)
+    unsigned final_cap = multi ? (unsigned)std::min<int>(BRK_FINAL_CAP, BRK_GATHER_CAP / BRK_MAXTASK) : (unsigned)BRK_FINAL_CAP;
     if (const char *fc = getenv("NDS_BRK_FINALCAP")) final_cap = std::min<unsigned>((unsigned)atoi(fc), BRK_FINAL_CAP);  // tests
     brk_begin_kernel<Key><<<1, 32, 0, st>>>(buf, n, final_cap);
     if ((e = count()) != cudaSuccess) return e;
@@ -2054,8 +2166,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         if ((e = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(kc0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         const int max_rounds = (int)sizeof(Key) + 1;
-        brk_final_kernel<Key><<<sm, 256, 0, st>>>(buf);
-        if ((e = count()) != cudaSuccess) return e;
+        if ((e = finish_small()) != cudaSuccess) return e;
         for (int round = 0; round < max_rounds; ++round) {
             if (round == 0) kc0<<<sm * 2, BRK_THREADS, smem, st>>>(buf);
             else kc<<<sm, BRK_THREADS, smem, st>>>(buf);
@@ -2072,8 +2183,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
             if ((e = count()) != cudaSuccess) return e;
             brk_refine_advance_kernel<Key><<<1, 32, 0, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
-            brk_final_kernel<Key><<<sm, 256, 0, st>>>(buf);
-            if ((e = count()) != cudaSuccess) return e;
+            if ((e = finish_small()) != cudaSuccess) return e;
             // every rank sees the same (reduced) counts and fail words, so all of them leave the loop together
             if (synchronous && (multi || round >= 1)) {
                 unsigned long long h[H_WORDS];
@@ -2153,7 +2263,7 @@ cudaError_t launch_bracket_typed(nds_ctx *ctx, const DeviceCall &c, void *scratc
 bool bracket_supported(const nds_ctx *ctx, const DeviceCall &c, bool sharded, bool forced) {
     (void)ctx;
     // sharded over ranks: every rank contributes S0 / nranks keys of its sample to the common S0
-    if (sharded && (ctx->nranks < 1 || BRK_S0 % ctx->nranks != 0)) return false;
+    if (sharded && (ctx->nranks < 1 || ctx->nranks > BRK_MAX_RANKS || BRK_S0 % ctx->nranks != 0)) return false;
     switch (c.dtype) {
     case NDS_F32: case NDS_I32: case NDS_U32: case NDS_F64: case NDS_I64: case NDS_U64: break;
     default: return false;

@@ -46,7 +46,8 @@ typedef enum nds_status {
     NDS_NCCL_ERROR = 6,
     NDS_BAD_ARGUMENT = 7,     /* null pointer, ndim out of range, axis out of bounds (the reference panics) */
     NDS_CAST_OVERFLOW = 8,    /* integer Linear: T::from_f64(..).unwrap() would panic, interpolate.rs:142 */
-    NDS_INDEX_OUT_OF_BOUNDS = 9 /* Sort1dExt: index >= n (the reference panics, src/sort.rs:27,38) */
+    NDS_INDEX_OUT_OF_BOUNDS = 9, /* Sort1dExt: index >= n (the reference panics, src/sort.rs:27,38) */
+    NDS_UNDEFINED_ORDER = 10    /* MinMaxError::UndefinedOrder (a NaN met min/max/argmin/argmax)  src/errors.rs:24-25 */
 } nds_status;
 
 typedef enum nds_dtype {
@@ -142,6 +143,20 @@ nds_status nds_quantiles_axis_masked(nds_ctx *ctx, nds_dtype dtype, const void *
  */
 nds_status nds_get_many_from_sorted(nds_ctx *ctx, nds_dtype dtype, const void *data, size_t n,
                                     ptrdiff_t stride_elems, const size_t *indexes, size_t k, void *out_values);
+
+/*
+ * QuantileExt::{argmin, argmax, min, max}                          src/quantile/mod.rs:283-300, 320-333, 347-363, 384-397
+ * QuantileExt::{argmin_skipnan, argmax_skipnan, min_skipnan, max_skipnan}   mod.rs:302-318, 335-345, 365-382, 399-409
+ * over the WHOLE array (any shape / strides).  `out_value` (host, one element, optional) receives the extremum,
+ * `out_index` (host, ndim entries, optional) its coordinates (`D::Pattern`).  Among equal extrema the first in logical
+ * (C) order is reported, as the reference's strict comparisons do; -0.0 and +0.0 are equal.
+ *   NDS_EMPTY_INPUT      the array has no element (MinMaxError::EmptyInput / EmptyInput), or -- skipnan -- none that is
+ *                        not NaN (arg*_skipnan: EmptyInput; min/max_skipnan: `out_value` holds the quiet NaN they return)
+ *   NDS_UNDEFINED_ORDER  skipnan == 0 and the array holds a NaN (MinMaxError::UndefinedOrder)
+ * For integer dtypes skipnan is a no-op.  Synchronous.
+ */
+nds_status nds_minmax(nds_ctx *ctx, nds_dtype dtype, const void *data, int ndim, const size_t *shape,
+                      const ptrdiff_t *strides_elems, int want_max, int skipnan, void *out_value, size_t *out_index);
 
 /* ---- one 1-D array sharded over several GPUs (one process per GPU) ------------------------ */
 

@@ -18,6 +18,7 @@ Arrays are numpy arrays (host; staged through the context's device arena) or tor
 (device-resident; nothing is copied).  There is no CPU fallback: importing works anywhere, but every
 compute call needs the CUDA library and a GPU and raises otherwise.
 """
+import builtins
 import ctypes
 import os
 
@@ -26,14 +27,15 @@ import numpy as np
 from . import _cabi
 from ._cabi import (  # noqa: F401  (re-exported status codes)
     NDS_BAD_ARGUMENT, NDS_CAST_OVERFLOW, NDS_CUDA_ERROR, NDS_EMPTY_INPUT, NDS_INDEX_OUT_OF_BOUNDS,
-    NDS_INVALID_QUANTILE, NDS_NAN_IN_INPUT, NDS_NCCL_ERROR, NDS_OK, NDS_UNSUPPORTED, library_path,
+    NDS_INVALID_QUANTILE, NDS_NAN_IN_INPUT, NDS_NCCL_ERROR, NDS_OK, NDS_UNDEFINED_ORDER, NDS_UNSUPPORTED, library_path,
 )
 
 __all__ = [
     "Axis", "Lower", "Higher", "Nearest", "Midpoint", "Linear", "QuantileError", "EmptyInput", "InvalidQuantile",
     "NanInInput", "CastOverflow", "Context", "default_context", "quantile_axis_mut", "quantiles_axis_mut",
     "quantile_axis_skipnan_mut", "quantile_mut", "quantiles_mut", "get_from_sorted_mut", "get_many_from_sorted_mut",
-    "shard_lanes",
+    "shard_lanes", "MinMaxError", "MinMaxEmptyInput", "UndefinedOrder", "argmin", "argmax", "min", "max",
+    "argmin_skipnan", "argmax_skipnan", "min_skipnan", "max_skipnan",
 ]
 
 
@@ -100,6 +102,22 @@ class InvalidQuantile(QuantileError):
 
     def __str__(self):
         return f"{self.q} is not between 0. and 1. (inclusive)."  # errors.rs:129-131
+
+
+class MinMaxError(Exception):
+    """src/errors.rs:18-26"""
+
+
+class MinMaxEmptyInput(MinMaxError, EmptyInput):
+    """MinMaxError::EmptyInput (also an EmptyInput: `impl From<EmptyInput> for MinMaxError`, errors.rs:40-44)"""
+
+    def __str__(self):
+        return "Empty input."
+
+
+class UndefinedOrder(MinMaxError):
+    def __str__(self):
+        return "Undefined ordering between a tested pair of values."  # errors.rs:31-33
 
 
 class NanInInput(ValueError):
@@ -322,6 +340,20 @@ class Context:
         self._raise(st)
         return out
 
+    def minmax(self, a, want_max, skipnan):
+        """``nds_minmax`` -> (status, value or None, index tuple or None); the callers map the status."""
+        code, ptr, shape, strides, keep, is_torch = self._describe(a)
+        ndim = len(shape)
+        np_dtype = keep.dtype if not is_torch else {v: k for k, v in _NP_DTYPES.items()}[code]
+        val = np.zeros(1, dtype=np_dtype)
+        idx = (ctypes.c_size_t * (ndim or 1))()
+        st = self._lib.nds_minmax(self._h, code, ctypes.c_void_p(ptr if a_size(shape) else 0), ndim,
+                                  (ctypes.c_size_t * (ndim or 1))(*shape), (ctypes.c_ssize_t * (ndim or 1))(*strides),
+                                  int(bool(want_max)), int(bool(skipnan)), ctypes.c_void_p(val.ctypes.data), idx)
+        if st not in (NDS_OK, NDS_EMPTY_INPUT, NDS_UNDEFINED_ORDER):
+            self._raise(st)
+        return st, val[0], tuple(int(idx[d]) for d in range(ndim))
+
     # -- one 1-D array sharded over ranks -------------------------------------------------------
     @staticmethod
     def comm_unique_id():
@@ -358,6 +390,13 @@ class Context:
             int(bool(skipnan)), ctypes.c_void_p(out_ptr), ctypes.byref(bad))
         self._raise(st, qs_arr, bad.value)
         return out
+
+
+def a_size(shape):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return n
 
 
 _default = {}
@@ -451,11 +490,87 @@ def shard_lanes(a, axis, rank, world):
     dims = [d for d in range(len(a.shape)) if d != axis]
     if not dims:
         raise ValueError("a single lane cannot be sharded by lanes; use quantiles_1d_sharded")
-    d = max(dims, key=lambda k: a.shape[k])
+    d = builtins.max(dims, key=lambda k: a.shape[k])  # (`max` below is the reference's QuantileExt::max)
     n = a.shape[d]
     base, rem = divmod(n, world)
-    start = rank * base + min(rank, rem)
+    start = rank * base + builtins.min(rank, rem)
     stop = start + base + (1 if rank < rem else 0)
     index = [slice(None)] * len(a.shape)
     index[d] = slice(start, stop)
     return a[tuple(index)], d, (start, stop)
+
+
+# ---- QuantileExt: min / max / argmin / argmax ----------------------------------------
+def _pattern(idx):
+    """ndarray's D::Pattern: a bare usize for 1-D arrays, a tuple otherwise."""
+    return idx[0] if len(idx) == 1 else idx
+
+
+def _minmax(a, want_max, skipnan, ctx):
+    return _ctx_for(a, ctx).minmax(a, want_max, skipnan)
+
+
+def argmin(a, ctx=None):
+    """QuantileExt::argmin (src/quantile/mod.rs:283-300)."""
+    st, _, idx = _minmax(a, False, False, ctx)
+    if st == NDS_EMPTY_INPUT:
+        raise MinMaxEmptyInput()
+    if st == NDS_UNDEFINED_ORDER:
+        raise UndefinedOrder()
+    return _pattern(idx)
+
+
+def argmax(a, ctx=None):
+    """QuantileExt::argmax (src/quantile/mod.rs:347-363)."""
+    st, _, idx = _minmax(a, True, False, ctx)
+    if st == NDS_EMPTY_INPUT:
+        raise MinMaxEmptyInput()
+    if st == NDS_UNDEFINED_ORDER:
+        raise UndefinedOrder()
+    return _pattern(idx)
+
+
+def min(a, ctx=None):  # noqa: A001  (the reference's name)
+    """QuantileExt::min (src/quantile/mod.rs:320-333)."""
+    st, v, _ = _minmax(a, False, False, ctx)
+    if st == NDS_EMPTY_INPUT:
+        raise MinMaxEmptyInput()
+    if st == NDS_UNDEFINED_ORDER:
+        raise UndefinedOrder()
+    return v
+
+
+def max(a, ctx=None):  # noqa: A001
+    """QuantileExt::max (src/quantile/mod.rs:384-397)."""
+    st, v, _ = _minmax(a, True, False, ctx)
+    if st == NDS_EMPTY_INPUT:
+        raise MinMaxEmptyInput()
+    if st == NDS_UNDEFINED_ORDER:
+        raise UndefinedOrder()
+    return v
+
+
+def argmin_skipnan(a, ctx=None):
+    """QuantileExt::argmin_skipnan (src/quantile/mod.rs:302-318): EmptyInput when no non-NaN value exists."""
+    st, _, idx = _minmax(a, False, True, ctx)
+    if st == NDS_EMPTY_INPUT:
+        raise EmptyInput()
+    return _pattern(idx)
+
+
+def argmax_skipnan(a, ctx=None):
+    """QuantileExt::argmax_skipnan (src/quantile/mod.rs:365-382)."""
+    st, _, idx = _minmax(a, True, True, ctx)
+    if st == NDS_EMPTY_INPUT:
+        raise EmptyInput()
+    return _pattern(idx)
+
+
+def min_skipnan(a, ctx=None):
+    """QuantileExt::min_skipnan (src/quantile/mod.rs:335-345): NaN when no non-NaN value exists."""
+    return _minmax(a, False, True, ctx)[1]
+
+
+def max_skipnan(a, ctx=None):
+    """QuantileExt::max_skipnan (src/quantile/mod.rs:399-409)."""
+    return _minmax(a, True, True, ctx)[1]

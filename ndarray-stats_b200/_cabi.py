@@ -5,7 +5,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 (NDS_OK, NDS_EMPTY_INPUT, NDS_INVALID_QUANTILE, NDS_NAN_IN_INPUT, NDS_UNSUPPORTED, NDS_CUDA_ERROR, NDS_NCCL_ERROR,
- NDS_BAD_ARGUMENT, NDS_CAST_OVERFLOW, NDS_INDEX_OUT_OF_BOUNDS) = range(10)
+ NDS_BAD_ARGUMENT, NDS_CAST_OVERFLOW, NDS_INDEX_OUT_OF_BOUNDS, NDS_UNDEFINED_ORDER) = range(11)
 
 _vp, _int, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
 _psz = ctypes.POINTER(ctypes.c_size_t)
@@ -31,6 +31,7 @@ PROTOTYPES = {
     "nds_quantiles_axis_enqueue": (_int, [_vp, _int, _vp, _int, _psz, _pss, _int, _pd, _sz, _int, _int, _vp, _psz]),
     "nds_quantiles_axis_masked": (_int, [_vp, _int, _vp, _vp, _int, _psz, _pss, _int, _pd, _sz, _int, _vp, _vp, _psz]),
     "nds_get_many_from_sorted": (_int, [_vp, _int, _vp, _sz, ctypes.c_ssize_t, _psz, _sz, _vp]),
+    "nds_minmax": (_int, [_vp, _int, _vp, _int, _psz, _pss, _int, _int, _vp, _psz]),
     "nds_comm_get_unique_id": (_int, [_vp]),
     "nds_comm_init_rank": (_int, [_vp, _int, _int, _vp]),
     "nds_comm_destroy": (_int, [_vp]),

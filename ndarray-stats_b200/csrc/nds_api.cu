@@ -313,6 +313,7 @@ const char *nds_status_string(nds_status s) {
     case NDS_BAD_ARGUMENT: return "bad argument";
     case NDS_CAST_OVERFLOW: return "integer interpolation overflow";
     case NDS_INDEX_OUT_OF_BOUNDS: return "index out of bounds";
+    case NDS_UNDEFINED_ORDER: return "Undefined ordering between a tested pair of values.";  // src/errors.rs:31-33
     }
     return "unknown status";
 }

@@ -12,6 +12,7 @@ pub const NDS_EMPTY_INPUT: c_int = 1;
 pub const NDS_INVALID_QUANTILE: c_int = 2;
 pub const NDS_NAN_IN_INPUT: c_int = 3;
 pub const NDS_CAST_OVERFLOW: c_int = 8;
+pub const NDS_UNDEFINED_ORDER: c_int = 10;
 
 extern "C" {
     pub fn nds_ctx_create(device: c_int, out: *mut *mut nds_ctx) -> c_int;
@@ -22,6 +23,11 @@ extern "C" {
         ctx: *mut nds_ctx, dtype: c_int, data: *const c_void, ndim: c_int, shape: *const usize,
         strides_elems: *const isize, axis: c_int, qs: *const f64, nq: usize, interp: c_int, skipnan: c_int,
         out: *mut c_void, bad_q_index: *mut usize,
+    ) -> c_int;
+    /// QuantileExt::{argmin, argmax, min, max}(+_skipnan)
+    pub fn nds_minmax(
+        ctx: *mut nds_ctx, dtype: c_int, data: *const c_void, ndim: c_int, shape: *const usize,
+        strides_elems: *const isize, want_max: c_int, skipnan: c_int, out_value: *mut c_void, out_index: *mut usize,
     ) -> c_int;
     /// Sort1dExt::get_many_from_sorted_mut / get_from_sorted_mut
     pub fn nds_get_many_from_sorted(

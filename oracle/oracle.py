@@ -161,3 +161,23 @@ def index_fraction(q, n):
 
 def max_threads():
     return lib().oracle_max_threads()
+
+
+# ---- QuantileExt::{min, max, argmin, argmax} and the *_skipnan variants -----------------
+# TEST INFRASTRUCTURE like the rest of this module.  A plain restatement of src/quantile/mod.rs:283-409: the array is
+# walked in logical (C) order, the current extremum is replaced only on a strict improvement, so among equal extrema
+# the first one wins and -0.0 == +0.0; a NaN makes the plain calls fail (every element is compared), the skipnan
+# calls ignore it.  Returns (status, value, index tuple): status "ok" | "EmptyInput" | "UndefinedOrder".
+def minmax(a, want_max=False, skipnan=False):
+    a = np.asarray(a)
+    if a.size == 0:
+        return "EmptyInput", (np.nan if skipnan and a.dtype.kind == "f" else None), None   # mod.rs:287, 336-345
+    flat = a.reshape(-1)  # logical C order (copy for strided views)
+    isnan = np.isnan(flat) if a.dtype.kind == "f" else np.zeros(flat.size, dtype=bool)
+    if not skipnan and isnan.any():
+        return "UndefinedOrder", None, None                                               # mod.rs:292, 321
+    if isnan.all():
+        return "EmptyInput", np.nan, None                                                 # mod.rs:314-318 / NaN for min_skipnan
+    vals = np.where(isnan, (-np.inf if want_max else np.inf), flat) if a.dtype.kind == "f" else flat
+    i = int(np.argmax(vals) if want_max else np.argmin(vals))   # numpy: first occurrence, -0.0 == +0.0
+    return "ok", flat[i], tuple(int(c) for c in np.unravel_index(i, a.shape))

@@ -35,7 +35,7 @@ __all__ = [
     "NanInInput", "CastOverflow", "Context", "default_context", "quantile_axis_mut", "quantiles_axis_mut",
     "quantile_axis_skipnan_mut", "quantile_mut", "quantiles_mut", "get_from_sorted_mut", "get_many_from_sorted_mut",
     "shard_lanes", "MinMaxError", "MinMaxEmptyInput", "UndefinedOrder", "argmin", "argmax", "min", "max",
-    "argmin_skipnan", "argmax_skipnan", "min_skipnan", "max_skipnan",
+    "argmin_skipnan", "argmax_skipnan", "min_skipnan", "max_skipnan", "FreedmanDiaconis", "BinsBuildError",
 ]
 
 
@@ -574,3 +574,6 @@ def min_skipnan(a, ctx=None):
 def max_skipnan(a, ctx=None):
     """QuantileExt::max_skipnan (src/quantile/mod.rs:399-409)."""
     return _minmax(a, True, True, ctx)[1]
+
+
+from .strategies import BinsBuildError, EquiSpaced, FreedmanDiaconis  # noqa: E402,F401  (SURVEY.md §8f row N3)

@@ -1,0 +1,96 @@
+"""histogram::strategies::FreedmanDiaconis — the one in-tree CALLER of the quantile path.
+
+Mirror of ``FreedmanDiaconis::from_array`` (src/histogram/strategies.rs:394-433) and of the ``EquiSpaced`` builder it
+wraps (strategies.rs:214-254).  The two quartiles come from ONE bulk device call (``quantiles_mut([0.25, 0.75],
+&Nearest)`` — the reference issues two single-q calls on its copy, the values are the same), minimum and maximum from
+the device reductions; the few scalar operations that follow are done on the host in the element type, with the
+reference's conversions (``T::from_usize``, ``T::from_f64``: truncation for integers).
+"""
+import numpy as np
+
+
+class BinsBuildError(Exception):
+    """src/histogram/errors.rs:23-48"""
+
+    def __init__(self, kind):
+        super().__init__(kind)
+        self.kind = kind
+
+    def is_empty_input(self):
+        return self.kind == "EmptyInput"
+
+    def is_strategy(self):
+        return self.kind == "Strategy"
+
+
+def _from_f64(dtype, x):
+    """num-traits FromPrimitive::from_f64 into the element type: floats round, integers truncate toward zero."""
+    dtype = np.dtype(dtype)
+    return dtype.type(x) if dtype.kind == "f" else dtype.type(int(x))
+
+
+class EquiSpaced:
+    """strategies.rs:214-254"""
+
+    def __init__(self, bin_width, lo, hi):
+        if bin_width <= 0 or lo >= hi:          # strategies.rs:221-222
+            raise BinsBuildError("Strategy")
+        self.bin_width, self.min, self.max = bin_width, lo, hi
+
+    def n_bins(self):                           # strategies.rs:243-251: repeated addition in the element type
+        max_edge, n = self.min, 0
+        while max_edge <= self.max:
+            max_edge = max_edge + self.bin_width
+            n += 1
+        return n
+
+    def build(self):                            # strategies.rs:232-241: min + from_usize(i) * bin_width
+        t = type(self.bin_width)
+        return np.array([self.min + t(i) * self.bin_width for i in range(self.n_bins() + 1)], dtype=np.dtype(t))
+
+
+class FreedmanDiaconis:
+    """bin_width = 2 * IQR * n^(-1/3) (strategies.rs:156-180, 394-433)."""
+
+    def __init__(self, builder):
+        self.builder = builder
+
+    @staticmethod
+    def compute_bin_width(n_points, iqr):       # strategies.rs:421-427
+        dtype = np.asarray(iqr).dtype
+        denominator = float(n_points) ** (1.0 / 3.0)
+        with np.errstate(over="ignore"):
+            return dtype.type(2) * iqr // _from_f64(dtype, denominator) if dtype.kind in "iu" \
+                else dtype.type(2) * iqr / _from_f64(dtype, denominator)
+
+    @classmethod
+    def from_array(cls, a, ctx=None):
+        """``a``: 1-D numpy array or CUDA tensor of a NaN-free ordered type."""
+        from . import Nearest, _ctx_for, _is_torch, NDS_EMPTY_INPUT, NDS_UNDEFINED_ORDER
+        if len(a.shape) != 1:
+            raise ValueError("from_array is defined on 1-D arrays")
+        n_points = int(a.shape[0])
+        if n_points == 0:
+            raise BinsBuildError("EmptyInput")  # strategies.rs:397-399
+        c = _ctx_for(a, ctx)
+        q = c.quantiles_axis(a, 0, [0.25, 0.75], Nearest)        # strategies.rs:402-403
+        q = q.cpu().numpy() if _is_torch(q) else q
+        with np.errstate(over="ignore"):
+            iqr = q[1] - q[0]
+        bin_width = cls.compute_bin_width(n_points, iqr)
+        st_lo, lo, _ = c.minmax(a, False, False)                 # a.min()?, a.max()?  strategies.rs:407-408
+        st_hi, hi, _ = c.minmax(a, True, False)
+        if NDS_UNDEFINED_ORDER in (st_lo, st_hi):
+            raise BinsBuildError("Strategy")                     # From<MinMaxError>, src/histogram/errors.rs
+        if NDS_EMPTY_INPUT in (st_lo, st_hi):
+            raise BinsBuildError("EmptyInput")
+        return cls(EquiSpaced(bin_width, lo, hi))
+
+    def build(self):
+        return self.builder.build()
+
+    def n_bins(self):
+        return self.builder.n_bins()
+
+    def bin_width(self):
+        return self.builder.bin_width

@@ -181,3 +181,32 @@ def minmax(a, want_max=False, skipnan=False):
     vals = np.where(isnan, (-np.inf if want_max else np.inf), flat) if a.dtype.kind == "f" else flat
     i = int(np.argmax(vals) if want_max else np.argmin(vals))   # numpy: first occurrence, -0.0 == +0.0
     return "ok", flat[i], tuple(int(c) for c in np.unravel_index(i, a.shape))
+
+
+# ---- histogram::strategies::FreedmanDiaconis::from_array (src/histogram/strategies.rs:394-433) ----
+# TEST INFRASTRUCTURE.  Quartiles through the restated quantile path above (two single-q Nearest calls, like the
+# reference), the rest in the element type.  Returns ("ok", bin_width, min, max, n_bins) or ("EmptyInput"|"Strategy",).
+def freedman_diaconis(a):
+    a = np.asarray(a)
+    n = a.size
+    if n == 0:
+        return ("EmptyInput",)
+    st, q1, _ = quantiles_axis(a, 0, [0.25], NEAREST)
+    st2, q3, _ = quantiles_axis(a, 0, [0.75], NEAREST)
+    assert st == OK and st2 == OK
+    with np.errstate(over="ignore"):
+        iqr = q3[0] - q1[0]
+        denom = float(n) ** (1.0 / 3.0)
+        if a.dtype.kind in "iu":
+            d = a.dtype.type(int(denom))                      # T::from_f64 truncates
+            bw = a.dtype.type(2) * iqr // d
+        else:
+            bw = a.dtype.type(2) * iqr / a.dtype.type(denom)
+    lo, hi = a.min(), a.max()
+    if bw <= 0 or lo >= hi:                                   # EquiSpaced::new, strategies.rs:221-222
+        return ("Strategy",)
+    edge, nb = lo, 0
+    while edge <= hi:                                         # strategies.rs:243-251
+        edge = edge + bw
+        nb += 1
+    return ("ok", bw, lo, hi, nb)

@@ -57,9 +57,12 @@ constexpr int BRK_FINAL_CAP = 4096;       // a segment this small is sorted by o
 constexpr int BRK_RCHUNK = 4096;          // refine passes: elements per chunk
 constexpr int BRK_GATHER_CAP = 1 << 15;   // sharded lanes: keys of the small segments one rank may contribute per round
 constexpr int BRK_MAX_RANKS = 8;
-constexpr int STR_THREADS = 512;          // streaming pass: 16 warps per SM, the table-lookup chains are latency bound
+#ifndef NDS_STR_THREADS
+#define NDS_STR_THREADS 1024
+#endif
+constexpr int STR_THREADS = NDS_STR_THREADS;  // streaming pass: 32 warps per SM (62 registers), the table-lookup chains are latency bound
 constexpr int STR_WARPS = STR_THREADS / 32;
-constexpr int STR_TILE = STR_THREADS * 8;
+constexpr int STR_TILE = 4096;
 
 constexpr unsigned ENT_COMPACT = 0x100u, ENT_MIXED = 0x200u, ENT_SPECIAL = 0x400u;
 
@@ -682,14 +685,14 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
 // ------------------------------------------------------------------------------------------------
 // 4. the streaming pass
 // ------------------------------------------------------------------------------------------------
-constexpr int STR_EPT = 8;                // keys per thread per tile
+constexpr int STR_EPT = STR_TILE / STR_THREADS;  // keys per thread per tile
 static_assert(STR_TILE == STR_THREADS * STR_EPT, "tile size");
-constexpr int STR_SPILL_TILES = 31;       // 8-bit private counters: 31 * 8 < 256
+constexpr int STR_SPILL_TILES = 255 / STR_EPT;  // 8-bit private counters
 
 template <typename Key> __host__ __device__ constexpr size_t stream_smem_bytes() {
     return (size_t)BRK_NCLS * STR_THREADS + (size_t)BRK_NC1 * 4 + (((size_t)BRK_L2N * 2 + 15) & ~(size_t)15) +
            2 * (size_t)BRK_MAXB * sizeof(Key) + 128 + (size_t)BRK_MAXB * 8 + (size_t)BRK_MAXB * 4 +
-           (size_t)BRK_MAXB * 4 + (size_t)BRK_NCLS * 4 + (size_t)STR_WARPS * 256 * (sizeof(Key) + 1) + 64;
+           (size_t)BRK_MAXB * 4 + (size_t)BRK_NCLS * 4 + (size_t)STR_WARPS * (32 * STR_EPT) * (sizeof(Key) + 1) + 64;
 }
 
 // slow path of the classification: a (sub-)cell that holds a bracket edge, or (floats) a cell on the border to
@@ -733,7 +736,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     unsigned *pcap = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;                         // capacity of one piece
     unsigned *pfill = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;                        // fill of this CTA's pieces
     unsigned *cta_cnt = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_NCLS * 4;                      // spilled private counters
-    Key *__restrict__ wkey = reinterpret_cast<Key *>(p); p += (size_t)STR_WARPS * 256 * sizeof(Key);                  // per-warp candidate staging
+    Key *__restrict__ wkey = reinterpret_cast<Key *>(p); p += (size_t)STR_WARPS * (32 * STR_EPT) * sizeof(Key);        // per-warp candidate staging
     unsigned char *wbrk = p;
 
     if (buf.hdr[H_FAIL]) return;  // the plan already gave up: the caller falls back
@@ -895,8 +898,8 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         }
         const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
         if (total == 0) return;
-        Key *mykey = wkey + warp * 256;
-        unsigned char *mybrk = wbrk + warp * 256;
+        Key *mykey = wkey + warp * (32 * STR_EPT);
+        unsigned char *mybrk = wbrk + warp * (32 * STR_EPT);
         unsigned pos = incl - cnt;
 #pragma unroll
         for (int e = 0; e < STR_EPT; ++e) {

@@ -1254,9 +1254,9 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_count_kernel(BrkBuf
 // CTA (fills in buf.fill).  A group of `cpb` CTAs shares one bracket and walks its pieces, so a CTA never mixes
 // brackets in its private counters.  `COMPACT` = second pass: keep the keys whose digit was chosen.
 template <typename Key, bool COMPACT>
-__global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_round0_kernel(BrkBuf<Key> buf) {
+__global__ void __launch_bounds__(BRK_THREADS, 2) brk_refine_round0_kernel(BrkBuf<Key> buf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned short *counters = reinterpret_cast<unsigned short *>(smem_raw);  // [256][THREADS]  (count pass only)
+    unsigned char *counters = smem_raw;  // [256 digits][THREADS] private 8-bit counters (count pass only): 64 KB, 3 CTAs per SM
     __shared__ short sid[256];
     __shared__ int wanted[256];   // the digits of this bracket that some rank chose (usually one or two)
     __shared__ int n_wanted;
@@ -1273,7 +1273,7 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_round0_kernel(BrkBu
     const int cpb = (int)gridDim.x / groups;                             // CTAs per bracket
     if ((int)blockIdx.x >= groups * cpb) return;
     const int part = blockIdx.x % cpb;
-    unsigned short *myctr = counters + counter_slot();
+    unsigned char *myctr = counters + (warp >> 2) * 128 + lane * 4 + (warp & 3);  // conflict-free (see the streaming pass)
     BrkSeg<Key> *nsegs = buf.seg[1];
     Key *dst = buf.cand[1];
     for (int b = blockIdx.x / cpb; b < B; b += groups) {
@@ -1290,7 +1290,7 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_round0_kernel(BrkBu
             if (n_wanted == 0) continue;
         } else {
             __syncthreads();
-            for (int i = tid; i < 256 * BRK_THREADS / 2; i += BRK_THREADS) reinterpret_cast<unsigned *>(counters)[i] = 0;
+            for (int i = tid; i < 256 * BRK_THREADS / 4; i += BRK_THREADS) reinterpret_cast<unsigned *>(counters)[i] = 0;
             __syncthreads();
         }
         const unsigned *fills = buf.fill + (size_t)b * nw;
@@ -1307,10 +1307,12 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_round0_kernel(BrkBu
         auto spill = [&]() {
             __syncthreads();
             for (int c = warp; c < 256; c += WARPS) {
+                unsigned *row = reinterpret_cast<unsigned *>(counters + (size_t)c * BRK_THREADS);
                 unsigned sum = 0;
-                for (int i = lane; i < BRK_THREADS; i += 32) {
-                    sum += counters[c * BRK_THREADS + i];
-                    counters[c * BRK_THREADS + i] = 0;
+#pragma unroll
+                for (int i = 0; i < BRK_THREADS / 4 / 32; ++i) {
+                    sum = __dp4a(row[i * 32 + lane], 0x01010101u, sum);
+                    row[i * 32 + lane] = 0;
                 }
                 sum = __reduce_add_sync(0xffffffffu, sum);
                 if (lane == 0 && sum) atomicAdd(&buf.loc_refine[(size_t)b * 256 + c], (unsigned long long)sum);
@@ -1412,15 +1414,15 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_round0_kernel(BrkBu
 #pragma unroll
                 for (int g = 0; g < KPT; g += 4) {  // 4 loads, equal digits merged, 4 stores (see the count kernel)
                     const unsigned c0 = digit(k[g]), c1 = digit(k[g + 1]), c2 = digit(k[g + 2]), c3 = digit(k[g + 3]);
-                    unsigned short *p0 = myctr + c0 * BRK_THREADS, *p1 = myctr + c1 * BRK_THREADS,
-                                   *p2 = myctr + c2 * BRK_THREADS, *p3 = myctr + c3 * BRK_THREADS;
+                    unsigned char *p0 = myctr + c0 * BRK_THREADS, *p1 = myctr + c1 * BRK_THREADS,
+                                  *p2 = myctr + c2 * BRK_THREADS, *p3 = myctr + c3 * BRK_THREADS;
                     const unsigned x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
                     const unsigned m0 = 1u + (c1 == c0) + (c2 == c0) + (c3 == c0), m1 = 1u + (c0 == c1) + (c2 == c1) + (c3 == c1);
                     const unsigned m2 = 1u + (c0 == c2) + (c1 == c2) + (c3 == c2), m3 = 1u + (c0 == c3) + (c1 == c3) + (c2 == c3);
-                    *p0 = (unsigned short)(x0 + m0);
-                    *p1 = (unsigned short)(x1 + m1);
-                    *p2 = (unsigned short)(x2 + m2);
-                    *p3 = (unsigned short)(x3 + m3);
+                    *p0 = (unsigned char)(x0 + m0);
+                    *p1 = (unsigned char)(x1 + m1);
+                    *p2 = (unsigned char)(x2 + m2);
+                    *p3 = (unsigned char)(x3 + m3);
                 }
             } else {
 #pragma unroll
@@ -1436,7 +1438,7 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_round0_kernel(BrkBu
                 bool more = seek(nw_, ne0);
                 if (more) vb = load(nw_, ne0, kb);
                 process(ka, va);
-                if (!COMPACT && ++chunks_since_spill >= 4000) {  // CTA-uniform (the chunk sequence is)
+                if (!COMPACT && ++chunks_since_spill >= 255 / KPT) {  // 8-bit counters; CTA-uniform (the chunk sequence is)
                     spill();
                     chunks_since_spill = 0;
                 }
@@ -1446,7 +1448,7 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_round0_kernel(BrkBu
                 more = seek(nw_, ne0);
                 if (more) va = load(nw_, ne0, ka);
                 process(kb, vb);
-                if (!COMPACT && ++chunks_since_spill >= 4000) {
+                if (!COMPACT && ++chunks_since_spill >= 255 / KPT) {
                     spill();
                     chunks_since_spill = 0;
                 }
@@ -2167,11 +2169,12 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         auto kp0 = brk_refine_round0_kernel<Key, true>;
         const size_t smem = (size_t)256 * BRK_THREADS * 2;
         if ((e = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(kc0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        const size_t smem0 = (size_t)256 * BRK_THREADS;  // 8-bit counters
+        if ((e = cudaFuncSetAttribute(kc0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0)) != cudaSuccess) return e;
         const int max_rounds = (int)sizeof(Key) + 1;
         if ((e = finish_small()) != cudaSuccess) return e;
         for (int round = 0; round < max_rounds; ++round) {
-            if (round == 0) kc0<<<sm * 2, BRK_THREADS, smem, st>>>(buf);
+            if (round == 0) kc0<<<sm * 3, BRK_THREADS, smem0, st>>>(buf);
             else kc<<<sm, BRK_THREADS, smem, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
             if (multi) {  // the exchange step: digit counts of every active segment, summed over ranks
@@ -2181,7 +2184,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
             }
             brk_refine_decide_kernel<Key><<<1, 256, 0, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
-            if (round == 0) kp0<<<sm * 2, BRK_THREADS, 0, st>>>(buf);
+            if (round == 0) kp0<<<sm * 6, BRK_THREADS, 0, st>>>(buf);
             else brk_refine_compact_kernel<Key><<<sm * 2, BRK_THREADS, 0, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
             brk_refine_advance_kernel<Key><<<1, 32, 0, st>>>(buf);

@@ -75,34 +75,44 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
 
     // ---- cp.async tile stream of this CTA: tile gt = (iteration, tile of the strip) ----------------------------
     const unsigned tiles = (n + COLS_TILE_ROWS - 1) / COLS_TILE_ROWS;
-    auto issue_tile = [&](unsigned long long gt) {
+    // issue state: tile iss_t of strip iss_strip goes to stage iss_stage (no divisions on this path)
+    unsigned iss_t = 0, iss_stage = 0;
+    unsigned long long iss_strip = blockIdx.x;
+    const T *iss_src = nullptr;
+    auto issue_tile = [&]() {
         if constexpr (ASYNC) {
-            const unsigned long long it = gt / tiles;
-            const unsigned t = (unsigned)(gt - it * tiles);
-            const unsigned long long strip_i = blockIdx.x + it * gridDim.x;
-            if (strip_i < n_strips) {
-                const unsigned long long grp_i = strip_i / strips_per_group;
-                const unsigned long long col_i = (strip_i - grp_i * strips_per_group) * COLS_CW;
-                long long io, oo;
-                lane_offsets(g, grp_i * ncols + col_i, io, oo);
-                const T *src = data + io;
-                uint32_t *st = stage_base + (size_t)(gt % COLS_STAGES) * COLS_STAGE_WORDS;
+            if (iss_strip < n_strips) {
+                if (iss_t == 0) {  // first tile of a strip: where it starts
+                    const unsigned long long grp_i = iss_strip / strips_per_group;
+                    const unsigned long long col_i = (iss_strip - grp_i * strips_per_group) * COLS_CW;
+                    long long io, oo;
+                    lane_offsets(g, grp_i * ncols + col_i, io, oo);
+                    iss_src = data + io;
+                }
+                uint32_t *st = stage_base + (size_t)iss_stage * COLS_STAGE_WORDS;
+                // chunk q = j * 256 + tid of the tile: row q >> 1, first / second four lanes q & 1.  j moves the row by 128
+                // = four 32-row blocks, so source and destination advance by constants
+                const unsigned rl0 = (unsigned)tid >> 1, half = (unsigned)tid & 1u;
+                const unsigned row0 = iss_t * COLS_TILE_ROWS + rl0;
+                const T *src = iss_src + (long long)row0 * pitch + half * 4;
+                uint32_t *dst = st + (rl0 >> 5) * COLS_RB_WORDS + (rl0 & 31u) * COLS_CW + half * 4;
+                const long long src_step = 128 * pitch;
 #pragma unroll
                 for (int j = 0; j < COLS_TILE_ROWS * COLS_CW * 4 / 16 / COLS_THREADS; ++j) {  // 8 chunks of 16 bytes per thread
-                    const unsigned q = (unsigned)j * COLS_THREADS + tid;
-                    const unsigned rl = q >> 1, half = q & 1u;          // row inside the tile, first / second four lanes
-                    const unsigned row = t * COLS_TILE_ROWS + rl;
-                    if (row < n)
-                        cp_async16(st + (rl >> 5) * COLS_RB_WORDS + (rl & 31u) * COLS_CW + half * 4,
-                                   src + (long long)row * pitch + half * 4);
+                    if (row0 + (unsigned)j * 128u < n) cp_async16(dst + j * 4 * COLS_RB_WORDS, src + j * src_step);
+                }
+                if (++iss_t == tiles) {
+                    iss_t = 0;
+                    iss_strip += gridDim.x;
                 }
             }
+            iss_stage = (iss_stage + 1 == COLS_STAGES) ? 0 : iss_stage + 1;
             cp_async_commit();  // (an empty group past the end keeps the group count uniform)
         }
     };
     if constexpr (ASYNC) {
-        issue_tile(0);
-        issue_tile(1);
+        issue_tile();
+        issue_tile();
     }
     unsigned long long iter = 0;
     for (unsigned long long strip = blockIdx.x; strip < n_strips; strip += gridDim.x, ++iter) {
@@ -127,7 +137,7 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
 #pragma unroll
                 for (int i = 0; i < 32; ++i) x[i] = st[i * COLS_CW];
                 __syncthreads();                    // the stage is free again
-                issue_tile(gt + COLS_STAGES);       // next tile of this strip, or the first tiles of the next one
+                issue_tile();                       // next tile of this strip, or the first tiles of the next one
                 if (rb < nrb) {                     // rows past the end of the lane are masked out in the walk
                     uint32_t w[16];
 #pragma unroll

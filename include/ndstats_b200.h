@@ -82,9 +82,12 @@ nds_status nds_ctx_synchronize(nds_ctx *ctx);
 const char *nds_ctx_last_error(nds_ctx *ctx);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches is a difference of these). */
 uint64_t nds_ctx_kernel_launches(nds_ctx *ctx);
-/* Name of the selection path the last call dispatched to ("short_bitslice", "generic_cta", "long_radix", ...). */
+/* Name of the selection path the last call dispatched to: "short_bitslice", "cols_bitslice", "bracket",
+ * "bracket_sharded", "bracket->long_radix" (a rank escaped its sampled bracket and the radix passes re-ran the call),
+ * "long_radix", "long_radix_sharded", "generic_cta", "minmax". */
 const char *nds_ctx_last_path(nds_ctx *ctx);
-/* Force a selection path for testing (NULL or "auto" = default dispatch). Returns NDS_BAD_ARGUMENT for unknown names. */
+/* Force a selection path for testing: "short_bitslice", "cols_bitslice", "bracket", "long_radix", "generic_cta"
+ * (NULL or "auto" = default dispatch).  Returns NDS_BAD_ARGUMENT for unknown names. */
 nds_status nds_ctx_force_path(nds_ctx *ctx, const char *name);
 
 /* Host-only argument check with the reference's precedence (src/quantile/mod.rs:440-455): first q outside
@@ -117,7 +120,8 @@ nds_status nds_quantiles_axis(nds_ctx *ctx, nds_dtype dtype, const void *data, i
 /*
  * Same computation for device-resident `data` and `out`, enqueued on the ctx stream without a host
  * synchronisation.  Argument errors are returned immediately; data-dependent conditions
- * (NDS_NAN_IN_INPUT, NDS_CAST_OVERFLOW) are reported by the next nds_ctx_synchronize().
+ * (NDS_NAN_IN_INPUT, NDS_CAST_OVERFLOW) are reported by the next nds_ctx_synchronize().  `data` and `out` must stay
+ * valid until that call: a long lane whose sampled brackets missed a rank is re-run there on the radix passes.
  */
 nds_status nds_quantiles_axis_enqueue(nds_ctx *ctx, nds_dtype dtype, const void *data, int ndim,
                                       const size_t *shape, const ptrdiff_t *strides_elems, int axis,
@@ -167,9 +171,11 @@ nds_status nds_comm_init_rank(nds_ctx *ctx, int nranks, int rank, const void *id
 nds_status nds_comm_destroy(nds_ctx *ctx);
 /*
  * Quantile1dExt::quantiles_mut (src/quantile/mod.rs:623-633) over the concatenation of every rank's
- * shard.  Collective: all ranks call with the same qs / interp / skipnan.  Per selection round each rank
- * builds digit histograms of its own shard and the histograms are summed with ncclAllReduce on the ctx
- * stream; element data never leaves its GPU.  Every rank receives the full result in `out` (nq values).
+ * shard.  Collective: all ranks call with the same qs / interp / skipnan (1, 2, 4 or 8 ranks take the one-pass
+ * bracket select, other counts the radix passes).  Every rank streams its own shard once; what is exchanged on the
+ * ctx stream are counts (ncclAllReduce: element count, sample bucket counts, class counts, digit histograms) and a few
+ * thousand keys (ncclAllGather: the common splitter sample, the last survivors); the elements of the array never
+ * leave their GPU.  Every rank receives the full result in `out` (nq values).
  */
 nds_status nds_quantiles_1d_sharded(nds_ctx *ctx, nds_dtype dtype, const void *local_shard, size_t n_local,
                                     const double *qs, size_t nq, nds_interp interp, int skipnan, void *out,

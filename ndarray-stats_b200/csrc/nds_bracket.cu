@@ -42,9 +42,6 @@ constexpr int BRK_MAXB = 120;             // brackets per call
 constexpr int BRK_NCLS = 128;             // counter classes of the streaming pass (127 = invalid: NaN)
 constexpr int BRK_INVALID_CLS = 127;
 constexpr int BRK_THREADS = 256;
-constexpr int BRK_EPT = 16;               // elements per thread per tile
-constexpr int BRK_TILE = BRK_THREADS * BRK_EPT;
-constexpr int BRK_STAGE_CAP = 2 * BRK_TILE;
 constexpr int BRK_NC1 = 4096;             // top-level cells
 constexpr int BRK_L2_PURE = 260;          // 2 * 128 pure (class, inside) combinations + 2 special entries
 constexpr int BRK_L2_SUB = 16384;         // sub-cell entries
@@ -143,7 +140,6 @@ __device__ __forceinline__ unsigned counter_slot() {
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     return (warp >> 1) * 64 + lane * 2 + (warp & 1);
 }
-template <typename T> struct KeyOf { using Key = typename Traits<T>::Key; };
 
 // floats: keys of NaNs lie outside [key(-inf), key(+inf)]
 template <typename T> __device__ __forceinline__ bool key_is_nan(typename Traits<T>::Key k) {
@@ -2024,8 +2020,6 @@ double brk_csigma() {
     return 5.0;
 }
 namespace {
-
-template <typename T> constexpr bool brk_type_ok() { return sizeof(T) == 4 || sizeof(T) == 8; }
 
 template <typename T>
 cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long n, const QuantArgs &qa, T *out,

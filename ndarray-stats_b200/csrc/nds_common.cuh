@@ -31,7 +31,9 @@ __host__ __device__ inline void lane_offsets(const LaneGeom &g, unsigned long lo
                                              long long &out_off) {
     in_off = 0;
     out_off = 0;
+#ifdef __CUDA_ARCH__
 #pragma unroll 1
+#endif
     for (int d = g.n_outer - 1; d >= 1; --d) {  // 64-bit division only for arrays with >= 3 dims
         const unsigned long long q = lane / g.oshape[d];
         const unsigned long long c = lane - q * g.oshape[d];

@@ -158,10 +158,13 @@ __global__ void brk_sample_kernel(const T *__restrict__ data, unsigned long long
     using Tr = Traits<T>;
     using Key = typename Tr::Key;
     unsigned valid = 0;
+    // stratum i = [i q + min(i, r), + q + (i < r)) with q = n / s1, r = n % s1 partitions [0, n) exactly; one element per
+    // stratum at a hashed offset (multiply-high instead of a modulo: the strata are narrower than 2^32)
+    const unsigned long long q = n / s1, r = n % s1;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += gridDim.x * blockDim.x) {
-        // stratum i = [i n / s1, (i + 1) n / s1): one element at a hashed offset (s1 <= n < 2^40, i < 2^24)
-        const unsigned long long p0 = (unsigned long long)i * n / s1, p1 = (unsigned long long)(i + 1) * n / s1;
-        unsigned long long pos = p0 + (p1 - p0 > 1 ? (unsigned long long)mix32(i) % (p1 - p0) : 0ull);
+        const unsigned long long p0 = (unsigned long long)i * q + (i < r ? i : r);
+        const unsigned long long width = q + (i < r ? 1ull : 0ull);
+        unsigned long long pos = p0 + (((unsigned long long)mix32(i) * width) >> 32);
         if (pos >= n) pos = n - 1;
         Key k = Tr::to_key(data[pos]);
         const bool inv = key_is_nan<T>(k);
@@ -229,20 +232,44 @@ __global__ void __launch_bounds__(1024) brk_sort_s0_kernel(BrkBuf<Key> buf, unsi
 }
 
 // 2b. exact sample ranks of the S0 keys: hist[i] = #{ s1 keys k : S0[i-1] < k <= S0[i] }
+constexpr int BRK_BLUT = 4096;  // cells of the bucket kernel's search table
+
 template <typename Key, bool IS_FLOAT>
 __global__ void __launch_bounds__(256) brk_bucket_kernel(BrkBuf<Key> buf, unsigned s1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Key *s = reinterpret_cast<Key *>(smem_raw);
+    unsigned short *start = reinterpret_cast<unsigned short *>(s + BRK_S0);  // [BLUT + 1]: lower_bound of every cell start
     for (unsigned i = threadIdx.x; i < BRK_S0; i += blockDim.x) s[i] = buf.s0[i];
+    __syncthreads();
+    auto lower_bound = [&](Key k, unsigned lo, unsigned hi) -> unsigned {  // #{ S0[lo..hi) < k } + lo
+        while (lo < hi) {
+            const unsigned mid = (lo + hi) >> 1;
+            if (s[mid] < k) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    };
+    // A key-linear table over [S0[0], S0[last]] narrows the 13-step binary search to the few splitters of one cell.
+    const Key k0 = s[0], k1 = s[BRK_S0 - 1];
+    const Key range = k1 - k0;
+    int sh = key_bits_used(range) - 12;
+    if (sh < 0) sh = 0;
+    while ((range >> sh) >= (Key)BRK_BLUT) ++sh;
+    for (unsigned c = threadIdx.x; c <= BRK_BLUT; c += blockDim.x) {
+        const Key off = (Key)c << sh;
+        const bool past = c && (off >> sh) != (Key)c;  // shifted out of the key type
+        start[c] = (unsigned short)((past || off > range) ? BRK_S0 : lower_bound((Key)(k0 + off), 0, BRK_S0));
+    }
     __syncthreads();
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += gridDim.x * blockDim.x) {
         const Key k = buf.s1[i];
         if (IS_FLOAT && k == (Key) ~(Key)0) continue;
-        unsigned lo = 0, hi = BRK_S0;  // lower_bound: #{ S0 < k }
-        while (lo < hi) {
-            unsigned mid = (lo + hi) >> 1;
-            if (s[mid] < k) lo = mid + 1;
-            else hi = mid;
+        unsigned lo;
+        if (k <= k0) lo = 0;
+        else if (k > k1) lo = BRK_S0;
+        else {
+            const unsigned c = (unsigned)((Key)(k - k0) >> sh);  // < BLUT; cell_start(c) <= k < cell_start(c + 1)
+            lo = lower_bound(k, start[c], start[c + 1]);
         }
         atomicAdd(&buf.s0hist[lo], 1ull);
         if (lo < BRK_S0 && s[lo] == k) atomicAdd(&buf.s0hist[BRK_S0 + 2 + lo], 1ull);  // #{ s1 == S0[lo] }, first of its run
@@ -1943,7 +1970,8 @@ template <typename Key> BrkSizes brk_sizes(unsigned long long n, int nq, double 
         z.s1 = (unsigned)cap;
     }
     // candidates: up to ~0.3 n, plus the head room of the per-warp pieces (<= MAXB * 148 * 16 pieces)
-    z.cap0 = n / 2 + (unsigned long long)BRK_MAXB * 148 * 2 * STR_TILE + (1ull << 16);
+    const unsigned long long pieces = std::min<unsigned long long>(148, n / STR_TILE + 1);  // streaming CTAs
+    z.cap0 = n / 2 + (unsigned long long)BRK_MAXB * pieces * 2 * STR_TILE + (1ull << 16);
     z.cap1 = z.cap0 / 4 + (1ull << 16);
     size_t t = 0;
     t += align256(H_WORDS * 8) + align256(2 * 8) + align256(2 * (BRK_S0 + 2) * 8) + align256((BRK_NCLS + BRK_MAXB + 2) * 8) +
@@ -2117,7 +2145,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     }
     {
         auto k = brk_bucket_kernel<Key, IS_FLOAT>;
-        const size_t smem = BRK_S0 * sizeof(Key);
+        const size_t smem = BRK_S0 * sizeof(Key) + (BRK_BLUT + 1) * 2 + 16;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         if (s1) {
             k<<<std::min<unsigned>((s1 + 255) / 256, sm * 4), 256, smem, st>>>(buf, s1);

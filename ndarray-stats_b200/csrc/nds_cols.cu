@@ -63,8 +63,10 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
     const unsigned col_pitch = 16u * nrbp + 4u;       // +4: the 8 lanes of a strip hit different banks
     unsigned *clist = reinterpret_cast<unsigned *>(planes + COLS_CW * col_pitch);  // [warp][COLS_CAND]
     Key *ckeys = reinterpret_cast<Key *>(clist + COLS_CW * COLS_CAND);             // [warp][COLS_CAND]
-    uint32_t *stage_base = reinterpret_cast<uint32_t *>(                             // [COLS_STAGES][COLS_STAGE_WORDS]
-        (reinterpret_cast<uintptr_t>(ckeys + COLS_CW * COLS_CAND) + 15) & ~(uintptr_t)15);
+    // [COLS_STAGES][COLS_STAGE_WORDS], 16-byte aligned; derived from smem_raw by an OFFSET so that the compiler keeps
+    // the shared address space (a pointer -> integer -> pointer round trip turns every access into a generic LD/ST)
+    const size_t stage_off = ((size_t)(reinterpret_cast<unsigned char *>(ckeys + COLS_CW * COLS_CAND) - smem_raw) + 15) & ~(size_t)15;
+    uint32_t *stage_base = reinterpret_cast<uint32_t *>(smem_raw + stage_off);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bc = tid % COLS_CW, brg = tid / COLS_CW;  // build role: lane (column) and row group

@@ -17,17 +17,20 @@
 namespace nds {
 namespace {
 
-constexpr int COLS_CW = 8;           // lanes per strip: 8 x 4 B = one 32-byte sector per row (f32)
-constexpr int COLS_THREADS = 256;    // 8 lanes x 32 row groups
+constexpr int COLS_CW_SYNC = 8;      // lanes per strip of the direct-load path: 8 x 4 B = one 32-byte sector per row (f32)
 constexpr int COLS_KMAX = 8;         // plane words per thread in the walk: 8 x 32 x 32 = 8192 elements
 constexpr unsigned FULLMASK = 0xffffffffu;
 constexpr int COLS_CAND = 64;        // candidates ranked directly once the walk has narrowed a lane down to this many
 
 constexpr int COLS_TILE_ROWS = 1024;                    // rows of a strip staged per cp.async group (4-byte types)
-constexpr int COLS_RB_WORDS = 32 * COLS_CW + 8;         // one 32-row block of a staged tile: +8 words of padding
-                                                        // so that the four row groups of a warp read 32 banks
-constexpr int COLS_STAGE_WORDS = 32 * COLS_RB_WORDS;    // 32 row blocks = 1024 rows x 8 lanes
+// one 32-row block of a staged tile is padded so that the row groups of a warp (4 for 8-lane strips, 8 for 4-lane
+// strips) read 32 different banks
+__host__ __device__ constexpr int cols_rb_words(int cw) { return 32 * cw + (cw == 8 ? 8 : 4); }
+__host__ __device__ constexpr int cols_stage_words(int cw) { return 32 * cols_rb_words(cw); }  // 32 row blocks = 1024 rows
 constexpr int COLS_STAGES = 2;
+constexpr int COLS_CW_ASYNC = 8;   // lanes per strip of the staged path.  (4-lane strips -- 16 bytes per row, half the shared
+                                   // memory, two CTAs per SM so that one streams while the other walks -- measured slower on
+                                   // C3: 1.03 ms vs 0.91 ms; the two half-sector strips of a row do not pair up well enough in L2)
 
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
@@ -38,10 +41,14 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 // ASYNC (4-byte types, full aligned strips): the strip is staged through shared memory by cp.async (LDGSTS), two tiles
 // of 1024 rows in flight, the first tiles of the NEXT strip already during the bit walk of this one.
-template <typename T, bool ASYNC>
-__global__ void __launch_bounds__(COLS_THREADS, 1)
+template <typename T, bool ASYNC, int CW>
+__global__ void __launch_bounds__(CW * 32, CW == 4 ? 2 : 1)
 cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__restrict__ out,
                      unsigned long long n_strips, unsigned strips_per_group) {
+    constexpr int COLS_CW = CW;                       // lanes per strip = warps per CTA
+    constexpr int COLS_THREADS = CW * 32;             // CW lanes x 32 row groups
+    constexpr int COLS_RB_WORDS = cols_rb_words(CW);
+    constexpr int COLS_STAGE_WORDS = cols_stage_words(CW);
     using Tr = Traits<T>;
     using Key = typename Tr::Key;
     using Raw = typename RawBits<T>::U;
@@ -94,14 +101,17 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                 uint32_t *st = stage_base + (size_t)iss_stage * COLS_STAGE_WORDS;
                 // chunk q = j * 256 + tid of the tile: row q >> 1, first / second four lanes q & 1.  j moves the row by 128
                 // = four 32-row blocks, so source and destination advance by constants
-                const unsigned rl0 = (unsigned)tid >> 1, half = (unsigned)tid & 1u;
+                constexpr unsigned CPR = COLS_CW * 4 / 16;            // 16-byte chunks per row (2 or 1)
+                constexpr unsigned RSTEP = COLS_THREADS / CPR;         // rows between a thread's chunks: 128
+                static_assert(RSTEP == 128, "a thread's chunks are four 32-row blocks apart");
+                const unsigned rl0 = (unsigned)tid / CPR, half = (unsigned)tid % CPR;
                 const unsigned row0 = iss_t * COLS_TILE_ROWS + rl0;
                 const T *src = iss_src + (long long)row0 * pitch + half * 4;
                 uint32_t *dst = st + (rl0 >> 5) * COLS_RB_WORDS + (rl0 & 31u) * COLS_CW + half * 4;
-                const long long src_step = 128 * pitch;
+                const long long src_step = (long long)RSTEP * pitch;
 #pragma unroll
-                for (int j = 0; j < COLS_TILE_ROWS * COLS_CW * 4 / 16 / COLS_THREADS; ++j) {  // 8 chunks of 16 bytes per thread
-                    if (row0 + (unsigned)j * 128u < n) cp_async16(dst + j * 4 * COLS_RB_WORDS, src + j * src_step);
+                for (int j = 0; j < COLS_TILE_ROWS / (int)RSTEP; ++j) {  // 8 chunks of 16 bytes per thread
+                    if (row0 + (unsigned)j * RSTEP < n) cp_async16(dst + j * 4 * COLS_RB_WORDS, src + j * src_step);
                 }
                 if (++iss_t == tiles) {
                     iss_t = 0;
@@ -469,45 +479,51 @@ ColsPlan plan_cols(const nds_ctx *ctx, const DeviceCall &c) {
     if (g.in_ostride[last] != 1 || g.oshape[last] < 32) return p;  // neighbouring lanes must be contiguous
     if (g.axis_len < 64 || g.axis_len > 8192) return p;             // 8 lanes x 16 planes x n/32 words of smem
     if (g.axis_stride < (long long)g.oshape[last]) return p;        // rows must not overlap
-    const unsigned long long spg = (g.oshape[last] + COLS_CW - 1) / COLS_CW;
-    if (spg > 0xffffffffull) return p;
-    p.strips_per_group = (unsigned)spg;
-    p.n_strips = (g.nlanes / g.oshape[last]) * spg;
     const unsigned nrb = (unsigned)((g.axis_len + 31) / 32), nrbp = (nrb + 31) / 32 * 32;
-    p.smem = (size_t)COLS_CW * (16 * nrbp + 4) * 4 + COLS_CW * COLS_CAND * 4 + COLS_CW * COLS_CAND * 8 + 64;
-    if (p.smem > (size_t)ctx->max_smem_optin) return p;
-    p.ok = true;
-    // the staged build wants every row of every strip to be two aligned 16-byte chunks
-    bool aligned = es == 4 && g.oshape[last] % COLS_CW == 0 && ((uintptr_t)c.data % 16) == 0 && (g.axis_stride * 4) % 16 == 0;
+    auto smem_for = [&](int cw) { return (size_t)cw * (16 * nrbp + 4) * 4 + (size_t)cw * COLS_CAND * 4 + (size_t)cw * COLS_CAND * 8 + 64; };
+    auto strips_for = [&](int cw) {
+        const unsigned long long spg = (g.oshape[last] + cw - 1) / cw;
+        p.strips_per_group = (unsigned)spg;
+        p.n_strips = (g.nlanes / g.oshape[last]) * spg;
+        return spg <= 0xffffffffull;
+    };
+    // the staged build (4-byte types) wants every row of every strip to be aligned 16-byte chunks
+    bool aligned = es == 4 && g.oshape[last] % COLS_CW_ASYNC == 0 && ((uintptr_t)c.data % 16) == 0 && (g.axis_stride * 4) % 16 == 0;
     for (int d = 0; d < last; ++d)
         if (g.oshape[d] > 1 && (g.in_ostride[d] * 4) % 16 != 0) aligned = false;
-    const size_t smem_async = ((p.smem + 15) & ~(size_t)15) + (size_t)COLS_STAGES * COLS_STAGE_WORDS * 4 + 16;
+    const size_t smem_async = ((smem_for(COLS_CW_ASYNC) + 15) & ~(size_t)15) + (size_t)COLS_STAGES * cols_stage_words(COLS_CW_ASYNC) * 4 + 16;
     if (aligned && smem_async <= (size_t)ctx->max_smem_optin && !getenv("NDS_COLS_NO_ASYNC")) {
+        if (!strips_for(COLS_CW_ASYNC)) return p;
         p.async = true;
         p.smem = smem_async;
+        p.ok = true;
+        return p;
     }
+    if (!strips_for(COLS_CW_SYNC)) return p;
+    p.smem = smem_for(COLS_CW_SYNC);
+    if (p.smem > (size_t)ctx->max_smem_optin) return p;
+    p.ok = true;
     return p;
 }
 
-template <typename T, bool ASYNC> cudaError_t launch_cols_typed2(nds_ctx *ctx, const DeviceCall &c, const ColsPlan &p) {
-    auto kernel = cols_bitslice_kernel<T, ASYNC>;
+template <typename T, bool ASYNC, int CW> cudaError_t launch_cols_typed2(nds_ctx *ctx, const DeviceCall &c, const ColsPlan &p) {
+    auto kernel = cols_bitslice_kernel<T, ASYNC, CW>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, COLS_THREADS, p.smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, CW * 32, p.smem);
     if (occ < 1) occ = 1;
     unsigned grid = (unsigned)std::min<unsigned long long>(p.n_strips, (unsigned long long)ctx->sm_count * occ);
-    kernel<<<grid, COLS_THREADS, p.smem, ctx->stream>>>((const T *)c.data, c.geom, c.q, (T *)c.out, p.n_strips,
-                                                         p.strips_per_group);
+    kernel<<<grid, CW * 32, p.smem, ctx->stream>>>((const T *)c.data, c.geom, c.q, (T *)c.out, p.n_strips, p.strips_per_group);
     ctx->launches += 1;
     return cudaGetLastError();
 }
 
 template <typename T> cudaError_t launch_cols_typed(nds_ctx *ctx, const DeviceCall &c, const ColsPlan &p) {
     if constexpr (sizeof(T) == 4) {
-        if (p.async) return launch_cols_typed2<T, true>(ctx, c, p);
+        if (p.async) return launch_cols_typed2<T, true, COLS_CW_ASYNC>(ctx, c, p);
     }
-    return launch_cols_typed2<T, false>(ctx, c, p);
+    return launch_cols_typed2<T, false, COLS_CW_SYNC>(ctx, c, p);
 }
 
 }  // namespace

@@ -65,7 +65,7 @@ constexpr unsigned ENT_COMPACT = 0x100u, ENT_MIXED = 0x200u, ENT_SPECIAL = 0x400
 
 enum : int {
     H_NTOTAL = 0, H_NINVALID, H_NEFF, H_FAIL, H_B, H_NSEG, H_NTASK, H_NACTIVE, H_S1VALID, H_EMPTY, H_NCHUNK_COUNT,
-    H_NCHUNK_COMPACT, H_NCLS_USED, H_NTIE, H_CUR, H_NEXT_NCHUNK, H_NEXT_NSEG, H_OLD_NSEG, H_NW, H_ROUND, H_DID, H_FINALCAP, H_SPARE, H_WORDS = 28
+    H_NCHUNK_COMPACT, H_NCLS_USED, H_NTIE, H_CUR, H_NEXT_NCHUNK, H_NEXT_NSEG, H_OLD_NSEG, H_NW, H_ROUND, H_DID, H_FINALCAP, H_NFINAL, H_MULTI, H_LOCALFAIL, H_WORDS = 30
 };
 enum : int { FAIL_ESCAPED = 1, FAIL_CAPACITY = 2, FAIL_TOO_MANY = 4, FAIL_INCONSISTENT = 8, FAIL_REMOTE = 16 };
 enum : int { TASK_ACTIVE = 0, TASK_DONE = 1 };
@@ -123,9 +123,15 @@ template <typename Key> struct BrkBuf {
 __device__ __forceinline__ unsigned long long ld_now(const unsigned long long *p) {
     return *reinterpret_cast<const volatile unsigned long long *>(p);
 }
+// A lane sharded over ranks must take every collective on every rank, so a failure seen by ONE rank must not change
+// that rank's control flow on its own: it is parked in H_LOCALFAIL (which only mutes the data kernels), travels with the
+// next collective, and comes back to every rank as FAIL_REMOTE in H_FAIL -- the word the host and the deciding kernels
+// look at.  On one GPU the two are the same thing.
 __device__ __forceinline__ void raise_fail(unsigned long long *hdr, int bits) {
-    atomicOr(&hdr[H_FAIL], (unsigned long long)bits);
+    const bool park = hdr[H_MULTI] != 0 && !(bits & FAIL_REMOTE);
+    atomicOr(&hdr[park ? H_LOCALFAIL : H_FAIL], (unsigned long long)bits);
 }
+__device__ __forceinline__ bool failed_any(const unsigned long long *hdr) { return (hdr[H_FAIL] | hdr[H_LOCALFAIL]) != 0; }
 __device__ __forceinline__ unsigned mix32(unsigned x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
@@ -158,12 +164,15 @@ __global__ void brk_sample_kernel(const T *__restrict__ data, unsigned long long
     using Tr = Traits<T>;
     using Key = typename Tr::Key;
     unsigned valid = 0;
-    // stratum i = [i q + min(i, r), + q + (i < r)) with q = n / s1, r = n % s1 partitions [0, n) exactly; one element per
-    // stratum at a hashed offset (multiply-high instead of a modulo: the strata are narrower than 2^32)
+    // stratum i starts at floor(i n / s1) = i q + floor(i r / s1) (q = n / s1, r = n % s1): the strata must be spread EVENLY
+    // over the lane -- a sorted lane sampled at two different rates puts its quantiles in the wrong place.  The second
+    // term comes from one double multiplication (i r < 2^48 is exact; being off by one element does not matter), the
+    // offset inside the stratum from a multiply-high instead of a modulo (strata are narrower than 2^32).
     const unsigned long long q = n / s1, r = n % s1;
+    const double inv_s1 = 1.0 / (double)s1;
+    const unsigned long long width = q + (r ? 1ull : 0ull);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += gridDim.x * blockDim.x) {
-        const unsigned long long p0 = (unsigned long long)i * q + (i < r ? i : r);
-        const unsigned long long width = q + (i < r ? 1ull : 0ull);
+        const unsigned long long p0 = (unsigned long long)i * q + (unsigned long long)((double)((unsigned long long)i * r) * inv_s1);
         unsigned long long pos = p0 + (((unsigned long long)mix32(i) * width) >> 32);
         if (pos >= n) pos = n - 1;
         Key k = Tr::to_key(data[pos]);
@@ -176,10 +185,12 @@ __global__ void brk_sample_kernel(const T *__restrict__ data, unsigned long long
 }
 
 // 0. this rank's element count (summed over ranks by the caller when the lane is sharded); final-sort threshold
-template <typename Key> __global__ void brk_begin_kernel(BrkBuf<Key> buf, unsigned long long n_local, unsigned final_cap) {
+template <typename Key>
+__global__ void brk_begin_kernel(BrkBuf<Key> buf, unsigned long long n_local, unsigned final_cap, int multi) {
     if (threadIdx.x == 0) {
         buf.red_n[0] = n_local;
         buf.hdr[H_FINALCAP] = final_cap;
+        buf.hdr[H_MULTI] = multi ? 1ull : 0ull;
     }
 }
 // sharded lanes: this rank's share of the S0 keys (all-gathered, then sorted identically on every rank)
@@ -192,13 +203,13 @@ template <typename Key> __global__ void brk_merge_fail_kernel(BrkBuf<Key> buf, c
     if (threadIdx.x == 0 && *word) raise_fail(buf.hdr, FAIL_REMOTE);
 }
 template <typename Key> __global__ void brk_post_fail_kernel(BrkBuf<Key> buf, unsigned long long *word) {
-    if (threadIdx.x == 0) *word = buf.hdr[H_FAIL] ? 1ull : 0ull;
+    if (threadIdx.x == 0) *word = failed_any(buf.hdr) ? 1ull : 0ull;
 }
 template <typename Key> __global__ void brk_copy_counts_kernel(BrkBuf<Key> buf) {  // red_refine = loc_refine (+ fail word)
     const int nseg = (int)buf.hdr[H_NSEG];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BRK_MAXSEG * 256; i += gridDim.x * blockDim.x)
         buf.red_refine[i] = i < nseg * 256 ? buf.loc_refine[i] : 0ull;
-    if (blockIdx.x == 0 && threadIdx.x == 0) buf.red_refine[BRK_MAXSEG * 256] = buf.hdr[H_FAIL] ? 1ull : 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) buf.red_refine[BRK_MAXSEG * 256] = failed_any(buf.hdr) ? 1ull : 0ull;
 }
 
 // 2a. S0 = every (s1 / S0)-th sample (or the gathered shares of all ranks), sorted by one CTA (bitonic network)
@@ -762,7 +773,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     Key *__restrict__ wkey = reinterpret_cast<Key *>(p); p += (size_t)STR_WARPS * (32 * STR_EPT) * sizeof(Key);        // per-warp candidate staging
     unsigned char *wbrk = p;
 
-    if (buf.hdr[H_FAIL]) return;  // the plan already gave up: the caller falls back
+    if (failed_any(buf.hdr)) return;  // the plan already gave up: the caller falls back
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const BrkLutConst<Key> lc = *buf.lutc;
     if ((lc.hi32 != 0) != HI32) return;
@@ -1007,7 +1018,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
 template <typename Key> __global__ void brk_publish_fill_kernel(BrkBuf<Key> buf) {
     const int B = (int)buf.hdr[H_B];
     for (int b = threadIdx.x; b < B; b += blockDim.x) buf.red_stream[BRK_NCLS + b] = buf.cur_local[b];
-    if (threadIdx.x == 0) buf.red_stream[BRK_NCLS + BRK_MAXB] = buf.hdr[H_FAIL] ? 1ull : 0ull;  // summed over ranks
+    if (threadIdx.x == 0) buf.red_stream[BRK_NCLS + BRK_MAXB] = failed_any(buf.hdr) ? 1ull : 0ull;  // summed over ranks
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1152,11 +1163,13 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
     }
     __syncthreads();
     if (tid == 0) {
-        int active = 0;
+        int active = 0, nfinal = 0;
         for (int b = 0; b < B; ++b) {
             const BrkSeg<Key> &s = buf.seg[0][b];
             if ((s.flags & SEG_USED) && !(s.flags & (SEG_FINAL | SEG_TIE))) ++active;
+            if ((s.flags & SEG_USED) && (s.flags & SEG_FINAL) && !(s.flags & SEG_TIE)) ++nfinal;
         }
+        buf.hdr[H_NFINAL] = (unsigned long long)nfinal;   // small segments waiting for brk_final_kernel
         buf.hdr[H_NCHUNK_COUNT] = 0;   // round 0 walks the pieces (brk_refine_count0_kernel), not a chunk table
         buf.hdr[H_NACTIVE] = (unsigned long long)active;
         buf.hdr[H_ROUND] = 0;
@@ -1199,7 +1212,7 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_count_kernel(BrkBuf
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned short *counters = reinterpret_cast<unsigned short *>(smem_raw);  // [256][THREADS]
     __shared__ unsigned long long sprefix[BRK_MAXSEG + 1];
-    if (buf.hdr[H_FAIL] || buf.hdr[H_ROUND] == 0 || buf.hdr[H_NACTIVE] == 0) return;
+    if (failed_any(buf.hdr) || buf.hdr[H_ROUND] == 0 || buf.hdr[H_NACTIVE] == 0) return;
     const unsigned long long nchunks = buf.hdr[H_NCHUNK_COUNT];
     if (nchunks == 0) return;
     const int cur = (int)buf.hdr[H_CUR];
@@ -1285,7 +1298,7 @@ __global__ void __launch_bounds__(BRK_THREADS, 2) brk_refine_round0_kernel(BrkBu
     __shared__ int n_wanted;
     __shared__ unsigned sfill[148];                       // fills of this bracket's pieces
     __shared__ unsigned long long wseg_off[4], wseg_cap[4];  // destination segments of the first wanted digits
-    if (buf.hdr[H_FAIL] || buf.hdr[H_ROUND] != 0 || buf.hdr[H_NACTIVE] == 0) return;
+    if (failed_any(buf.hdr) || buf.hdr[H_ROUND] != 0 || buf.hdr[H_NACTIVE] == 0) return;
     if (COMPACT && !buf.hdr[H_DID]) return;
     const int B = (int)(COMPACT ? buf.hdr[H_OLD_NSEG] : buf.hdr[H_NSEG]);
     const unsigned nw = (unsigned)buf.hdr[H_NW];
@@ -1485,7 +1498,7 @@ __global__ void __launch_bounds__(BRK_THREADS, 2) brk_refine_round0_kernel(BrkBu
 
 // One CTA: every active task picks its digit; the chosen (segment, digit) pairs become the next segments.
 template <typename Key>
-__global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf) {
+__global__ void __launch_bounds__(1024) brk_refine_decide_kernel(BrkBuf<Key> buf) {
     __shared__ int want[BRK_MAXTASK];                 // seg * 256 + digit of the task, or -1
     __shared__ int newseg_of[BRK_MAXTASK];            // id of the segment the task moves to
     __shared__ unsigned long long pad_cnt[BRK_MAXTASK];
@@ -1504,6 +1517,7 @@ __global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf)
         if (tid == 0) {
             buf.hdr[H_NCHUNK_COMPACT] = 0;
             buf.hdr[H_DID] = 0;
+            buf.hdr[H_NFINAL] = 0;
         }
         return;
     }
@@ -1632,14 +1646,17 @@ __global__ void __launch_bounds__(256) brk_refine_decide_kernel(BrkBuf<Key> buf)
             if (seg_any[s]) chunks_compact += (old_cnt_local[s] + BRK_RCHUNK - 1) / BRK_RCHUNK;
         }
         for (int s = nseg; s <= BRK_MAXSEG; ++s) buf.cprefix_compact[s] = chunks_compact;
-        int active = 0;
+        int active = 0, nfinal = 0;
         for (int s = 0; s < nid; ++s) {
             buf.cprefix_count[s] = chunks_count;
             if (!new_final[s]) {
                 chunks_count += (new_cnt_local[s] + BRK_RCHUNK - 1) / BRK_RCHUNK;
                 ++active;
+            } else {
+                ++nfinal;
             }
         }
+        buf.hdr[H_NFINAL] = (unsigned long long)nfinal;
         for (int s = nid; s <= BRK_MAXSEG; ++s) buf.cprefix_count[s] = chunks_count;
         buf.hdr[H_NCHUNK_COMPACT] = chunks_compact;
         // the next count pass must see the new table only after the compaction of this round has read the
@@ -1662,7 +1679,7 @@ template <typename Key>
 __global__ void __launch_bounds__(BRK_THREADS) brk_refine_compact_kernel(BrkBuf<Key> buf) {
     __shared__ unsigned long long sprefix[BRK_MAXSEG + 1];
     __shared__ short sid[256];
-    if (buf.hdr[H_FAIL] || buf.hdr[H_ROUND] == 0 || !buf.hdr[H_DID]) return;
+    if (failed_any(buf.hdr) || buf.hdr[H_ROUND] == 0 || !buf.hdr[H_DID]) return;
     const unsigned long long nchunks = buf.hdr[H_NCHUNK_COMPACT];
     if (nchunks == 0) return;
     const int nseg = (int)buf.hdr[H_OLD_NSEG];
@@ -1735,7 +1752,7 @@ __global__ void __launch_bounds__(1024) brk_pack_final_kernel(BrkBuf<Key> buf) {
     const int tid = threadIdx.x;
     for (int i = tid; i < BRK_MAXSEG; i += blockDim.x) { cnt[i] = 0; off[i] = 0; wanted[i] = 0; hdr_out[i] = 0; }
     __syncthreads();
-    if (buf.hdr[H_FAIL] || buf.hdr[H_EMPTY]) return;
+    if (failed_any(buf.hdr) || buf.hdr[H_EMPTY]) return;
     const int nseg = (int)buf.hdr[H_NSEG], ntask = (int)buf.hdr[H_NTASK];
     const int cur = (int)buf.hdr[H_CUR];
     for (int t = tid; t < ntask; t += blockDim.x) {
@@ -1792,7 +1809,7 @@ __global__ void __launch_bounds__(256) brk_final_kernel(BrkBuf<Key> buf, int nra
     __shared__ int tseg[BRK_MAXTASK];  // segment of every still active task, -1 otherwise
     __shared__ int s_any;
     __shared__ unsigned roff[BRK_MAX_RANKS], rcnt[BRK_MAX_RANKS];
-    if (buf.hdr[H_FAIL] || buf.hdr[H_EMPTY]) return;
+    if (failed_any(buf.hdr) || buf.hdr[H_EMPTY]) return;
     const int nseg = (int)buf.hdr[H_NSEG], ntask = (int)buf.hdr[H_NTASK];
     const int cur = (int)buf.hdr[H_CUR];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -1902,7 +1919,7 @@ __global__ void brk_output_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs
                                   long long out_axis_stride, int last) {
     using Tr = Traits<T>;
     using Key = typename Tr::Key;
-    if (buf.hdr[H_FAIL]) {  // the caller re-runs this lane on the radix passes (immediately, or at the next synchronize)
+    if (failed_any(buf.hdr)) {  // the caller re-runs this lane on the radix passes (immediately, or at the next synchronize)
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(qa.status, STATUS_BIT_FALLBACK);
         return;
     }
@@ -2099,7 +2116,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     //    that all tasks' segments fit one rank's send buffer)
     unsigned final_cap = multi ? (unsigned)std::min<int>(BRK_FINAL_CAP, BRK_GATHER_CAP / BRK_MAXTASK) : (unsigned)BRK_FINAL_CAP;
     if (const char *fc = getenv("NDS_BRK_FINALCAP")) final_cap = std::min<unsigned>((unsigned)atoi(fc), BRK_FINAL_CAP);  // tests
-    brk_begin_kernel<Key><<<1, 32, 0, st>>>(buf, n, final_cap);
+    brk_begin_kernel<Key><<<1, 32, 0, st>>>(buf, n, final_cap, multi ? 1 : 0);
     if ((e = count()) != cudaSuccess) return e;
     unsigned long long n_total = n;
     if (multi) {
@@ -2194,7 +2211,17 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         const size_t smem0 = (size_t)256 * BRK_THREADS;  // 8-bit counters
         if ((e = cudaFuncSetAttribute(kc0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0)) != cudaSuccess) return e;
         const int max_rounds = (int)sizeof(Key) + 1;
-        if ((e = finish_small()) != cudaSuccess) return e;
+        // over ranks the host follows the (rank-identical) header: it skips the exchange of small segments when there
+        // are none and reduces only the rows of the live segments
+        unsigned long long hh[H_WORDS];
+        size_t live_rows = BRK_MAXSEG;
+        bool small_pending = true;
+        if (multi) {
+            if ((e = read_hdr(hh)) != cudaSuccess) return e;
+            small_pending = hh[H_NFINAL] != 0 && !hh[H_FAIL];
+            live_rows = std::min<size_t>(BRK_MAXSEG, (size_t)hh[H_NSEG]);
+        }
+        if (small_pending && (e = finish_small()) != cudaSuccess) return e;
         for (int round = 0; round < max_rounds; ++round) {
             if (round == 0) kc0<<<sm * 3, BRK_THREADS, smem0, st>>>(buf);
             else kc<<<sm, BRK_THREADS, smem, st>>>(buf);
@@ -2202,21 +2229,29 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
             if (multi) {  // the exchange step: digit counts of every active segment, summed over ranks
                 brk_copy_counts_kernel<Key><<<64, 256, 0, st>>>(buf);
                 if ((e = count()) != cudaSuccess) return e;
-                if ((e = allreduce(buf.red_refine, (size_t)BRK_MAXSEG * 256 + 2)) != cudaSuccess) return e;
+                // rows of the live segments, then (at a fixed place) the fail word: two small collectives beat one of 512 KB
+                if ((e = allreduce(buf.red_refine, live_rows * 256)) != cudaSuccess) return e;
+                if ((e = allreduce(buf.red_refine + (size_t)BRK_MAXSEG * 256, 2)) != cudaSuccess) return e;
             }
-            brk_refine_decide_kernel<Key><<<1, 256, 0, st>>>(buf);
+            brk_refine_decide_kernel<Key><<<1, 1024, 0, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
             if (round == 0) kp0<<<sm * 6, BRK_THREADS, 0, st>>>(buf);
             else brk_refine_compact_kernel<Key><<<sm * 2, BRK_THREADS, 0, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
             brk_refine_advance_kernel<Key><<<1, 32, 0, st>>>(buf);
             if ((e = count()) != cudaSuccess) return e;
-            if ((e = finish_small()) != cudaSuccess) return e;
-            // every rank sees the same (reduced) counts and fail words, so all of them leave the loop together
-            if (synchronous && (multi || round >= 1)) {
-                unsigned long long h[H_WORDS];
-                if ((e = read_hdr(h)) != cudaSuccess) return e;
-                if (h[H_FAIL] || h[H_NACTIVE] == 0) break;
+            // every rank sees the same (reduced) counts and fail words, so all of them take the same branches
+            if (multi) {
+                if ((e = read_hdr(hh)) != cudaSuccess) return e;
+                if (hh[H_NFINAL] != 0 && !hh[H_FAIL] && (e = finish_small()) != cudaSuccess) return e;
+                live_rows = std::min<size_t>(BRK_MAXSEG, (size_t)hh[H_NSEG]);
+                if (hh[H_FAIL] || hh[H_NACTIVE] == 0) break;
+            } else {
+                if ((e = finish_small()) != cudaSuccess) return e;
+                if (synchronous && round >= 1) {
+                    if ((e = read_hdr(hh)) != cudaSuccess) return e;
+                    if (hh[H_FAIL] || hh[H_NACTIVE] == 0) break;
+                }
             }
         }
     }
@@ -2231,7 +2266,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     if (synchronous) {
         unsigned long long h[H_WORDS];
         if ((e = read_hdr(h)) != cudaSuccess) return e;
-        *failed = (int)h[H_FAIL];
+        *failed = (int)(h[H_FAIL] | h[H_LOCALFAIL]);
         if (n_total_out) *n_total_out = n_total;
         if (multi) {
             unsigned long long agreed = 0;

@@ -61,7 +61,7 @@ constexpr int STR_THREADS = NDS_STR_THREADS;  // streaming pass: 32 warps per SM
 constexpr int STR_WARPS = STR_THREADS / 32;
 constexpr int STR_TILE = 4096;
 
-constexpr unsigned ENT_COMPACT = 0x100u, ENT_MIXED = 0x200u, ENT_SPECIAL = 0x400u;
+constexpr unsigned ENT_COMPACT = 0x100u, ENT_MIXED = 0x200u;
 
 enum : int {
     H_NTOTAL = 0, H_NINVALID, H_NEFF, H_FAIL, H_B, H_NSEG, H_NTASK, H_NACTIVE, H_S1VALID, H_EMPTY, H_NCHUNK_COUNT,
@@ -390,10 +390,8 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             buf.lutc->submask = 0;
             buf.lutc->ncls_used = 1;
         }
-        for (int c = tid; c < BRK_NC1; c += nthreads) buf.lut1[c] = 256u;  // everything is "outside": class 0 or NaN
-        for (int i = tid; i < BRK_L2_PURE; i += nthreads)
-            buf.lut2[i] = i == 256 ? (unsigned short)(ENT_MIXED | ENT_SPECIAL | 0xffu)
-                                   : (i == 258 ? (unsigned short)BRK_INVALID_CLS : (unsigned short)0);
+        for (int c = tid; c < BRK_NC1; c += nthreads) buf.lut1[c] = 0u;  // every number is class 0 (NaNs: invalid class)
+        for (int i = tid; i < BRK_L2_PURE; i += nthreads) buf.lut2[i] = (unsigned short)0;
         return;
     }
 
@@ -538,11 +536,19 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             hi32 = 1;
             kmin_lut = (Key)((unsigned long long)blo[0] & 0xFFFFFFFF00000000ull);
         }
-        const Key range = bhi[B - 1] - kmin_lut;
-        int shift1 = key_bits_used(range) - 12;
+        // The origin of the cells lies one whole cell BELOW the first bracket: the streaming pass clamps every key
+        // below the origin onto it, i.e. into sub-cell 0 of cell 0, which then holds no key of a bracket (or, when
+        // the origin is clipped at key 0, no key below the origin exists).  Cells past the last bracket are pure
+        // "above"; the last cell takes everything beyond the table.
+        const Key kbase = kmin_lut;
+        int shift1 = key_bits_used((Key)(bhi[B - 1] - kbase)) - 12;
         if (shift1 < 0) shift1 = 0;
         if (hi32 && shift1 < 32) shift1 = 32;
-        while ((range >> shift1) > (Key)(BRK_NC1 - 2)) ++shift1;
+        for (;; ++shift1) {
+            const Key step = (Key)1 << shift1;
+            kmin_lut = kbase >= step ? kbase - step : (Key)0;
+            if (((Key)(bhi[B - 1] - kmin_lut) >> shift1) <= (Key)(BRK_NC1 - 2)) break;
+        }
         sShift1 = shift1;
         sHi32 = hi32;
         sKminLut = kmin_lut;
@@ -604,44 +610,26 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
         buf.bhi[b] = bhi[b];
         buf.btie[b] = btie[b];
     }
-    // pure entries + the two special ones (floats: below / above the bracket range may hold NaN keys)
+    // pure entries (NaN keys never reach the tables: the streaming pass finds them with a floating-point compare)
     for (int i = tid; i < BRK_L2_PURE; i += nthreads) {
         unsigned short e = 0;
         if (i < 256) {
             const int j = i >> 1;
             const bool in = i & 1;
             if (j <= B && (!in || j > 0)) e = (unsigned short)pure_entry(j, in, btie);
-        } else if (i == 256) {
-            e = (unsigned short)(ENT_MIXED | ENT_SPECIAL | 0xffu);       // outside [kmin, kmax]: below, above or NaN
-        } else if (i == 258) {
-            e = (unsigned short)BRK_INVALID_CLS;                           // a range of NaN keys only
         }
         buf.lut2[i] = e;
     }
     // ---- level 1: which cells hold a bracket edge -----------------------------------------------------
-    // cell c (0 .. NC1-2) covers keys [kmin + (c << shift1), +2^shift1); cell NC1-1 is everything outside
-    // [kmin, kmax] (k - kmin wraps around below kmin)
+    // cell c (0 .. NC1-2) covers keys [kmin + (c << shift1), +2^shift1); cell NC1-1 is everything beyond the table
+    // (keys below kmin are clamped onto kmin by the streaming pass)
     const Key width1 = ((Key)1 << shift1) - 1;
     auto cell_ends = [&](int c, Key &a, Key &e) {
         a = kmin + ((Key)c << shift1);
         e = (a > KMAX - width1) ? KMAX : a + width1;
     };
-    // Kind of the key range [a, e]: 0 = one class throughout (pa), 1 = holds a bracket edge, 2 = NaN keys only,
-    // 3 = holds the border between numbers and NaN keys (floats: keys outside [key(-inf), key(+inf)] are NaNs)
-    const Key NINF = sizeof(Key) == 8 ? (Key)0x000FFFFFFFFFFFFFull : (Key)0x007FFFFFu;
-    const Key PINF = sizeof(Key) == 8 ? (Key)0xFFF0000000000000ull : (Key)0xFF800000u;
-    const Key kmax = bhi[B - 1];
+    // Kind of the key range [a, e]: 0 = one class throughout (pa), 1 = holds a bracket edge
     auto range_kind = [&](Key a, Key e, PointClass<Key> &pa) -> int {
-        // past the last bracket: keys BELOW kmin alias into these cells (k - kmin wraps around), so they resolve
-        // like the outside cell
-        if (a > kmax) return 4;
-        if (IS_FLOAT) {
-            if (a > PINF || e < NINF) return 2;
-            if (e > PINF || a < NINF) {
-                pa = classify_point(blo, bhi, B, a);
-                return 3;
-            }
-        }
         pa = classify_point(blo, bhi, B, a);
         const PointClass<Key> pe = classify_point(blo, bhi, B, e);
         return (pa.j == pe.j && pa.in == pe.in) ? 0 : 1;
@@ -649,22 +637,15 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
     const Key max_cell = (KMAX - kmin) >> shift1;  // cells past the end of the key space can never be hit
     for (int c = tid; c < BRK_NC1; c += nthreads) {
         unsigned e1;
-        if (c == BRK_NC1 - 1) {
-            e1 = 256u;
-        } else if ((Key)c > max_cell) {
-            e1 = 256u;
+        if (c == BRK_NC1 - 1 || (Key)c > max_cell) {
+            e1 = (unsigned)(2 * B);  // beyond the last bracket (or beyond the key space): pure "above"
         } else {
             Key a, e;
             cell_ends(c, a, e);
             PointClass<Key> pa;
-            int kind = range_kind(a, e, pa);
-            // the cell that runs past the end of the key space also receives the keys below kmin (k - kmin wraps
-            // around): it must not be "pure"
-            if (a > KMAX - width1 && kmin > 0 && (kind == 0 || kind == 2)) kind = 1;
-            if (kind == 0) e1 = (unsigned)(2 * pa.j + (pa.in ? 1 : 0));
-            else if (kind == 2) e1 = 258u;
-            else if (kind == 4) e1 = 256u;
-            else {
+            if (range_kind(a, e, pa) == 0) {
+                e1 = (unsigned)(2 * pa.j + (pa.in ? 1 : 0));
+            } else {
                 const int slot = atomicAdd(&sNmixed, 1);
                 mixcell[slot] = (unsigned short)c;
                 e1 = 0x80000000u | (unsigned)slot;  // the table base is filled in once M is known
@@ -704,14 +685,8 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
         if (e2 > e) e2 = e;
         PointClass<Key> p2;
         const int k2 = range_kind(a2, e2, p2);
-        unsigned short ent;
-        const bool straddles_wrap = a2 >= a && a2 > KMAX - width2 && kmin > 0;  // same aliasing, at sub-cell level
-        if (straddles_wrap && (k2 == 0 || k2 == 2))
-            ent = (unsigned short)(ENT_MIXED | (IS_FLOAT ? ENT_SPECIAL : 0u) | (unsigned)classify_point(blo, bhi, B, a2).j);
-        else if (k2 == 0) ent = (unsigned short)pure_entry(p2.j, p2.in, btie);
-        else if (k2 == 2) ent = (unsigned short)BRK_INVALID_CLS;
-        else if (k2 == 4) ent = (unsigned short)(ENT_MIXED | ENT_SPECIAL | 0xffu);
-        else ent = (unsigned short)(ENT_MIXED | (k2 == 3 ? ENT_SPECIAL : 0u) | (unsigned)p2.j);
+        const unsigned short ent = k2 == 0 ? (unsigned short)pure_entry(p2.j, p2.in, btie)
+                                           : (unsigned short)(ENT_MIXED | (unsigned)p2.j);
         buf.lut2[BRK_L2_PURE + g] = ent;
     }
 }
@@ -722,29 +697,54 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
 constexpr int STR_EPT = STR_TILE / STR_THREADS;  // keys per thread per tile
 static_assert(STR_TILE == STR_THREADS * STR_EPT, "tile size");
 constexpr int STR_SPILL_TILES = 255 / STR_EPT;  // 8-bit private counters
+constexpr int STR_RING = 32 * STR_EPT;          // per-warp candidate ring (a power of two): one tile's worth
+static_assert((STR_RING & (STR_RING - 1)) == 0, "ring size");
+
+// shared-window accesses of the streaming pass (32-bit addresses: no generic-to-shared conversion in the hot loop)
+__device__ __forceinline__ unsigned sm_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned lds_u8(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8(unsigned a, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// predicated pair of stores (candidate key + its bracket) without a branch
+__device__ __forceinline__ void sts_key64_if(unsigned flag, unsigned akey, unsigned long long k, unsigned abrk, unsigned b) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u64 [%1], %2;\n\t@p st.shared.u8 [%3], %4;\n\t}"
+                 ::"r"(flag), "r"(akey), "l"(k), "r"(abrk), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts_key32_if(unsigned flag, unsigned akey, unsigned k, unsigned abrk, unsigned b) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u32 [%1], %2;\n\t@p st.shared.u8 [%3], %4;\n\t}"
+                 ::"r"(flag), "r"(akey), "r"(k), "r"(abrk), "r"(b) : "memory");
+}
+
+// this CTA's piece of one bracket's candidate segment: first element (index into cand[0]) and capacity
+struct __align__(16) StrPiece { unsigned long long base; unsigned cap, pad; };
 
 template <typename Key> __host__ __device__ constexpr size_t stream_smem_bytes() {
     return (size_t)BRK_NCLS * STR_THREADS + (size_t)BRK_NC1 * 4 + (((size_t)BRK_L2N * 2 + 15) & ~(size_t)15) +
-           2 * (size_t)BRK_MAXB * sizeof(Key) + 128 + (size_t)BRK_MAXB * 8 + (size_t)BRK_MAXB * 4 +
-           (size_t)BRK_MAXB * 4 + (size_t)BRK_NCLS * 4 + (size_t)STR_WARPS * (32 * STR_EPT) * (sizeof(Key) + 1) + 64;
+           2 * (size_t)BRK_MAXB * sizeof(Key) + 128 + (size_t)BRK_MAXB * sizeof(StrPiece) +
+           (size_t)BRK_MAXB * 4 + (size_t)BRK_NCLS * 4 + (size_t)STR_WARPS * STR_RING * (sizeof(Key) + 1) + 64;
 }
 
-// slow path of the classification: a (sub-)cell that holds a bracket edge, or (floats) a cell on the border to
-// the NaN keys.  (Keys outside [kmin, kmax] are handled inline by the caller.)
-template <typename Key, bool IS_FLOAT>
-__device__ __noinline__ unsigned brk_resolve_entry(Key k, unsigned ent, Key kmin, const Key *blo, const Key *bhi,
-                                                   const unsigned char *btie, int B) {
-    if (IS_FLOAT && (ent & ENT_SPECIAL)) {
-        const bool nan = sizeof(Key) == 8 ? (k > (Key)0xFFF0000000000000ull || k < (Key)0x000FFFFFFFFFFFFFull)
-                                          : (k > (Key)0xFF800000u || k < (Key)0x007FFFFFu);
-        if (nan) return BRK_INVALID_CLS;
-    }
-    if (k < kmin) return 0u;  // below every bracket (k - origin wrapped around into a cell at or past the last bracket)
-    if ((ent & 0xffu) == 0xffu) return (unsigned)B;  // above every bracket
+// slow path of the classification: a sub-cell that holds a bracket edge.  `ent` carries the class at the lower end of
+// the sub-cell; the edges inside it are walked -- two steps without a branch (tie-heavy lanes send a fifth of their keys
+// here, and the lanes of a warp must not diverge), more in a loop.  Keys below the table origin were clamped into
+// sub-cell 0 of cell 0 by the caller, whose entry says class 0: no bracket edge is <= such a key, so they stay there.
+template <typename Key>
+__device__ __forceinline__ unsigned brk_resolve_entry(Key k, unsigned ent, const Key *blo, const Key *bhi,
+                                                      const unsigned char *btie, int B) {
     int j = (int)(ent & 0xffu);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int jj = j < B ? j : B - 1;
+        j += (j < B && blo[jj] <= k) ? 1 : 0;
+    }
     while (j < B && blo[j] <= k) ++j;
-    const bool in = j > 0 && k <= bhi[j - 1];
-    return pure_entry(j, in, btie);
+    const int jm = j > 0 ? j - 1 : 0;
+    const bool in = j > 0 && k <= bhi[jm];
+    const unsigned t = btie[jm];
+    return in ? (t != 0xffu ? t : ((unsigned)j | ENT_COMPACT)) : (unsigned)j;
 }
 
 // HI32: 64-bit keys, tables indexed with the high word (see brk_plan_kernel); the kernel of the other mode returns
@@ -766,11 +766,10 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     Key *blo = reinterpret_cast<Key *>(p); p += (size_t)BRK_MAXB * sizeof(Key);
     Key *bhi = reinterpret_cast<Key *>(p); p += (size_t)BRK_MAXB * sizeof(Key);
     unsigned char *btie = p; p += 128;
-    unsigned long long *pbase = reinterpret_cast<unsigned long long *>(p); p += (size_t)BRK_MAXB * 8;  // first piece of a bracket
-    unsigned *pcap = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;                         // capacity of one piece
-    unsigned *pfill = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;                        // fill of this CTA's pieces
+    StrPiece *piece = reinterpret_cast<StrPiece *>(p); p += (size_t)BRK_MAXB * sizeof(StrPiece);       // this CTA's pieces
+    unsigned *pfill = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_MAXB * 4;                        // their fills
     unsigned *cta_cnt = reinterpret_cast<unsigned *>(p); p += (size_t)BRK_NCLS * 4;                      // spilled private counters
-    Key *__restrict__ wkey = reinterpret_cast<Key *>(p); p += (size_t)STR_WARPS * (32 * STR_EPT) * sizeof(Key);        // per-warp candidate staging
+    Key *__restrict__ wkey = reinterpret_cast<Key *>(p); p += (size_t)STR_WARPS * STR_RING * sizeof(Key);  // per-warp candidate ring
     unsigned char *wbrk = p;
 
     if (failed_any(buf.hdr)) return;  // the plan already gave up: the caller falls back
@@ -778,7 +777,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     const BrkLutConst<Key> lc = *buf.lutc;
     if ((lc.hi32 != 0) != HI32) return;
     const int B = lc.B;
-    const Key kmin = lc.kmin, kmin_true = lc.kmin_true;
+    const Key kmin = lc.kmin;
     const int shift1 = lc.shift1, subshift = lc.subshift;
     const unsigned submask = lc.submask;
     const int ncls_used = lc.ncls_used;
@@ -790,10 +789,14 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         blo[i] = i < B ? buf.blo[i] : (Key)0;
         bhi[i] = i < B ? buf.bhi[i] : (Key)0;
         btie[i] = i < B ? buf.btie[i] : (unsigned char)0xff;
-        pbase[i] = i < B ? buf.boff[i] : 0ull;
-        pcap[i] = i < B ? (unsigned)buf.bcap[i] : 0u;
+        const unsigned cap = i < B ? (unsigned)buf.bcap[i] : 0u;
+        StrPiece pc;
+        pc.base = i < B ? buf.boff[i] + (unsigned long long)blockIdx.x * cap : 0ull;
+        pc.cap = cap;
+        pc.pad = 0;
+        piece[i] = pc;
+        pfill[i] = 0;
     }
-    for (int i = tid; i < BRK_MAXB; i += STR_THREADS) pfill[i] = 0;
     for (int i = tid; i < BRK_NCLS; i += STR_THREADS) cta_cnt[i] = 0;
     for (int i = tid; i < BRK_NCLS * STR_THREADS / 4; i += STR_THREADS) reinterpret_cast<unsigned *>(counters)[i] = 0;
     __syncthreads();
@@ -801,19 +804,27 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     // conflict-free private counter of this thread in a class row of 512 bytes: the 32 lanes of a warp hit 32
     // different banks, four warps share a 128-byte line (byte 0..3 of each word)
     unsigned char *__restrict__ myctr = counters + (warp >> 2) * 128 + lane * 4 + (warp & 3);
+    const unsigned myctr_a = sm_addr(myctr);
     Key *cand = buf.cand[0];
+    Key *mykey = wkey + warp * STR_RING;
+    unsigned char *mybrk = wbrk + warp * STR_RING;
+    const unsigned mykey_a = sm_addr(mykey), mybrk_a = sm_addr(mybrk);
+    unsigned whead = 0, wpend = 0;  // the warp's ring of candidates that wait for a full group of 32 (warp-uniform)
 
-    // two table reads per key, no side effects (k - origin wraps to a huge value below it: the "outside" cell)
+    // Two table reads per key, no side effects.  Keys below the table origin are clamped onto it: the origin lies a
+    // whole cell below the first bracket (brk_plan_kernel), so they read a "below every bracket" entry; keys past the
+    // last bracket fall into cells that are pure "above" (the last cell takes everything beyond the table).
     auto lookup = [&](Key k) -> unsigned {
         if constexpr (HI32) {
-            const unsigned d = (unsigned)(k >> 32) - (unsigned)(kmin >> 32);
+            const unsigned hk = (unsigned)(k >> 32), h0 = (unsigned)(kmin >> 32);
+            const unsigned d = umax(hk, h0) - h0;
             const unsigned cc = d >> (shift1 - 32);
             const unsigned cell = cc < (unsigned)(BRK_NC1 - 1) ? cc : (unsigned)(BRK_NC1 - 1);
             const unsigned e1 = lut1[cell];
             const unsigned sub = (d >> (subshift - 32)) & submask & (unsigned)((int)e1 >> 31);
             return lut2[(e1 & 0x7fffffffu) + sub];
         } else {
-            const Key d = k - kmin;
+            const Key d = (k > kmin ? k : kmin) - kmin;
             const Key cc = d >> shift1;
             const unsigned cell = (unsigned)(cc < (Key)(BRK_NC1 - 1) ? cc : (Key)(BRK_NC1 - 1));
             const unsigned e1 = lut1[cell];
@@ -821,33 +832,36 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             return lut2[(e1 & 0x7fffffffu) + sub];
         }
     };
-    // entries that need a second look: outside [kmin, kmax] is decided inline (no NaN: class 0 below, B above),
-    // everything else (a sub-cell with a bracket edge, the border to the NaN keys) by the out-of-line scan
-    auto settle = [&](Key k, unsigned ent) -> unsigned {
-        if ((ent & 0xffu) == 0xffu) {
-            bool nan = false;
-            if (IS_FLOAT)
-                nan = sizeof(Key) == 8 ? (k > (Key)0xFFF0000000000000ull || k < (Key)0x000FFFFFFFFFFFFFull)
-                                       : (k > (Key)0xFF800000u || k < (Key)0x007FFFFFu);
-            return nan ? (unsigned)BRK_INVALID_CLS : (k < kmin_true ? 0u : (unsigned)B);
-        }
-        return brk_resolve_entry<Key, IS_FLOAT>(k, ent, kmin_true, blo, bhi, btie, B);
-    };
-    // Append this lane's candidate `k` of bracket `b` (if `has`) to this CTA's piece of the bracket's segment.
-    // Lanes with the same bracket are grouped with match.any and the group leader reserves the positions with ONE
-    // shared-memory atomic on the CTA's fill of that bracket.  Called by all 32 lanes; no CTA barrier anywhere.
+    // One group of up to 32 candidates: lane i appends `k` to this CTA's piece of bracket `b` (if `has`).  Lanes with
+    // the same bracket are grouped with match.any and the group leader reserves the positions with ONE shared-memory
+    // atomic on the CTA's fill of that bracket.  Called by all 32 lanes; no CTA barrier anywhere.
     auto append = [&](bool has, Key k, unsigned b) {
-        const unsigned hasmask = __ballot_sync(0xffffffffu, has);
-        if (!has) return;
-        const unsigned peers = __match_any_sync(hasmask, b);
+        const unsigned bb = has ? b : 0xffffffffu;               // the idle lanes form a group of their own
+        const unsigned peers = __match_any_sync(0xffffffffu, bb);
         const int leader = __ffs(peers) - 1;
         const unsigned rank = __popc(peers & ((1u << lane) - 1u));
         unsigned base = 0;
-        if (lane == leader) base = atomicAdd(&pfill[b], (unsigned)__popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        const unsigned pos = base + rank;
-        if (pos < pcap[b]) cand[pbase[b] + (unsigned long long)blockIdx.x * pcap[b] + pos] = k;
-        else raise_fail(buf.hdr, FAIL_CAPACITY);
+        if (has && lane == leader) base = atomicAdd(&pfill[b], (unsigned)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (has) {
+            const StrPiece pc = piece[b];
+            const unsigned pos = base + rank;
+            if (pos < pc.cap) cand[pc.base + pos] = k;
+            else raise_fail(buf.hdr, FAIL_CAPACITY);
+        }
+    };
+    // full groups of the ring (`all`: the rest too)
+    auto drain = [&](bool all) {
+#pragma unroll 1
+        while (wpend >= 32u || (all && wpend > 0u)) {
+            const unsigned take = wpend < 32u ? wpend : 32u;
+            const unsigned i = (whead + (unsigned)lane) & (unsigned)(STR_RING - 1);
+            const bool has = (unsigned)lane < take;
+            append(has, mykey[i], (unsigned)mybrk[i] - 1u);
+            whead = (whead + take) & (unsigned)(STR_RING - 1);
+            wpend -= take;
+        }
+        __syncwarp();
     };
     // private 8-bit counters -> 32-bit CTA counters (every STR_SPILL_TILES tiles)
     auto spill_counters = [&]() {
@@ -883,17 +897,25 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     };
     auto process_tile = [&](const uint4 (&q)[NLD]) {
         Key k[STR_EPT];
+        bool nan = false;  // floats: NaNs are found with one floating-point compare per key (their keys lie outside
+                           // [key(-inf), key(+inf)] and the tables do not know about them)
 #pragma unroll
         for (int j = 0; j < NLD; ++j) {
             if constexpr (ES == 4) {
                 const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) k[j * 4 + u] = Tr::to_key(from_raw<T>(w[u]));
+                for (int u = 0; u < 4; ++u) {
+                    const T v = from_raw<T>(w[u]);
+                    if constexpr (IS_FLOAT) nan |= v != v;
+                    k[j * 4 + u] = Tr::to_key(v);
+                }
             } else {
                 const uint64_t w0 = (uint64_t)q[j].x | ((uint64_t)q[j].y << 32);
                 const uint64_t w1 = (uint64_t)q[j].z | ((uint64_t)q[j].w << 32);
-                k[j * 2] = Tr::to_key(from_raw<T>(w0));
-                k[j * 2 + 1] = Tr::to_key(from_raw<T>(w1));
+                const T v0 = from_raw<T>(w0), v1 = from_raw<T>(w1);
+                if constexpr (IS_FLOAT) nan |= (v0 != v0) | (v1 != v1);
+                k[j * 2] = Tr::to_key(v0);
+                k[j * 2 + 1] = Tr::to_key(v1);
             }
         }
         // phase 1: all table reads of the tile are independent of each other
@@ -904,26 +926,34 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             ent[e] = lookup(k[e]);
             slow |= ent[e];
         }
-        // phase 2: the few keys next to a bracket edge or outside all brackets
-        if (slow & (ENT_MIXED | ENT_SPECIAL)) {
+        if constexpr (IS_FLOAT) {
+            if (__any_sync(0xffffffffu, nan)) {  // rare: NaNs get the invalid class, whatever the tables said
+                slow = 0;
+#pragma unroll
+                for (int e = 0; e < STR_EPT; ++e) {
+                    if (key_is_nan<T>(k[e])) ent[e] = (unsigned)BRK_INVALID_CLS;
+                    slow |= ent[e];
+                }
+            }
+        }
+        // phase 2: the few keys in a sub-cell with a bracket edge
+        if (slow & ENT_MIXED) {
 #pragma unroll
             for (int e = 0; e < STR_EPT; ++e)
-                if (ent[e] & (ENT_MIXED | ENT_SPECIAL)) ent[e] = settle(k[e], ent[e]);
+                if (ent[e] & ENT_MIXED) ent[e] = brk_resolve_entry<Key>(k[e], ent[e], blo, bhi, btie, B);
         }
-        // phase 3: private counters (plain read-modify-write of this thread's own bytes), candidate mask
-        unsigned cmask = 0;
+        // phase 3: private counters (plain read-modify-write of this thread's own bytes, one after the other: two
+        // keys of a thread may share a class), candidate mask
+        unsigned cflag[STR_EPT], cnt = 0;
 #pragma unroll
-        for (int e = 0; e < STR_EPT; e += 2) {  // pairs: both loads go out together; equal classes store old + 2 twice
-            const unsigned c0 = ent[e] & 0xffu, c1 = ent[e + 1] & 0xffu;
-            unsigned char *p0 = myctr + c0 * STR_THREADS, *p1 = myctr + c1 * STR_THREADS;
-            const unsigned x0 = *p0, x1 = *p1, same = c0 == c1 ? 1u : 0u;
-            *p0 = (unsigned char)(x0 + 1u + same);
-            *p1 = (unsigned char)(x1 + 1u + same);
-            cmask |= (((ent[e] >> 8) & 1u) << e) | (((ent[e + 1] >> 8) & 1u) << (e + 1));
+        for (int e = 0; e < STR_EPT; ++e) {
+            const unsigned a = myctr_a + (ent[e] & 0xffu) * (unsigned)STR_THREADS;
+            sts_u8(a, lds_u8(a) + 1u);
+            cflag[e] = (ent[e] >> 8) & 1u;
+            cnt += cflag[e];
         }
-        // phase 4: the ~10 % of keys inside a bracket are packed into the warp's staging area (warp prefix sum),
-        // then appended 32 at a time
-        const unsigned cnt = __popc(cmask);
+        // phase 4: the ~10 % of keys inside a bracket are packed into the warp's ring (warp prefix sum); full groups
+        // of 32 are appended to the brackets' segments, the rest waits for the next tile
         unsigned incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -932,24 +962,18 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         }
         const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
         if (total == 0) return;
-        Key *mykey = wkey + warp * (32 * STR_EPT);
-        unsigned char *mybrk = wbrk + warp * (32 * STR_EPT);
-        unsigned pos = incl - cnt;
+        if (wpend + total > (unsigned)STR_RING) drain(true);  // rare: make room for a tile full of candidates
+        unsigned pos = whead + wpend + incl - cnt;
 #pragma unroll
-        for (int e = 0; e < STR_EPT; ++e) {
-            if (cmask & (1u << e)) {
-                mykey[pos] = k[e];
-                mybrk[pos] = (unsigned char)((ent[e] & 0xffu) - 1u);
-                ++pos;
-            }
+        for (int e = 0; e < STR_EPT; ++e) {  // the ring keeps the class (= bracket + 1) of a candidate
+            const unsigned i = pos & (unsigned)(STR_RING - 1);
+            if constexpr (sizeof(Key) == 8) sts_key64_if(cflag[e], mykey_a + i * 8u, (unsigned long long)k[e], mybrk_a + i, ent[e]);
+            else sts_key32_if(cflag[e], mykey_a + i * 4u, (unsigned)k[e], mybrk_a + i, ent[e]);
+            pos += cflag[e];
         }
+        wpend += total;
         __syncwarp();
-        for (unsigned i0 = 0; i0 < total; i0 += 32) {
-            const unsigned i = i0 + lane;
-            const bool has = i < total;
-            append(has, has ? mykey[i] : (Key)0, has ? (unsigned)mybrk[i] : 0u);
-        }
-        __syncwarp();
+        if (wpend >= 32u) drain(false);
     };
 
     unsigned tiles_since_spill = 0;
@@ -977,6 +1001,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             tile = next2;
         }
     }
+    drain(true);
     spill_counters();
     // ---- ragged head and tail: the last CTA, element by element ---------------------------------------
     if (blockIdx.x == gridDim.x - 1) {
@@ -991,8 +1016,12 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             if (have) {
                 const unsigned long long idx = i < head ? i : tail0 + (i - head);
                 k = Tr::to_key(data[idx]);
-                ent = lookup(k);
-                if (ent & (ENT_MIXED | ENT_SPECIAL)) ent = settle(k, ent);
+                if (key_is_nan<T>(k)) {
+                    ent = (unsigned)BRK_INVALID_CLS;
+                } else {
+                    ent = lookup(k);
+                    if (ent & ENT_MIXED) ent = brk_resolve_entry<Key>(k, ent, blo, bhi, btie, B);
+                }
                 myctr[(ent & 0xffu) * STR_THREADS] += 1;
             }
             append(have && (ent & ENT_COMPACT), k, ((ent & 0xffu) - 1u) & 0xffu);

@@ -638,13 +638,13 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
     for (int c = tid; c < BRK_NC1; c += nthreads) {
         unsigned e1;
         if (c == BRK_NC1 - 1 || (Key)c > max_cell) {
-            e1 = (unsigned)(2 * B);  // beyond the last bracket (or beyond the key space): pure "above"
+            e1 = (unsigned)B;  // beyond the last bracket (or beyond the key space): pure "above"
         } else {
             Key a, e;
             cell_ends(c, a, e);
             PointClass<Key> pa;
             if (range_kind(a, e, pa) == 0) {
-                e1 = (unsigned)(2 * pa.j + (pa.in ? 1 : 0));
+                e1 = pure_entry(pa.j, pa.in, btie);  // a pure cell: the final entry, no second table read
             } else {
                 const int slot = atomicAdd(&sNmixed, 1);
                 mixcell[slot] = (unsigned short)c;
@@ -814,22 +814,28 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     // Two table reads per key, no side effects.  Keys below the table origin are clamped onto it: the origin lies a
     // whole cell below the first bracket (brk_plan_kernel), so they read a "below every bracket" entry; keys past the
     // last bracket fall into cells that are pure "above" (the last cell takes everything beyond the table).
+    const unsigned lut2_a = sm_addr(lut2);
+    // second table read only for the lanes whose cell is subdivided (e1 < 0): a predicated load, so that the others do
+    // not take part in its bank conflicts
+    auto second = [&](unsigned e1, unsigned sub) -> unsigned {
+        unsigned ent;
+        const unsigned a = lut2_a + 2u * ((e1 & 0x7fffffffu) + (sub & submask));
+        asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, 0;\n\tmov.u32 %0, %1;\n\t@p ld.shared.u16 %0, [%2];\n\t}"
+            : "=r"(ent) : "r"(e1), "r"(a));
+        return ent;
+    };
     auto lookup = [&](Key k) -> unsigned {
         if constexpr (HI32) {
             const unsigned hk = (unsigned)(k >> 32), h0 = (unsigned)(kmin >> 32);
             const unsigned d = umax(hk, h0) - h0;
             const unsigned cc = d >> (shift1 - 32);
             const unsigned cell = cc < (unsigned)(BRK_NC1 - 1) ? cc : (unsigned)(BRK_NC1 - 1);
-            const unsigned e1 = lut1[cell];
-            const unsigned sub = (d >> (subshift - 32)) & submask & (unsigned)((int)e1 >> 31);
-            return lut2[(e1 & 0x7fffffffu) + sub];
+            return second(lut1[cell], d >> (subshift - 32));
         } else {
             const Key d = (k > kmin ? k : kmin) - kmin;
             const Key cc = d >> shift1;
             const unsigned cell = (unsigned)(cc < (Key)(BRK_NC1 - 1) ? cc : (Key)(BRK_NC1 - 1));
-            const unsigned e1 = lut1[cell];
-            const unsigned sub = (unsigned)(d >> subshift) & submask & (unsigned)((int)e1 >> 31);
-            return lut2[(e1 & 0x7fffffffu) + sub];
+            return second(lut1[cell], (unsigned)(d >> subshift));
         }
     };
     // One group of up to 32 candidates: lane i appends `k` to this CTA's piece of bracket `b` (if `has`).  Lanes with

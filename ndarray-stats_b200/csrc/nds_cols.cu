@@ -58,6 +58,10 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
     constexpr bool IS_FLOAT = Tr::is_float;
     constexpr bool TOP_INVERTED = IS_FLOAT || std::is_signed<T>::value;
     constexpr int EXP_LO = (ES == 4) ? 7 : 4;  // exponent bits of the top 16-bit field are [EXP_LO, 14]
+    // floats: two more plane words per 32-row block, made while the block is still in registers -- rows whose top 16 bits
+    // say NaN (all-ones exponent, a high mantissa bit), and rows that are inf or a NaN with a low payload (decided by
+    // looking at the element again).  The walk then needs two shared-memory reads per block for its skipnan masks.
+    constexpr int NPL = IS_FLOAT ? 18 : 16;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *planes = reinterpret_cast<uint32_t *>(smem_raw);
@@ -67,7 +71,7 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
     const unsigned nrb = (n + 31u) / 32u;             // 32-row blocks per lane
     const unsigned nrbp = (nrb + 31u) / 32u * 32u;    // padded to a multiple of 32 (<= 256)
     const unsigned kw = nrbp / 32u;                   // plane words per thread in the walk
-    const unsigned col_pitch = 16u * nrbp + 4u;       // +4: the 8 lanes of a strip hit different banks
+    const unsigned col_pitch = (unsigned)NPL * nrbp + 4u;  // +4: the 8 lanes of a strip hit different banks
     unsigned *clist = reinterpret_cast<unsigned *>(planes + COLS_CW * col_pitch);  // [warp][COLS_CAND]
     Key *ckeys = reinterpret_cast<Key *>(clist + COLS_CW * COLS_CAND);             // [warp][COLS_CAND]
     // [COLS_STAGES][COLS_STAGE_WORDS], 16-byte aligned; derived from smem_raw by an OFFSET so that the compiler keeps
@@ -126,6 +130,17 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
         issue_tile();
         issue_tile();
     }
+    auto store_nan_planes = [&](const uint32_t (&w)[16], uint32_t *dst) {  // dst = this block's word of plane 0
+        if constexpr (IS_FLOAT) {
+            uint32_t e = 0xffffffffu, mhi = 0;
+#pragma unroll
+            for (int b = EXP_LO; b <= 14; ++b) e &= w[b];
+#pragma unroll
+            for (int b = 0; b < EXP_LO; ++b) mhi |= w[b];
+            dst[16 * nrbp] = e & mhi;
+            dst[17 * nrbp] = e & ~mhi;
+        }
+    };
     unsigned long long iter = 0;
     for (unsigned long long strip = blockIdx.x; strip < n_strips; strip += gridDim.x, ++iter) {
         const unsigned long long grp = strip / strips_per_group;
@@ -157,6 +172,7 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                     transpose16(w);
 #pragma unroll
                     for (int b = 0; b < 16; ++b) pdst[b * nrbp + rb] = w[b];
+                    store_nan_planes(w, pdst + rb);
                 }
             }
         } else {
@@ -181,6 +197,7 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                 transpose16(w);
 #pragma unroll
                 for (int b = 0; b < 16; ++b) pdst[b * nrbp + rb] = w[b];
+                store_nan_planes(w, pdst + rb);
             }
         }
         __syncthreads();
@@ -206,23 +223,16 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                         for (int p = 0; p < 32; ++p)
                             if (base + (unsigned)slot_of_pos(p) < n) v |= 1u << p;
                     if (IS_FLOAT && v) {
-                        uint32_t e = v, mhi = 0;
-#pragma unroll
-                        for (int b = EXP_LO; b <= 14; ++b) e &= pl[b * nrbp + 32 * k];
-                        if (e) {
-#pragma unroll
-                            for (int b = 0; b < EXP_LO; ++b) mhi |= pl[b * nrbp + 32 * k];
-                            uint32_t nanm = e & mhi;        // all-ones exponent and a high mantissa bit: NaN
-                            uint32_t amb = e & ~mhi;        // inf, or a NaN whose payload sits in the low bits
-                            while (amb) {
-                                int p = __ffs(amb) - 1;
-                                amb &= amb - 1;
-                                T xv = lp[(long long)(base + slot_of_pos(p)) * pitch];
-                                if (xv != xv) nanm |= 1u << p;
-                            }
-                            v &= ~nanm;
-                            my_nan += __popc(nanm);
+                        uint32_t nanm = pl[16 * nrbp + 32 * k] & v;   // NaN by the top 16 bits
+                        uint32_t amb = pl[17 * nrbp + 32 * k] & v;    // inf, or a NaN whose payload sits in the low bits
+                        while (amb) {
+                            int p = __ffs(amb) - 1;
+                            amb &= amb - 1;
+                            T xv = lp[(long long)(base + slot_of_pos(p)) * pitch];
+                            if (xv != xv) nanm |= 1u << p;
                         }
+                        v &= ~nanm;
+                        my_nan += __popc(nanm);
                     }
                 }
                 init[k] = v;
@@ -359,41 +369,40 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                                     myraw[c] = to_raw<T>(xv);
                                     mykey[c] = Tr::to_key(xv);
                                 }
-                                mykeys[idx] = mykey[c];
                             }
-                            __syncwarp();
-                            unsigned less[CPT];
+                            // The candidates share the key bits the walk has consumed; the remaining bits are walked on
+                            // the registers (one ballot per candidate slot and bit) until one key is left -- a handful of
+                            // bits for distinct keys.  Equal keys are the same element value, any of them will do.
+                            auto fetch_rank = [&](unsigned want) -> Raw {
+                                bool alive[CPT];
 #pragma unroll
-                            for (int c = 0; c < CPT; ++c) less[c] = 0;
-                            const unsigned jmax = (total + 31u) & ~31u;
+                                for (int c = 0; c < CPT; ++c) alive[c] = (unsigned)lane + 32u * c < total;
+                                unsigned tot2 = total, rem2 = want;
 #pragma unroll 1
-                            for (unsigned j0 = 0; j0 < jmax; j0 += 32) {
-#pragma unroll
-                                for (unsigned jj = 0; jj < 32; ++jj) {
-                                    const unsigned j = j0 + jj;
-                                    const Key kj = mykeys[j];
+                                for (int b = KEYBITS - 1 - bits_done; b >= 0 && tot2 > 1u; --b) {
+                                    bool one[CPT];
+                                    unsigned ones = 0;
 #pragma unroll
                                     for (int c = 0; c < CPT; ++c) {
-                                        if (32u * c >= jmax) continue;
-                                        const unsigned idx = (unsigned)lane + 32u * c;
-                                        less[c] += (kj < mykey[c] || (kj == mykey[c] && j < idx)) ? 1u : 0u;
+                                        one[c] = ((mykey[c] >> b) & (Key)1) != 0;
+                                        ones += __popc(__ballot_sync(FULLMASK, alive[c] && one[c]));
                                     }
-                                }
-                            }
-                            __syncwarp();
-                            // the candidate of rank `want` lives in exactly one (thread, slot)
-                            auto fetch_rank = [&](unsigned want) -> Raw {
-                                Raw v = 0;
-                                int src = -1;
+                                    const unsigned zeros = tot2 - ones;
+                                    const bool take0 = rem2 < zeros;
+                                    tot2 = take0 ? zeros : ones;
+                                    rem2 = take0 ? rem2 : rem2 - zeros;
 #pragma unroll
-                                for (int c = 0; c < CPT; ++c) {
-                                    const unsigned idx = (unsigned)lane + 32u * c;
-                                    if (idx < total && less[c] == want) {
-                                        v = myraw[c];
-                                        src = lane;
-                                    }
+                                    for (int c = 0; c < CPT; ++c) alive[c] = alive[c] && (one[c] != take0);
                                 }
-                                const unsigned hit = __ballot_sync(FULLMASK, src >= 0);
+                                Raw v = 0;
+                                bool mine = false;
+#pragma unroll
+                                for (int c = 0; c < CPT; ++c)
+                                    if (alive[c] && !mine) {
+                                        v = myraw[c];
+                                        mine = true;
+                                    }
+                                const unsigned hit = __ballot_sync(FULLMASK, mine);
                                 return __shfl_sync(FULLMASK, v, __ffs(hit) - 1);
                             };
                             found = fetch_rank(rem);
@@ -480,7 +489,8 @@ ColsPlan plan_cols(const nds_ctx *ctx, const DeviceCall &c) {
     if (g.axis_len < 64 || g.axis_len > 8192) return p;             // 8 lanes x 16 planes x n/32 words of smem
     if (g.axis_stride < (long long)g.oshape[last]) return p;        // rows must not overlap
     const unsigned nrb = (unsigned)((g.axis_len + 31) / 32), nrbp = (nrb + 31) / 32 * 32;
-    auto smem_for = [&](int cw) { return (size_t)cw * (16 * nrbp + 4) * 4 + (size_t)cw * COLS_CAND * 4 + (size_t)cw * COLS_CAND * 8 + 64; };
+    const unsigned npl = (c.dtype == NDS_F32 || c.dtype == NDS_F64) ? 18 : 16;  // floats: + the two NaN planes
+    auto smem_for = [&](int cw) { return (size_t)cw * (npl * nrbp + 4) * 4 + (size_t)cw * COLS_CAND * 4 + (size_t)cw * COLS_CAND * 8 + 64; };
     auto strips_for = [&](int cw) {
         const unsigned long long spg = (g.oshape[last] + cw - 1) / cw;
         p.strips_per_group = (unsigned)spg;

@@ -187,12 +187,18 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
             c_parity ^= 1u << c_stage;
             c_stage = (c_stage + 1 == S) ? 0 : c_stage + 1;
             uint4 q[LD_PER_BLK];
+            if (nchunks_blk == BLK_BYTES / 16) {  // a full block (warp-uniform): no index clamping
 #pragma unroll
-            for (int j = 0; j < LD_PER_BLK; ++j) {
-                // chunks past the end of the lane are clamped onto the last one: their positions are
-                // masked out by vm, so any in-bounds value will do and no predicate is needed
-                const unsigned chunk = min((unsigned)(j * 32 + lane), nchunks_blk - 1);
-                q[j] = *reinterpret_cast<const uint4 *>(src + (size_t)chunk * 16);
+                for (int j = 0; j < LD_PER_BLK; ++j)
+                    q[j] = *reinterpret_cast<const uint4 *>(src + (size_t)(j * 32 + lane) * 16);
+            } else {
+#pragma unroll
+                for (int j = 0; j < LD_PER_BLK; ++j) {
+                    // chunks past the end of the lane are clamped onto the last one: their positions are
+                    // masked out by vm, so any in-bounds value will do and no predicate is needed
+                    const unsigned chunk = min((unsigned)(j * 32 + lane), nchunks_blk - 1);
+                    q[j] = *reinterpret_cast<const uint4 *>(src + (size_t)chunk * 16);
+                }
             }
             __syncwarp();
             produce();  // this stage is free again: fetch the block S positions ahead

@@ -118,6 +118,8 @@ template <typename Key> struct BrkBuf {
     Key *cand[2];
     unsigned long long cand_cap[2];
     unsigned s1cap, nw_cap;
+    unsigned str_rot;                // streaming pass: rotation of the tile assignment per round (tuning knob NDS_STR_ROT, default 0)
+    unsigned str_mode;               // tuning knob NDS_STR_MODE: bit 0 = streaming (evict-first) loads, bits 4.. = L2 prefetch distance in rounds
 };
 
 __device__ __forceinline__ unsigned long long ld_now(const unsigned long long *p) {
@@ -776,6 +778,10 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const BrkLutConst<Key> lc = *buf.lutc;
     if ((lc.hi32 != 0) != HI32) return;
+#ifdef NDS_STR_TIMING  // diagnostic build (make strvar TIMING=1): per-CTA cycle counts of the streaming pass
+    const long long t_begin = clock64();
+    long long t_loop = 0;
+#endif
     const int B = lc.B;
     const Key kmin = lc.kmin;
     const int shift1 = lc.shift1, subshift = lc.subshift;
@@ -896,10 +902,23 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     const T *adata = data + head;
     const uint4 *vdata = reinterpret_cast<const uint4 *>(adata);
 
+    const bool ld_cs = (buf.str_mode & 1u) != 0;
+    const unsigned pf_dist = buf.str_mode >> 4;
     auto load_tile = [&](unsigned long long tile, uint4 (&q)[NLD]) {
         const uint4 *src = vdata + tile * (STR_TILE / VEC);
+        if (ld_cs) {
 #pragma unroll
-        for (int j = 0; j < NLD; ++j) q[j] = __ldg(src + j * STR_THREADS + tid);
+            for (int j = 0; j < NLD; ++j) q[j] = __ldcs(src + j * STR_THREADS + tid);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NLD; ++j) q[j] = __ldg(src + j * STR_THREADS + tid);
+        }
+        if (pf_dist && tid == 0) {  // one thread asks L2 for the tile this CTA reads pf_dist rounds later
+            const unsigned long long pt = tile + (unsigned long long)pf_dist * gridDim.x;
+            if (pt < n_tiles)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vdata + pt * (STR_TILE / VEC)), "r"((unsigned)(STR_TILE * ES))
+                             : "memory");
+        }
     };
     auto process_tile = [&](const uint4 (&q)[NLD]) {
         Key k[STR_EPT];
@@ -982,31 +1001,50 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         if (wpend >= 32u) drain(false);
     };
 
+    // Round r deals the tiles r * G .. r * G + G - 1 to the G CTAs, CTA i taking tile r * G + (i + r) mod G.  The rotation
+    // matters: with a fixed offset every CTA would walk the lane with a stride of G tiles (148 x 32 KB), which keeps all
+    // of its loads on the same residue of the memory interleave -- some SMs then finish a third later than others.
     unsigned tiles_since_spill = 0;
     {
         uint4 qa[NLD], qb[NLD];
-        unsigned long long tile = blockIdx.x;
-        if (tile < n_tiles) load_tile(tile, qa);
-        while (tile < n_tiles) {
-            const unsigned long long next = tile + gridDim.x;
-            if (next < n_tiles) load_tile(next, qb);
-            process_tile(qa);
+        const unsigned G = gridDim.x;
+        unsigned long long base = 0;   // first tile of the round
+        unsigned rot = blockIdx.x;     // this CTA's tile inside the round
+        const unsigned rstep = buf.str_rot % G;
+        auto next_round = [&]() {
+            base += G;
+            rot += rstep;
+            rot = rot >= G ? rot - G : rot;
+        };
+        auto after_tile = [&]() {
             if (++tiles_since_spill >= STR_SPILL_TILES) {
                 spill_counters();
                 tiles_since_spill = 0;
             }
-            tile = next;
-            if (tile >= n_tiles) break;
-            const unsigned long long next2 = tile + gridDim.x;
-            if (next2 < n_tiles) load_tile(next2, qa);
-            process_tile(qb);
-            if (++tiles_since_spill >= STR_SPILL_TILES) {
-                spill_counters();
-                tiles_since_spill = 0;
+        };
+        bool have_a = base + rot < n_tiles, have_b = false;  // (only the last round can miss a tile)
+        if (have_a) load_tile(base + rot, qa);
+        while (base < n_tiles) {
+            next_round();
+            have_b = base + rot < n_tiles;
+            if (have_b) load_tile(base + rot, qb);
+            if (have_a) {
+                process_tile(qa);
+                after_tile();
             }
-            tile = next2;
+            if (base >= n_tiles) break;
+            next_round();
+            have_a = base + rot < n_tiles;
+            if (have_a) load_tile(base + rot, qa);
+            if (have_b) {
+                process_tile(qb);
+                after_tile();
+            }
         }
     }
+#ifdef NDS_STR_TIMING
+    t_loop = clock64();
+#endif
     drain(true);
     spill_counters();
     // ---- ragged head and tail: the last CTA, element by element ---------------------------------------
@@ -1047,6 +1085,13 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         buf.fill[(size_t)b * nw + blockIdx.x] = f;
         if (f) atomicAdd(&buf.cur_local[b], (unsigned long long)f);
     }
+#ifdef NDS_STR_TIMING
+    if (tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        printf("strtime cta %d sm %u loop %lld total %lld\n", (int)blockIdx.x, smid, t_loop - t_begin, clock64() - t_begin);
+    }
+#endif
 }
 
 // in-counts of the non-tie brackets are their segment fills
@@ -2059,6 +2104,12 @@ template <typename Key> BrkBuf<Key> brk_carve(void *scratch, const BrkSizes &z, 
     b.loc_refine = (unsigned long long *)take((size_t)BRK_MAXSEG * 256 * 8);
     b.fill = (unsigned *)take((size_t)BRK_MAXB * 148 * STR_WARPS * 4);
     b.nw_cap = 148 * STR_WARPS;
+    {
+        static const unsigned rot = getenv("NDS_STR_ROT") ? (unsigned)atoi(getenv("NDS_STR_ROT")) : 0u;
+        static const unsigned mode = getenv("NDS_STR_MODE") ? (unsigned)strtoul(getenv("NDS_STR_MODE"), nullptr, 0) : 0u;
+        b.str_rot = rot;
+        b.str_mode = mode;
+    }
     *zero_bytes = (size_t)(p - (char *)scratch);
     // --- the rest is written before it is read ---
     b.s1 = (Key *)take((size_t)z.s1 * sizeof(Key));

@@ -91,7 +91,7 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
     // issue state: tile iss_t of strip iss_strip goes to stage iss_stage (no divisions on this path)
     unsigned iss_t = 0, iss_stage = 0;
     unsigned long long iss_strip = blockIdx.x;
-    const T *iss_src = nullptr;
+    const T *iss_src = nullptr, *iss_ptr = nullptr;  // strip origin; this thread's first chunk of the tile to issue
     auto issue_tile = [&]() {
         if constexpr (ASYNC) {
             if (iss_strip < n_strips) {
@@ -104,19 +104,26 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                 }
                 uint32_t *st = stage_base + (size_t)iss_stage * COLS_STAGE_WORDS;
                 // chunk q = j * 256 + tid of the tile: row q >> 1, first / second four lanes q & 1.  j moves the row by 128
-                // = four 32-row blocks, so source and destination advance by constants
+                // = four 32-row blocks, so source and destination advance by constants (one 64-bit add per chunk; the
+                // row * pitch products are formed once per strip)
                 constexpr unsigned CPR = COLS_CW * 4 / 16;            // 16-byte chunks per row (2 or 1)
                 constexpr unsigned RSTEP = COLS_THREADS / CPR;         // rows between a thread's chunks: 128
                 static_assert(RSTEP == 128, "a thread's chunks are four 32-row blocks apart");
                 const unsigned rl0 = (unsigned)tid / CPR, half = (unsigned)tid % CPR;
+                if (iss_t == 0) iss_ptr = iss_src + (long long)rl0 * pitch + half * 4;
                 const unsigned row0 = iss_t * COLS_TILE_ROWS + rl0;
-                const T *src = iss_src + (long long)row0 * pitch + half * 4;
                 uint32_t *dst = st + (rl0 >> 5) * COLS_RB_WORDS + (rl0 & 31u) * COLS_CW + half * 4;
                 const long long src_step = (long long)RSTEP * pitch;
+                const T *s = iss_ptr;
+                if ((iss_t + 1u) * COLS_TILE_ROWS <= n) {  // a whole tile (uniform): no row checks
 #pragma unroll
-                for (int j = 0; j < COLS_TILE_ROWS / (int)RSTEP; ++j) {  // 8 chunks of 16 bytes per thread
-                    if (row0 + (unsigned)j * RSTEP < n) cp_async16(dst + j * 4 * COLS_RB_WORDS, src + j * src_step);
+                    for (int j = 0; j < COLS_TILE_ROWS / (int)RSTEP; ++j, s += src_step) cp_async16(dst + j * 4 * COLS_RB_WORDS, s);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < COLS_TILE_ROWS / (int)RSTEP; ++j, s += src_step)  // 8 chunks of 16 bytes per thread
+                        if (row0 + (unsigned)j * RSTEP < n) cp_async16(dst + j * 4 * COLS_RB_WORDS, s);
                 }
+                iss_ptr = s;  // first chunk of the next tile
                 if (++iss_t == tiles) {
                     iss_t = 0;
                     iss_strip += gridDim.x;

@@ -169,7 +169,8 @@ def cpu_reference_run(name, threads, budget_s, shape_lanes=None):
         nl = shape_lanes or max(threads * 64, 512)
         sample_shape = (nl, lane_len) if axis == 1 else (lane_len, nl)
     else:
-        sample_shape = (min(shape[0], 1 << 24),)
+        # c5: the faithful quickselect is quadratic on equal runs; 2^16 keys keep the sample to seconds
+        sample_shape = (min(shape[0], 1 << 16 if name == "c5" else 1 << 24),)
     if dt.kind == "f":
         a = rng.random(sample_shape, dtype=dt.type if dt == np.float32 else np.float64).astype(dt, copy=False)
         if name == "c3":
@@ -187,6 +188,8 @@ def cpu_reference_run(name, threads, budget_s, shape_lanes=None):
         assert st == 0, f"oracle status {st}"
     sec = t_total / reps
     sample = f"{'x'.join(map(str, sample_shape))} {dtype} of the {name} workload, {reps} repetitions, {threads} thread(s)"
+    if name == "c5":
+        sample += "; the reference quickselect is quadratic on equal runs: 2^24 keys of this workload ran at 3.97e4 elems/s (round 1)"
     return elems * dt.itemsize / sec / 1e9, elems / sec, sample, t_total
 
 

@@ -65,7 +65,7 @@ constexpr unsigned ENT_COMPACT = 0x100u, ENT_MIXED = 0x200u;
 
 enum : int {
     H_NTOTAL = 0, H_NINVALID, H_NEFF, H_FAIL, H_B, H_NSEG, H_NTASK, H_NACTIVE, H_S1VALID, H_EMPTY, H_NCHUNK_COUNT,
-    H_NCHUNK_COMPACT, H_NCLS_USED, H_NTIE, H_CUR, H_NEXT_NCHUNK, H_NEXT_NSEG, H_OLD_NSEG, H_NW, H_ROUND, H_DID, H_FINALCAP, H_NFINAL, H_MULTI, H_LOCALFAIL, H_WORDS = 30
+    H_NCHUNK_COMPACT, H_NCLS_USED, H_NTIE, H_CUR, H_NEXT_NCHUNK, H_NEXT_NSEG, H_OLD_NSEG, H_NW, H_ROUND, H_DID, H_FINALCAP, H_NFINAL, H_MULTI, H_LOCALFAIL, H_PSTRIDE, H_WORDS = 30
 };
 enum : int { FAIL_ESCAPED = 1, FAIL_CAPACITY = 2, FAIL_TOO_MANY = 4, FAIL_INCONSISTENT = 8, FAIL_REMOTE = 16 };
 enum : int { TASK_ACTIVE = 0, TASK_DONE = 1 };
@@ -76,6 +76,7 @@ template <typename Key> struct BrkSeg {
     int shift, flags;
     unsigned long long off, cnt_local, cnt_global, cursor;
     unsigned long long piece_cap;  // round 0: the segment is H_NW pieces of this capacity (one per streaming CTA), fills in buf.fill
+    unsigned long long piece_stride;  // round 0: distance between the pieces of consecutive CTAs (all pieces of ONE CTA are contiguous)
 };
 struct BrkTask {
     unsigned long long r;      // rank inside its segment (over all ranks when sharded)
@@ -118,8 +119,6 @@ template <typename Key> struct BrkBuf {
     Key *cand[2];
     unsigned long long cand_cap[2];
     unsigned s1cap, nw_cap;
-    unsigned str_rot;                // streaming pass: rotation of the tile assignment per round (tuning knob NDS_STR_ROT, default 0)
-    unsigned str_mode;               // tuning knob NDS_STR_MODE: bit 0 = streaming (evict-first) loads, bits 4.. = L2 prefetch distance in rounds
 };
 
 __device__ __forceinline__ unsigned long long ld_now(const unsigned long long *p) {
@@ -597,13 +596,17 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
         }
         __syncthreads();
         if (tid == 0) {
+            // CTA-major layout: the pieces of ONE streaming CTA (one per bracket) are contiguous, so that a CTA appends
+            // into a handful of 2 MB pages instead of one page per bracket (the scattered stores of 148 CTAs x ~100
+            // brackets thrash the TLBs: measured as 40 SMs running 15 % behind the others)
             unsigned long long off = 0;
             for (int b = 0; b < B; ++b) {
-                buf.boff[b] = off;
+                buf.boff[b] = off;              // offset of the bracket's piece inside a CTA's block
                 buf.bcap[b] = scap[b];          // capacity of ONE piece
-                off += scap[b] * (unsigned long long)nw;
+                off += scap[b];
             }
-            if (off > buf.cand_cap[0]) raise_fail(buf.hdr, FAIL_CAPACITY);
+            buf.hdr[H_PSTRIDE] = off;           // block of one CTA
+            if (off * (unsigned long long)nw > buf.cand_cap[0]) raise_fail(buf.hdr, FAIL_CAPACITY);
         }
     }
     const Key kmin = sKminLut;  // origin of the cells
@@ -797,7 +800,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         btie[i] = i < B ? buf.btie[i] : (unsigned char)0xff;
         const unsigned cap = i < B ? (unsigned)buf.bcap[i] : 0u;
         StrPiece pc;
-        pc.base = i < B ? buf.boff[i] + (unsigned long long)blockIdx.x * cap : 0ull;
+        pc.base = i < B ? buf.boff[i] + (unsigned long long)blockIdx.x * buf.hdr[H_PSTRIDE] : 0ull;
         pc.cap = cap;
         pc.pad = 0;
         piece[i] = pc;
@@ -902,23 +905,10 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     const T *adata = data + head;
     const uint4 *vdata = reinterpret_cast<const uint4 *>(adata);
 
-    const bool ld_cs = (buf.str_mode & 1u) != 0;
-    const unsigned pf_dist = buf.str_mode >> 4;
     auto load_tile = [&](unsigned long long tile, uint4 (&q)[NLD]) {
         const uint4 *src = vdata + tile * (STR_TILE / VEC);
-        if (ld_cs) {
 #pragma unroll
-            for (int j = 0; j < NLD; ++j) q[j] = __ldcs(src + j * STR_THREADS + tid);
-        } else {
-#pragma unroll
-            for (int j = 0; j < NLD; ++j) q[j] = __ldg(src + j * STR_THREADS + tid);
-        }
-        if (pf_dist && tid == 0) {  // one thread asks L2 for the tile this CTA reads pf_dist rounds later
-            const unsigned long long pt = tile + (unsigned long long)pf_dist * gridDim.x;
-            if (pt < n_tiles)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vdata + pt * (STR_TILE / VEC)), "r"((unsigned)(STR_TILE * ES))
-                             : "memory");
-        }
+        for (int j = 0; j < NLD; ++j) q[j] = __ldg(src + j * STR_THREADS + tid);
     };
     auto process_tile = [&](const uint4 (&q)[NLD]) {
         Key k[STR_EPT];
@@ -1001,45 +991,31 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         if (wpend >= 32u) drain(false);
     };
 
-    // Round r deals the tiles r * G .. r * G + G - 1 to the G CTAs, CTA i taking tile r * G + (i + r) mod G.  The rotation
-    // matters: with a fixed offset every CTA would walk the lane with a stride of G tiles (148 x 32 KB), which keeps all
-    // of its loads on the same residue of the memory interleave -- some SMs then finish a third later than others.
+    // (Measured and dropped: rotating the tile assignment per round, evict-first loads, L2 bulk prefetch two to eight
+    // rounds ahead -- none of them moves the pass; what did was the CTA-major layout of the candidate pieces.)
     unsigned tiles_since_spill = 0;
     {
         uint4 qa[NLD], qb[NLD];
-        const unsigned G = gridDim.x;
-        unsigned long long base = 0;   // first tile of the round
-        unsigned rot = blockIdx.x;     // this CTA's tile inside the round
-        const unsigned rstep = buf.str_rot % G;
-        auto next_round = [&]() {
-            base += G;
-            rot += rstep;
-            rot = rot >= G ? rot - G : rot;
-        };
-        auto after_tile = [&]() {
+        unsigned long long tile = blockIdx.x;
+        if (tile < n_tiles) load_tile(tile, qa);
+        while (tile < n_tiles) {
+            const unsigned long long next = tile + gridDim.x;
+            if (next < n_tiles) load_tile(next, qb);
+            process_tile(qa);
             if (++tiles_since_spill >= STR_SPILL_TILES) {
                 spill_counters();
                 tiles_since_spill = 0;
             }
-        };
-        bool have_a = base + rot < n_tiles, have_b = false;  // (only the last round can miss a tile)
-        if (have_a) load_tile(base + rot, qa);
-        while (base < n_tiles) {
-            next_round();
-            have_b = base + rot < n_tiles;
-            if (have_b) load_tile(base + rot, qb);
-            if (have_a) {
-                process_tile(qa);
-                after_tile();
+            tile = next;
+            if (tile >= n_tiles) break;
+            const unsigned long long next2 = tile + gridDim.x;
+            if (next2 < n_tiles) load_tile(next2, qa);
+            process_tile(qb);
+            if (++tiles_since_spill >= STR_SPILL_TILES) {
+                spill_counters();
+                tiles_since_spill = 0;
             }
-            if (base >= n_tiles) break;
-            next_round();
-            have_a = base + rot < n_tiles;
-            if (have_a) load_tile(base + rot, qa);
-            if (have_b) {
-                process_tile(qb);
-                after_tile();
-            }
+            tile = next2;
         }
     }
 #ifdef NDS_STR_TIMING
@@ -1235,6 +1211,7 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
         if (seg_used[b]) s.flags |= SEG_USED;
         s.off = buf.boff[b];
         s.piece_cap = buf.bcap[b];
+        s.piece_stride = buf.hdr[H_PSTRIDE];
         s.cnt_local = (s.flags & SEG_TIE) ? 0 : buf.cur_local[b];  // sum over this GPU's pieces
         s.cnt_global = incnt[b];
         s.cursor = 0;
@@ -1460,7 +1437,7 @@ __global__ void __launch_bounds__(BRK_THREADS, 2) brk_refine_round0_kernel(BrkBu
         auto load = [&](unsigned w, unsigned e0, Key (&k)[KPT]) -> unsigned {
             constexpr int VEC = 16 / (int)sizeof(Key);
             const unsigned cnt = sfill[w] - e0 < (unsigned)BRK_RCHUNK ? sfill[w] - e0 : (unsigned)BRK_RCHUNK;
-            const Key *ptr = src + (unsigned long long)w * sg.piece_cap + e0;  // 16-byte aligned
+            const Key *ptr = src + (unsigned long long)w * sg.piece_stride + e0;  // 16-byte aligned
             unsigned valid = 0;
 #pragma unroll
             for (int j = 0; j < KPT / VEC; ++j) {
@@ -1698,6 +1675,7 @@ __global__ void __launch_bounds__(1024) brk_refine_decide_kernel(BrkBuf<Key> buf
             ns.cnt_global = buf.red_refine[(size_t)w];
             ns.cursor = 0;
             ns.piece_cap = 0;
+            ns.piece_stride = 0;
             if (ns.cnt_global <= buf.hdr[H_FINALCAP]) ns.flags |= SEG_FINAL;
             if (off + pad_cnt[t] > buf.cand_cap[cur ^ 1]) raise_fail(buf.hdr, FAIL_CAPACITY);
             nsegs[id] = ns;
@@ -1873,7 +1851,7 @@ __global__ void __launch_bounds__(1024) brk_pack_final_kernel(BrkBuf<Key> buf) {
                 for (unsigned u = lane; u < w; u += 32) before += fills[u];
                 before = __reduce_add_sync(0xffffffffu, before);
                 const unsigned f = fills[w];
-                const Key *piece = src + (unsigned long long)w * sg.piece_cap;
+                const Key *piece = src + (unsigned long long)w * sg.piece_stride;
                 for (unsigned i = lane; i < f; i += 32)
                     if (before + i < c) keys_out[off[sidx] + before + i] = piece[i];
             }
@@ -1956,7 +1934,7 @@ __global__ void __launch_bounds__(256) brk_final_kernel(BrkBuf<Key> buf, int nra
                 unsigned base = 0;
                 if (lane == 0) base = (unsigned)atomicAdd(&s_any, (int)f);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                const Key *piece = src + (unsigned long long)w * sg.piece_cap;
+                const Key *piece = src + (unsigned long long)w * sg.piece_stride;
                 for (unsigned i = lane; i < f; i += 32)
                     if (base + i < BRK_FINAL_CAP) s[base + i] = piece[i];
             }
@@ -2104,12 +2082,6 @@ template <typename Key> BrkBuf<Key> brk_carve(void *scratch, const BrkSizes &z, 
     b.loc_refine = (unsigned long long *)take((size_t)BRK_MAXSEG * 256 * 8);
     b.fill = (unsigned *)take((size_t)BRK_MAXB * 148 * STR_WARPS * 4);
     b.nw_cap = 148 * STR_WARPS;
-    {
-        static const unsigned rot = getenv("NDS_STR_ROT") ? (unsigned)atoi(getenv("NDS_STR_ROT")) : 0u;
-        static const unsigned mode = getenv("NDS_STR_MODE") ? (unsigned)strtoul(getenv("NDS_STR_MODE"), nullptr, 0) : 0u;
-        b.str_rot = rot;
-        b.str_mode = mode;
-    }
     *zero_bytes = (size_t)(p - (char *)scratch);
     // --- the rest is written before it is read ---
     b.s1 = (Key *)take((size_t)z.s1 * sizeof(Key));

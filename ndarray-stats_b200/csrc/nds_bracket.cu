@@ -8,13 +8,17 @@
 //   2. bucket      count S1 against the sorted S0 (binary search): exact sample ranks of every S0 key
 //   3. plan        per requested quantile pick a value bracket [lo, hi] of S0 keys whose sample-rank span
 //                  is the expected position +- 5 sigma; merge overlapping brackets; build a two-level
-//                  key -> class lookup table (4096 top cells, the cells that hold a bracket edge
-//                  subdivided again) so that one element costs two shared-memory reads to classify
+//                  key -> class lookup table: 4096 top cells starting one cell BELOW the first bracket (keys
+//                  below the origin are clamped onto it and read "below everything"; cells past the last
+//                  bracket are "above everything"); a cell without a bracket edge carries its final entry,
+//                  the cells that hold an edge are subdivided again
 //   4. stream      THE pass over the lane: every element is classified (class = number of bracket lower
-//                  edges <= key), counted in per-thread private 16-bit shared-memory counters (a plain
+//                  edges <= key; one table read, a second, predicated one for the ~12 % of keys in a
+//                  subdivided cell), counted in per-thread private 8-bit shared-memory counters (a plain
 //                  LDS/ADD/STS on a conflict-free layout: shared atomics would cap the pass at 0.5
-//                  element/cycle/SM), and the ~10 % of elements that fall inside a bracket are staged in
-//                  shared memory and appended to that bracket's candidate segment
+//                  element/cycle/SM), and the ~14 % of elements that fall inside a bracket are packed into
+//                  a per-warp ring and appended, 32 at a time, to that bracket's candidate segment (this
+//                  CTA's piece of it; the pieces of one CTA are contiguous)
 //   5. resolve     exact counts below / inside every bracket (summed over ranks with ncclAllReduce when the
 //                  lane is sharded) turn each requested rank into (bracket, rank inside the bracket); a rank
 //                  that escaped its bracket raises FAIL and the caller falls back to the radix passes

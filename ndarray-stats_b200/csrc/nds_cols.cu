@@ -44,7 +44,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <typename T, bool ASYNC, int CW>
 __global__ void __launch_bounds__(CW * 32, CW == 4 ? 2 : 1)
 cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__restrict__ out,
-                     unsigned long long n_strips, unsigned strips_per_group) {
+                     unsigned long long n_strips, unsigned strips_per_group, unsigned pair_sync) {
     constexpr int COLS_CW = CW;                       // lanes per strip = warps per CTA
     constexpr int COLS_THREADS = CW * 32;             // CW lanes x 32 row groups
     constexpr int COLS_RB_WORDS = cols_rb_words(CW);
@@ -150,6 +150,10 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
     };
     unsigned long long iter = 0;
     for (unsigned long long strip = blockIdx.x; strip < n_strips; strip += gridDim.x, ++iter) {
+        // 4-lane strips, launched as clusters of two CTAs that own the two halves of the same 32-byte sectors: the pair
+        // starts every strip together, so that the second request for a sector finds it in L2 (same trip count in both
+        // CTAs: the host sets pair_sync only for an even grid and an even number of strips)
+        if (pair_sync) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
         const unsigned long long grp = strip / strips_per_group;
         const unsigned long long col0 = (strip - grp * strips_per_group) * COLS_CW;
         long long in_off, out_off;
@@ -473,6 +477,7 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
 }
 
 struct ColsPlan {
+    int cw = 8;           // lanes per strip of the staged path (tuning knob NDS_COLS_CW=4: 4-lane strips, two CTAs per SM, paired in clusters)
     bool ok = false;
     unsigned long long n_strips = 0;
     unsigned strips_per_group = 0;
@@ -508,9 +513,12 @@ ColsPlan plan_cols(const nds_ctx *ctx, const DeviceCall &c) {
     bool aligned = es == 4 && g.oshape[last] % COLS_CW_ASYNC == 0 && ((uintptr_t)c.data % 16) == 0 && (g.axis_stride * 4) % 16 == 0;
     for (int d = 0; d < last; ++d)
         if (g.oshape[d] > 1 && (g.in_ostride[d] * 4) % 16 != 0) aligned = false;
-    const size_t smem_async = ((smem_for(COLS_CW_ASYNC) + 15) & ~(size_t)15) + (size_t)COLS_STAGES * cols_stage_words(COLS_CW_ASYNC) * 4 + 16;
+    static const int cw_knob = getenv("NDS_COLS_CW") ? atoi(getenv("NDS_COLS_CW")) : COLS_CW_ASYNC;
+    const int cwa = (cw_knob == 4 && g.oshape[last] % 8 == 0) ? 4 : COLS_CW_ASYNC;
+    const size_t smem_async = ((smem_for(cwa) + 15) & ~(size_t)15) + (size_t)COLS_STAGES * cols_stage_words(cwa) * 4 + 16;
     if (aligned && smem_async <= (size_t)ctx->max_smem_optin && !getenv("NDS_COLS_NO_ASYNC")) {
-        if (!strips_for(COLS_CW_ASYNC)) return p;
+        if (!strips_for(cwa)) return p;
+        p.cw = cwa;
         p.async = true;
         p.smem = smem_async;
         p.ok = true;
@@ -531,13 +539,32 @@ template <typename T, bool ASYNC, int CW> cudaError_t launch_cols_typed2(nds_ctx
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, CW * 32, p.smem);
     if (occ < 1) occ = 1;
     unsigned grid = (unsigned)std::min<unsigned long long>(p.n_strips, (unsigned long long)ctx->sm_count * occ);
-    kernel<<<grid, CW * 32, p.smem, ctx->stream>>>((const T *)c.data, c.geom, c.q, (T *)c.out, p.n_strips, p.strips_per_group);
+    if (ASYNC && CW == 4 && grid >= 2 && p.n_strips % 2 == 0) {  // pairs of CTAs on the two halves of the same sectors
+        grid &= ~1u;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(CW * 32);
+        cfg.dynamicSmemBytes = p.smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kernel, (const T *)c.data, c.geom, c.q, (T *)c.out, p.n_strips, p.strips_per_group, 1u);
+        ctx->launches += 1;
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
+    kernel<<<grid, CW * 32, p.smem, ctx->stream>>>((const T *)c.data, c.geom, c.q, (T *)c.out, p.n_strips, p.strips_per_group, 0u);
     ctx->launches += 1;
     return cudaGetLastError();
 }
 
 template <typename T> cudaError_t launch_cols_typed(nds_ctx *ctx, const DeviceCall &c, const ColsPlan &p) {
     if constexpr (sizeof(T) == 4) {
+        if (p.async && p.cw == 4) return launch_cols_typed2<T, true, 4>(ctx, c, p);
         if (p.async) return launch_cols_typed2<T, true, COLS_CW_ASYNC>(ctx, c, p);
     }
     return launch_cols_typed2<T, false, COLS_CW_SYNC>(ctx, c, p);

@@ -73,7 +73,7 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
     const unsigned kw = nrbp / 32u;                   // plane words per thread in the walk
     const unsigned col_pitch = (unsigned)NPL * nrbp + 4u;  // +4: the 8 lanes of a strip hit different banks
     unsigned *clist = reinterpret_cast<unsigned *>(planes + COLS_CW * col_pitch);  // [warp][COLS_CAND]
-    Key *ckeys = reinterpret_cast<Key *>(clist + COLS_CW * COLS_CAND);             // [warp][COLS_CAND]
+    Key *ckeys = reinterpret_cast<Key *>(clist + COLS_CW * COLS_CAND);             // [warp][COLS_CAND] (spare: the survivors' keys stay in registers)
     // [COLS_STAGES][COLS_STAGE_WORDS], 16-byte aligned; derived from smem_raw by an OFFSET so that the compiler keeps
     // the shared address space (a pointer -> integer -> pointer round trip turns every access into a generic LD/ST)
     const size_t stage_off = ((size_t)(reinterpret_cast<unsigned char *>(ckeys + COLS_CW * COLS_CAND) - smem_raw) + 15) & ~(size_t)15;
@@ -218,7 +218,6 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
             const T *lp = sp + warp;  // element (row, this lane) = lp[row * pitch]
             uint32_t *pl = planes + (size_t)warp * col_pitch + lane;  // word k of plane b: pl[b * nrbp + 32 * k]
             unsigned *mylist = clist + warp * COLS_CAND;
-            Key *mykeys = ckeys + warp * COLS_CAND;
 
             // valid rows and (floats) NaN positions, from the planes of round 0
             uint32_t init[COLS_KMAX];
@@ -366,7 +365,7 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                                 }
                             }
                             __syncwarp();
-                            // up to 4 candidates per thread: fetch (L2), publish keys, rank each against all
+                            // up to COLS_CAND / 32 candidates per thread: fetch them again (L2)
                             constexpr int CPT = COLS_CAND / 32;
                             Raw myraw[CPT];
                             Key mykey[CPT];

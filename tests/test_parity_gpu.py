@@ -3,6 +3,7 @@
 Bars: bit-exact for every order statistic and for Lower/Higher/Nearest/Midpoint (-0.0 folded onto +0.0,
 SURVEY.md note Z); Linear <= 1 ulp (and in fact 0 — asserted as such where noted)."""
 import math
+import os
 import zlib
 
 import numpy as np
@@ -329,6 +330,10 @@ def test_short_bitslice_nan(nds, gpu_ctx, oracle, dtype):
         gpu_ctx.force_path("auto")
 
 
+# NDS_COLS_V2=1 routes the qualifying calls to the experimental pipelined strip kernel (nds_cols.cu); the same cases apply
+COLS_PATHS = ("cols_bitslice", "cols_pipelined") if os.environ.get("NDS_COLS_V2") else ("cols_bitslice",)
+
+
 @pytest.mark.parametrize("dtype", SHORT_DTYPES, ids=lambda d: np.dtype(d).name)
 def test_cols_bitslice_path(nds, gpu_ctx, oracle, dtype):
     """Column lanes (strided axis, contiguous neighbours): the CTA-per-strip kernel, incl. ragged strip
@@ -351,10 +356,10 @@ def test_cols_bitslice_path(nds, gpu_ctx, oracle, dtype):
                 for interp, qs in (("nearest", [0.5]), ("midpoint", [0.5, 0.25]), ("linear", [0.1, 0.9, 0.5]),
                                    ("lower", [0.0, 1.0]), ("higher", [0.33])):
                     check(gpu_ctx, oracle, a, 0, qs, interp, select_impl=1 if kind == "ties" else 0)
-                    assert gpu_ctx.last_path == "cols_bitslice"
+                    assert gpu_ctx.last_path in COLS_PATHS
         b = (rng.standard_normal((3, 500, 40)) * 100).astype(dtype)
         check(gpu_ctx, oracle, b, 1, [0.5, 0.75], "lower")
-        assert gpu_ctx.last_path == "cols_bitslice"
+        assert gpu_ctx.last_path in COLS_PATHS
     finally:
         gpu_ctx.force_path("auto")
 
@@ -378,7 +383,7 @@ def test_cols_bitslice_skipnan(nds, gpu_ctx, oracle, dtype):
         for interp in INTERPS:
             for q in (0.0, 0.5, 0.61, 1.0):
                 check(gpu_ctx, oracle, a, 0, [q], interp, skipnan=True)
-                assert gpu_ctx.last_path == "cols_bitslice"
+                assert gpu_ctx.last_path in COLS_PATHS
         with pytest.raises(nds.NanInInput):
             gpu_ctx.quantiles_axis(a, 0, [0.5], "lower")
     finally:

@@ -162,6 +162,24 @@ nds_status nds_get_many_from_sorted(nds_ctx *ctx, nds_dtype dtype, const void *d
 nds_status nds_minmax(nds_ctx *ctx, nds_dtype dtype, const void *data, int ndim, const size_t *shape,
                       const ptrdiff_t *strides_elems, int want_max, int skipnan, void *out_value, size_t *out_index);
 
+/* ---- synthetic benchmark inputs ---------------------------------------- */
+
+/* Counter-based splitmix64 streams: element i is a function of mix(seed + first_index + i) only, so bench.py's
+ * device-resident inputs and the host arrays of its CPU reference arm hold the same bytes (tests/test_synth.py
+ * restates the streams in numpy).  Not part of the reference's surface: bench / test tooling that ships with the
+ * library so that the inputs are generated at HBM speed. */
+typedef enum nds_synth_kind {
+    NDS_SYNTH_F64_UNIFORM = 0,       /* (z >> 11) * 2^-53 */
+    NDS_SYNTH_F32_UNIFORM = 1,       /* (z >> 40) * 2^-24 */
+    NDS_SYNTH_F32_UNIFORM_NAN10 = 2, /* the same, NaN (0x7FC00000) where mix(0x9E37 + seed + i) % 10 == 0 */
+    NDS_SYNTH_U32_16VALUES = 3,      /* (z & 15) * 0x11111111 */
+    NDS_SYNTH_U32_16VALUES_ADV = 4,  /* 0x80000000 + (z & 15) */
+    NDS_SYNTH_I64_16VALUES = 5       /* ((z & 15) - 8) * 2^40 */
+} nds_synth_kind;
+/* Fills n elements at dst_device (device memory) on the ctx stream; asynchronous. */
+nds_status nds_synth_fill(nds_ctx *ctx, nds_synth_kind kind, void *dst_device, size_t n, uint64_t seed,
+                          uint64_t first_index);
+
 /* ---- one 1-D array sharded over several GPUs (one process per GPU) ------------------------ */
 
 #define NDS_UNIQUE_ID_BYTES 128
@@ -169,13 +187,19 @@ nds_status nds_minmax(nds_ctx *ctx, nds_dtype dtype, const void *data, int ndim,
 nds_status nds_comm_get_unique_id(void *id_out /* NDS_UNIQUE_ID_BYTES */);
 nds_status nds_comm_init_rank(nds_ctx *ctx, int nranks, int rank, const void *id);
 nds_status nds_comm_destroy(nds_ctx *ctx);
+/* How the ranks of this context exchange data in sharded calls, and how much of it has happened so far:
+ * out[0] = 1 when the exchange steps run as our own kernels over peer memory (every rank has mapped every peer's inbox
+ * at nds_comm_init_rank: NVLink / NVSwitch P2P), 0 when they are NCCL collectives; out[1] = exchange steps enqueued so
+ * far; out[2] = host round trips inside sharded calls so far; out[3] = ranks. */
+nds_status nds_comm_stats(nds_ctx *ctx, uint64_t out[4]);
 /*
  * Quantile1dExt::quantiles_mut (src/quantile/mod.rs:623-633) over the concatenation of every rank's
  * shard.  Collective: all ranks call with the same qs / interp / skipnan (1, 2, 4 or 8 ranks take the one-pass
  * bracket select, other counts the radix passes).  Every rank streams its own shard once; what is exchanged on the
- * ctx stream are counts (ncclAllReduce: element count, sample bucket counts, class counts, digit histograms) and a few
- * thousand keys (ncclAllGather: the common splitter sample, the last survivors); the elements of the array never
- * leave their GPU.  Every rank receives the full result in `out` (nq values).
+ * ctx stream are counts (element count, sample bucket counts, class counts, digit histograms) and a few thousand keys
+ * (the common splitter sample, the last survivors) -- written straight into the peers' memory over NVLink by the
+ * library's own kernels when the GPUs can map each other (nds_comm_stats), NCCL collectives otherwise; the elements of
+ * the array never leave their GPU.  Every rank receives the full result in `out` (nq values).
  */
 nds_status nds_quantiles_1d_sharded(nds_ctx *ctx, nds_dtype dtype, const void *local_shard, size_t n_local,
                                     const double *qs, size_t nq, nds_interp interp, int skipnan, void *out,

@@ -370,6 +370,13 @@ class Context:
     def comm_destroy(self):
         self._lib.nds_comm_destroy(self._h)
 
+    def comm_info(self):
+        """``nds_comm_stats``: how sharded calls exchange data between the ranks, and the counters so far."""
+        out = (ctypes.c_uint64 * 4)()
+        self._raise(self._lib.nds_comm_stats(self._h, out))
+        return {"transport": "peer memory (own kernels over NVLink)" if out[0] else ("nccl" if out[3] > 1 else "none (one rank)"),
+                "exchange_steps": int(out[1]), "host_syncs": int(out[2]), "ranks": int(out[3])}
+
     def quantiles_1d_sharded(self, local, qs, interpolate, skipnan=False):
         """``nds_quantiles_1d_sharded``: collective over every rank of the communicator."""
         code, ptr, shape, strides, keep, is_torch = self._describe(local)
@@ -577,3 +584,4 @@ def max_skipnan(a, ctx=None):
 
 
 from .strategies import BinsBuildError, EquiSpaced, FreedmanDiaconis  # noqa: E402,F401  
+from . import synth  # noqa: E402,F401  (synthetic benchmark inputs)

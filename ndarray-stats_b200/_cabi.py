@@ -35,7 +35,9 @@ PROTOTYPES = {
     "nds_comm_get_unique_id": (_int, [_vp]),
     "nds_comm_init_rank": (_int, [_vp, _int, _int, _vp]),
     "nds_comm_destroy": (_int, [_vp]),
+    "nds_comm_stats": (_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "nds_quantiles_1d_sharded": (_int, [_vp, _int, _vp, _sz, _pd, _sz, _int, _int, _vp, _psz]),
+    "nds_synth_fill": (_int, [_vp, _int, _vp, _sz, ctypes.c_uint64, ctypes.c_uint64]),
 }
 
 _lib = None

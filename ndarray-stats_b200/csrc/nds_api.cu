@@ -109,6 +109,7 @@ nds_status parse_call(nds_ctx *ctx, int dtype, int ndim, const size_t *shape, co
 
 nds_status status_from_bits(nds_ctx *ctx, int bits) {
     // STATUS_BIT_FALLBACK is consumed by nds_ctx_synchronize before this is called
+    if (bits & STATUS_BIT_XCHG) return fail(ctx, NDS_NCCL_ERROR, "peer-memory exchange timed out waiting for another rank");
     if (bits & STATUS_BIT_NAN) return fail(ctx, NDS_NAN_IN_INPUT, "NaN in a non-skipnan float input (N32/N64 cannot hold NaN)");
     if (bits & STATUS_BIT_CAST_OVERFLOW)
         return fail(ctx, NDS_CAST_OVERFLOW, "integer Linear interpolation: T::from_f64 out of range (the reference panics)");

@@ -33,7 +33,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "nds_bitslice.cuh"
@@ -56,7 +58,7 @@ constexpr int BRK_MAXTASK = 2 * BRK_MAXQ; // unique ranks
 constexpr int BRK_MAXSEG = 2 * BRK_MAXQ;
 constexpr int BRK_FINAL_CAP = 4096;       // a segment this small is sorted by one CTA
 constexpr int BRK_RCHUNK = 4096;          // refine passes: elements per chunk
-constexpr int BRK_GATHER_CAP = 1 << 15;   // sharded lanes: keys of the small segments one rank may contribute per round
+constexpr int BRK_GATHER_CAP = 1 << 17;   // sharded lanes: keys of the small segments one rank may contribute per round
 constexpr int BRK_MAX_RANKS = 8;
 #ifndef NDS_STR_THREADS
 #define NDS_STR_THREADS 1024
@@ -69,7 +71,11 @@ constexpr unsigned ENT_COMPACT = 0x100u, ENT_MIXED = 0x200u;
 
 enum : int {
     H_NTOTAL = 0, H_NINVALID, H_NEFF, H_FAIL, H_B, H_NSEG, H_NTASK, H_NACTIVE, H_S1VALID, H_EMPTY, H_NCHUNK_COUNT,
-    H_NCHUNK_COMPACT, H_NCLS_USED, H_NTIE, H_CUR, H_NEXT_NCHUNK, H_NEXT_NSEG, H_OLD_NSEG, H_NW, H_ROUND, H_DID, H_FINALCAP, H_NFINAL, H_MULTI, H_LOCALFAIL, H_PSTRIDE, H_WORDS = 30
+    H_NCHUNK_COMPACT, H_NCLS_USED, H_NTIE, H_CUR, H_NEXT_NCHUNK, H_NEXT_NSEG, H_OLD_NSEG, H_NW, H_ROUND, H_DID, H_FINALCAP, H_NFINAL, H_MULTI, H_LOCALFAIL, H_PSTRIDE,
+    H_S1,           // keys this rank samples (sharded lanes: computed on the device from the total length)
+    H_GATE_ROUND,   // 1 while refinement rounds have work (identical on every rank: derived from reduced counts)
+    H_GATE_SMALL,   // sharded lanes: 1 when small segments wait to be gathered and sorted
+    H_NEXT_ACTIVE, H_XWORDS, H_GWORDS, H_WORDS = 40
 };
 enum : int { FAIL_ESCAPED = 1, FAIL_CAPACITY = 2, FAIL_TOO_MANY = 4, FAIL_INCONSISTENT = 8, FAIL_REMOTE = 16 };
 enum : int { TASK_ACTIVE = 0, TASK_DONE = 1 };
@@ -106,7 +112,9 @@ template <typename Key> struct BrkBuf {
     unsigned long long *red_refine;  // [MAXSEG * 256]                               (allreduce per refine round)
     unsigned long long *loc_refine;  // [MAXSEG * 256] local copy (== red_refine on one GPU)
     Key *s1, *s0, *blo, *bhi;
-    Key *s0part, *s0all;             // sharded lanes: this rank's share of S0, the all-gathered S0
+    Key *s0all;                      // sharded lanes: the all-gathered S0
+    unsigned long long *xsend, *xrecv;  // sharded lanes, first exchange: [n_local, 0, this rank's share of the S0 keys] / of all ranks
+    unsigned long long *red_refine_fail;  // sharded lanes: the fail word that travels in front of red_refine
     unsigned long long *red_end;     // [2] final agreement on FAIL over ranks
     unsigned char *gsend, *grecv;    // sharded lanes: packed small segments of this rank / of all ranks (header + keys)
     unsigned long long *boff, *bcap;
@@ -163,11 +171,35 @@ template <typename T> __device__ __forceinline__ bool key_is_nan(typename Traits
 // ------------------------------------------------------------------------------------------------
 // 1. sample
 // ------------------------------------------------------------------------------------------------
+// sample size for a lane of n elements: `need` keys (what the requested quantiles ask for), between 2^16 and
+// min(n / 8, 2^24), never more than the lane holds
+__host__ __device__ inline unsigned pick_s1_from_need(unsigned long long n, double need) {
+    unsigned long long hi = n / 8;
+    if (hi < (1ull << 16)) hi = 1ull << 16;
+    if (hi > (1ull << 24)) hi = 1ull << 24;
+    unsigned long long s1 = need < 65536.0 ? 65536ull : (need > (double)hi ? hi : (unsigned long long)need);
+    if (s1 > n) s1 = n;
+    return (unsigned)s1;
+}
+
+// `sharded`: the lane is this rank's shard of a longer one whose total length red_n[0] is only known on the device; every
+// rank samples at the same rate, so the sample size follows from the shard's share (and is published in H_S1)
 template <typename T>
-__global__ void brk_sample_kernel(const T *__restrict__ data, unsigned long long n, unsigned s1,
+__global__ void brk_sample_kernel(const T *__restrict__ data, unsigned long long n, unsigned s1, double need, int sharded,
                                   BrkBuf<typename Traits<T>::Key> buf) {
     using Tr = Traits<T>;
     using Key = typename Tr::Key;
+    if (sharded) {
+        const unsigned long long n_total = buf.red_n[0];
+        const unsigned s1_total = pick_s1_from_need(n_total, need);
+        const double share = n_total ? (double)n / (double)n_total : 0.0;
+        unsigned long long want = (unsigned long long)ceil(share * (double)s1_total);
+        if (want > n) want = n;
+        if (want > buf.s1cap) want = buf.s1cap;
+        s1 = (unsigned)want;
+        if (blockIdx.x == 0 && threadIdx.x == 0) buf.hdr[H_S1] = s1;
+    }
+    if (s1 == 0) return;
     unsigned valid = 0;
     // stratum i starts at floor(i n / s1) = i q + floor(i r / s1) (q = n / s1, r = n % s1): the strata must be spread EVENLY
     // over the lane -- a sorted lane sampled at two different rates puts its quantiles in the wrong place.  The second
@@ -176,14 +208,30 @@ __global__ void brk_sample_kernel(const T *__restrict__ data, unsigned long long
     const unsigned long long q = n / s1, r = n % s1;
     const double inv_s1 = 1.0 / (double)s1;
     const unsigned long long width = q + (r ? 1ull : 0ull);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += gridDim.x * blockDim.x) {
+    // four independent loads in flight per thread: the pass is bound by the latency of its scattered 32-byte reads
+    const unsigned step = gridDim.x * blockDim.x;
+    auto position = [&](unsigned i) -> unsigned long long {
         const unsigned long long p0 = (unsigned long long)i * q + (unsigned long long)((double)((unsigned long long)i * r) * inv_s1);
         unsigned long long pos = p0 + (((unsigned long long)mix32(i) * width) >> 32);
-        if (pos >= n) pos = n - 1;
-        Key k = Tr::to_key(data[pos]);
-        const bool inv = key_is_nan<T>(k);
-        buf.s1[i] = inv ? (Key) ~(Key)0 : k;  // NaN samples sort last and are not counted
-        valid += inv ? 0u : 1u;
+        return pos >= n ? n - 1 : pos;
+    };
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += 4 * step) {
+        T x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned iu = i + (unsigned)u * step;
+            if (iu < s1 && iu >= i) x[u] = data[position(iu)];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned iu = i + (unsigned)u * step;
+            if (iu < s1 && iu >= i) {
+                Key k = Tr::to_key(x[u]);
+                const bool inv = key_is_nan<T>(k);
+                buf.s1[iu] = inv ? (Key) ~(Key)0 : k;  // NaN samples sort last and are not counted
+                valid += inv ? 0u : 1u;
+            }
+        }
     }
     valid = __reduce_add_sync(0xffffffffu, valid);
     if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&buf.hdr[H_S1VALID], (unsigned long long)valid);
@@ -191,17 +239,53 @@ __global__ void brk_sample_kernel(const T *__restrict__ data, unsigned long long
 
 // 0. this rank's element count (summed over ranks by the caller when the lane is sharded); final-sort threshold
 template <typename Key>
-__global__ void brk_begin_kernel(BrkBuf<Key> buf, unsigned long long n_local, unsigned final_cap, int multi) {
+__global__ void brk_begin_kernel(BrkBuf<Key> buf, unsigned long long n_local, unsigned final_cap, int multi, unsigned s1) {
     if (threadIdx.x == 0) {
         buf.red_n[0] = n_local;
         buf.hdr[H_FINALCAP] = final_cap;
         buf.hdr[H_MULTI] = multi ? 1ull : 0ull;
+        buf.hdr[H_S1] = s1;  // (sharded lanes: overwritten by the sample kernel once the total length is known)
     }
 }
-// sharded lanes: this rank's share of the S0 keys (all-gathered, then sorted identically on every rank)
-template <typename Key> __global__ void brk_pick_s0_kernel(BrkBuf<Key> buf, unsigned s1, Key *dst, unsigned count) {
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
-        dst[i] = s1 ? buf.s1[(unsigned long long)i * s1 / count] : (Key) ~(Key)0;
+// sharded lanes, first exchange: this rank's element count and its share of the S0 keys (drawn at hashed, evenly
+// spread positions of the local shard), packed as [n_local, 0, keys ...]; the all-gathered keys are sorted identically
+// on every rank and the counts add up to the total length -- ONE exchange step for both
+template <typename T>
+__global__ void brk_pick_local_s0_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typename Traits<T>::Key> buf,
+                                         unsigned count) {
+    using Tr = Traits<T>;
+    using Key = typename Tr::Key;
+    Key *dst = reinterpret_cast<Key *>(buf.xsend + 2);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        buf.xsend[0] = n;
+        buf.xsend[1] = 0;
+    }
+    const unsigned long long q = n / count, r = n % count;
+    const double inv = 1.0 / (double)count;
+    const unsigned long long width = q + (r ? 1ull : 0ull);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        Key k = (Key) ~(Key)0;
+        if (n) {
+            const unsigned long long p0 = (unsigned long long)i * q + (unsigned long long)((double)((unsigned long long)i * r) * inv);
+            unsigned long long pos = p0 + (((unsigned long long)mix32(i ^ 0x5bd1e995u) * width) >> 32);
+            if (pos >= n) pos = n - 1;
+            k = Tr::to_key(data[pos]);
+            if (key_is_nan<T>(k)) k = (Key) ~(Key)0;
+        }
+        dst[i] = k;
+    }
+}
+template <typename Key> __global__ void brk_unpack_s0_kernel(BrkBuf<Key> buf, int nranks, unsigned count) {
+    const size_t words_per_rank = 2 + ((size_t)count * sizeof(Key) + 7) / 8;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long total = 0;
+        for (int r = 0; r < nranks; ++r) total += buf.xrecv[(size_t)r * words_per_rank];
+        buf.red_n[0] = total;
+    }
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)nranks * count; i += gridDim.x * blockDim.x) {
+        const unsigned r = i / count, j = i - r * count;
+        buf.s0all[i] = reinterpret_cast<const Key *>(buf.xrecv + (size_t)r * words_per_rank + 2)[j];
+    }
 }
 // local fail bits travel with the counts of every exchange step, so that all ranks give up together
 template <typename Key> __global__ void brk_merge_fail_kernel(BrkBuf<Key> buf, const unsigned long long *word) {
@@ -210,49 +294,70 @@ template <typename Key> __global__ void brk_merge_fail_kernel(BrkBuf<Key> buf, c
 template <typename Key> __global__ void brk_post_fail_kernel(BrkBuf<Key> buf, unsigned long long *word) {
     if (threadIdx.x == 0) *word = failed_any(buf.hdr) ? 1ull : 0ull;
 }
-template <typename Key> __global__ void brk_copy_counts_kernel(BrkBuf<Key> buf) {  // red_refine = loc_refine (+ fail word)
+template <typename Key> __global__ void brk_copy_counts_kernel(BrkBuf<Key> buf) {  // [fail word, red_refine = loc_refine]
+    if (!buf.hdr[H_GATE_ROUND]) return;
     const int nseg = (int)buf.hdr[H_NSEG];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BRK_MAXSEG * 256; i += gridDim.x * blockDim.x)
-        buf.red_refine[i] = i < nseg * 256 ? buf.loc_refine[i] : 0ull;
-    if (blockIdx.x == 0 && threadIdx.x == 0) buf.red_refine[BRK_MAXSEG * 256] = failed_any(buf.hdr) ? 1ull : 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nseg * 256; i += gridDim.x * blockDim.x)
+        buf.red_refine[i] = buf.loc_refine[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        buf.red_refine_fail[0] = failed_any(buf.hdr) ? 1ull : 0ull;
+        buf.hdr[H_XWORDS] = 1ull + (unsigned long long)nseg * 256ull;
+    }
 }
 
-// 2a. S0 = every (s1 / S0)-th sample (or the gathered shares of all ranks), sorted by one CTA (bitonic network)
+// 2a. S0 = every (s1 / S0)-th sample (or the gathered shares of all ranks), sorted by counting: the place of key i is
+// #{ j : S0[j] < S0[i], or S0[j] == S0[i] and j < i }.  8192^2 comparisons spread over 128 CTAs (64 keys each, eight
+// warps that each scan an eighth of S0 from shared memory with broadcast reads) take ~15 us; the bitonic network that
+// one CTA ran before took 100 us -- a fixed cost that a lane sharded over eight GPUs cannot amortise.
+constexpr int SORT_KEYS_PER_CTA = 64;
+constexpr int SORT_CTAS = BRK_S0 / SORT_KEYS_PER_CTA;
+constexpr int SORT_THREADS = 256;
+static_assert(BRK_S0 % (SORT_THREADS / 32) == 0 && SORT_KEYS_PER_CTA == 64, "sort geometry");
+
 template <typename Key>
-__global__ void __launch_bounds__(1024) brk_sort_s0_kernel(BrkBuf<Key> buf, unsigned s1, const Key *gathered) {
+__global__ void __launch_bounds__(SORT_THREADS) brk_sort_s0_kernel(BrkBuf<Key> buf, const Key *gathered) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Key *s = reinterpret_cast<Key *>(smem_raw);
+    __shared__ unsigned place[SORT_KEYS_PER_CTA];
+    const unsigned s1 = (unsigned)buf.hdr[H_S1];
     for (unsigned i = threadIdx.x; i < BRK_S0; i += blockDim.x) {
         if (gathered) {
             s[i] = gathered[i];
+        } else if (s1 == 0) {
+            s[i] = (Key) ~(Key)0;  // an empty lane
         } else {
             unsigned long long pos = (unsigned long long)i * s1 / BRK_S0;
             s[i] = buf.s1[pos];
         }
     }
+    if (threadIdx.x < SORT_KEYS_PER_CTA) place[threadIdx.x] = 0;
     __syncthreads();
-    for (unsigned k = 2; k <= BRK_S0; k <<= 1) {
-        for (unsigned j = k >> 1; j > 0; j >>= 1) {
-            for (unsigned i = threadIdx.x; i < BRK_S0; i += blockDim.x) {
-                unsigned ixj = i ^ j;
-                if (ixj > i) {
-                    Key a = s[i], b = s[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { s[i] = b; s[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned i0 = blockIdx.x * SORT_KEYS_PER_CTA + lane, i1 = i0 + 32;
+    const Key a = s[i0], b = s[i1];
+    constexpr unsigned SPAN = BRK_S0 / (SORT_THREADS / 32);
+    const unsigned j0 = warp * SPAN;
+    unsigned ca = 0, cb = 0;
+#pragma unroll 8
+    for (unsigned j = j0; j < j0 + SPAN; ++j) {
+        const Key k = s[j];  // the same address for the whole warp: a broadcast
+        ca += (k < a || (k == a && j < i0)) ? 1u : 0u;
+        cb += (k < b || (k == b && j < i1)) ? 1u : 0u;
     }
-    for (unsigned i = threadIdx.x; i < BRK_S0; i += blockDim.x) buf.s0[i] = s[i];
+    atomicAdd(&place[lane], ca);
+    atomicAdd(&place[lane + 32], cb);
+    __syncthreads();
+    if (threadIdx.x < SORT_KEYS_PER_CTA) buf.s0[place[threadIdx.x]] = s[blockIdx.x * SORT_KEYS_PER_CTA + threadIdx.x];
 }
 
 // 2b. exact sample ranks of the S0 keys: hist[i] = #{ s1 keys k : S0[i-1] < k <= S0[i] }
 constexpr int BRK_BLUT = 4096;  // cells of the bucket kernel's search table
 
 template <typename Key, bool IS_FLOAT>
-__global__ void __launch_bounds__(256) brk_bucket_kernel(BrkBuf<Key> buf, unsigned s1) {
+__global__ void __launch_bounds__(256) brk_bucket_kernel(BrkBuf<Key> buf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned s1 = (unsigned)buf.hdr[H_S1];
+    if (s1 == 0) return;
     Key *s = reinterpret_cast<Key *>(smem_raw);
     unsigned short *start = reinterpret_cast<unsigned short *>(s + BRK_S0);  // [BLUT + 1]: lower_bound of every cell start
     for (unsigned i = threadIdx.x; i < BRK_S0; i += blockDim.x) s[i] = buf.s0[i];
@@ -1234,6 +1339,10 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
         buf.hdr[H_NCHUNK_COUNT] = 0;   // round 0 walks the pieces (brk_refine_count0_kernel), not a chunk table
         buf.hdr[H_NACTIVE] = (unsigned long long)active;
         buf.hdr[H_ROUND] = 0;
+        // what the exchange steps of the refinement look at: identical on every rank (H_FAIL, not the local fail word)
+        const bool ok = ld_now(&buf.hdr[H_FAIL]) == 0;
+        buf.hdr[H_GATE_ROUND] = (ok && active != 0) ? 1ull : 0ull;
+        buf.hdr[H_GATE_SMALL] = (ok && nfinal != 0 && buf.hdr[H_MULTI]) ? 1ull : 0ull;
     }
 }
 
@@ -1569,8 +1678,8 @@ __global__ void __launch_bounds__(1024) brk_refine_decide_kernel(BrkBuf<Key> buf
     __shared__ unsigned char new_final[BRK_MAXSEG];
     __shared__ int s_nid;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    if (buf.red_refine != buf.loc_refine && buf.red_refine[BRK_MAXSEG * 256]) {
-        if (tid == 0) raise_fail(buf.hdr, FAIL_REMOTE);
+    if (buf.red_refine != buf.loc_refine && buf.hdr[H_GATE_ROUND] && buf.red_refine_fail[0]) {
+        if (tid == 0) raise_fail(buf.hdr, FAIL_REMOTE);  // some rank gave up: everybody does
         return;
     }
     if (buf.hdr[H_FAIL]) return;
@@ -1726,7 +1835,7 @@ __global__ void __launch_bounds__(1024) brk_refine_decide_kernel(BrkBuf<Key> buf
         buf.hdr[H_NEXT_NCHUNK] = chunks_count;
         buf.hdr[H_NEXT_NSEG] = (unsigned long long)nid;
         buf.hdr[H_OLD_NSEG] = (unsigned long long)nseg;
-        buf.hdr[H_WORDS - 1] = (unsigned long long)active;  // becomes H_NACTIVE once the compaction has run
+        buf.hdr[H_NEXT_ACTIVE] = (unsigned long long)active;  // becomes H_NACTIVE once the compaction has run
         buf.hdr[H_DID] = 1;
     }
     // the counts of this round are consumed: clear them for the next one
@@ -1792,14 +1901,18 @@ __global__ void __launch_bounds__(BRK_THREADS) brk_refine_compact_kernel(BrkBuf<
 
 // publish the next round's segment table sizes (after the compaction has read the old ones)
 template <typename Key> __global__ void brk_refine_advance_kernel(BrkBuf<Key> buf) {
-    if (threadIdx.x == 0 && !buf.hdr[H_FAIL] && buf.hdr[H_DID]) {
+    if (threadIdx.x != 0) return;
+    if (!buf.hdr[H_FAIL] && buf.hdr[H_DID]) {
         buf.hdr[H_NCHUNK_COUNT] = buf.hdr[H_NEXT_NCHUNK];
         buf.hdr[H_NSEG] = buf.hdr[H_NEXT_NSEG];
-        buf.hdr[H_NACTIVE] = buf.hdr[H_WORDS - 1];
+        buf.hdr[H_NACTIVE] = buf.hdr[H_NEXT_ACTIVE];
         buf.hdr[H_CUR] = buf.hdr[H_CUR] ^ 1ull;
         buf.hdr[H_ROUND] = buf.hdr[H_ROUND] + 1;
         buf.hdr[H_DID] = 0;
     }
+    const bool ok = buf.hdr[H_FAIL] == 0;
+    buf.hdr[H_GATE_ROUND] = (ok && buf.hdr[H_NACTIVE] != 0) ? 1ull : 0ull;
+    buf.hdr[H_GATE_SMALL] = (ok && buf.hdr[H_NFINAL] != 0 && buf.hdr[H_MULTI]) ? 1ull : 0ull;
 }
 
 // Sharded lanes: the small (FINAL) segments that still have a task are packed into one send buffer per rank --
@@ -1812,7 +1925,9 @@ __global__ void __launch_bounds__(1024) brk_pack_final_kernel(BrkBuf<Key> buf) {
     unsigned *hdr_out = reinterpret_cast<unsigned *>(buf.gsend);
     Key *keys_out = reinterpret_cast<Key *>(buf.gsend + (size_t)BRK_MAXSEG * 4);
     const int tid = threadIdx.x;
+    if (!buf.hdr[H_GATE_SMALL]) return;  // nothing to gather (the same on every rank): the exchange step is skipped, too
     for (int i = tid; i < BRK_MAXSEG; i += blockDim.x) { cnt[i] = 0; off[i] = 0; wanted[i] = 0; hdr_out[i] = 0; }
+    if (tid == 0) buf.hdr[H_GWORDS] = (unsigned long long)BRK_MAXSEG * 4 / 8;  // the header alone
     __syncthreads();
     if (failed_any(buf.hdr) || buf.hdr[H_EMPTY]) return;
     const int nseg = (int)buf.hdr[H_NSEG], ntask = (int)buf.hdr[H_NTASK];
@@ -1836,6 +1951,7 @@ __global__ void __launch_bounds__(1024) brk_pack_final_kernel(BrkBuf<Key> buf) {
             off[sidx] = run;
             run += c;
         }
+        buf.hdr[H_GWORDS] = ((unsigned long long)BRK_MAXSEG * 4 + (unsigned long long)run * sizeof(Key) + 7) / 8;
     }
     __syncthreads();
     const unsigned nw = (unsigned)buf.hdr[H_NW];
@@ -1872,6 +1988,7 @@ __global__ void __launch_bounds__(256) brk_final_kernel(BrkBuf<Key> buf, int nra
     __shared__ int s_any;
     __shared__ unsigned roff[BRK_MAX_RANKS], rcnt[BRK_MAX_RANKS];
     if (failed_any(buf.hdr) || buf.hdr[H_EMPTY]) return;
+    if (nranks > 0 && !buf.hdr[H_GATE_SMALL]) return;  // nothing was gathered
     const int nseg = (int)buf.hdr[H_NSEG], ntask = (int)buf.hdr[H_NTASK];
     const int cur = (int)buf.hdr[H_CUR];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -1994,7 +2111,7 @@ __global__ void brk_output_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs
         }
         const BrkTask tl = buf.task[(int)buf.slot_rank[2 * t]], th = buf.task[(int)buf.slot_rank[2 * t + 1]];
         if (tl.state != TASK_DONE || th.state != TASK_DONE) {
-            if (last) {
+            if (last && buf.hdr[H_NACTIVE] == 0) {
                 raise_fail(buf.hdr, FAIL_INCONSISTENT);
                 atomicOr(qa.status, STATUS_BIT_FALLBACK);
             }
@@ -2021,20 +2138,16 @@ struct BrkSizes {
 
 // Sample size: large enough that the brackets of all requested quantiles together hold ~12 % of the lane.
 // wsum = sum over quantiles of 2 c sqrt(p (1 - p)) (the +-c sigma widths in units of sqrt(sample size)).
-unsigned pick_s1(unsigned long long n, double wsum) {
+double sample_need(double wsum) {
     const double f_target = 0.12;
     double need = (wsum / f_target) * (wsum / f_target);
     if (const char *e = getenv("NDS_BRK_SAMPLE")) {
         const double v = atof(e);
         if (v >= 1.0) need = v;
     }
-    unsigned long long hi = n / 8;
-    if (hi < (1ull << 16)) hi = 1ull << 16;
-    if (hi > (1ull << 24)) hi = 1ull << 24;
-    unsigned long long s1 = need < 65536.0 ? 65536ull : (need > (double)hi ? hi : (unsigned long long)need);
-    if (s1 > n) s1 = n;
-    return (unsigned)s1;
+    return need;
 }
+unsigned pick_s1(unsigned long long n, double wsum) { return pick_s1_from_need(n, sample_need(wsum)); }
 double predicted_fraction(unsigned long long n, int nq, double wsum) {
     const unsigned s1 = pick_s1(n, wsum);
     return s1 ? wsum / std::sqrt((double)s1) + (double)nq / 4096.0 : 1.0;
@@ -2055,7 +2168,8 @@ template <typename Key> BrkSizes brk_sizes(unsigned long long n, int nq, double 
     size_t t = 0;
     t += align256(H_WORDS * 8) + align256(2 * 8) + align256(2 * (BRK_S0 + 2) * 8) + align256((BRK_NCLS + BRK_MAXB + 2) * 8) +
          align256(BRK_MAXB * 8) + 2 * align256(((size_t)BRK_MAXSEG * 256 + 2) * 8) + align256(16) + align256((size_t)BRK_MAXB * 148 * STR_WARPS * 4);
-    t += align256((size_t)z.s1 * sizeof(Key)) + 3 * align256(BRK_S0 * sizeof(Key)) + 2 * align256(BRK_MAXB * sizeof(Key));
+    t += align256((size_t)z.s1 * sizeof(Key)) + 2 * align256(BRK_S0 * sizeof(Key)) + 2 * align256(BRK_MAXB * sizeof(Key)) +
+         align256(16 + BRK_S0 * sizeof(Key)) * (1 + BRK_MAX_RANKS);
     t += align256(gather_bytes<Key>()) + align256(gather_bytes<Key>() * BRK_MAX_RANKS);
     t += 2 * align256(BRK_MAXB * 8) + align256(BRK_MAXB) + align256(BRK_NC1 * 4) + align256(BRK_L2N * 2) +
          align256(sizeof(BrkLutConst<Key>));
@@ -2081,7 +2195,8 @@ template <typename Key> BrkBuf<Key> brk_carve(void *scratch, const BrkSizes &z, 
     b.s0hist = (unsigned long long *)take(2 * (BRK_S0 + 2) * 8);
     b.red_stream = (unsigned long long *)take((BRK_NCLS + BRK_MAXB + 2) * 8);
     b.cur_local = (unsigned long long *)take(BRK_MAXB * 8);
-    b.red_refine = (unsigned long long *)take(((size_t)BRK_MAXSEG * 256 + 2) * 8);
+    b.red_refine_fail = (unsigned long long *)take(((size_t)BRK_MAXSEG * 256 + 2) * 8);  // [fail word | digit counts]
+    b.red_refine = b.red_refine_fail + 1;
     b.red_end = (unsigned long long *)take(2 * 8);
     b.loc_refine = (unsigned long long *)take((size_t)BRK_MAXSEG * 256 * 8);
     b.fill = (unsigned *)take((size_t)BRK_MAXB * 148 * STR_WARPS * 4);
@@ -2090,8 +2205,9 @@ template <typename Key> BrkBuf<Key> brk_carve(void *scratch, const BrkSizes &z, 
     // --- the rest is written before it is read ---
     b.s1 = (Key *)take((size_t)z.s1 * sizeof(Key));
     b.s0 = (Key *)take(BRK_S0 * sizeof(Key));
-    b.s0part = (Key *)take(BRK_S0 * sizeof(Key));
     b.s0all = (Key *)take(BRK_S0 * sizeof(Key));
+    b.xsend = (unsigned long long *)take(16 + BRK_S0 * sizeof(Key));
+    b.xrecv = (unsigned long long *)take((16 + BRK_S0 * sizeof(Key)) * BRK_MAX_RANKS);
     b.gsend = (unsigned char *)take(gather_bytes<Key>());
     b.grecv = (unsigned char *)take(gather_bytes<Key>() * BRK_MAX_RANKS);
     b.blo = (Key *)take(BRK_MAXB * sizeof(Key));
@@ -2128,6 +2244,42 @@ double brk_csigma() {
 }
 namespace {
 
+// Stage timer (NDS_BRK_TIMING=1): CUDA events between the stages of one call, printed after the call has finished.
+struct BrkTimer {
+    bool on = false;
+    cudaStream_t st = nullptr;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
+    void mark(const char *name) {
+        if (!on) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        marks.emplace_back(name, ev);
+    }
+    void report(int rank) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        std::string line = "[bracket-timing] rank " + std::to_string(rank) + ":";
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            char b[96];
+            std::snprintf(b, sizeof b, " %s %.1fus", marks[i].first, ms * 1000.f);
+            line += b;
+        }
+        if (marks.size() > 1) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks.front().second, marks.back().second);
+            char b[64];
+            std::snprintf(b, sizeof b, " | total %.1fus", ms * 1000.f);
+            line += b;
+        }
+        fprintf(stderr, "%s\n", line.c_str());
+        for (auto &m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+    }
+};
+
 template <typename T>
 cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long n, const QuantArgs &qa, T *out,
                                 uint8_t *out_valid, long long out_axis_stride, void *scratch, bool sharded,
@@ -2136,6 +2288,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     constexpr bool IS_FLOAT = Traits<T>::is_float;
     cudaStream_t st = ctx->stream;
     const bool multi = sharded && ctx->nccl_comm && ctx->nranks > 1;
+    const bool p2p = multi && xchg_ready(ctx);   // our own exchange kernels over peer memory; otherwise NCCL collectives
     const BrkSizes z = brk_sizes<Key>(n, qa.nq, wsum, sharded);
     size_t zero_bytes = 0;
     BrkBuf<Key> buf = brk_carve<Key>(scratch, z, qa.nq, &zero_bytes);
@@ -2143,11 +2296,33 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     cudaError_t e = cudaMemsetAsync(scratch, 0, zero_bytes, st);
     if (e != cudaSuccess) return e;
     const int sm = ctx->sm_count;
+    static const bool timing_knob = getenv("NDS_BRK_TIMING") && atoi(getenv("NDS_BRK_TIMING")) != 0;
+    BrkTimer timer;
+    timer.on = timing_knob && synchronous;
+    timer.st = st;
+    timer.mark("start");
     auto count = [&]() { ctx->launches += 1; return cudaGetLastError(); };
-    auto allreduce = [&](unsigned long long *p, size_t words) -> cudaError_t {
+    // The exchange steps of a lane sharded over ranks.  `dev_words` / `gate` (device words holding the same value on every
+    // rank) size / skip a step on the device; NCCL cannot do either and moves `words` unconditionally (harmless: the
+    // kernels that consume the result look at the same words).
+    auto allreduce = [&](unsigned long long *p, size_t words, const unsigned long long *dev_words,
+                         const unsigned long long *gate) -> cudaError_t {
         if (!multi) return cudaSuccess;
+        if (p2p) return xchg_allreduce_u64(ctx, p, words, dev_words, gate);
         std::string err;
+        ctx->xchg_steps += 1;
         if (nccl_allreduce_sum_u64(ctx, p, words, st, &err) != 0) {
+            ctx->last_error = err;
+            return cudaErrorUnknown;
+        }
+        return cudaSuccess;
+    };
+    auto allgather = [&](const void *send, void *recv, size_t bytes_per_rank, const unsigned long long *dev_words,
+                         const unsigned long long *gate) -> cudaError_t {
+        if (p2p) return xchg_allgather(ctx, send, recv, bytes_per_rank, dev_words, gate);
+        std::string err;
+        ctx->xchg_steps += 1;
+        if (nccl_allgather_bytes(ctx, send, recv, bytes_per_rank, st, &err) != 0) {
             ctx->last_error = err;
             return cudaErrorUnknown;
         }
@@ -2156,6 +2331,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     auto read_hdr = [&](unsigned long long (&h)[H_WORDS]) -> cudaError_t {
         cudaError_t e2 = cudaMemcpyAsync(h, buf.hdr, sizeof h, cudaMemcpyDeviceToHost, st);
         if (e2 != cudaSuccess) return e2;
+        if (sharded) ctx->host_syncs += 1;
         return cudaStreamSynchronize(st);
     };
 
@@ -2165,73 +2341,54 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         if (multi) {
             brk_pack_final_kernel<Key><<<1, 1024, 0, st>>>(buf);
             if ((e2 = count()) != cudaSuccess) return e2;
-            std::string err;
-            if (nccl_allgather_bytes(ctx, buf.gsend, buf.grecv, gather_bytes<Key>(), st, &err) != 0) {
-                ctx->last_error = err;
-                return cudaErrorUnknown;
-            }
+            if ((e2 = allgather(buf.gsend, buf.grecv, gather_bytes<Key>(), &buf.hdr[H_GWORDS], &buf.hdr[H_GATE_SMALL])) != cudaSuccess)
+                return e2;
         }
         brk_final_kernel<Key><<<sm, 256, 0, st>>>(buf, multi ? ctx->nranks : 0);
         return count();
     };
-    // 0. element count (over all ranks), threshold below which a segment is sorted by one CTA (sharded: small enough
-    //    that all tasks' segments fit one rank's send buffer)
-    unsigned final_cap = multi ? (unsigned)std::min<int>(BRK_FINAL_CAP, BRK_GATHER_CAP / BRK_MAXTASK) : (unsigned)BRK_FINAL_CAP;
+    // 0. threshold below which a segment is sorted by one CTA (sharded: small enough that all tasks' segments fit one
+    //    rank's send buffer); sample size of an unsharded lane
+    unsigned final_cap = multi ? (unsigned)std::min<int>(BRK_FINAL_CAP, BRK_GATHER_CAP / (2 * std::max(qa.nq, 1))) : (unsigned)BRK_FINAL_CAP;
     if (const char *fc = getenv("NDS_BRK_FINALCAP")) final_cap = std::min<unsigned>((unsigned)atoi(fc), BRK_FINAL_CAP);  // tests
-    brk_begin_kernel<Key><<<1, 32, 0, st>>>(buf, n, final_cap, multi ? 1 : 0);
+    const double need = sample_need(wsum);
+    const unsigned s1_host = sharded ? 0u : z.s1;
+    brk_begin_kernel<Key><<<1, 32, 0, st>>>(buf, n, final_cap, multi ? 1 : 0, s1_host);
     if ((e = count()) != cudaSuccess) return e;
-    unsigned long long n_total = n;
+    // 1. over ranks: ONE exchange step carries every rank's element count and its share of the common splitters S0
+    const Key *gathered = nullptr;
     if (multi) {
-        if ((e = allreduce(buf.red_n, 2)) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(&n_total, buf.red_n, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-    }
-    // 1-2. sample (every rank at the same rate), sort S0, bucket S1
-    unsigned s1 = z.s1;
-    if (multi) {
-        const unsigned s1_total = pick_s1(n_total, wsum);
-        const double share = n_total ? (double)n / (double)n_total : 0.0;
-        unsigned long long want = (unsigned long long)std::ceil(share * (double)s1_total);
-        if (want > n) want = n;
-        if (want > z.s1) want = z.s1;
-        s1 = (unsigned)want;
-    }
-    if (s1) {
-        brk_sample_kernel<T><<<std::min<unsigned>((s1 + 255) / 256, sm * 8), 256, 0, st>>>(lane, n, s1, buf);
+        const unsigned share = BRK_S0 / (unsigned)ctx->nranks;
+        brk_pick_local_s0_kernel<T><<<8, 256, 0, st>>>(lane, n, buf, share);
         if ((e = count()) != cudaSuccess) return e;
+        if ((e = allgather(buf.xsend, buf.xrecv, 16 + (size_t)share * sizeof(Key), nullptr, nullptr)) != cudaSuccess) return e;
+        brk_unpack_s0_kernel<Key><<<8, 256, 0, st>>>(buf, ctx->nranks, share);
+        if ((e = count()) != cudaSuccess) return e;
+        gathered = buf.s0all;
+        timer.mark("count+S0-exchange");
     }
+    // 2. sample (every rank at the same rate: the size follows on the device from the total length), sort S0, bucket S1
     {
-        const Key *gathered = nullptr;
-        if (multi) {
-            // every rank contributes S0 / nranks keys of its sample; the union, sorted, is the same on every rank
-            const unsigned share = BRK_S0 / (unsigned)ctx->nranks;
-            brk_pick_s0_kernel<Key><<<8, 256, 0, st>>>(buf, s1, buf.s0part, share);
-            if ((e = count()) != cudaSuccess) return e;
-            std::string err;
-            if (nccl_allgather_bytes(ctx, buf.s0part, buf.s0all, (size_t)share * sizeof(Key), st, &err) != 0) {
-                ctx->last_error = err;
-                return cudaErrorUnknown;
-            }
-            gathered = buf.s0all;
-        }
+        const unsigned bound = sharded ? z.s1 : s1_host;
+        const unsigned grid = std::max(1u, std::min<unsigned>((bound + 255) / 256, (unsigned)sm * 8));
+        brk_sample_kernel<T><<<grid, 256, 0, st>>>(lane, n, s1_host, need, sharded ? 1 : 0, buf);
+        if ((e = count()) != cudaSuccess) return e;
+        timer.mark("sample");
         auto k = brk_sort_s0_kernel<Key>;
         const size_t smem = BRK_S0 * sizeof(Key);
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if (s1 || gathered) {
-            k<<<1, 1024, smem, st>>>(buf, s1, gathered);
-            if ((e = count()) != cudaSuccess) return e;
-        }
+        k<<<SORT_CTAS, SORT_THREADS, smem, st>>>(buf, gathered);
+        if ((e = count()) != cudaSuccess) return e;
+        timer.mark("sort-S0");
+        auto kb = brk_bucket_kernel<Key, IS_FLOAT>;
+        const size_t smemb = BRK_S0 * sizeof(Key) + (BRK_BLUT + 1) * 2 + 16;
+        if ((e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemb)) != cudaSuccess) return e;
+        kb<<<std::max(1u, std::min<unsigned>((bound + 255) / 256, (unsigned)sm * 4)), 256, smemb, st>>>(buf);
+        if ((e = count()) != cudaSuccess) return e;
+        timer.mark("bucket");
     }
-    {
-        auto k = brk_bucket_kernel<Key, IS_FLOAT>;
-        const size_t smem = BRK_S0 * sizeof(Key) + (BRK_BLUT + 1) * 2 + 16;
-        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if (s1) {
-            k<<<std::min<unsigned>((s1 + 255) / 256, sm * 4), 256, smem, st>>>(buf, s1);
-            if ((e = count()) != cudaSuccess) return e;
-        }
-    }
-    if ((e = allreduce(buf.s0hist, 2 * (BRK_S0 + 2))) != cudaSuccess) return e;
+    if ((e = allreduce(buf.s0hist, 2 * (BRK_S0 + 2), nullptr, nullptr)) != cudaSuccess) return e;
+    if (multi) timer.mark("hist-exchange");
     // 3. plan
     const unsigned long long tiles = n / STR_TILE + 1;
     const unsigned sgrid = (unsigned)std::min<unsigned long long>(tiles, (unsigned long long)std::min(sm, 148));
@@ -2242,6 +2399,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<1, 1024, smem, st>>>(buf, qa, brk_csigma(), n, multi ? 1 : 0, nw);
         if ((e = count()) != cudaSuccess) return e;
+        timer.mark("plan");
     }
     // 4. stream (the kernel of the table mode the plan did not choose returns at once)
     {
@@ -2258,12 +2416,22 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         }
         brk_publish_fill_kernel<Key><<<1, 128, 0, st>>>(buf);
         if ((e = count()) != cudaSuccess) return e;
+        timer.mark("stream");
     }
-    if ((e = allreduce(buf.red_stream, BRK_NCLS + BRK_MAXB + 2)) != cudaSuccess) return e;
+    if ((e = allreduce(buf.red_stream, BRK_NCLS + BRK_MAXB + 2, nullptr, nullptr)) != cudaSuccess) return e;
+    if (multi) timer.mark("count-exchange");
     // 5. resolve
     brk_resolve_kernel<T><<<1, 256, 0, st>>>(buf, qa, qa.skipnan);
     if ((e = count()) != cudaSuccess) return e;
-    // 6. refine
+    timer.mark("resolve");
+    // 6. refine.  Every decision is taken on the device from counts that are the same on every rank, so rounds are
+    //    enqueued without looking: an idle round is a handful of kernels that return at once (over peer memory its
+    //    exchange steps are skipped on the device, too).  One GPU: all possible rounds for an enqueued call, a look at
+    //    the header after the second round of a synchronous one.  Over ranks: two rounds, then one look; more only when
+    //    segments are still active (tie-heavy or adversarial lanes).
+    unsigned long long hh[H_WORDS];
+    unsigned long long agreed = 0;
+    bool have_hdr = false;
     {
         auto kc = brk_refine_count_kernel<Key>;
         auto kc0 = brk_refine_round0_kernel<Key, false>;
@@ -2273,68 +2441,76 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         const size_t smem0 = (size_t)256 * BRK_THREADS;  // 8-bit counters
         if ((e = cudaFuncSetAttribute(kc0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0)) != cudaSuccess) return e;
         const int max_rounds = (int)sizeof(Key) + 1;
-        // over ranks the host follows the (rank-identical) header: it skips the exchange of small segments when there
-        // are none and reduces only the rows of the live segments
-        unsigned long long hh[H_WORDS];
-        size_t live_rows = BRK_MAXSEG;
-        bool small_pending = true;
-        if (multi) {
-            if ((e = read_hdr(hh)) != cudaSuccess) return e;
-            small_pending = hh[H_NFINAL] != 0 && !hh[H_FAIL];
-            live_rows = std::min<size_t>(BRK_MAXSEG, (size_t)hh[H_NSEG]);
-        }
-        if (small_pending && (e = finish_small()) != cudaSuccess) return e;
-        for (int round = 0; round < max_rounds; ++round) {
+        if ((e = finish_small()) != cudaSuccess) return e;
+        timer.mark("small-segments");
+        auto one_round = [&](int round) -> cudaError_t {
+            cudaError_t e2;
             if (round == 0) kc0<<<sm * 3, BRK_THREADS, smem0, st>>>(buf);
             else kc<<<sm, BRK_THREADS, smem, st>>>(buf);
-            if ((e = count()) != cudaSuccess) return e;
-            if (multi) {  // the exchange step: digit counts of every active segment, summed over ranks
+            if ((e2 = count()) != cudaSuccess) return e2;
+            timer.mark(round == 0 ? "r0:count" : "r:count");
+            if (multi) {  // the exchange step: digit counts of every active segment, summed over ranks, behind the fail word
                 brk_copy_counts_kernel<Key><<<64, 256, 0, st>>>(buf);
-                if ((e = count()) != cudaSuccess) return e;
-                // rows of the live segments, then (at a fixed place) the fail word: two small collectives beat one of 512 KB
-                if ((e = allreduce(buf.red_refine, live_rows * 256)) != cudaSuccess) return e;
-                if ((e = allreduce(buf.red_refine + (size_t)BRK_MAXSEG * 256, 2)) != cudaSuccess) return e;
+                if ((e2 = count()) != cudaSuccess) return e2;
+                if ((e2 = allreduce(buf.red_refine_fail, 1 + (size_t)BRK_MAXSEG * 256, &buf.hdr[H_XWORDS], &buf.hdr[H_GATE_ROUND])) != cudaSuccess)
+                    return e2;
+                timer.mark("exch");
             }
             brk_refine_decide_kernel<Key><<<1, 1024, 0, st>>>(buf);
-            if ((e = count()) != cudaSuccess) return e;
+            if ((e2 = count()) != cudaSuccess) return e2;
+            timer.mark("decide");
             if (round == 0) kp0<<<sm * 6, BRK_THREADS, 0, st>>>(buf);
             else brk_refine_compact_kernel<Key><<<sm * 2, BRK_THREADS, 0, st>>>(buf);
-            if ((e = count()) != cudaSuccess) return e;
+            if ((e2 = count()) != cudaSuccess) return e2;
             brk_refine_advance_kernel<Key><<<1, 32, 0, st>>>(buf);
-            if ((e = count()) != cudaSuccess) return e;
-            // every rank sees the same (reduced) counts and fail words, so all of them take the same branches
-            if (multi) {
+            if ((e2 = count()) != cudaSuccess) return e2;
+            timer.mark("compact");
+            if ((e2 = finish_small()) != cudaSuccess) return e2;
+            timer.mark("small");
+            return cudaSuccess;
+        };
+        // 7. output (a slot whose ranks are not known yet is left alone while segments are still active)
+        auto output = [&]() -> cudaError_t {
+            brk_output_kernel<T><<<(qa.nq + 127) / 128, 128, 0, st>>>(buf, qa, out, out_valid, out_axis_stride, 1);
+            return count();
+        };
+        if (multi) {
+            int round = 0;
+            for (;;) {
+                const int stop = std::min(round + 2, max_rounds);
+                for (; round < stop; ++round)
+                    if ((e = one_round(round)) != cudaSuccess) return e;
+                if ((e = output()) != cudaSuccess) return e;
+                // agree on the outcome: either every rank keeps its result or all of them fall back
+                brk_post_fail_kernel<Key><<<1, 32, 0, st>>>(buf, buf.red_end);
+                if ((e = count()) != cudaSuccess) return e;
+                if ((e = allreduce(buf.red_end, 2, nullptr, nullptr)) != cudaSuccess) return e;
+                timer.mark("output+agree");
+                if ((e = cudaMemcpyAsync(&agreed, buf.red_end, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
                 if ((e = read_hdr(hh)) != cudaSuccess) return e;
-                if (hh[H_NFINAL] != 0 && !hh[H_FAIL] && (e = finish_small()) != cudaSuccess) return e;
-                live_rows = std::min<size_t>(BRK_MAXSEG, (size_t)hh[H_NSEG]);
-                if (hh[H_FAIL] || hh[H_NACTIVE] == 0) break;
-            } else {
-                if ((e = finish_small()) != cudaSuccess) return e;
+                have_hdr = true;
+                // (H_FAIL, H_NACTIVE and the agreed word are the same on every rank: all of them leave together)
+                if (hh[H_FAIL] || agreed || hh[H_NACTIVE] == 0 || round >= max_rounds) break;
+            }
+        } else {
+            for (int round = 0; round < max_rounds; ++round) {
+                if ((e = one_round(round)) != cudaSuccess) return e;
                 if (synchronous && round >= 1) {
                     if ((e = read_hdr(hh)) != cudaSuccess) return e;
                     if (hh[H_FAIL] || hh[H_NACTIVE] == 0) break;
                 }
             }
+            if ((e = output()) != cudaSuccess) return e;
+            timer.mark("output");
         }
-    }
-    // 7. output
-    brk_output_kernel<T><<<(qa.nq + 127) / 128, 128, 0, st>>>(buf, qa, out, out_valid, out_axis_stride, 1);
-    if ((e = count()) != cudaSuccess) return e;
-    if (multi) {  // agree on the outcome: either every rank keeps its result or all of them fall back
-        brk_post_fail_kernel<Key><<<1, 32, 0, st>>>(buf, buf.red_end);
-        if ((e = count()) != cudaSuccess) return e;
-        if ((e = allreduce(buf.red_end, 2)) != cudaSuccess) return e;
     }
     if (synchronous) {
-        unsigned long long h[H_WORDS];
-        if ((e = read_hdr(h)) != cudaSuccess) return e;
+        unsigned long long (&h)[H_WORDS] = hh;
+        if (!have_hdr && (e = read_hdr(h)) != cudaSuccess) return e;
         *failed = (int)(h[H_FAIL] | h[H_LOCALFAIL]);
-        if (n_total_out) *n_total_out = n_total;
-        if (multi) {
-            unsigned long long agreed = 0;
-            if ((e = cudaMemcpy(&agreed, buf.red_end, 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
-            if (agreed) *failed |= FAIL_REMOTE;
-        }
+        if (n_total_out) *n_total_out = h[H_NTOTAL];
+        if (multi && agreed) *failed |= FAIL_REMOTE;
+        timer.report(ctx->rank);
         if (const char *dbg = getenv("NDS_BRK_DEBUG")) {
             if (atoi(dbg) >= 2) {  // brackets and exact class counts, for tools/dbg_bracket2.py
                 const int B = (int)h[H_B];
@@ -2354,9 +2530,9 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
                             (unsigned long long)lo[b], (unsigned long long)hi[b], (int)tie[b], red[b], red[BRK_NCLS + b]);
                 fprintf(stderr, "[bracket-b] %d (above) cls_count=%llu\n", B, red[B]);
             }
-            fprintf(stderr, "[bracket] rank=%d n=%llu n_total=%llu s1=%u fail=%llu B=%llu ties=%llu tasks=%llu n_eff=%llu invalid=%llu active=%llu round=%llu\n",
-                    ctx->rank, n, n_total, s1, h[H_FAIL], h[H_B], h[H_NTIE], h[H_NTASK], h[H_NEFF], h[H_NINVALID], h[H_NACTIVE],
-                    h[H_ROUND]);
+            fprintf(stderr, "[bracket] rank=%d n=%llu n_total=%llu s1=%llu fail=%llu localfail=%llu B=%llu ties=%llu tasks=%llu n_eff=%llu invalid=%llu active=%llu round=%llu\n",
+                    ctx->rank, n, h[H_NTOTAL], h[H_S1], h[H_FAIL], h[H_LOCALFAIL], h[H_B], h[H_NTIE], h[H_NTASK], h[H_NEFF], h[H_NINVALID],
+                    h[H_NACTIVE], h[H_ROUND]);
         }
     } else {
         // asynchronous call: the FAIL word is folded into the ctx status at the next synchronize

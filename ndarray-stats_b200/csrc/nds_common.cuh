@@ -9,7 +9,7 @@
 namespace nds {
 
 // deferred, data-dependent status bits accumulated in the ctx's device status word
-enum : int { STATUS_BIT_NAN = 1, STATUS_BIT_CAST_OVERFLOW = 2, STATUS_BIT_FALLBACK = 4 };
+enum : int { STATUS_BIT_NAN = 1, STATUS_BIT_CAST_OVERFLOW = 2, STATUS_BIT_FALLBACK = 4, STATUS_BIT_XCHG = 8 };
 
 // ---------------------------------------------------------------------------------------------
 // Lane geometry: every 1-D lane along `axis` of an ndarray-style view (what the reference's

@@ -10,6 +10,21 @@
 
 namespace nds { struct PendingCall; }
 
+// ---- peer-memory exchange between the ranks of a sharded call (nds_xchg.cu) ------------------------------------
+constexpr int XCHG_MAX_RANKS = 8;
+constexpr int XCHG_SLOTS = 4;                          // exchange steps whose payloads may be in flight
+constexpr size_t XCHG_SRC_BYTES = 1040 * 1024;         // largest payload of one rank in one step (the keys of the small segments: 1 MB + header)
+namespace nds {
+struct XchgDev {                                       // passed by value to the exchange kernels
+    unsigned char *inbox[XCHG_MAX_RANKS];              // rank r's inbox as mapped into this process ([me]: local memory)
+    unsigned long long *flags[XCHG_MAX_RANKS];         // rank r's flags: [slot][source rank] = sequence number + 1
+    unsigned long long *done;                          // local: CTAs of a push kernel that have finished, per slot
+    size_t src_stride, slot_stride;
+    unsigned long long timeout_ns;
+    int nranks, me;
+};
+}
+
 struct nds_ctx {
     int device = 0;
     int sm_count = 148;
@@ -32,6 +47,11 @@ struct nds_ctx {
     void *nccl_comm = nullptr;
     int nranks = 1;
     int rank = 0;
+    // peer-memory exchange (nds_xchg.cu): set up by nds_comm_init_rank when every rank can map every peer's inbox
+    void *xchg = nullptr;
+    unsigned long long xseq = 0;     // sequence number of the next exchange step (identical on every rank)
+    uint64_t xchg_steps = 0;         // exchange steps enqueued so far (peer-memory or NCCL)
+    uint64_t host_syncs = 0;         // host round trips inside sharded calls so far
 };
 
 namespace nds {
@@ -84,6 +104,16 @@ cudaError_t launch_short_bitslice(nds_ctx *ctx, const DeviceCall &c);
 // Strided lanes whose neighbours are contiguous (column lanes): CTA per strip of 8 lanes, bit-sliced.
 bool cols_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c);
 cudaError_t launch_cols_bitslice(nds_ctx *ctx, const DeviceCall &c);
+
+// Peer-memory exchange (nds_xchg.cu).  `dev_words` (optional, device): the number of 8-byte words to exchange, `gate`
+// (optional, device): skip the step when the word is 0 -- both must hold the same value on every rank.
+bool xchg_setup(nds_ctx *ctx);                      // collective; false = stay on NCCL
+void xchg_teardown(nds_ctx *ctx, bool collective);
+bool xchg_ready(const nds_ctx *ctx);
+cudaError_t xchg_allreduce_u64(nds_ctx *ctx, unsigned long long *buf, size_t words, const unsigned long long *dev_words,
+                               const unsigned long long *gate);
+cudaError_t xchg_allgather(nds_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank,
+                           const unsigned long long *dev_words, const unsigned long long *gate);
 
 // NCCL shim (nds_nccl.cpp)
 int nccl_allreduce_sum_u64(nds_ctx *ctx, void *buf, size_t count, cudaStream_t stream, std::string *err);

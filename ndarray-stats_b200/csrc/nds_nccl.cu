@@ -117,11 +117,22 @@ nds_status nds_comm_init_rank(nds_ctx *ctx, int nranks, int rank, const void *id
     ctx->nccl_comm = comm;
     ctx->nranks = nranks;
     ctx->rank = rank;
+    nds::xchg_setup(ctx);  // collective: every rank maps every peer's inbox, or all of them stay on the NCCL collectives
+    return NDS_OK;
+}
+
+nds_status nds_comm_stats(nds_ctx *ctx, uint64_t out[4]) {
+    if (!ctx || !out) return NDS_BAD_ARGUMENT;
+    out[0] = nds::xchg_ready(ctx) ? 1 : 0;
+    out[1] = ctx->xchg_steps;
+    out[2] = ctx->host_syncs;
+    out[3] = (uint64_t)ctx->nranks;
     return NDS_OK;
 }
 
 nds_status nds_comm_destroy(nds_ctx *ctx) {
     if (!ctx) return NDS_BAD_ARGUMENT;
+    if (ctx->xchg) nds::xchg_teardown(ctx, true);
     if (ctx->nccl_comm) {
         cudaStreamSynchronize(ctx->stream);
         api().CommDestroy((ncclComm_t)ctx->nccl_comm);

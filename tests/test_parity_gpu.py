@@ -537,3 +537,37 @@ def test_bracket_c4_shape(nds, gpu_ctx, oracle, dtype):
     b = (rng.standard_normal(1 << 25) * 3.0).astype(dtype)
     check(gpu_ctx, oracle, b, 0, qs, "linear", select_impl=1)
     assert gpu_ctx.last_path == "bracket"
+
+
+def test_full_size_c3_against_oracle(nds, gpu_ctx, oracle):
+    """BASELINE config 3 at full size (8192 x 65536 f32, Axis(0), skipnan, 10 % NaN, Nearest; the splitmix64 stream of
+    SURVEY.md section 8d generated on the device): 128 column lanes spread over the array against the oracle, and -- a
+    size-independent property -- every result is an element of its own lane with the right rank among the non-NaNs."""
+    import torch
+    rows, cols = 8192, 65536
+    t = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
+    nds.synth.fill(gpu_ctx, t, "f32_uniform_nan10", 1003)
+    out = gpu_ctx.quantiles_axis(t, 0, [0.5], "nearest", skipnan=True)
+    assert gpu_ctx.last_path.startswith("cols")
+    pick = np.linspace(0, cols - 1, num=128).astype(np.int64)
+    idx = torch.from_numpy(pick).cuda()
+    sub = t.index_select(1, idx).cpu().numpy()
+    got = out.index_select(1, idx).cpu().numpy()
+    # the device generator and its numpy restatement agree on these lanes
+    lane_idx = np.arange(rows, dtype=np.uint64)[:, None] * np.uint64(cols) + pick.astype(np.uint64)[None, :]
+    host = nds.synth.host_at("f32_uniform_nan10", lane_idx, 1003)
+    assert np.array_equal(sub.view(np.uint32), host.view(np.uint32))
+    st, want, _ = oracle.quantiles_axis(sub, 0, [0.5], "nearest", skipnan=True)
+    assert st == oracle.OK
+    assert_bit_equal(got, want, msg="c3 full size")
+    # rank property on ALL 65536 lanes: Nearest selects one order statistic r of the n' non-NaN values
+    valid = ~torch.isnan(t)
+    n_eff = valid.sum(dim=0)
+    x = 0.5 * (n_eff.double() - 1.0)
+    r = torch.where((x - torch.trunc(x)) < 0.5, torch.floor(x), torch.ceil(x)).long()
+    v = out[0]
+    lt = ((t < v[None, :]) & valid).sum(dim=0)
+    le = ((t <= v[None, :]) & valid).sum(dim=0)
+    assert bool(((lt <= r) & (r < le)).all())
+    del t, valid
+    torch.cuda.empty_cache()

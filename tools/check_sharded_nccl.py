@@ -77,7 +77,7 @@ def main():
         pass
     dist.barrier()
     if rank == 0:
-        print(f"sharded NCCL check ok on {world} GPUs; paths: {paths}")
+        print(f"sharded NCCL check ok on {world} GPUs; paths: {paths}; exchange: {ctx.comm_info()}")
     ctx.comm_destroy()
     dist.destroy_process_group()
 

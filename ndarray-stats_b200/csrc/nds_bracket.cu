@@ -208,24 +208,25 @@ __global__ void brk_sample_kernel(const T *__restrict__ data, unsigned long long
     const unsigned long long q = n / s1, r = n % s1;
     const double inv_s1 = 1.0 / (double)s1;
     const unsigned long long width = q + (r ? 1ull : 0ull);
-    // four independent loads in flight per thread: the pass is bound by the latency of its scattered 32-byte reads
+    // eight independent loads in flight per thread: the pass is bound by the latency of its scattered 32-byte reads
     const unsigned step = gridDim.x * blockDim.x;
     auto position = [&](unsigned i) -> unsigned long long {
         const unsigned long long p0 = (unsigned long long)i * q + (unsigned long long)((double)((unsigned long long)i * r) * inv_s1);
         unsigned long long pos = p0 + (((unsigned long long)mix32(i) * width) >> 32);
         return pos >= n ? n - 1 : pos;
     };
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += 4 * step) {
-        T x[4];
+    constexpr int MLP = 8;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += (unsigned long long)MLP * step) {
+        T x[MLP];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const unsigned iu = i + (unsigned)u * step;
-            if (iu < s1 && iu >= i) x[u] = data[position(iu)];
+        for (int u = 0; u < MLP; ++u) {
+            const unsigned long long iu = i + (unsigned long long)u * step;
+            if (iu < s1) x[u] = data[position((unsigned)iu)];
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const unsigned iu = i + (unsigned)u * step;
-            if (iu < s1 && iu >= i) {
+        for (int u = 0; u < MLP; ++u) {
+            const unsigned long long iu = i + (unsigned long long)u * step;
+            if (iu < s1) {
                 Key k = Tr::to_key(x[u]);
                 const bool inv = key_is_nan<T>(k);
                 buf.s1[iu] = inv ? (Key) ~(Key)0 : k;  // NaN samples sort last and are not counted
@@ -233,8 +234,7 @@ __global__ void brk_sample_kernel(const T *__restrict__ data, unsigned long long
             }
         }
     }
-    valid = __reduce_add_sync(0xffffffffu, valid);
-    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&buf.hdr[H_S1VALID], (unsigned long long)valid);
+    (void)valid;  // (the number of valid samples comes out of the bucket counts; ten thousand atomics on one word cost 40 us)
 }
 
 // 0. this rank's element count (summed over ranks by the caller when the lane is sharded); final-sort threshold
@@ -382,18 +382,28 @@ __global__ void __launch_bounds__(256) brk_bucket_kernel(BrkBuf<Key> buf) {
         start[c] = (unsigned short)((past || off > range) ? BRK_S0 : lower_bound((Key)(k0 + off), 0, BRK_S0));
     }
     __syncthreads();
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += gridDim.x * blockDim.x) {
-        const Key k = buf.s1[i];
-        if (IS_FLOAT && k == (Key) ~(Key)0) continue;
-        unsigned lo;
-        if (k <= k0) lo = 0;
-        else if (k > k1) lo = BRK_S0;
-        else {
-            const unsigned c = (unsigned)((Key)(k - k0) >> sh);  // < BLUT; cell_start(c) <= k < cell_start(c + 1)
-            lo = lower_bound(k, start[c], start[c + 1]);
+    // four keys per thread in flight: the loop is bound by the latency of the key loads, the searches are short
+    constexpr int MLP = 4;
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += MLP * step) {
+        Key kk[MLP];
+#pragma unroll
+        for (int u = 0; u < MLP; ++u) kk[u] = (i + u * step < s1) ? buf.s1[i + u * step] : (Key) ~(Key)0;
+#pragma unroll
+        for (int u = 0; u < MLP; ++u) {
+            const Key k = kk[u];
+            if (i + u * step >= s1) continue;
+            if (IS_FLOAT && k == (Key) ~(Key)0) continue;
+            unsigned lo;
+            if (k <= k0) lo = 0;
+            else if (k > k1) lo = BRK_S0;
+            else {
+                const unsigned c = (unsigned)((Key)(k - k0) >> sh);  // < BLUT; cell_start(c) <= k < cell_start(c + 1)
+                lo = lower_bound(k, start[c], start[c + 1]);
+            }
+            atomicAdd(&buf.s0hist[lo], 1ull);
+            if (lo < BRK_S0 && s[lo] == k) atomicAdd(&buf.s0hist[BRK_S0 + 2 + lo], 1ull);  // #{ s1 == S0[lo] }, first of its run
         }
-        atomicAdd(&buf.s0hist[lo], 1ull);
-        if (lo < BRK_S0 && s[lo] == k) atomicAdd(&buf.s0hist[BRK_S0 + 2 + lo], 1ull);  // #{ s1 == S0[lo] }, first of its run
     }
 }
 
@@ -430,6 +440,7 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
     unsigned *cum = reinterpret_cast<unsigned *>(smem_raw);            // [S0 + 1] inclusive: #{ s1 <= S0[i] }
     Key *s0 = reinterpret_cast<Key *>(smem_raw + ((BRK_S0 + 1) * 4 + 15) / 16 * 16);  // [S0] the sorted sample
     unsigned short *mixcell = reinterpret_cast<unsigned short *>(s0 + BRK_S0);          // [NC1] cells that hold an edge
+    unsigned *eqc = reinterpret_cast<unsigned *>(mixcell + BRK_NC1);                    // [S0 + 2] #{ s1 == S0[i] } (first of its run)
     __shared__ unsigned long long scap[BRK_MAXB];
     __shared__ Key qlo[BRK_MAXQ], qhi[BRK_MAXQ], slo[BRK_MAXQ], shi[BRK_MAXQ];
     __shared__ Key blo[BRK_MAXB], bhi[BRK_MAXB];
@@ -480,6 +491,7 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
         }
         if (tid == 0) sFail = 0;
         for (int i = tid; i < BRK_S0; i += nthreads) s0[i] = buf.s0[i];
+        for (int i = tid; i < BRK_S0 + 2; i += nthreads) eqc[i] = (unsigned)buf.s0hist[BRK_S0 + 2 + i];
         __syncthreads();
     }
     const unsigned s1v = cum[BRK_S0];  // valid samples (over all ranks when sharded)
@@ -527,7 +539,7 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
                     if (s0[m2] < v) f0 = m2 + 1;
                     else f1 = m2;
                 }
-                const unsigned cum_lt = cum[f0] - (unsigned)buf.s0hist[BRK_S0 + 2 + f0];
+                const unsigned cum_lt = cum[f0] - eqc[f0];
                 if (cum_lt <= target) a = mid + 1;
                 else b = mid;
             }
@@ -561,7 +573,7 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
                 if (s0[m2] < v) f0 = m2 + 1;
                 else f1 = m2;
             }
-            return (f0 < BRK_S0 && s0[f0] == v) ? (unsigned)buf.s0hist[BRK_S0 + 2 + f0] : 0u;
+            return (f0 < BRK_S0 && s0[f0] == v) ? eqc[f0] : 0u;
         };
         qheavy[t] = (unsigned char)((sample_multiplicity(lo) >= 4 ? 1 : 0) | (sample_multiplicity(hi) >= 4 ? 2 : 0));
     }
@@ -683,7 +695,7 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
                 while (a < e) { int mid = (a + e) >> 1; if (s0[mid] <= bhi[b]) a = mid + 1; else e = mid; }
                 unsigned all_hi;
                 if (a > 0 && s0[a - 1] == bhi[b]) all_hi = cum[a - 1];   // hi is an S0 key: exact
-                else all_hi = cum[a] - (a < BRK_S0 ? (unsigned)buf.s0hist[BRK_S0 + 2 + a] : 0u);  // #{ s1 < next S0 key }, or everything
+                else all_hi = cum[a] - (a < BRK_S0 ? eqc[a] : 0u);  // #{ s1 < next S0 key }, or everything
                 a = 0; e = BRK_S0;      // lower_bound(lo)
                 while (a < e) { int mid = (a + e) >> 1; if (s0[mid] < blo[b]) a = mid + 1; else e = mid; }
                 const unsigned lt_lo = a > 0 ? cum[a - 1] : 0u;
@@ -1196,6 +1208,13 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
     using Key = typename Tr::Key;
     __shared__ unsigned long long below[BRK_MAXB], incnt[BRK_MAXB];
     __shared__ int seg_used[BRK_MAXB];
+    // everything the single-threaded parts look at is staged in shared memory first (this kernel sits between the
+    // streaming pass and the refinement on the critical path of every call: one memory latency per table entry adds up)
+    __shared__ unsigned long long s_red[BRK_NCLS + BRK_MAXB + 2];
+    __shared__ unsigned char s_btie[BRK_MAXB], s_segkind[BRK_MAXB];
+    __shared__ Key s_blo[BRK_MAXB], s_bhi[BRK_MAXB];
+    __shared__ unsigned long long s_rank[BRK_MAXTASK];
+    __shared__ int s_first[BRK_MAXTASK], s_id[BRK_MAXTASK];
     const int tid = threadIdx.x;
     if (buf.red_stream[BRK_NCLS + BRK_MAXB]) {  // some rank gave up in the streaming pass: everybody does
         if (tid == 0) raise_fail(buf.hdr, FAIL_REMOTE);
@@ -1205,7 +1224,15 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
     const int B = (int)buf.hdr[H_B];
     const int R = 2 * qa.nq;
     const unsigned long long n_total = buf.hdr[H_NTOTAL];
-    const unsigned long long n_invalid = buf.red_stream[BRK_INVALID_CLS];
+    for (int i = tid; i < BRK_NCLS + BRK_MAXB + 2; i += blockDim.x) s_red[i] = buf.red_stream[i];
+    for (int b = tid; b < BRK_MAXB; b += blockDim.x) {
+        seg_used[b] = 0;
+        s_btie[b] = b < B ? buf.btie[b] : (unsigned char)0xff;
+        s_blo[b] = b < B ? buf.blo[b] : (Key)0;
+        s_bhi[b] = b < B ? buf.bhi[b] : (Key)0;
+    }
+    __syncthreads();
+    const unsigned long long n_invalid = s_red[BRK_INVALID_CLS];
     const bool drop = masked_or_skip != 0;
     const unsigned long long n_eff = drop ? n_total - n_invalid : n_total;
     if (tid == 0) {
@@ -1215,7 +1242,6 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
         buf.hdr[H_EMPTY] = n_eff == 0;
         buf.hdr[H_NSEG] = (unsigned long long)B;
     }
-    for (int b = tid; b < BRK_MAXB; b += blockDim.x) seg_used[b] = 0;
     if (n_eff == 0) {
         if (tid == 0) {
             buf.hdr[H_NTASK] = 0;
@@ -1229,18 +1255,18 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
     if (tid == 0) {  // exact counts below / inside each bracket
         unsigned long long run = 0, check = 0;
         for (int b = 0; b < B; ++b) {
-            const unsigned char t = buf.btie[b];
-            const unsigned long long in_b = t != 0xff ? buf.red_stream[t] : buf.red_stream[BRK_NCLS + b];
+            const unsigned char t = s_btie[b];
+            const unsigned long long in_b = t != 0xff ? s_red[t] : s_red[BRK_NCLS + b];
             // class j counts the gap before bracket j plus (non-tie) the inside of bracket j-1
-            unsigned long long gap = buf.red_stream[b];
-            if (b > 0 && buf.btie[b - 1] == 0xff) gap -= incnt[b - 1];
+            unsigned long long gap = s_red[b];
+            if (b > 0 && s_btie[b - 1] == 0xff) gap -= incnt[b - 1];
             run += gap;
             below[b] = run;
             incnt[b] = in_b;
             run += in_b;
         }
-        unsigned long long gap = buf.red_stream[B];
-        if (B > 0 && buf.btie[B - 1] == 0xff) gap -= incnt[B - 1];
+        unsigned long long gap = s_red[B];
+        if (B > 0 && s_btie[B - 1] == 0xff) gap -= incnt[B - 1];
         check = run + gap;
         if (check != n_total - n_invalid) raise_fail(buf.hdr, FAIL_INCONSISTENT);  // every non-NaN element is in one class
     }
@@ -1248,25 +1274,31 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
     for (int t = tid; t < qa.nq; t += blockDim.x) {
         RankMath rm = slot_rank_math(qa, t, n_eff);
         const bool nl = needs_lower(qa.interp, rm.frac), nh = needs_higher(qa.interp, rm.frac);
-        buf.slot_rank[2 * t] = nl ? rm.lower : rm.higher;
-        buf.slot_rank[2 * t + 1] = nh ? rm.higher : rm.lower;
+        s_rank[2 * t] = nl ? rm.lower : rm.higher;
+        s_rank[2 * t + 1] = nh ? rm.higher : rm.lower;
     }
     __syncthreads();
     if (ld_now(&buf.hdr[H_FAIL])) return;
     for (int i = tid; i < R; i += blockDim.x) {  // first occurrence of each rank, numbered in slot order
-        const unsigned long long ri = buf.slot_rank[i];
+        const unsigned long long ri = s_rank[i];
         int first = i;
         for (int k = 0; k < i; ++k)
-            if (buf.slot_rank[k] == ri) { first = k; break; }
-        buf.slot_task[i] = first == i ? -1 - i : first;  // negative: "I am a first occurrence"
+            if (s_rank[k] == ri) { first = k; break; }
+        s_first[i] = first == i ? -1 - i : first;  // negative: "I am a first occurrence"
+    }
+    __syncthreads();
+    for (int i = tid; i < R; i += blockDim.x) {  // dense task ids in slot order: every slot learns the id of its rank
+        const int f = s_first[i] < 0 ? i : s_first[i];
+        int id = 0;
+        for (int k = 0; k < f; ++k) id += s_first[k] < 0 ? 1 : 0;
+        s_id[i] = id;
     }
     __syncthreads();
     for (int i = tid; i < R; i += blockDim.x) {
-        if (buf.slot_task[i] < 0) {
-            int id = 0;
-            for (int k = 0; k < i; ++k) id += buf.slot_task[k] < 0 ? 1 : 0;
-            // (ids are dense in slot order)
-            const unsigned long long r = buf.slot_rank[i];
+        buf.slot_task[i] = s_first[i];
+        buf.slot_rank[i] = (unsigned long long)s_id[i];  // slot -> task id (what the output kernel reads)
+        if (s_first[i] < 0) {
+            const unsigned long long r = s_rank[i];
             BrkTask tk;
             tk.r = 0;
             tk.value = 0;
@@ -1284,56 +1316,52 @@ brk_resolve_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs qa, int masked
             } else {
                 tk.seg = lo;
                 tk.r = r - below[lo];
-                if (buf.btie[lo] != 0xff || buf.blo[lo] == buf.bhi[lo]) {
+                if (s_btie[lo] != 0xff || s_blo[lo] == s_bhi[lo]) {
                     tk.state = TASK_DONE;
-                    tk.value = (unsigned long long)buf.blo[lo];
+                    tk.value = (unsigned long long)s_blo[lo];
                 } else {
                     seg_used[lo] = 1;
                 }
             }
-            buf.task[id] = tk;
+            buf.task[s_id[i]] = tk;
         }
     }
-    __syncthreads();
-    // slot -> task id (second pass: first occurrences know their id by counting)
-    for (int i = tid; i < R; i += blockDim.x) {
-        int f = buf.slot_task[i] < 0 ? i : buf.slot_task[i];
-        int id = 0;
-        for (int k = 0; k < f; ++k) id += buf.slot_task[k] < 0 ? 1 : 0;
-        buf.slot_rank[i] = (unsigned long long)id;  // reuse: slot -> task id
-    }
-    __syncthreads();
     if (tid == 0) {
         int nt = 0;
-        for (int i = 0; i < R; ++i) nt += buf.slot_task[i] < 0 ? 1 : 0;
+        for (int i = 0; i < R; ++i) nt += s_first[i] < 0 ? 1 : 0;
         buf.hdr[H_NTASK] = (unsigned long long)nt;
     }
+    __syncthreads();
     // ---- round-0 segments are the brackets -------------------------------------------------------------
+    const unsigned long long final_cap = buf.hdr[H_FINALCAP], pstride = buf.hdr[H_PSTRIDE];
     for (int b = tid; b < B; b += blockDim.x) {
         BrkSeg<Key> s;
-        s.lo = buf.blo[b];
-        s.hi = buf.bhi[b];
+        s.lo = s_blo[b];
+        s.hi = s_bhi[b];
         const int bits = key_bits_used<Key>((Key)(s.hi - s.lo));
         s.shift = bits > 8 ? bits - 8 : 0;
         s.flags = 0;
-        if (buf.btie[b] != 0xff) s.flags |= SEG_TIE;
+        if (s_btie[b] != 0xff) s.flags |= SEG_TIE;
         if (seg_used[b]) s.flags |= SEG_USED;
         s.off = buf.boff[b];
         s.piece_cap = buf.bcap[b];
-        s.piece_stride = buf.hdr[H_PSTRIDE];
+        s.piece_stride = pstride;
         s.cnt_local = (s.flags & SEG_TIE) ? 0 : buf.cur_local[b];  // sum over this GPU's pieces
         s.cnt_global = incnt[b];
         s.cursor = 0;
-        if ((s.flags & SEG_USED) && s.cnt_global <= buf.hdr[H_FINALCAP]) s.flags |= SEG_FINAL;
+        if ((s.flags & SEG_USED) && s.cnt_global <= final_cap) s.flags |= SEG_FINAL;
         buf.seg[0][b] = s;
+        unsigned char kind = 0;  // 1 = goes through the refinement rounds, 2 = small enough to be sorted at once
+        if ((s.flags & SEG_USED) && !(s.flags & (SEG_FINAL | SEG_TIE))) kind = 1;
+        if ((s.flags & SEG_USED) && (s.flags & SEG_FINAL) && !(s.flags & SEG_TIE)) kind = 2;
+        s_segkind[b] = kind;
     }
     __syncthreads();
     if (tid == 0) {
         int active = 0, nfinal = 0;
         for (int b = 0; b < B; ++b) {
-            const BrkSeg<Key> &s = buf.seg[0][b];
-            if ((s.flags & SEG_USED) && !(s.flags & (SEG_FINAL | SEG_TIE))) ++active;
-            if ((s.flags & SEG_USED) && (s.flags & SEG_FINAL) && !(s.flags & SEG_TIE)) ++nfinal;
+            active += s_segkind[b] == 1 ? 1 : 0;
+            nfinal += s_segkind[b] == 2 ? 1 : 0;
         }
         buf.hdr[H_NFINAL] = (unsigned long long)nfinal;   // small segments waiting for brk_final_kernel
         buf.hdr[H_NCHUNK_COUNT] = 0;   // round 0 walks the pieces (brk_refine_count0_kernel), not a chunk table
@@ -1677,6 +1705,12 @@ __global__ void __launch_bounds__(1024) brk_refine_decide_kernel(BrkBuf<Key> buf
     __shared__ unsigned long long new_cnt_local[BRK_MAXSEG], old_cnt_local[BRK_MAXSEG];
     __shared__ unsigned char new_final[BRK_MAXSEG];
     __shared__ int s_nid;
+    // the tasks and what they need of their segments, staged once by all threads: a warp (or a single thread) that
+    // walks the tables in global memory pays one memory latency per entry, and this kernel sits on the critical path
+    // of every refinement round
+    __shared__ BrkTask s_task[BRK_MAXTASK];
+    __shared__ Key s_lo[BRK_MAXTASK];
+    __shared__ int s_shift[BRK_MAXTASK], s_flags[BRK_MAXTASK];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     if (buf.red_refine != buf.loc_refine && buf.hdr[H_GATE_ROUND] && buf.red_refine_fail[0]) {
         if (tid == 0) raise_fail(buf.hdr, FAIL_REMOTE);  // some rank gave up: everybody does
@@ -1698,12 +1732,23 @@ __global__ void __launch_bounds__(1024) brk_refine_decide_kernel(BrkBuf<Key> buf
     for (int i = tid; i < nseg * 256; i += blockDim.x) buf.newid[i] = -1;
     for (int i = tid; i < BRK_MAXTASK; i += blockDim.x) { want[i] = -1; newseg_of[i] = -1; pad_cnt[i] = 0; first[i] = 0; }
     for (int i = tid; i < BRK_MAXSEG; i += blockDim.x) seg_any[i] = 0;
+    for (int t = tid; t < ntask; t += blockDim.x) {
+        const BrkTask tk = buf.task[t];
+        s_task[t] = tk;
+        s_flags[t] = SEG_FINAL;  // "nothing to decide"
+        if (tk.state == TASK_ACTIVE && tk.seg >= 0) {
+            const BrkSeg<Key> sg = segs[tk.seg];
+            s_flags[t] = sg.flags;
+            s_shift[t] = sg.shift;
+            s_lo[t] = sg.lo;
+        }
+    }
     __syncthreads();
     // ---- digit of every active task --------------------------------------------------------------------
     for (int t = warp; t < ntask; t += nwarps) {
-        BrkTask tk = buf.task[t];
+        BrkTask tk = s_task[t];
         if (tk.state != TASK_ACTIVE) continue;
-        const BrkSeg<Key> sg = segs[tk.seg];
+        struct { Key lo; int shift, flags; } sg = {s_lo[t], s_shift[t], s_flags[t]};
         if (sg.flags & (SEG_FINAL | SEG_TIE)) continue;  // resolved by the final kernel
         const unsigned long long *row = buf.red_refine + (size_t)tk.seg * 256;
         unsigned long long c[8], sum = 0;
@@ -1748,7 +1793,7 @@ __global__ void __launch_bounds__(1024) brk_refine_decide_kernel(BrkBuf<Key> buf
                 pad_cnt[t] = (buf.loc_refine[(size_t)tk.seg * 256 + digit] + 3) & ~3ull;
                 tk.r = rem;
             }
-            buf.task[t] = tk;
+            s_task[t] = tk;
         }
     }
     __syncthreads();
@@ -1777,7 +1822,7 @@ __global__ void __launch_bounds__(1024) brk_refine_decide_kernel(BrkBuf<Key> buf
         newseg_of[t] = id;
         if (first[t]) {
             const int s = w >> 8, d = w & 255;
-            const BrkSeg<Key> sg = segs[s];
+            struct { Key lo; int shift; } sg = {s_lo[t], s_shift[t]};  // (task t still points at its old segment s)
             BrkSeg<Key> ns;
             ns.lo = sg.lo + ((Key)d << sg.shift);
             ns.hi = ns.lo + (((Key)1 << sg.shift) - 1);
@@ -1802,9 +1847,8 @@ __global__ void __launch_bounds__(1024) brk_refine_decide_kernel(BrkBuf<Key> buf
     __syncthreads();
     // ---- re-point the tasks; chunk tables of the compaction pass (old segments) and the next count pass ----
     for (int t = tid; t < ntask; t += blockDim.x) {
-        if (want[t] < 0) continue;
-        BrkTask tk = buf.task[t];
-        tk.seg = newseg_of[t];
+        BrkTask tk = s_task[t];  // (tasks this round did not touch are written back unchanged)
+        if (want[t] >= 0) tk.seg = newseg_of[t];
         buf.task[t] = tk;
     }
     for (int s = tid; s < nseg; s += blockDim.x) old_cnt_local[s] = seg_any[s] ? segs[s].cnt_local : 0ull;
@@ -1937,43 +1981,71 @@ __global__ void __launch_bounds__(1024) brk_pack_final_kernel(BrkBuf<Key> buf) {
         if (tk.state == TASK_ACTIVE && tk.seg >= 0) wanted[tk.seg] = 1;
     }
     __syncthreads();
-    if (tid == 0) {
-        unsigned run = 0;
-        for (int sidx = 0; sidx < nseg; ++sidx) {
-            const BrkSeg<Key> &sg = buf.seg[cur][sidx];
-            if (!wanted[sidx] || !(sg.flags & SEG_FINAL) || (sg.flags & SEG_TIE)) continue;
-            unsigned c = (unsigned)sg.cnt_local;
-            if (run + c > (unsigned)BRK_GATHER_CAP) {  // cannot happen with FINAL_CAP * tasks <= GATHER_CAP; be safe
-                raise_fail(buf.hdr, FAIL_CAPACITY);
-                c = 0;
+    // sizes and offsets of the segments to send: one thread per segment (independent loads of the segment table -- a
+    // single thread walking it pays one memory latency per segment), then a scan by the first warps
+    __shared__ unsigned long long soff[BRK_MAXSEG], spstride[BRK_MAXSEG];
+    __shared__ unsigned spcap[BRK_MAXSEG];
+    __shared__ unsigned wsum[BRK_MAXSEG / 32];
+    __shared__ int overflow;
+    if (tid == 0) overflow = 0;
+    if (tid < BRK_MAXSEG) {
+        unsigned c = 0;
+        if (tid < nseg && wanted[tid]) {
+            const BrkSeg<Key> sg = buf.seg[cur][tid];
+            if ((sg.flags & SEG_FINAL) && !(sg.flags & SEG_TIE)) {
+                c = (unsigned)sg.cnt_local;
+                soff[tid] = sg.off;
+                spcap[tid] = (unsigned)sg.piece_cap;
+                spstride[tid] = sg.piece_stride;
             }
-            cnt[sidx] = c;
-            off[sidx] = run;
-            run += c;
         }
-        buf.hdr[H_GWORDS] = ((unsigned long long)BRK_MAXSEG * 4 + (unsigned long long)run * sizeof(Key) + 7) / 8;
+        cnt[tid] = c;
+        unsigned incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((tid & 31) >= d) incl += v;
+        }
+        off[tid] = incl - c;
+        if ((tid & 31) == 31) wsum[tid >> 5] = incl;
     }
     __syncthreads();
+    if (tid < BRK_MAXSEG) {
+        unsigned before = 0;
+        for (int w = 0; w < (tid >> 5); ++w) before += wsum[w];
+        off[tid] += before;
+        if (cnt[tid] && off[tid] + cnt[tid] > (unsigned)BRK_GATHER_CAP) overflow = 1;  // cannot happen with FINAL_CAP * tasks <= GATHER_CAP
+    }
+    __syncthreads();
+    if (overflow) {  // be safe: send nothing, every rank falls back
+        if (tid == 0) raise_fail(buf.hdr, FAIL_CAPACITY);
+        return;
+    }
+    if (tid < BRK_MAXSEG) hdr_out[tid] = cnt[tid];
+    if (tid == 0) {
+        unsigned run = 0;
+        for (int w = 0; w < BRK_MAXSEG / 32; ++w) run += wsum[w];
+        buf.hdr[H_GWORDS] = ((unsigned long long)BRK_MAXSEG * 4 + (unsigned long long)run * sizeof(Key) + 7) / 8;
+    }
+    // the keys: one warp per segment
     const unsigned nw = (unsigned)buf.hdr[H_NW];
-    for (int sidx = 0; sidx < nseg; ++sidx) {
+    const int lane = tid & 31;
+    for (int sidx = tid >> 5; sidx < nseg; sidx += (int)(blockDim.x >> 5)) {
         const unsigned c = cnt[sidx];
-        if (tid == 0) hdr_out[sidx] = c;
         if (c == 0) continue;
-        const BrkSeg<Key> sg = buf.seg[cur][sidx];
-        const Key *src = buf.cand[cur] + sg.off;
-        if (sg.piece_cap == 0) {
-            for (unsigned i = tid; i < c; i += blockDim.x) keys_out[off[sidx] + i] = src[i];
-        } else {  // a round-0 segment: pieces (fills in buf.fill); one warp per piece, positions by prefix over the pieces
+        const Key *src = buf.cand[cur] + soff[sidx];
+        Key *dst = keys_out + off[sidx];
+        if (spcap[sidx] == 0) {
+            for (unsigned i = lane; i < c; i += 32) dst[i] = src[i];
+        } else {  // a round-0 segment: one piece per streaming CTA (fills in buf.fill), laid end to end
             const unsigned *fills = buf.fill + (size_t)sidx * nw;
-            const int lane = tid & 31;
-            for (unsigned w = tid >> 5; w < nw; w += blockDim.x >> 5) {
-                unsigned before = 0;
-                for (unsigned u = lane; u < w; u += 32) before += fills[u];
-                before = __reduce_add_sync(0xffffffffu, before);
-                const unsigned f = fills[w];
-                const Key *piece = src + (unsigned long long)w * sg.piece_stride;
+            unsigned before = 0;
+            for (unsigned w = 0; w < nw; ++w) {
+                const unsigned f = min(fills[w], spcap[sidx]);
+                const Key *piece = src + (unsigned long long)w * spstride[sidx];
                 for (unsigned i = lane; i < f; i += 32)
-                    if (before + i < c) keys_out[off[sidx] + before + i] = piece[i];
+                    if (before + i < c) dst[before + i] = piece[i];
+                before += f;
             }
         }
     }
@@ -2395,7 +2467,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     const unsigned nw = sgrid;  // streaming CTAs = pieces per bracket segment
     {
         auto k = brk_plan_kernel<Key, IS_FLOAT>;
-        const size_t smem = ((BRK_S0 + 1) * 4 + 15) / 16 * 16 + BRK_S0 * sizeof(Key) + BRK_NC1 * 2;
+        const size_t smem = ((BRK_S0 + 1) * 4 + 15) / 16 * 16 + BRK_S0 * sizeof(Key) + BRK_NC1 * 2 + (BRK_S0 + 2) * 4;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<1, 1024, smem, st>>>(buf, qa, brk_csigma(), n, multi ? 1 : 0, nw);
         if ((e = count()) != cudaSuccess) return e;

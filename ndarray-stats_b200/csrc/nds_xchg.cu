@@ -22,6 +22,7 @@
 // raises STATUS_BIT_XCHG and the call returns NDS_NCCL_ERROR instead of hanging the box.
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,6 +55,11 @@ struct XchgHost {
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+constexpr int XCHG_SEQ_BITS = 40;  // flag word = (sequence number + 1) | payload length in 16-byte units << 40
+constexpr unsigned long long XCHG_SEQ_MASK = (1ull << XCHG_SEQ_BITS) - 1ull;
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -73,42 +79,54 @@ __device__ __forceinline__ size_t step_bytes(size_t bytes, const unsigned long l
     return bytes;
 }
 
-// payload -> slot (seq % XCHG_SLOTS, me) of every rank's inbox; the last CTA releases the flags
-__global__ void __launch_bounds__(256)
-xchg_push_kernel(XchgDev x, unsigned long long seq, const uint4 *__restrict__ src, size_t bytes,
-                 const unsigned long long *dev_words, const unsigned long long *gate) {
-    if (gate && *gate == 0) return;
-    bytes = step_bytes(bytes, dev_words);
-    const size_t n16 = bytes / 16;
+// Phase 1 of a step: this CTA's share of the payload -> slot (seq % XCHG_SLOTS, me) of EVERY rank's inbox; the last CTA
+// of the grid to finish releases one flag per rank.  Plain stores, one barrier, then ONE system-scope fence by thread 0:
+// the barrier orders the CTA's stores before the fence (PTX causality is cumulative over bar.sync), the fence orders
+// them before the counter update, and the last CTA fences again before it releases the flags.
+__device__ __forceinline__ void xchg_push(const XchgDev &x, unsigned long long seq, const uint4 *__restrict__ src, size_t n16) {
     const unsigned slot = (unsigned)(seq % XCHG_SLOTS);
     const size_t off = (size_t)slot * x.slot_stride + (size_t)x.me * x.src_stride;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (int j = 0; j < x.nranks; ++j) {
-        const int r = (x.me + j) % x.nranks;  // start with the local copy, then the peers in a rank-dependent order
-        uint4 *dst = reinterpret_cast<uint4 *>(x.inbox[r] + off);
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = src[i];
+#pragma unroll 1
+        for (int j = 0; j < x.nranks; ++j) {
+            int r = x.me + j;  // the local copy first, then the peers in a rank-dependent order
+            if (r >= x.nranks) r -= x.nranks;
+            reinterpret_cast<uint4 *>(x.inbox[r] + off)[i] = v;
+        }
     }
-    __threadfence_system();
+    // One system-scope fence per CTA (thread 0, after the barrier that orders the CTA's stores before it), a counter
+    // that tells the last CTA it is the last, and then ONE more fence in each of the first nranks threads, all at the
+    // same time, before each of them releases the flag of "its" rank with a relaxed store.  (A st.release per flag from
+    // one thread costs one NVLink round trip per rank, one after the other: 8 ranks, ~25 us.)  The flag word carries the
+    // payload's length in its upper bits.
+    __shared__ int s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned long long old = atomicAdd(&x.done[slot], 1ull);
-        if (old == (unsigned long long)gridDim.x - 1ull) {
-            x.done[slot] = 0;
+        int last = 1;
+        if (gridDim.x > 1) {
             __threadfence_system();
-            for (int r = 0; r < x.nranks; ++r)
-                st_release_sys(x.flags[r] + (size_t)slot * XCHG_MAX_RANKS + x.me, seq + 1ull);
+            const unsigned long long old = atomicAdd(&x.done[slot], 1ull);
+            last = old == (unsigned long long)gridDim.x - 1ull;
+            if (last) x.done[slot] = 0;
         }
+        s_last = last;
+    }
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < x.nranks) {
+        __threadfence_system();
+        st_relaxed_sys(x.flags[threadIdx.x] + (size_t)slot * XCHG_MAX_RANKS + x.me, (seq + 1ull) | ((unsigned long long)n16 << XCHG_SEQ_BITS));
     }
 }
 
-// wait until every rank's payload of step `seq` sits in this rank's inbox (thread r waits for rank r)
+// Phase 2: wait until every rank's payload of step `seq` sits in this rank's inbox (thread r waits for rank r).
 __device__ __forceinline__ void xchg_wait(const XchgDev &x, unsigned long long seq, int *status) {
     if ((int)threadIdx.x < x.nranks) {
         const unsigned long long *f = x.flags[x.me] + (size_t)(seq % XCHG_SLOTS) * XCHG_MAX_RANKS + threadIdx.x;
-        if (ld_acquire_sys(f) != seq + 1ull && !(*reinterpret_cast<volatile int *>(status) & STATUS_BIT_XCHG)) {
+        if ((ld_acquire_sys(f) & XCHG_SEQ_MASK) != seq + 1ull && !(*reinterpret_cast<volatile int *>(status) & STATUS_BIT_XCHG)) {
             const unsigned long long t0 = global_ns();
-            while (ld_acquire_sys(f) != seq + 1ull) {
-                __nanosleep(200);
+            while ((ld_acquire_sys(f) & XCHG_SEQ_MASK) != seq + 1ull) {
                 if (global_ns() - t0 > x.timeout_ns) {
                     atomicOr(status, STATUS_BIT_XCHG);
                     break;
@@ -119,41 +137,56 @@ __device__ __forceinline__ void xchg_wait(const XchgDev &x, unsigned long long s
     __syncthreads();
 }
 
+// One exchange step as ONE kernel: push, wait, then sum what the peers have left in this rank's inbox.  Every CTA reduces
+// exactly the 16-byte chunks it pushed itself, so the sum may overwrite the payload in place.  All CTAs wait inside the
+// kernel, hence the grid is kept far below the SM count (they are all resident).
 __global__ void __launch_bounds__(256)
-xchg_reduce_u64_kernel(XchgDev x, unsigned long long seq, unsigned long long *__restrict__ dst, size_t words,
-                       const unsigned long long *dev_words, const unsigned long long *gate, int *status) {
+xchg_allreduce_kernel(XchgDev x, unsigned long long seq, unsigned long long *__restrict__ buf, size_t bytes,
+                      const unsigned long long *dev_words, const unsigned long long *gate, int *status) {
     if (gate && *gate == 0) return;
-    if (dev_words && *dev_words < words) words = (size_t)*dev_words;
+    bytes = step_bytes(bytes, dev_words);
+    const size_t n16 = bytes / 16;
+    xchg_push(x, seq, reinterpret_cast<const uint4 *>(buf), n16);
     xchg_wait(x, seq, status);
     const unsigned char *base = x.inbox[x.me] + (size_t)(seq % XCHG_SLOTS) * x.slot_stride;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) {
-        unsigned long long sum = 0;
-        for (int r = 0; r < x.nranks; ++r)
-            sum += __ldcg(reinterpret_cast<const unsigned long long *>(base + (size_t)r * x.src_stride) + i);
-        dst[i] = sum;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        unsigned long long s0 = 0, s1 = 0;
+        for (int r = 0; r < x.nranks; ++r) {
+            const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(base + (size_t)r * x.src_stride) + i);
+            s0 += (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+            s1 += (unsigned long long)v.z | ((unsigned long long)v.w << 32);
+        }
+        buf[2 * i] = s0;
+        buf[2 * i + 1] = s1;
     }
 }
 
 __global__ void __launch_bounds__(256)
-xchg_gather_kernel(XchgDev x, unsigned long long seq, uint4 *__restrict__ dst, size_t bytes_per_rank,
-                   const unsigned long long *gate, int *status) {
+xchg_allgather_kernel(XchgDev x, unsigned long long seq, const uint4 *__restrict__ send, uint4 *__restrict__ recv,
+                      size_t bytes_per_rank, const unsigned long long *dev_words, const unsigned long long *gate, int *status) {
     if (gate && *gate == 0) return;
+    const size_t n16_max = bytes_per_rank / 16;
+    const size_t n16 = step_bytes(bytes_per_rank, dev_words) / 16;  // what THIS rank sends; the peers' lengths may differ
+    xchg_push(x, seq, send, n16);
     xchg_wait(x, seq, status);
     const unsigned char *base = x.inbox[x.me] + (size_t)(seq % XCHG_SLOTS) * x.slot_stride;
-    const size_t n16 = bytes_per_rank / 16;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (int r = 0; r < x.nranks; ++r) {
+    const unsigned long long *fl = x.flags[x.me] + (size_t)(seq % XCHG_SLOTS) * XCHG_MAX_RANKS;
+    for (int r = 0; r < x.nranks; ++r) {  // every rank's payload has its own length (it came with the flag)
+        size_t ncopy = (size_t)(__ldcg(fl + r) >> XCHG_SEQ_BITS);
+        if (ncopy > n16_max) ncopy = n16_max;
         const uint4 *s = reinterpret_cast<const uint4 *>(base + (size_t)r * x.src_stride);
-        uint4 *d = dst + (size_t)r * n16;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) d[i] = __ldcg(s + i);
+        uint4 *d = recv + (size_t)r * n16_max;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncopy; i += stride) d[i] = __ldcg(s + i);
     }
 }
 
 unsigned grid_for(const nds_ctx *ctx, size_t bytes) {
-    size_t g = (bytes + 16 * 256 * 8 - 1) / (16 * 256 * 8);  // ~32 KB per CTA
+    size_t g = (bytes + 16 * 256 * 2 - 1) / (16 * 256 * 2);  // ~8 KB per CTA
     if (g < 1) g = 1;
-    if (g > (size_t)ctx->sm_count) g = (size_t)ctx->sm_count;
+    const size_t cap = (size_t)std::min(ctx->sm_count / 2, 32);  // every CTA waits inside the kernel: all must be resident
+    if (g > cap) g = cap;
     return (unsigned)g;
 }
 
@@ -168,10 +201,8 @@ cudaError_t xchg_allreduce_u64(nds_ctx *ctx, unsigned long long *buf, size_t wor
     const size_t bytes = (words * 8 + 15) & ~(size_t)15;
     if (bytes > h->dev.src_stride) return cudaErrorInvalidValue;
     const unsigned long long seq = ctx->xseq++;
-    const unsigned grid = grid_for(ctx, bytes);
-    xchg_push_kernel<<<grid, 256, 0, ctx->stream>>>(h->dev, seq, (const uint4 *)buf, bytes, dev_words, gate);
-    xchg_reduce_u64_kernel<<<grid, 256, 0, ctx->stream>>>(h->dev, seq, buf, words, dev_words, gate, ctx->d_status);
-    ctx->launches += 2;
+    xchg_allreduce_kernel<<<grid_for(ctx, bytes), 256, 0, ctx->stream>>>(h->dev, seq, buf, bytes, dev_words, gate, ctx->d_status);
+    ctx->launches += 1;
     ctx->xchg_steps += 1;
     return cudaGetLastError();
 }
@@ -182,10 +213,9 @@ cudaError_t xchg_allgather(nds_ctx *ctx, const void *send, void *recv, size_t by
     if (!h) return cudaErrorNotSupported;
     if (bytes_per_rank % 16 != 0 || bytes_per_rank > h->dev.src_stride) return cudaErrorInvalidValue;
     const unsigned long long seq = ctx->xseq++;
-    const unsigned grid = grid_for(ctx, bytes_per_rank);
-    xchg_push_kernel<<<grid, 256, 0, ctx->stream>>>(h->dev, seq, (const uint4 *)send, bytes_per_rank, dev_words, gate);
-    xchg_gather_kernel<<<grid, 256, 0, ctx->stream>>>(h->dev, seq, (uint4 *)recv, bytes_per_rank, gate, ctx->d_status);
-    ctx->launches += 2;
+    xchg_allgather_kernel<<<grid_for(ctx, bytes_per_rank), 256, 0, ctx->stream>>>(h->dev, seq, (const uint4 *)send, (uint4 *)recv,
+                                                                               bytes_per_rank, dev_words, gate, ctx->d_status);
+    ctx->launches += 1;
     ctx->xchg_steps += 1;
     return cudaGetLastError();
 }
@@ -223,7 +253,7 @@ bool xchg_setup(nds_ctx *ctx) {
     const size_t src_stride = XCHG_SRC_BYTES;
     const size_t slot_stride = src_stride * XCHG_MAX_RANKS;
     const size_t inbox_bytes = slot_stride * XCHG_SLOTS;
-    const size_t flag_bytes = (size_t)XCHG_SLOTS * XCHG_MAX_RANKS * 8;
+    const size_t flag_bytes = (size_t)2 * XCHG_SLOTS * XCHG_MAX_RANKS * 8;  // flags, then the payload lengths
     const size_t total = inbox_bytes + flag_bytes + 256 /* done counters */ + 256;
     XchgRecord mine;
     std::memset(&mine, 0, sizeof mine);

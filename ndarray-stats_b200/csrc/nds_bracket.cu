@@ -68,6 +68,11 @@ constexpr int STR_WARPS = STR_THREADS / 32;
 constexpr int STR_TILE = 4096;
 
 constexpr unsigned ENT_COMPACT = 0x100u, ENT_MIXED = 0x200u;
+// a table cell that holds exactly ONE bracket and that bracket is a single key v (a tie bracket b, the low byte): the
+// class follows from two compares -- below v: gap b, equal: the tie's own class, above: gap b + 1 -- instead of the walk
+// over the bracket edges.  Tie-heavy lanes send most of their keys through such cells.
+constexpr unsigned ENT_TIE1 = 0x400u;
+constexpr int BRK_LOWCARD_MAX = 63;       // distinct sample keys up to which a lane is counted per key (2 K + 1 classes)
 
 enum : int {
     H_NTOTAL = 0, H_NINVALID, H_NEFF, H_FAIL, H_B, H_NSEG, H_NTASK, H_NACTIVE, H_S1VALID, H_EMPTY, H_NCHUNK_COUNT,
@@ -100,6 +105,7 @@ template <typename Key> struct BrkLutConst {
     unsigned submask;
     int B, ncls_used;
     int hi32;          // 64-bit keys: the tables are indexed with the high word only (shift1, subshift >= 32)
+    int count_only;    // low-cardinality lane: every bracket is one distinct key, nothing is compacted (tie class = B + 1 + b)
 };
 
 template <typename Key> struct BrkBuf {
@@ -435,7 +441,8 @@ __device__ __forceinline__ unsigned pure_entry(int j, bool in, const unsigned ch
 
 template <typename Key, bool IS_FLOAT>
 __global__ void __launch_bounds__(1024)
-brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long n_local, int sharded, unsigned nw) {
+brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long n_local, int sharded, unsigned nw,
+                int lowcard_allowed) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned *cum = reinterpret_cast<unsigned *>(smem_raw);            // [S0 + 1] inclusive: #{ s1 <= S0[i] }
     Key *s0 = reinterpret_cast<Key *>(smem_raw + ((BRK_S0 + 1) * 4 + 15) / 16 * 16);  // [S0] the sorted sample
@@ -448,8 +455,9 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
     __shared__ unsigned char qheavy[BRK_MAXQ];
     __shared__ Key hv[2 * BRK_MAXQ];
     __shared__ unsigned warp_tot[32];
-    __shared__ int sB, sM, sShift1, sNmixed, sFail, sHi32;
+    __shared__ int sB, sM, sShift1, sNmixed, sFail, sHi32, sLow, sK;
     __shared__ Key sKminLut;
+    __shared__ Key dkey[BRK_LOWCARD_MAX + 1];
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const Key KMAX = (Key) ~(Key)0;
     const int nq = qa.nq;
@@ -511,14 +519,43 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             buf.lutc->subshift = 0;
             buf.lutc->submask = 0;
             buf.lutc->ncls_used = 1;
+            buf.lutc->count_only = 0;
         }
         for (int c = tid; c < BRK_NC1; c += nthreads) buf.lut1[c] = 0u;  // every number is class 0 (NaNs: invalid class)
         for (int i = tid; i < BRK_L2_PURE; i += nthreads) buf.lut2[i] = (unsigned short)0;
         return;
     }
 
-    // ---- one bracket per requested quantile ----------------------------------------------------------
-    for (int t = tid; t < nq; t += nthreads) {
+    // ---- low-cardinality lanes: when the sorted sample S0 holds at most 63 distinct keys, every one of them becomes
+    //      a bracket of its own (a tie: counted in its own class, never compacted) and the streaming pass only COUNTS.
+    //      Any requested rank then resolves from the counts; a rank that falls between the known keys (a key the
+    //      sample has not seen) escapes and the call falls back to the radix passes, as always. -------------------
+    if (tid == 0) { sK = 0; sLow = 0; }
+    __syncthreads();
+    for (int i = tid; i < BRK_S0; i += nthreads) {
+        const Key v = s0[i];
+        if (IS_FLOAT && v == KMAX) continue;  // NaN samples
+        if (i == 0 || s0[i - 1] != v) {
+            const int slot = atomicAdd(&sK, 1);
+            if (slot <= BRK_LOWCARD_MAX) dkey[slot] = v;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) sLow = (sK >= 1 && sK <= BRK_LOWCARD_MAX && lowcard_allowed) ? 1 : 0;
+    __syncthreads();
+    const bool low = sLow != 0;
+    if (low) {  // the distinct keys, ascending (rank sort of <= 63 keys)
+        const int K = sK;
+        if (tid < K) {
+            const Key v = dkey[tid];
+            int r = 0;
+            for (int u = 0; u < K; ++u) r += dkey[u] < v ? 1 : 0;
+            blo[r] = v;
+            bhi[r] = v;
+        }
+    }
+    // ---- otherwise: one bracket per requested quantile -------------------------------------------------
+    for (int t = tid; t < (low ? 0 : nq); t += nthreads) {
         double p;
         if (qa.ranks) p = n_total > 1 ? (double)qa.ranks[t] / (double)(n_total - 1) : 0.0;
         else p = qa.qs[t];
@@ -579,7 +616,7 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
     }
     __syncthreads();
     // sort by (lo, hi) with a rank sort (nq <= 128), then merge overlapping brackets sequentially
-    for (int t = tid; t < nq; t += nthreads) {
+    for (int t = tid; t < (low ? 0 : nq); t += nthreads) {
         int rank = 0;
         const Key l = qlo[t], h = qhi[t];
         for (int u = 0; u < nq; ++u) {
@@ -593,7 +630,7 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
     if (tid == 0) {
         // heavy edge keys, sorted and unique
         int nh = 0;
-        for (int t = 0; t < nq; ++t) {
+        for (int t = 0; t < (low ? 0 : nq); ++t) {
             for (int side = 0; side < 2; ++side) {
                 if (!(qheavy[t] & (1 << side))) continue;
                 const Key v = side ? qhi[t] : qlo[t];
@@ -628,17 +665,21 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             }
             if (open) emit(cur, h);
         };
-        Key cl = slo[0], ch = shi[0];
-        for (int t = 1; t < nq; ++t) {
-            if (slo[t] <= ch || (ch != KMAX && slo[t] == ch + 1)) {
-                if (shi[t] > ch) ch = shi[t];
-            } else {
-                emit_span(cl, ch);
-                cl = slo[t];
-                ch = shi[t];
+        if (low) {
+            B = sK;  // blo / bhi hold the distinct keys already
+        } else {
+            Key cl = slo[0], ch = shi[0];
+            for (int t = 1; t < nq; ++t) {
+                if (slo[t] <= ch || (ch != KMAX && slo[t] == ch + 1)) {
+                    if (shi[t] > ch) ch = shi[t];
+                } else {
+                    emit_span(cl, ch);
+                    cl = slo[t];
+                    ch = shi[t];
+                }
             }
+            emit_span(cl, ch);
         }
-        emit_span(cl, ch);
         int fail = 0;
         if (B > BRK_MAXB) { fail |= FAIL_TOO_MANY; B = BRK_MAXB; }
         // tie brackets (a single key) get their own counter class while classes last
@@ -760,6 +801,20 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
         const PointClass<Key> pe = classify_point(blo, bhi, B, e);
         return (pa.j == pe.j && pa.in == pe.in) ? 0 : 1;
     };
+    // index of the tie bracket (a single key with a class of its own) that is ALL the range [a, e] holds, or -1
+    auto tie1_of = [&](Key a, Key e) -> int {
+        int lo = 0, hi = B;  // first bracket that ends at or after a
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (bhi[mid] < a) lo = mid + 1;
+            else hi = mid;
+        }
+        const int b = lo;
+        if (b >= B || blo[b] != bhi[b] || btie[b] == 0xff) return -1;
+        if (blo[b] < a || blo[b] > e) return -1;
+        if (b + 1 < B && blo[b + 1] <= e) return -1;
+        return b;
+    };
     const Key max_cell = (KMAX - kmin) >> shift1;  // cells past the end of the key space can never be hit
     for (int c = tid; c < BRK_NC1; c += nthreads) {
         unsigned e1;
@@ -769,8 +824,11 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             Key a, e;
             cell_ends(c, a, e);
             PointClass<Key> pa;
+            int tb;
             if (range_kind(a, e, pa) == 0) {
                 e1 = pure_entry(pa.j, pa.in, btie);  // a pure cell: the final entry, no second table read
+            } else if ((tb = tie1_of(a, e)) >= 0) {
+                e1 = ENT_TIE1 | (unsigned)tb;         // one tie key and nothing else: final as well
             } else {
                 const int slot = atomicAdd(&sNmixed, 1);
                 mixcell[slot] = (unsigned short)c;
@@ -795,6 +853,7 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
         buf.lutc->submask = (1u << M) - 1u;
         buf.lutc->B = B;
         buf.lutc->ncls_used = (int)buf.hdr[H_NCLS_USED];
+        buf.lutc->count_only = sLow;
     }
     __syncthreads();
     const int M = sM, subshift = shift1 - M;
@@ -811,8 +870,10 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
         if (e2 > e) e2 = e;
         PointClass<Key> p2;
         const int k2 = range_kind(a2, e2, p2);
+        const int tb2 = k2 == 0 ? -1 : tie1_of(a2, e2);
         const unsigned short ent = k2 == 0 ? (unsigned short)pure_entry(p2.j, p2.in, btie)
-                                           : (unsigned short)(ENT_MIXED | (unsigned)p2.j);
+                                           : (tb2 >= 0 ? (unsigned short)(ENT_TIE1 | (unsigned)tb2)
+                                                       : (unsigned short)(ENT_MIXED | (unsigned)p2.j));
         buf.lut2[BRK_L2_PURE + g] = ent;
     }
 }
@@ -872,9 +933,18 @@ __device__ __forceinline__ unsigned brk_resolve_entry(Key k, unsigned ent, const
     const unsigned t = btie[jm];
     return in ? (t != 0xffu ? t : ((unsigned)j | ENT_COMPACT)) : (unsigned)j;
 }
+// a cell that holds one tie key and nothing else (ENT_TIE1): two compares
+template <typename Key>
+__device__ __forceinline__ unsigned brk_tie1_entry(Key k, unsigned ent, const Key *blo, const unsigned char *btie) {
+    const unsigned b = ent & 0xffu;
+    const Key v = blo[b];
+    const unsigned t = btie[b];
+    return k < v ? b : (k == v ? t : b + 1u);
+}
 
-// HI32: 64-bit keys, tables indexed with the high word (see brk_plan_kernel); the kernel of the other mode returns
-template <typename T, bool HI32>
+// HI32: 64-bit keys, tables indexed with the high word (see brk_plan_kernel); the kernel of the other mode returns.
+// COUNT: low-cardinality lanes (every bracket is one distinct key): classify and count only, nothing is compacted.
+template <typename T, bool HI32, bool COUNT>
 __global__ void __launch_bounds__(STR_THREADS, 1)
 brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typename Traits<T>::Key> buf) {
     using Tr = Traits<T>;
@@ -901,7 +971,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     if (failed_any(buf.hdr)) return;  // the plan already gave up: the caller falls back
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const BrkLutConst<Key> lc = *buf.lutc;
-    if ((lc.hi32 != 0) != HI32) return;
+    if ((lc.hi32 != 0) != HI32 || (lc.count_only != 0) != COUNT) return;
 #ifdef NDS_STR_TIMING  // diagnostic build (make strvar TIMING=1): per-CTA cycle counts of the streaming pass
     const long long t_begin = clock64();
     long long t_loop = 0;
@@ -1072,11 +1142,13 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
                 }
             }
         }
-        // phase 2: the few keys in a sub-cell with a bracket edge
-        if (slow & ENT_MIXED) {
+        // phase 2: keys in a cell with one tie key (two compares), the few keys in a sub-cell with a bracket edge (a walk)
+        if (slow & (ENT_MIXED | ENT_TIE1)) {
 #pragma unroll
-            for (int e = 0; e < STR_EPT; ++e)
-                if (ent[e] & ENT_MIXED) ent[e] = brk_resolve_entry<Key>(k[e], ent[e], blo, bhi, btie, B);
+            for (int e = 0; e < STR_EPT; ++e) {
+                if (ent[e] & ENT_TIE1) ent[e] = brk_tie1_entry<Key>(k[e], ent[e], blo, btie);
+                else if (ent[e] & ENT_MIXED) ent[e] = brk_resolve_entry<Key>(k[e], ent[e], blo, bhi, btie, B);
+            }
         }
         // phase 3: private counters (plain read-modify-write of this thread's own bytes, one after the other: two
         // keys of a thread may share a class), candidate mask
@@ -1088,6 +1160,8 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             cflag[e] = (ent[e] >> 8) & 1u;
             cnt += cflag[e];
         }
+        if constexpr (COUNT) return;  // nothing is ever compacted in this mode
+        if (!__any_sync(0xffffffffu, cnt != 0)) return;  // a tile without candidates (common when brackets are few)
         // phase 4: the ~10 % of keys inside a bracket are packed into the warp's ring (warp prefix sum); full groups
         // of 32 are appended to the brackets' segments, the rest waits for the next tile
         unsigned incl = cnt;
@@ -1161,7 +1235,8 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
                     ent = (unsigned)BRK_INVALID_CLS;
                 } else {
                     ent = lookup(k);
-                    if (ent & ENT_MIXED) ent = brk_resolve_entry<Key>(k, ent, blo, bhi, btie, B);
+                    if (ent & ENT_TIE1) ent = brk_tie1_entry<Key>(k, ent, blo, btie);
+                    else if (ent & ENT_MIXED) ent = brk_resolve_entry<Key>(k, ent, blo, bhi, btie, B);
                 }
                 myctr[(ent & 0xffu) * STR_THREADS] += 1;
             }
@@ -2469,22 +2544,25 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         auto k = brk_plan_kernel<Key, IS_FLOAT>;
         const size_t smem = ((BRK_S0 + 1) * 4 + 15) / 16 * 16 + BRK_S0 * sizeof(Key) + BRK_NC1 * 2 + (BRK_S0 + 2) * 4;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<1, 1024, smem, st>>>(buf, qa, brk_csigma(), n, multi ? 1 : 0, nw);
+        static const bool lowcard_knob = !(getenv("NDS_BRK_LOWCARD") && atoi(getenv("NDS_BRK_LOWCARD")) == 0);
+        k<<<1, 1024, smem, st>>>(buf, qa, brk_csigma(), n, multi ? 1 : 0, nw, lowcard_knob ? 1 : 0);
         if ((e = count()) != cudaSuccess) return e;
         timer.mark("plan");
     }
     // 4. stream (the kernel of the table mode the plan did not choose returns at once)
     {
         const size_t smem = stream_smem_bytes<Key>();
-        auto k0 = brk_stream_kernel<T, false>;
-        if ((e = cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k0<<<sgrid, STR_THREADS, smem, st>>>(lane, n, buf);
-        if ((e = count()) != cudaSuccess) return e;
+        auto launch_stream = [&](auto k) -> cudaError_t {
+            cudaError_t e2 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e2 != cudaSuccess) return e2;
+            k<<<sgrid, STR_THREADS, smem, st>>>(lane, n, buf);
+            return count();
+        };
+        if ((e = launch_stream(brk_stream_kernel<T, false, false>)) != cudaSuccess) return e;
+        if ((e = launch_stream(brk_stream_kernel<T, false, true>)) != cudaSuccess) return e;
         if constexpr (sizeof(Key) == 8) {
-            auto k1 = brk_stream_kernel<T, true>;
-            if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-            k1<<<sgrid, STR_THREADS, smem, st>>>(lane, n, buf);
-            if ((e = count()) != cudaSuccess) return e;
+            if ((e = launch_stream(brk_stream_kernel<T, true, false>)) != cudaSuccess) return e;
+            if ((e = launch_stream(brk_stream_kernel<T, true, true>)) != cudaSuccess) return e;
         }
         brk_publish_fill_kernel<Key><<<1, 128, 0, st>>>(buf);
         if ((e = count()) != cudaSuccess) return e;

@@ -571,3 +571,41 @@ def test_full_size_c3_against_oracle(nds, gpu_ctx, oracle):
     assert bool(((lt <= r) & (r < le)).all())
     del t, valid
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("dtype", [np.uint32, np.int64, np.float32, np.float64], ids=lambda d: np.dtype(d).name)
+def test_bracket_low_cardinality(nds, gpu_ctx, oracle, dtype):
+    """Tie-heavy long lanes (BASELINE config 5): at most 63 distinct keys in the sample -> every distinct key is counted in
+    a class of its own and nothing is compacted.  All five strategies, ranks all over the lane; a key the sample cannot
+    have seen (one occurrence, requested as the maximum) must still come out right (the call falls back)."""
+    rng = np.random.default_rng(55)
+    n = (1 << 21) + 12345
+    for nvals, adversarial in ((16, False), (16, True), (60, False), (2, False), (1, False)):
+        if np.dtype(dtype).kind == "f":
+            vals = np.sort(rng.standard_normal(nvals)).astype(dtype)
+            if nvals >= 2:
+                vals[0], vals[1] = dtype(-0.0), dtype(0.0)
+            if adversarial:
+                vals = (np.float64(1.0) + np.arange(nvals) * np.finfo(dtype).eps).astype(dtype)
+        elif adversarial:
+            vals = (np.int64(0x80000000 if dtype == np.uint32 else -3) + np.arange(nvals)).astype(dtype)
+        else:
+            vals = (np.arange(nvals, dtype=np.int64) * (0x11111111 if dtype == np.uint32 else (1 << 40))).astype(dtype)
+            if dtype == np.int64:
+                vals = vals - np.int64(8 << 40)
+        a = vals[rng.integers(0, nvals, n)]
+        qs = [0.0, 0.1, 0.25, 0.5, 0.75, 0.9, 0.999, 1.0]
+        for interp in INTERPS:
+            check(gpu_ctx, oracle, a, 0, qs, interp, select_impl=1)
+            assert gpu_ctx.last_path == "bracket", gpu_ctx.last_path
+    # a key the sample has not seen
+    a = np.asarray([3, 5, 7], dtype=dtype)[rng.integers(0, 3, n)]
+    a[n // 3] = 9
+    check(gpu_ctx, oracle, a, 0, [0.5, 1.0], "lower", select_impl=1)
+    assert gpu_ctx.last_path == "bracket->long_radix", gpu_ctx.last_path
+    if np.dtype(dtype).kind == "f":  # NaNs beside few values, skipnan and not
+        b = a.copy()
+        b[rng.random(n) < 0.05] = np.nan
+        check(gpu_ctx, oracle, b, 0, [0.2, 0.5, 0.9], "midpoint", skipnan=True, select_impl=1)
+        with pytest.raises(nds.NanInInput):
+            gpu_ctx.quantiles_axis(b, 0, [0.5], "lower")

@@ -116,11 +116,19 @@ nds_status status_from_bits(nds_ctx *ctx, int bits) {
     return NDS_OK;
 }
 
-bool use_long_path(const nds_ctx *ctx, const LaneGeom &g) {
+// Grid-wide selection of ONE lane at a time (bracket select, else the radix passes: every requested rank per pass) against
+// the CTA-per-lane kernel (one rank at a time, one CTA per lane).  `fast_lanes`: a bit-sliced lane kernel takes the call.
+bool use_long_path(const nds_ctx *ctx, const LaneGeom &g, size_t nq, bool fast_lanes) {
     if (ctx->forced_path == "long_radix") return true;
     if (ctx->forced_path != "auto") return false;
     if (g.axis_len >= (1ull << 32)) return true;
-    return g.axis_len >= (1ull << 18) && g.nlanes * 4 <= (unsigned long long)ctx->sm_count;
+    if (fast_lanes) return false;
+    if (g.axis_len >= (1ull << 18) && g.nlanes * 4 <= (unsigned long long)ctx->sm_count) return true;
+    // mid-length lanes that no lane kernel takes: a handful of lanes, or many quantiles of a few lanes, are quicker one
+    // after the other over the whole grid (~0.1 ms each) than as one CTA each that selects rank after rank
+    if (g.axis_len >= 8192 && g.nlanes <= 8) return true;
+    if (g.axis_len >= 8192 && nq >= 8 && g.nlanes <= 32) return true;
+    return false;
 }
 
 // Common body once everything is parsed. `host_io`: data/out (and masks) are host pointers to stage.
@@ -143,7 +151,18 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
     view_span(ndim, shape, strides, min_off, max_off);
     const size_t span_elems = (size_t)(max_off - min_off + 1);
 
-    const bool long_path = sharded || use_long_path(ctx, p.geom);
+    bool fast_lanes = false;
+    if (!sharded && ctx->forced_path == "auto") {
+        DeviceCall pre;
+        pre.dtype = dtype;
+        pre.data = data_on_device ? data : (const void *)nullptr;  // (a staged host array is 256-byte aligned)
+        pre.valid = valid;
+        pre.out_valid = out_valid;
+        pre.geom = p.geom;
+        pre.q.nq = (int)nq;
+        fast_lanes = short_bitslice_supported(ctx, pre) || cols_bitslice_supported(ctx, pre);
+    }
+    const bool long_path = sharded || use_long_path(ctx, p.geom, nq, fast_lanes);
     // ---- carve the arena ---------------------------------------------------------------------------
     size_t off = 0;
     auto carve = [&](size_t bytes) {

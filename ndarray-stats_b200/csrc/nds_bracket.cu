@@ -952,7 +952,12 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     constexpr bool IS_FLOAT = Tr::is_float;
     constexpr int ES = (int)sizeof(T);
     constexpr int VEC = 16 / ES;             // elements per 16-byte load
-    constexpr int NLD = STR_EPT / VEC;       // 16-byte loads per thread per tile
+    // keys per thread and tile: four -- eight for the 4-byte types when the pass only counts (then nothing but the loads in
+    // flight limits it: two 16-byte loads per thread keep 2 x 32 KB per SM on their way, as the 8-byte types do)
+    constexpr int EPT = (COUNT && ES == 4) ? 2 * STR_EPT : STR_EPT;
+    constexpr int TILE = STR_THREADS * EPT;
+    constexpr int SPILL_TILES = 255 / EPT;   // 8-bit private counters
+    constexpr int NLD = EPT / VEC;           // 16-byte loads per thread per tile
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // ---- carve shared memory -----------------------------------------------------------------------
     unsigned char *p = smem_raw;
@@ -1092,17 +1097,17 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     const uintptr_t addr = reinterpret_cast<uintptr_t>(data);
     unsigned long long head = ((16 - (addr & 15)) & 15) / ES;  // elements before the first aligned one
     if (head > n) head = n;
-    const unsigned long long n_tiles = (n - head) / STR_TILE;
+    const unsigned long long n_tiles = (n - head) / TILE;
     const T *adata = data + head;
     const uint4 *vdata = reinterpret_cast<const uint4 *>(adata);
 
     auto load_tile = [&](unsigned long long tile, uint4 (&q)[NLD]) {
-        const uint4 *src = vdata + tile * (STR_TILE / VEC);
+        const uint4 *src = vdata + tile * (TILE / VEC);
 #pragma unroll
         for (int j = 0; j < NLD; ++j) q[j] = __ldg(src + j * STR_THREADS + tid);
     };
     auto process_tile = [&](const uint4 (&q)[NLD]) {
-        Key k[STR_EPT];
+        Key k[EPT];
         bool nan = false;  // floats: NaNs are found with one floating-point compare per key (their keys lie outside
                            // [key(-inf), key(+inf)] and the tables do not know about them)
 #pragma unroll
@@ -1125,10 +1130,10 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             }
         }
         // phase 1: all table reads of the tile are independent of each other
-        unsigned ent[STR_EPT];
+        unsigned ent[EPT];
         unsigned slow = 0;
 #pragma unroll
-        for (int e = 0; e < STR_EPT; ++e) {
+        for (int e = 0; e < EPT; ++e) {
             ent[e] = lookup(k[e]);
             slow |= ent[e];
         }
@@ -1136,7 +1141,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             if (__any_sync(0xffffffffu, nan)) {  // rare: NaNs get the invalid class, whatever the tables said
                 slow = 0;
 #pragma unroll
-                for (int e = 0; e < STR_EPT; ++e) {
+                for (int e = 0; e < EPT; ++e) {
                     if (key_is_nan<T>(k[e])) ent[e] = (unsigned)BRK_INVALID_CLS;
                     slow |= ent[e];
                 }
@@ -1145,16 +1150,16 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         // phase 2: keys in a cell with one tie key (two compares), the few keys in a sub-cell with a bracket edge (a walk)
         if (slow & (ENT_MIXED | ENT_TIE1)) {
 #pragma unroll
-            for (int e = 0; e < STR_EPT; ++e) {
+            for (int e = 0; e < EPT; ++e) {
                 if (ent[e] & ENT_TIE1) ent[e] = brk_tie1_entry<Key>(k[e], ent[e], blo, btie);
                 else if (ent[e] & ENT_MIXED) ent[e] = brk_resolve_entry<Key>(k[e], ent[e], blo, bhi, btie, B);
             }
         }
         // phase 3: private counters (plain read-modify-write of this thread's own bytes, one after the other: two
         // keys of a thread may share a class), candidate mask
-        unsigned cflag[STR_EPT], cnt = 0;
+        unsigned cflag[EPT], cnt = 0;
 #pragma unroll
-        for (int e = 0; e < STR_EPT; ++e) {
+        for (int e = 0; e < EPT; ++e) {
             const unsigned a = myctr_a + (ent[e] & 0xffu) * (unsigned)STR_THREADS;
             sts_u8(a, lds_u8(a) + 1u);
             cflag[e] = (ent[e] >> 8) & 1u;
@@ -1175,7 +1180,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         if (wpend + total > (unsigned)STR_RING) drain(true);  // rare: make room for a tile full of candidates
         unsigned pos = whead + wpend + incl - cnt;
 #pragma unroll
-        for (int e = 0; e < STR_EPT; ++e) {  // the ring keeps the class (= bracket + 1) of a candidate
+        for (int e = 0; e < EPT; ++e) {  // the ring keeps the class (= bracket + 1) of a candidate
             const unsigned i = pos & (unsigned)(STR_RING - 1);
             if constexpr (sizeof(Key) == 8) sts_key64_if(cflag[e], mykey_a + i * 8u, (unsigned long long)k[e], mybrk_a + i, ent[e]);
             else sts_key32_if(cflag[e], mykey_a + i * 4u, (unsigned)k[e], mybrk_a + i, ent[e]);
@@ -1197,7 +1202,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             const unsigned long long next = tile + gridDim.x;
             if (next < n_tiles) load_tile(next, qb);
             process_tile(qa);
-            if (++tiles_since_spill >= STR_SPILL_TILES) {
+            if (++tiles_since_spill >= SPILL_TILES) {
                 spill_counters();
                 tiles_since_spill = 0;
             }
@@ -1206,7 +1211,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
             const unsigned long long next2 = tile + gridDim.x;
             if (next2 < n_tiles) load_tile(next2, qa);
             process_tile(qb);
-            if (++tiles_since_spill >= STR_SPILL_TILES) {
+            if (++tiles_since_spill >= SPILL_TILES) {
                 spill_counters();
                 tiles_since_spill = 0;
             }
@@ -1220,7 +1225,7 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     spill_counters();
     // ---- ragged head and tail: the last CTA, element by element ---------------------------------------
     if (blockIdx.x == gridDim.x - 1) {
-        const unsigned long long tail0 = head + n_tiles * STR_TILE;
+        const unsigned long long tail0 = head + n_tiles * TILE;
         const unsigned long long n_ragged = head + (n - tail0);
         unsigned rounds = 0;
         for (unsigned long long i0 = 0; i0 < n_ragged; i0 += STR_THREADS) {
@@ -2258,7 +2263,7 @@ __global__ void brk_output_kernel(BrkBuf<typename Traits<T>::Key> buf, QuantArgs
         }
         const BrkTask tl = buf.task[(int)buf.slot_rank[2 * t]], th = buf.task[(int)buf.slot_rank[2 * t + 1]];
         if (tl.state != TASK_DONE || th.state != TASK_DONE) {
-            if (last && buf.hdr[H_NACTIVE] == 0) {
+            if (last == 2 || (last && buf.hdr[H_NACTIVE] == 0)) {  // (2: no further round will be enqueued)
                 raise_fail(buf.hdr, FAIL_INCONSISTENT);
                 atomicOr(qa.status, STATUS_BIT_FALLBACK);
             }
@@ -2620,8 +2625,8 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
             return cudaSuccess;
         };
         // 7. output (a slot whose ranks are not known yet is left alone while segments are still active)
-        auto output = [&]() -> cudaError_t {
-            brk_output_kernel<T><<<(qa.nq + 127) / 128, 128, 0, st>>>(buf, qa, out, out_valid, out_axis_stride, 1);
+        auto output = [&](int last) -> cudaError_t {
+            brk_output_kernel<T><<<(qa.nq + 127) / 128, 128, 0, st>>>(buf, qa, out, out_valid, out_axis_stride, last);
             return count();
         };
         if (multi) {
@@ -2630,7 +2635,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
                 const int stop = std::min(round + 2, max_rounds);
                 for (; round < stop; ++round)
                     if ((e = one_round(round)) != cudaSuccess) return e;
-                if ((e = output()) != cudaSuccess) return e;
+                if ((e = output(round >= max_rounds ? 2 : 1)) != cudaSuccess) return e;
                 // agree on the outcome: either every rank keeps its result or all of them fall back
                 brk_post_fail_kernel<Key><<<1, 32, 0, st>>>(buf, buf.red_end);
                 if ((e = count()) != cudaSuccess) return e;
@@ -2643,14 +2648,18 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
                 if (hh[H_FAIL] || agreed || hh[H_NACTIVE] == 0 || round >= max_rounds) break;
             }
         } else {
-            for (int round = 0; round < max_rounds; ++round) {
+            // an enqueued call cannot look: three rounds (24 key bits below the bracket width; the idle ones return at
+            // once), and the rare lane whose segments are still active after them -- medium-sized runs of equal keys --
+            // goes to the radix passes like any other give-up
+            const int rounds = synchronous ? max_rounds : std::min(max_rounds, 3);
+            for (int round = 0; round < rounds; ++round) {
                 if ((e = one_round(round)) != cudaSuccess) return e;
                 if (synchronous && round >= 1) {
                     if ((e = read_hdr(hh)) != cudaSuccess) return e;
                     if (hh[H_FAIL] || hh[H_NACTIVE] == 0) break;
                 }
             }
-            if ((e = output()) != cudaSuccess) return e;
+            if ((e = output(2)) != cudaSuccess) return e;
             timer.mark("output");
         }
     }

@@ -1,4 +1,4 @@
-// Contiguous short lanes (up to 4096 elements of a 4- or 8-byte type): warp-per-lane, bit-sliced
+// Contiguous short lanes (up to 8192 elements of a 4- or 8-byte type): warp-per-lane, bit-sliced
 // MSB-first selection, lanes staged through shared memory by 1-D TMA bulk copies.
 //
 // Why not the shared-memory digit histogram: a shared atomic costs ~2 cycles per element per SM
@@ -287,9 +287,43 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
                 Raw prefix = 0;
                 int bits_done = 0;
                 bool small = total <= 32;
+                bool tie_done = false;
+                Raw tie_raw = 0;
 #pragma unroll 1
                 for (int round = 0; round < ROUNDS && !small; ++round) {
                     if (round > 0) {
+                        // Tie-heavy lanes: more than 32 candidates survive a whole 16-bit round.  Before the lane is read
+                        // and transposed again for the next 16 bits: are the survivors all one value?  (They usually
+                        // are once the bits that tell the lane's few distinct values apart have been walked.)  Every
+                        // thread compares its own candidates with the first one; the warp stops at the first mismatch.
+                        Raw mine = 0;
+                        bool have = false;
+#pragma unroll
+                        for (int blk = 0; blk < NB; ++blk)
+                            if (!have && m[blk]) {
+                                mine = to_raw<T>(lp[elem_index(blk, slot_of_pos(__ffs(m[blk]) - 1))]);
+                                have = true;
+                            }
+                        const unsigned owners = __ballot_sync(FULL, have);
+                        const Raw ref = __shfl_sync(FULL, mine, __ffs(owners) - 1);
+                        bool same = true, go = true;
+#pragma unroll
+                        for (int blk = 0; blk < NB; ++blk) {  // (unrolled: m[] must stay in registers)
+                            if (go) {
+                                uint32_t bits = m[blk];
+                                while (bits) {
+                                    const int p = __ffs(bits) - 1;
+                                    bits &= bits - 1;
+                                    same = same && (to_raw<T>(lp[elem_index(blk, slot_of_pos(p))]) == ref);
+                                }
+                                go = __all_sync(FULL, same);
+                            }
+                        }
+                        if (go) {
+                            tie_done = true;
+                            tie_raw = ref;
+                            break;
+                        }
                         __syncwarp();
                         build_from_global(reinterpret_cast<const unsigned char *>(lp), round);
                         __syncwarp();
@@ -334,7 +368,14 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
                 if (bits_done < KEYBITS) prefix <<= (KEYBITS - bits_done);
                 Raw found, found_next = 0;
                 bool have_next = false;
-                if (total > 32) {
+                if (tie_done) {
+                    // every remaining candidate is the same value (found by the check below)
+                    found = tie_raw;
+                    if (rem + 1 < total) {
+                        found_next = tie_raw;
+                        have_next = true;
+                    }
+                } else if (total > 32) {
                     // every key bit decided: all remaining candidates are equal to `prefix`
                     found = prefix;
                     if (rem + 1 < total) {
@@ -462,15 +503,15 @@ ShortPlan plan_short(const nds_ctx *ctx, const DeviceCall &c) {
     }
     const LaneGeom &g = c.geom;
     if (c.valid || c.out_valid) return p;
-    if (g.axis_stride != 1 || g.axis_len < 64 || g.axis_len > 4096) return p;
+    if (g.axis_stride != 1 || g.axis_len < 64 || g.axis_len > 8192) return p;
     if ((g.axis_len * es) % 16 != 0) return p;  // TMA bulk copies move multiples of 16 bytes from 16-byte aligned addresses
     if (((uintptr_t)c.data) % 16 != 0) return p;
     for (int d = 0; d < g.n_outer; ++d)
         if (g.oshape[d] > 1 && ((g.in_ostride[d] * (long long)es) % 16) != 0) return p;
     if (g.nlanes < 64) return p;  // too few lanes to fill the machine warp-per-lane
-    p.nb = g.axis_len <= 1024 ? 1 : (g.axis_len <= 2048 ? 2 : 4);
-    const size_t fixed = (p.nb == 1 ? short_warp_fixed_bytes<1>() : (p.nb == 2 ? short_warp_fixed_bytes<2>() : short_warp_fixed_bytes<4>())) +
-                         SHORT_WARP_TAIL_BYTES;
+    p.nb = g.axis_len <= 1024 ? 1 : (g.axis_len <= 2048 ? 2 : (g.axis_len <= 4096 ? 4 : 8));
+    const size_t fixed = (p.nb == 1 ? short_warp_fixed_bytes<1>() : (p.nb == 2 ? short_warp_fixed_bytes<2>()
+                          : (p.nb == 4 ? short_warp_fixed_bytes<4>() : short_warp_fixed_bytes<8>()))) + SHORT_WARP_TAIL_BYTES;
     const size_t blk_bytes = 1024 * es;
     const size_t budget = (size_t)ctx->max_smem_optin > 4096 ? (size_t)ctx->max_smem_optin - 1024 : 0;
     // Warps hide the latency of the serial bit walk; ring stages keep HBM requests in flight.  Measured on
@@ -508,7 +549,8 @@ cudaError_t launch_short_typed(nds_ctx *ctx, const DeviceCall &c, const ShortPla
     switch (p.nb) {
     case 1: return launch_short_nb<T, 1>(ctx, c, p);
     case 2: return launch_short_nb<T, 2>(ctx, c, p);
-    default: return launch_short_nb<T, 4>(ctx, c, p);
+    case 4: return launch_short_nb<T, 4>(ctx, c, p);
+    default: return launch_short_nb<T, 8>(ctx, c, p);
     }
 }
 

@@ -255,7 +255,7 @@ def test_short_bitslice_path(gpu_ctx, oracle, dtype):
     vec = 16 // dtype.itemsize
     try:
         gpu_ctx.force_path("short_bitslice")
-        for n in (4096, 2048, 1024, 64, 100, 4096 - vec, 1028, 2052):
+        for n in (4096, 2048, 1024, 64, 100, 4096 - vec, 1028, 2052, 8192, 8192 - vec, 5000 // vec * vec):
             lanes = 150
             kinds = ["normal", "uniform", "clustered", "ties", "equal", "extremes"]
             for kind in kinds:
@@ -609,3 +609,39 @@ def test_bracket_low_cardinality(nds, gpu_ctx, oracle, dtype):
         check(gpu_ctx, oracle, b, 0, [0.2, 0.5, 0.9], "midpoint", skipnan=True, select_impl=1)
         with pytest.raises(nds.NanInInput):
             gpu_ctx.quantiles_axis(b, 0, [0.5], "lower")
+
+
+def test_c5_i64_lane_shape(nds, gpu_ctx, oracle):
+    """BASELINE config 5's lane half: 8192-element i64 lanes with 16 distinct values ((z & 15) - 8) * 2^40 (the splitmix64
+    stream of SURVEY.md section 8d), Lower and Higher -- the warp-per-lane kernel with its all-candidates-equal check."""
+    import torch
+    t = torch.empty((512, 8192), dtype=torch.int64, device="cuda")
+    nds.synth.fill(gpu_ctx, t, "i64_16values", 1005)
+    a = t.cpu().numpy()
+    for interp in ("lower", "higher", "midpoint"):
+        check(gpu_ctx, oracle, a, 1, [0.1, 0.5, 0.9], interp, select_impl=1)
+        assert gpu_ctx.last_path == "short_bitslice", gpu_ctx.last_path
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int16, np.uint8], ids=lambda d: np.dtype(d).name)
+def test_mid_length_lanes_dispatch(nds, gpu_ctx, oracle, dtype):
+    """Lanes too long for the lane kernels and too few for one CTA each to pay: a handful of lanes, or many quantiles of a few
+    lanes, run one after the other over the whole grid (every requested rank per pass); the call must not fall into the
+    rank-at-a-time CTA kernel.  The 65536-element x 99-percentile call of the smoke test is one of these."""
+    rng = np.random.default_rng(31)
+    pct = np.arange(1, 100) / 100.0
+    if np.dtype(dtype).kind == "f":
+        a = rng.standard_normal((3, 65536)).astype(dtype)
+    else:
+        info = np.iinfo(dtype)
+        a = rng.integers(info.min, info.max, size=(3, 65536), dtype=dtype, endpoint=True)
+    check(gpu_ctx, oracle, a, 1, pct, "linear" if np.dtype(dtype).kind == "f" else "lower", select_impl=1)
+    assert gpu_ctx.last_path in ("long_radix", "bracket", "bracket->long_radix"), gpu_ctx.last_path
+    check(gpu_ctx, oracle, a[0], 0, pct, "nearest", select_impl=1)          # the smoke shape
+    assert gpu_ctx.last_path in ("long_radix", "bracket", "bracket->long_radix"), gpu_ctx.last_path
+    b = a[:, :20001].T.copy()                                                 # 20001 x 3: strided lanes along axis 0
+    check(gpu_ctx, oracle, b, 0, [0.25, 0.5], "midpoint", select_impl=1)
+    assert gpu_ctx.last_path in ("long_radix", "bracket", "bracket->long_radix"), gpu_ctx.last_path
+    wide = np.tile(a[:, :9000], (20, 1))                                      # 60 lanes x 9000, 2 quantiles: one CTA per lane
+    check(gpu_ctx, oracle, wide, 1, [0.5, 0.9], "higher", select_impl=1)
+    assert gpu_ctx.last_path == "generic_cta", gpu_ctx.last_path

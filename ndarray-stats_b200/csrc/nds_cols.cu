@@ -8,6 +8,9 @@
 // strip has been streamed once, warp w walks the key bits of lane w MSB-first exactly like the short-lane
 // kernel (popc over the lane's plane words, one REDUX per bit), finishing on <= 32 candidates that are
 // fetched again from L2.  Input is read from HBM once; skipnan masks come out of the exponent planes.
+#include <cuda.h>
+
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -38,6 +41,7 @@ __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // ASYNC (4-byte types, full aligned strips): the strip is staged through shared memory by cp.async (LDGSTS), two tiles
 // of 1024 rows in flight, the first tiles of the NEXT strip already during the bit walk of this one.
@@ -476,438 +480,438 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (NDS_COLS_V2=1, 4-byte types; written at the end of round 1 without GPU time left to run it -- not
-// on any default path): the same selection with the build of one strip overlapped with the walk of the previous one.
+// TMA-staged strips (4-byte types, whole 16-byte aligned strips of a 2-D / 3-D array): the default for BASELINE config 3.
 //
-// cols_bitslice_kernel keeps 8 warps per SM whose phases (stream + build, NaN masks, walk, ranking) run one after
-// the other; while a strip is walked only two tiles of the next one are in flight.  Here a strip is 4 lanes wide
-// (16 bytes per row), its planes take half the shared memory, and TWO plane buffers fit: 8 builder warps stream and
-// transpose strip i + 1 into one buffer while 4 walker warps select from the other.  A CTA takes the two halves of
-// the same 32-byte sectors back to back, so the second half comes out of L2 and DRAM traffic stays at one read.
-// Hand-off by named barriers (bar.arrive / bar.sync, 384 threads): FULL[p] builders -> walkers, EMPTY[p] back.
+// What holds cols_bitslice_kernel at a third of the HBM roofline is the number of bytes it keeps in flight: two 32 KB
+// cp.async tiles, one of them always being consumed, none while the lanes are walked -- 148 SMs x 32 KB / ~1.2 us of
+// loaded latency is 4 TB/s for 60 % of the time.  (cols16_kernel, 16 warps on the same planes, showed that more warps
+// are not the cure: with its single 64 KB stage it is slower.)  Here a dedicated producer warp streams the strips
+// through a ring of 8 KB slots -- tensor-map TMA boxes of 256 rows x 8 lanes, cp.async.bulk.tensor + mbarrier, no
+// registers, no address arithmetic, no LSU -- and keeps every free slot of the ring (~70 KB) in flight at all times,
+// also while the previous strip is being walked.  A slot is consumed by one PAIR of warps (64 threads: 8 lanes x 8
+// blocks of 32 rows), the four pairs work on different slots and never meet at a CTA barrier during the build.
+// A thread reads rows r, r + 4, r + 8 ... of one lane (conflict-free on the unpadded TMA box: a warp touches 32
+// consecutive words), so plane word W of a lane holds the rows (W / 4) * 128 + (W % 4) + 4 * slot: the walk does not care
+// which rows a word holds, only the valid masks and the survivors' addresses do.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int C2_CW = 4;
-constexpr int C2_BUILD_THREADS = 256;
-constexpr int C2_WALK_WARPS = 4;
-constexpr int C2_THREADS = C2_BUILD_THREADS + 32 * C2_WALK_WARPS;
-constexpr int C2_TILE_ROWS = 2048;                                   // 64 row blocks x 4 lanes = one job per builder thread
-constexpr int C2_RB_WORDS = cols_rb_words(C2_CW);                   // 132: eight row groups of a warp hit 32 banks
-constexpr int C2_STAGE_WORDS = (C2_TILE_ROWS / 32) * C2_RB_WORDS;   // 8448 words
-constexpr int C2_STAGES = 2;
-enum : int { C2_BAR_BUILD = 1, C2_BAR_FULL0 = 2, C2_BAR_EMPTY0 = 4 };
+constexpr int CT_CW = 8;
+constexpr int CT_SLOT_ROWS = 256;
+constexpr unsigned CT_SLOT_BYTES = CT_SLOT_ROWS * CT_CW * 4;   // 8192
+constexpr int CT_CONSUMERS = 256;                             // 8 warps = 4 pairs
+constexpr int CT_THREADS = CT_CONSUMERS + 32;                 // + the producer warp
+constexpr int CT_MAX_SLOTS = 16;
 
-__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
-// One warp selects every requested quantile of one lane from its bit planes (the walk of cols_bitslice_kernel).
-template <typename T>
-__device__ __forceinline__ void cols_walk_lane(const T *sp, int wl, uint32_t *lane_planes, unsigned *lane_list, int lane,
-                                               unsigned n, long long pitch, unsigned nrbp, unsigned kw, const QuantArgs &qa,
-                                               const LaneGeom &g, T *__restrict__ out, long long out_off, long long out_col_stride) {
-    using Tr = Traits<T>;
-    using Key = typename Tr::Key;
-    using Raw = typename RawBits<T>::U;
-    constexpr int ES = (int)sizeof(T);
-    constexpr int ROUNDS = ES * 8 / 16;
-    constexpr int KEYBITS = ES * 8;
-    constexpr bool IS_FLOAT = Tr::is_float;
-    constexpr bool TOP_INVERTED = IS_FLOAT || std::is_signed<T>::value;
-    auto slot_of_pos = [](int p) -> int { return 2 * (p & 15) + (p >> 4); };
-    const T *lp = sp + wl;  // element (row, this lane) = lp[row * pitch]
-    uint32_t *pl = lane_planes + lane;  // word k of plane b: pl[b * nrbp + 32 * k]
-    unsigned *mylist = lane_list;
-
-    // valid rows and (floats) NaN positions, from the planes of round 0
-    uint32_t init[COLS_KMAX];
-    unsigned my_nan = 0;
-#pragma unroll
-    for (int k = 0; k < COLS_KMAX; ++k) {
-        uint32_t v = 0;
-        if ((unsigned)k < kw) {
-            const unsigned rb = (unsigned)lane + 32u * k;
-            const unsigned base = rb * 32u;
-            if (base + 32u <= n) v = 0xffffffffu;
-            else if (base < n)
-                for (int p = 0; p < 32; ++p)
-                    if (base + (unsigned)slot_of_pos(p) < n) v |= 1u << p;
-            if (IS_FLOAT && v) {
-                uint32_t nanm = pl[16 * nrbp + 32 * k] & v;   // NaN by the top 16 bits
-                uint32_t amb = pl[17 * nrbp + 32 * k] & v;    // inf, or a NaN whose payload sits in the low bits
-                while (amb) {
-                    int p = __ffs(amb) - 1;
-                    amb &= amb - 1;
-                    T xv = lp[(long long)(base + slot_of_pos(p)) * pitch];
-                    if (xv != xv) nanm |= 1u << p;
-                }
-                v &= ~nanm;
-                my_nan += __popc(nanm);
-            }
-        }
-        init[k] = v;
-    }
-    unsigned n_eff = n;
-    if (IS_FLOAT) {
-        const unsigned nan_total = __reduce_add_sync(FULLMASK, my_nan);
-        if (nan_total) {
-            if (!qa.skipnan && lane == 0) atomicOr(qa.status, STATUS_BIT_NAN);
-            n_eff = n - nan_total;
-        }
-    }
-    const long long my_out = out_off + (long long)wl * out_col_stride;
-
-    if (n_eff == 0) {
-        for (int t = lane; t < qa.nq; t += 32) out[my_out + (long long)t * g.out_axis_stride] = canonical_nan<T>();
-    } else {
-        bool planes_dirty = false;
-        // rebuild this lane's planes for `round` from global memory (L2-resident), warp-local
-        auto rebuild = [&](int round) {
-#pragma unroll 1
-            for (unsigned k = 0; k < kw; ++k) {
-                const unsigned rb = (unsigned)lane + 32u * k;
-                uint32_t w[16];
-#pragma unroll
-                for (int kk = 0; kk < 16; ++kk) {
-                    const unsigned r0 = min(rb * 32u + 2u * kk, n - 1u), r1 = min(rb * 32u + 2u * kk + 1u, n - 1u);
-                    const Raw a = to_raw<T>(__ldg(lp + (long long)r0 * pitch));
-                    const Raw b = to_raw<T>(__ldg(lp + (long long)r1 * pitch));
-                    const int sh = KEYBITS - 16 * (round + 1);
-                    w[kk] = (uint32_t)((a >> sh) & 0xffffu) | ((uint32_t)((b >> sh) & 0xffffu) << 16);
-                }
-                transpose16(w);
-#pragma unroll
-                for (int b = 0; b < 16; ++b) pl[b * nrbp + 32 * k] = w[b];
-            }
-            __syncwarp();
-        };
-
-        auto select = [&](unsigned r, bool want_next, Raw &raw_r, Raw &raw_next) {
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                if (planes_dirty) {
-                    rebuild(0);
-                    planes_dirty = false;
-                }
-                uint32_t m[COLS_KMAX];
-#pragma unroll
-                for (int k = 0; k < COLS_KMAX; ++k) m[k] = init[k];
-                unsigned total = n_eff, rem = r + (unsigned)pass;
-                bool neg = false;
-                Raw prefix = 0;
-                int bits_done = 0;
-                bool small = total <= COLS_CAND;
-#pragma unroll 1
-                for (int round = 0; round < ROUNDS && !small; ++round) {
-                    if (round > 0) {
-                        rebuild(round);
-                        planes_dirty = true;
-                    }
-                    uint32_t inv = (round == 0) ? (TOP_INVERTED ? 0xffffffffu : 0u)
-                                                : ((IS_FLOAT && neg) ? 0xffffffffu : 0u);
-                    const uint32_t *pp = pl + 15 * nrbp;
-#pragma unroll 1
-                    for (int b = 15; b >= 0; --b, pp -= nrbp) {
-                        uint32_t x[COLS_KMAX];
-                        unsigned ones = 0;
-#pragma unroll
-                        for (int k = 0; k < COLS_KMAX; ++k) {
-                            x[k] = ((unsigned)k < kw) ? pp[32 * k] : 0u;
-                            ones += __popc(m[k] & (x[k] ^ inv));
-                        }
-                        ones = __reduce_add_sync(FULLMASK, ones);
-                        const unsigned small_cnt = total - ones;
-                        const bool take_small = rem < small_cnt;
-                        total = take_small ? small_cnt : ones;
-                        rem = take_small ? rem : rem - small_cnt;
-                        const uint32_t keep = take_small ? inv : ~inv;
-                        prefix = (Raw)(prefix << 1) | (Raw)(keep & 1u);
-#pragma unroll
-                        for (int k = 0; k < COLS_KMAX; ++k) m[k] &= ~(x[k] ^ keep);
-                        if (round == 0 && b == 15) {
-                            neg = IS_FLOAT && (keep & 1u);
-                            inv = neg ? 0xffffffffu : 0u;
-                        }
-                        bits_done += 1;
-                        if (total <= COLS_CAND) {
-                            small = true;
-                            break;
-                        }
-                    }
-                }
-                if (bits_done < KEYBITS) prefix <<= (KEYBITS - bits_done);
-                Raw found, found_next = 0;
-                bool have_next = false;
-                if (total > COLS_CAND) {
-                    found = prefix;
-                    if (rem + 1 < total) {
-                        found_next = prefix;
-                        have_next = true;
-                    }
-                } else {
-                    unsigned mycnt = 0;
-#pragma unroll
-                    for (int k = 0; k < COLS_KMAX; ++k) mycnt += __popc(m[k]);
-                    unsigned incl = mycnt;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        unsigned tt = __shfl_up_sync(FULLMASK, incl, d);
-                        if (lane >= d) incl += tt;
-                    }
-                    unsigned base = incl - mycnt;
-#pragma unroll
-                    for (int k = 0; k < COLS_KMAX; ++k) {
-                        uint32_t bits = m[k];
-                        while (bits) {
-                            int p = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            mylist[base++] = ((unsigned)lane + 32u * k) * 32u + (unsigned)slot_of_pos(p);
-                        }
-                    }
-                    __syncwarp();
-                    // up to COLS_CAND / 32 candidates per thread: fetch them again (L2)
-                    constexpr int CPT = COLS_CAND / 32;
-                    Raw myraw[CPT];
-                    Key mykey[CPT];
-#pragma unroll
-                    for (int c = 0; c < CPT; ++c) {
-                        const unsigned idx = (unsigned)lane + 32u * c;
-                        myraw[c] = 0;
-                        mykey[c] = (Key) ~(Key)0;
-                        if (idx < total) {
-                            T xv = lp[(long long)mylist[idx] * pitch];
-                            myraw[c] = to_raw<T>(xv);
-                            mykey[c] = Tr::to_key(xv);
-                        }
-                    }
-                    // The candidates share the key bits the walk has consumed; the remaining bits are walked on
-                    // the registers (one ballot per candidate slot and bit) until one key is left -- a handful of
-                    // bits for distinct keys.  Equal keys are the same element value, any of them will do.
-                    auto fetch_rank = [&](unsigned want) -> Raw {
-                        bool alive[CPT];
-#pragma unroll
-                        for (int c = 0; c < CPT; ++c) alive[c] = (unsigned)lane + 32u * c < total;
-                        unsigned tot2 = total, rem2 = want;
-#pragma unroll 1
-                        for (int b = KEYBITS - 1 - bits_done; b >= 0 && tot2 > 1u; --b) {
-                            bool one[CPT];
-                            unsigned ones = 0;
-#pragma unroll
-                            for (int c = 0; c < CPT; ++c) {
-                                one[c] = ((mykey[c] >> b) & (Key)1) != 0;
-                                ones += __popc(__ballot_sync(FULLMASK, alive[c] && one[c]));
-                            }
-                            const unsigned zeros = tot2 - ones;
-                            const bool take0 = rem2 < zeros;
-                            tot2 = take0 ? zeros : ones;
-                            rem2 = take0 ? rem2 : rem2 - zeros;
-#pragma unroll
-                            for (int c = 0; c < CPT; ++c) alive[c] = alive[c] && (one[c] != take0);
-                        }
-                        Raw v = 0;
-                        bool mine = false;
-#pragma unroll
-                        for (int c = 0; c < CPT; ++c)
-                            if (alive[c] && !mine) {
-                                v = myraw[c];
-                                mine = true;
-                            }
-                        const unsigned hit = __ballot_sync(FULLMASK, mine);
-                        return __shfl_sync(FULLMASK, v, __ffs(hit) - 1);
-                    };
-                    found = fetch_rank(rem);
-                    if (rem + 1 < total) {
-                        found_next = fetch_rank(rem + 1);
-                        have_next = true;
-                    }
-                }
-                if (pass == 0) {
-                    raw_r = found;
-                    if (!want_next) return;
-                    if (have_next) {
-                        raw_next = found_next;
-                        return;
-                    }
-                } else {
-                    raw_next = found;
-                }
-            }
-        };
-
-        unsigned cache_rank[2] = {0xffffffffu, 0xffffffffu};
-        Raw cache_raw[2] = {0, 0};
-        auto remember = [&](unsigned r, Raw v) {
-            cache_rank[1] = cache_rank[0];
-            cache_raw[1] = cache_raw[0];
-            cache_rank[0] = r;
-            cache_raw[0] = v;
-        };
-        auto lookup = [&](unsigned r, Raw &v) -> bool {
-            if (r == cache_rank[0]) { v = cache_raw[0]; return true; }
-            if (r == cache_rank[1]) { v = cache_raw[1]; return true; }
-            return false;
-        };
-#pragma unroll 1
-        for (int t = 0; t < qa.nq; ++t) {
-            const RankMath rm = slot_rank_math(qa, t, n_eff);
-            const bool nl = needs_lower(qa.interp, rm.frac), nh = needs_higher(qa.interp, rm.frac);
-            const unsigned rl = (unsigned)rm.lower, rh = (unsigned)rm.higher;
-            Raw vl = 0, vh = 0;
-#pragma unroll 1
-            for (;;) {
-                const bool have_l = !nl || lookup(rl, vl);
-                const bool have_h = !nh || lookup(rh, vh);
-                if (have_l && have_h) break;
-                const unsigned r = !have_l ? rl : rh;
-                const bool want_next = !have_l && !have_h && rh == rl + 1;
-                Raw a = 0, b = 0;
-                select(r, want_next, a, b);
-                remember(r, a);
-                if (want_next) remember(r + 1, b);
-            }
-            if (lane == 0)
-                out[my_out + (long long)t * g.out_axis_stride] =
-                    interpolate<T>(qa.interp, from_raw<T>(vl), from_raw<T>(vh), rm.frac, qa.status);
-        }
-    }
+__device__ __forceinline__ uint32_t ct_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ct_mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ct_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ct_mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ct_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ct_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ct_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ct_mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "CT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra CT_DONE;\n"
+        "bra CT_WAIT;\n"
+        "CT_DONE:\n"
+        "}\n" ::"r"(ct_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// one box of the tensor map -> shared memory, completion on the mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void ct_tma_load_3d(void *dst_smem, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            ct_smem_u32(dst_smem)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(ct_smem_u32(bar))
+        : "memory");
 }
 
 template <typename T>
-__global__ void __launch_bounds__(C2_THREADS, 1)
-cols_pipelined_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__restrict__ out, unsigned long long n_strips,
-                      unsigned strips_per_group) {
+__global__ void __launch_bounds__(CT_THREADS, 1)
+cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ data, LaneGeom g, QuantArgs qa,
+                T *__restrict__ out, unsigned long long n_strips, unsigned strips_per_group, int nslots) {
+    static_assert(sizeof(T) == 4, "TMA boxes of 8 lanes x 4 bytes");
     using Tr = Traits<T>;
-    static_assert(sizeof(T) == 4, "staged 16-byte chunks: 4 lanes of a 4-byte type");
+    using Key = typename Tr::Key;
+    using Raw = typename RawBits<T>::U;
+    constexpr int KEYBITS = 32, ROUNDS = 2;
     constexpr bool IS_FLOAT = Tr::is_float;
+    constexpr bool TOP_INVERTED = IS_FLOAT || std::is_signed<T>::value;
     constexpr int EXP_LO = 7;
     constexpr int NPL = IS_FLOAT ? 18 : 16;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *planes = reinterpret_cast<uint32_t *>(smem_raw);       // [2 buffers][4 lanes][col_pitch]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const unsigned n = (unsigned)g.axis_len;
     const long long pitch = g.axis_stride;
-    const unsigned nrb = (n + 31u) / 32u;
-    const unsigned nrbp = (nrb + 31u) / 32u * 32u;
-    const unsigned kw = nrbp / 32u;
+    const unsigned sps = (n + CT_SLOT_ROWS - 1) / CT_SLOT_ROWS;   // slots per strip
+    const unsigned nw = sps * 8u;                                  // plane words per lane (one per 32 rows)
+    const unsigned kw = (nw + 31u) / 32u;                          // plane words per thread in the walk
+    const unsigned nrbp = kw * 32u;                                // plane pitch in words
     const unsigned col_pitch = (unsigned)NPL * nrbp + 4u;
-    unsigned *clist = reinterpret_cast<unsigned *>(planes + 2 * C2_CW * col_pitch);        // [walker warp][COLS_CAND]
-    const size_t stage_off = ((size_t)(reinterpret_cast<unsigned char *>(clist + C2_WALK_WARPS * COLS_CAND) - smem_raw) + 15) & ~(size_t)15;
-    uint32_t *stage_base = reinterpret_cast<uint32_t *>(smem_raw + stage_off);               // [C2_STAGES][C2_STAGE_WORDS]
+    uint32_t *planes = reinterpret_cast<uint32_t *>(smem_raw);
+    unsigned *clist = reinterpret_cast<unsigned *>(planes + CT_CW * col_pitch);     // [lane][COLS_CAND]
+    uint64_t *full = reinterpret_cast<uint64_t *>(clist + CT_CW * COLS_CAND);       // [CT_MAX_SLOTS]
+    uint64_t *empty = full + CT_MAX_SLOTS;                                           // [CT_MAX_SLOTS]
+    // the ring: 128-byte aligned shared addresses (derived by an offset from smem_raw, see cols_bitslice_kernel)
+    const uint32_t base_addr = ct_smem_u32(smem_raw);
+    const uint32_t ring_addr = (ct_smem_u32(empty + CT_MAX_SLOTS) + 127u) & ~127u;
+    unsigned char *ring = smem_raw + (ring_addr - base_addr);
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int last_outer = g.n_outer - 1;
     const unsigned long long ncols = g.oshape[last_outer];
     const long long out_col_stride = g.out_ostride[last_outer];
-    const unsigned tiles = (n + C2_TILE_ROWS - 1) / C2_TILE_ROWS;
+    auto slot_of_pos = [](int p) -> int { return 2 * (p & 15) + (p >> 4); };
+    // row held by bit p of plane word W
+    auto row_of = [&](unsigned W, int p) -> unsigned { return (W >> 2) * 128u + (W & 3u) + 4u * (unsigned)slot_of_pos(p); };
 
-    // the half-strips of this CTA: pairs P = blockIdx.x + j * gridDim.x of adjacent half-strips (n_strips is even)
-    const unsigned long long npairs = n_strips / 2;
-    const unsigned my_pairs = blockIdx.x < npairs ? (unsigned)((npairs - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
-    const unsigned h_count = 2u * my_pairs;
-    auto half_strip = [&](unsigned i) -> unsigned long long {
-        return 2ull * ((unsigned long long)blockIdx.x + (unsigned long long)(i >> 1) * gridDim.x) + (i & 1u);
-    };
-    auto strip_origin = [&](unsigned long long hs, long long &in_off, long long &out_off) {
-        const unsigned long long grp = hs / strips_per_group;
-        const unsigned long long col0 = (hs - grp * strips_per_group) * C2_CW;
-        lane_offsets(g, grp * ncols + col0, in_off, out_off);
-    };
+    if (tid == 0) {
+        for (int s = 0; s < nslots; ++s) {
+            ct_mbar_init(full + s, 1);
+            ct_mbar_init(empty + s, 2);   // the two warps that read a slot
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
-    if (tid < C2_BUILD_THREADS) {
-        // ================= builders: stream the half-strips through the stages into the plane buffers =================
-        const int bc = tid % C2_CW, brg = tid / C2_CW;  // lane of the half-strip, row block inside the tile (0..63)
-        unsigned iss_i = 0, iss_t = 0, iss_stage = 0;
-        const T *iss_ptr = nullptr;
-        auto issue_tile = [&]() {
-            if (iss_i < h_count) {
-                const unsigned rl0 = (unsigned)tid;  // one 16-byte chunk per row: rows rl0 + 256 j of the tile
-                if (iss_t == 0) {
-                    long long io, oo;
-                    strip_origin(half_strip(iss_i), io, oo);
-                    iss_ptr = data + io + (long long)rl0 * pitch;
-                }
-                uint32_t *dst = stage_base + (size_t)iss_stage * C2_STAGE_WORDS + (rl0 >> 5) * C2_RB_WORDS + (rl0 & 31u) * C2_CW;
-                const long long src_step = (long long)C2_BUILD_THREADS * pitch;
-                const unsigned row0 = iss_t * C2_TILE_ROWS + rl0;
-                const T *s = iss_ptr;
-                if ((iss_t + 1u) * C2_TILE_ROWS <= n) {
-#pragma unroll
-                    for (int j = 0; j < C2_TILE_ROWS / C2_BUILD_THREADS; ++j, s += src_step) cp_async16(dst + j * 8 * C2_RB_WORDS, s);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < C2_TILE_ROWS / C2_BUILD_THREADS; ++j, s += src_step)
-                        if (row0 + (unsigned)j * C2_BUILD_THREADS < n) cp_async16(dst + j * 8 * C2_RB_WORDS, s);
-                }
-                iss_ptr = s;
-                if (++iss_t == tiles) {
-                    iss_t = 0;
-                    ++iss_i;
+    const unsigned long long my_strips = blockIdx.x < n_strips ? (n_strips - blockIdx.x + gridDim.x - 1) / gridDim.x : 0ull;
+
+    if (warp == CT_CONSUMERS / 32) {
+        // ================= producer: every slot of every strip of this CTA, in order =================
+        if (lane == 0) {
+            unsigned long long q = 0;
+            for (unsigned long long it = 0; it < my_strips; ++it) {
+                const unsigned long long strip = blockIdx.x + it * gridDim.x;
+                const unsigned long long grp = strip / strips_per_group;
+                const int col0 = (int)((strip - grp * strips_per_group) * CT_CW);
+                for (unsigned j = 0; j < sps; ++j, ++q) {
+                    const unsigned r = (unsigned)(q % (unsigned)nslots);
+                    const unsigned long long turn = q / (unsigned)nslots;
+                    if (turn > 0) ct_mbar_wait(empty + r, (unsigned)((turn - 1) & 1ull));  // the readers are done with it
+                    ct_mbar_expect_tx(full + r, CT_SLOT_BYTES);
+                    ct_tma_load_3d(ring + (size_t)r * CT_SLOT_BYTES, &tmap, col0, (int)(j * CT_SLOT_ROWS), (int)grp, full + r);
                 }
             }
-            iss_stage ^= 1u;
-            cp_async_commit();  // (an empty group past the end keeps the group count uniform)
-        };
-        issue_tile();
-        issue_tile();
-        unsigned gt = 0;  // tiles consumed so far: tile gt sits in stage gt & 1
+        }
+        return;
+    }
+
+    // ================= consumers =================
+    const int pair = warp >> 1, ph = warp & 1;     // build role: which slots (j % 4 == pair), which 128 rows of the slot
+    const int bc = lane & 7, bsub = lane >> 3;     // lane (column) and row phase: rows bsub, bsub + 4, ... of the 128
+    for (unsigned long long it = 0; it < my_strips; ++it) {
+        const unsigned long long strip = blockIdx.x + it * gridDim.x;
+        const unsigned long long grp = strip / strips_per_group;
+        const unsigned long long col0 = (strip - grp * strips_per_group) * CT_CW;
+        long long in_off, out_off;
+        lane_offsets(g, grp * ncols + col0, in_off, out_off);
+        const T *sp = data + in_off;
+
+        // ---- build: this pair's slots of the strip ---------------------------------------------------------
+        {
+            uint32_t *pdst = planes + (size_t)bc * col_pitch;
 #pragma unroll 1
-        for (unsigned i = 0; i < h_count; ++i) {
-            const unsigned p = i & 1u;
-            if (i >= 2) named_bar_sync(C2_BAR_EMPTY0 + (int)p, C2_THREADS);  // the walkers are done with this buffer
-            uint32_t *pdst = planes + (size_t)(p * C2_CW + bc) * col_pitch;
-#pragma unroll 1
-            for (unsigned t = 0; t < tiles; ++t, ++gt) {
-                cp_async_wait<C2_STAGES - 1>();
-                named_bar_sync(C2_BAR_BUILD, C2_BUILD_THREADS);      // tile gt has landed for every builder
-                const uint32_t *st = stage_base + (size_t)(gt & 1u) * C2_STAGE_WORDS + brg * C2_RB_WORDS + bc;
-                uint32_t x[32];
+            for (unsigned j = (unsigned)pair; j < sps; j += 4u) {
+                const unsigned long long q = it * sps + j;
+                const unsigned r = (unsigned)(q % (unsigned)nslots);
+                ct_mbar_wait(full + r, (unsigned)((q / (unsigned)nslots) & 1ull));
+                const uint32_t *st = reinterpret_cast<const uint32_t *>(ring + (size_t)r * CT_SLOT_BYTES) + (ph * 128 + bsub) * CT_CW + bc;
+                uint32_t w[16];
+                {
+                    uint32_t x[32];
 #pragma unroll
-                for (int r = 0; r < 32; ++r) x[r] = st[r * C2_CW];
-                named_bar_sync(C2_BAR_BUILD, C2_BUILD_THREADS);      // the stage is free again
-                issue_tile();
-                const unsigned rb = t * (C2_TILE_ROWS / 32) + (unsigned)brg;
-                if (rb < nrb) {
-                    uint32_t w[16];
+                    for (int i = 0; i < 32; ++i) x[i] = st[i * 4 * CT_CW];   // a warp reads 32 consecutive words per step
 #pragma unroll
                     for (int k = 0; k < 16; ++k) w[k] = __byte_perm(x[2 * k], x[2 * k + 1], 0x7632);
-                    transpose16(w);
+                }
+                __syncwarp();
+                if (lane == 0) ct_mbar_arrive(empty + r);   // this warp has read its half of the slot
+                const unsigned W = (j * 2u + (unsigned)ph) * 4u + (unsigned)bsub;
+                transpose16(w);
 #pragma unroll
-                    for (int b = 0; b < 16; ++b) pdst[b * nrbp + rb] = w[b];
-                    if constexpr (IS_FLOAT) {
-                        uint32_t e = 0xffffffffu, mhi = 0;
+                for (int b = 0; b < 16; ++b) pdst[b * nrbp + W] = w[b];
+                if constexpr (IS_FLOAT) {
+                    uint32_t e = 0xffffffffu, mhi = 0;
 #pragma unroll
-                        for (int b = EXP_LO; b <= 14; ++b) e &= w[b];
+                    for (int b = EXP_LO; b <= 14; ++b) e &= w[b];
 #pragma unroll
-                        for (int b = 0; b < EXP_LO; ++b) mhi |= w[b];
-                        pdst[16 * nrbp + rb] = e & mhi;
-                        pdst[17 * nrbp + rb] = e & ~mhi;
-                    }
+                    for (int b = 0; b < EXP_LO; ++b) mhi |= w[b];
+                    pdst[16 * nrbp + W] = e & mhi;
+                    pdst[17 * nrbp + W] = e & ~mhi;
                 }
             }
-            __threadfence_block();
-            named_bar_arrive(C2_BAR_FULL0 + (int)p, C2_THREADS);     // buffer p holds half-strip i
         }
-        cp_async_wait<0>();
-    } else {
-        // ================= walkers: one warp per lane of the half-strip whose planes are complete =================
-        const int wl = (tid - C2_BUILD_THREADS) >> 5;
+        named_bar_sync(1, CT_CONSUMERS);   // the strip's planes are complete
+
+        // ---- warp w selects the quantiles of lane w ---------------------------------------------------------
+        {
+            const T *lp = sp + warp;
+            uint32_t *pl = planes + (size_t)warp * col_pitch + lane;  // word k of plane b: pl[b * nrbp + 32 * k]
+            unsigned *mylist = clist + warp * COLS_CAND;
+
+            uint32_t init[COLS_KMAX];
+            unsigned my_nan = 0;
+#pragma unroll
+            for (int k = 0; k < COLS_KMAX; ++k) {
+                uint32_t v = 0;
+                if ((unsigned)k < kw) {
+                    const unsigned W = (unsigned)lane + 32u * k;
+                    const unsigned first = (W >> 2) * 128u;   // the word's rows lie in [first, first + 128)
+                    if (first + 128u <= n) v = 0xffffffffu;
+                    else if (first < n)
+                        for (int p = 0; p < 32; ++p)
+                            if (row_of(W, p) < n) v |= 1u << p;
+                    if (IS_FLOAT && v) {
+                        uint32_t nanm = pl[16 * nrbp + 32 * k] & v;
+                        uint32_t amb = pl[17 * nrbp + 32 * k] & v;
+                        while (amb) {
+                            int p = __ffs(amb) - 1;
+                            amb &= amb - 1;
+                            T xv = lp[(long long)row_of(W, p) * pitch];
+                            if (xv != xv) nanm |= 1u << p;
+                        }
+                        v &= ~nanm;
+                        my_nan += __popc(nanm);
+                    }
+                }
+                init[k] = v;
+            }
+            unsigned n_eff = n;
+            if (IS_FLOAT) {
+                const unsigned nan_total = __reduce_add_sync(FULLMASK, my_nan);
+                if (nan_total) {
+                    if (!qa.skipnan && lane == 0) atomicOr(qa.status, STATUS_BIT_NAN);
+                    n_eff = n - nan_total;
+                }
+            }
+            const long long my_out = out_off + (long long)warp * out_col_stride;
+
+            if (n_eff == 0) {
+                for (int t = lane; t < qa.nq; t += 32) out[my_out + (long long)t * g.out_axis_stride] = canonical_nan<T>();
+            } else {
+                bool planes_dirty = false;
+                auto rebuild = [&](int round) {  // this lane's planes for `round` from global memory (L2-resident), warp-local
 #pragma unroll 1
-        for (unsigned i = 0; i < h_count; ++i) {
-            const unsigned p = i & 1u;
-            named_bar_sync(C2_BAR_FULL0 + (int)p, C2_THREADS);
-            long long in_off, out_off;
-            strip_origin(half_strip(i), in_off, out_off);
-            cols_walk_lane<T>(data + in_off, wl, planes + (size_t)(p * C2_CW + wl) * col_pitch, clist + wl * COLS_CAND, lane, n, pitch,
-                              nrbp, kw, qa, g, out, out_off, out_col_stride);
-            __syncwarp();
-            if (i + 2 < h_count) named_bar_arrive(C2_BAR_EMPTY0 + (int)p, C2_THREADS);  // (the builders wait for it from i + 2 on)
+                    for (unsigned k = 0; k < kw; ++k) {
+                        const unsigned W = (unsigned)lane + 32u * k;
+                        uint32_t w[16];
+#pragma unroll
+                        for (int kk = 0; kk < 16; ++kk) {
+                            const unsigned base = (W >> 2) * 128u + (W & 3u);
+                            const unsigned r0 = min(base + 8u * kk, n - 1u), r1 = min(base + 8u * kk + 4u, n - 1u);
+                            const Raw a = to_raw<T>(__ldg(lp + (long long)r0 * pitch));
+                            const Raw b = to_raw<T>(__ldg(lp + (long long)r1 * pitch));
+                            const int sh = KEYBITS - 16 * (round + 1);
+                            w[kk] = (uint32_t)((a >> sh) & 0xffffu) | ((uint32_t)((b >> sh) & 0xffffu) << 16);
+                        }
+                        transpose16(w);
+#pragma unroll
+                        for (int b = 0; b < 16; ++b) pl[b * nrbp + 32 * k] = w[b];
+                    }
+                    __syncwarp();
+                };
+
+                auto select = [&](unsigned r, bool want_next, Raw &raw_r, Raw &raw_next) {
+#pragma unroll 1
+                    for (int pass = 0; pass < 2; ++pass) {
+                        if (planes_dirty) {
+                            rebuild(0);
+                            planes_dirty = false;
+                        }
+                        uint32_t m[COLS_KMAX];
+#pragma unroll
+                        for (int k = 0; k < COLS_KMAX; ++k) m[k] = init[k];
+                        unsigned total = n_eff, rem = r + (unsigned)pass;
+                        bool neg = false;
+                        Raw prefix = 0;
+                        int bits_done = 0;
+                        bool small = total <= COLS_CAND;
+#pragma unroll 1
+                        for (int round = 0; round < ROUNDS && !small; ++round) {
+                            if (round > 0) {
+                                rebuild(round);
+                                planes_dirty = true;
+                            }
+                            uint32_t inv = (round == 0) ? (TOP_INVERTED ? 0xffffffffu : 0u)
+                                                        : ((IS_FLOAT && neg) ? 0xffffffffu : 0u);
+                            const uint32_t *pp = pl + 15 * nrbp;
+#pragma unroll 1
+                            for (int b = 15; b >= 0; --b, pp -= nrbp) {
+                                uint32_t x[COLS_KMAX];
+                                unsigned ones = 0;
+#pragma unroll
+                                for (int k = 0; k < COLS_KMAX; ++k) {
+                                    x[k] = ((unsigned)k < kw) ? pp[32 * k] : 0u;
+                                    ones += __popc(m[k] & (x[k] ^ inv));
+                                }
+                                ones = __reduce_add_sync(FULLMASK, ones);
+                                const unsigned small_cnt = total - ones;
+                                const bool take_small = rem < small_cnt;
+                                total = take_small ? small_cnt : ones;
+                                rem = take_small ? rem : rem - small_cnt;
+                                const uint32_t keep = take_small ? inv : ~inv;
+                                prefix = (Raw)(prefix << 1) | (Raw)(keep & 1u);
+#pragma unroll
+                                for (int k = 0; k < COLS_KMAX; ++k) m[k] &= ~(x[k] ^ keep);
+                                if (round == 0 && b == 15) {
+                                    neg = IS_FLOAT && (keep & 1u);
+                                    inv = neg ? 0xffffffffu : 0u;
+                                }
+                                bits_done += 1;
+                                if (total <= COLS_CAND) {
+                                    small = true;
+                                    break;
+                                }
+                            }
+                        }
+                        if (bits_done < KEYBITS) prefix <<= (KEYBITS - bits_done);
+                        Raw found, found_next = 0;
+                        bool have_next = false;
+                        if (total > COLS_CAND) {
+                            found = prefix;
+                            if (rem + 1 < total) {
+                                found_next = prefix;
+                                have_next = true;
+                            }
+                        } else {
+                            unsigned mycnt = 0;
+#pragma unroll
+                            for (int k = 0; k < COLS_KMAX; ++k) mycnt += __popc(m[k]);
+                            unsigned incl = mycnt;
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                unsigned tt = __shfl_up_sync(FULLMASK, incl, d);
+                                if (lane >= d) incl += tt;
+                            }
+                            unsigned base = incl - mycnt;
+#pragma unroll
+                            for (int k = 0; k < COLS_KMAX; ++k) {
+                                uint32_t bits = m[k];
+                                while (bits) {
+                                    int p = __ffs(bits) - 1;
+                                    bits &= bits - 1;
+                                    mylist[base++] = row_of((unsigned)lane + 32u * k, p);
+                                }
+                            }
+                            __syncwarp();
+                            constexpr int CPT = COLS_CAND / 32;
+                            Raw myraw[CPT];
+                            Key mykey[CPT];
+#pragma unroll
+                            for (int c = 0; c < CPT; ++c) {
+                                const unsigned idx = (unsigned)lane + 32u * c;
+                                myraw[c] = 0;
+                                mykey[c] = (Key) ~(Key)0;
+                                if (idx < total) {
+                                    T xv = lp[(long long)mylist[idx] * pitch];
+                                    myraw[c] = to_raw<T>(xv);
+                                    mykey[c] = Tr::to_key(xv);
+                                }
+                            }
+                            __syncwarp();
+                            auto fetch_rank = [&](unsigned want) -> Raw {
+                                bool alive[CPT];
+#pragma unroll
+                                for (int c = 0; c < CPT; ++c) alive[c] = (unsigned)lane + 32u * c < total;
+                                unsigned tot2 = total, rem2 = want;
+#pragma unroll 1
+                                for (int b = KEYBITS - 1 - bits_done; b >= 0 && tot2 > 1u; --b) {
+                                    bool one[CPT];
+                                    unsigned ones = 0;
+#pragma unroll
+                                    for (int c = 0; c < CPT; ++c) {
+                                        one[c] = ((mykey[c] >> b) & (Key)1) != 0;
+                                        ones += __popc(__ballot_sync(FULLMASK, alive[c] && one[c]));
+                                    }
+                                    const unsigned zeros = tot2 - ones;
+                                    const bool take0 = rem2 < zeros;
+                                    tot2 = take0 ? zeros : ones;
+                                    rem2 = take0 ? rem2 : rem2 - zeros;
+#pragma unroll
+                                    for (int c = 0; c < CPT; ++c) alive[c] = alive[c] && (one[c] != take0);
+                                }
+                                Raw v = 0;
+                                bool mine = false;
+#pragma unroll
+                                for (int c = 0; c < CPT; ++c)
+                                    if (alive[c] && !mine) {
+                                        v = myraw[c];
+                                        mine = true;
+                                    }
+                                const unsigned hit = __ballot_sync(FULLMASK, mine);
+                                return __shfl_sync(FULLMASK, v, __ffs(hit) - 1);
+                            };
+                            found = fetch_rank(rem);
+                            if (rem + 1 < total) {
+                                found_next = fetch_rank(rem + 1);
+                                have_next = true;
+                            }
+                        }
+                        if (pass == 0) {
+                            raw_r = found;
+                            if (!want_next) return;
+                            if (have_next) {
+                                raw_next = found_next;
+                                return;
+                            }
+                        } else {
+                            raw_next = found;
+                        }
+                    }
+                };
+
+                unsigned cache_rank[2] = {0xffffffffu, 0xffffffffu};
+                Raw cache_raw[2] = {0, 0};
+                auto remember = [&](unsigned r, Raw v) {
+                    cache_rank[1] = cache_rank[0];
+                    cache_raw[1] = cache_raw[0];
+                    cache_rank[0] = r;
+                    cache_raw[0] = v;
+                };
+                auto lookup = [&](unsigned r, Raw &v) -> bool {
+                    if (r == cache_rank[0]) { v = cache_raw[0]; return true; }
+                    if (r == cache_rank[1]) { v = cache_raw[1]; return true; }
+                    return false;
+                };
+#pragma unroll 1
+                for (int t = 0; t < qa.nq; ++t) {
+                    const RankMath rm = slot_rank_math(qa, t, n_eff);
+                    const bool nl = needs_lower(qa.interp, rm.frac), nh = needs_higher(qa.interp, rm.frac);
+                    const unsigned rl = (unsigned)rm.lower, rh = (unsigned)rm.higher;
+                    Raw vl = 0, vh = 0;
+#pragma unroll 1
+                    for (;;) {
+                        const bool have_l = !nl || lookup(rl, vl);
+                        const bool have_h = !nh || lookup(rh, vh);
+                        if (have_l && have_h) break;
+                        const unsigned r = !have_l ? rl : rh;
+                        const bool want_next = !have_l && !have_h && rh == rl + 1;
+                        Raw a = 0, b = 0;
+                        select(r, want_next, a, b);
+                        remember(r, a);
+                        if (want_next) remember(r + 1, b);
+                    }
+                    if (lane == 0)
+                        out[my_out + (long long)t * g.out_axis_stride] =
+                            interpolate<T>(qa.interp, from_raw<T>(vl), from_raw<T>(vh), rm.frac, qa.status);
+                }
+            }
         }
+        named_bar_sync(1, CT_CONSUMERS);  // the planes are rewritten by the next strip
     }
 }
 
 struct ColsPlan {
-    bool v2 = false;      // EXPERIMENTAL pipelined kernel (NDS_COLS_V2=1), see cols_pipelined_kernel
-    size_t smem_v2 = 0;
-    unsigned long long n_strips_v2 = 0;
-    unsigned strips_per_group_v2 = 0;
+    bool tma = false;     // TMA-staged strips (cols_tma_kernel): 4-byte types, aligned 8-lane strips of a 2-D / 3-D array
+    size_t smem_tma = 0;
+    int nslots = 0;
     int cw = 8;           // lanes per strip of the staged path (tuning knob NDS_COLS_CW=4: 4-lane strips, two CTAs per SM, paired in clusters)
     bool ok = false;
     unsigned long long n_strips = 0;
@@ -947,16 +951,18 @@ ColsPlan plan_cols(const nds_ctx *ctx, const DeviceCall &c) {
     static const int cw_knob = getenv("NDS_COLS_CW") ? atoi(getenv("NDS_COLS_CW")) : COLS_CW_ASYNC;
     const int cwa = (cw_knob == 4 && g.oshape[last] % 8 == 0) ? 4 : COLS_CW_ASYNC;
     const size_t smem_async = ((smem_for(cwa) + 15) & ~(size_t)15) + (size_t)COLS_STAGES * cols_stage_words(cwa) * 4 + 16;
-    static const bool v2_knob = getenv("NDS_COLS_V2") && atoi(getenv("NDS_COLS_V2")) != 0;
-    if (v2_knob && aligned && g.oshape[last] % 8 == 0) {
-        const size_t pl = (size_t)2 * C2_CW * (npl * nrbp + 4) * 4 + (size_t)C2_WALK_WARPS * COLS_CAND * 4;
-        const size_t need = ((pl + 15) & ~(size_t)15) + (size_t)C2_STAGES * C2_STAGE_WORDS * 4 + 16;
-        const unsigned long long spg = g.oshape[last] / C2_CW;
-        if (need <= (size_t)ctx->max_smem_optin && spg <= 0xffffffffull) {
-            p.v2 = true;
-            p.smem_v2 = need;
-            p.strips_per_group_v2 = (unsigned)spg;
-            p.n_strips_v2 = (g.nlanes / g.oshape[last]) * spg;
+    static const bool tma_knob = !(getenv("NDS_COLS_TMA") && atoi(getenv("NDS_COLS_TMA")) == 0);
+    if (tma_knob && aligned && cwa == 8 && g.n_outer <= 2 && g.axis_stride > 0 && (g.n_outer == 1 || g.in_ostride[0] > 0) &&
+        g.axis_len <= 0x7fffffffull && g.oshape[last] <= 0x7fffffffull && (g.n_outer == 1 || g.oshape[0] <= 0x7fffffffull)) {
+        const unsigned sps = (unsigned)((g.axis_len + CT_SLOT_ROWS - 1) / CT_SLOT_ROWS);
+        const unsigned kw = (sps * 8 + 31) / 32, pitch_w = npl * kw * 32 + 4;
+        if (kw <= COLS_KMAX) {
+            const size_t fixed = (size_t)CT_CW * pitch_w * 4 + (size_t)CT_CW * COLS_CAND * 4 + 2 * CT_MAX_SLOTS * 8 + 128;
+            if ((size_t)ctx->max_smem_optin > fixed + 4 * CT_SLOT_BYTES) {
+                p.nslots = (int)std::min<size_t>(CT_MAX_SLOTS, ((size_t)ctx->max_smem_optin - fixed) / CT_SLOT_BYTES);
+                p.smem_tma = fixed + (size_t)p.nslots * CT_SLOT_BYTES;
+                p.tma = true;
+            }
         }
     }
     if (aligned && smem_async <= (size_t)ctx->max_smem_optin && !getenv("NDS_COLS_NO_ASYNC")) {
@@ -1005,18 +1011,54 @@ template <typename T, bool ASYNC, int CW> cudaError_t launch_cols_typed2(nds_ctx
     return cudaGetLastError();
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {  // the driver entry point, without linking libcuda
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+template <typename T> cudaError_t launch_cols_tma(nds_ctx *ctx, const DeviceCall &c, const ColsPlan &p) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return cudaErrorNotSupported;
+    const LaneGeom &g = c.geom;
+    const int last = g.n_outer - 1;
+    // the array as a rank-3 tensor {lanes (contiguous), rows along the quantile axis, groups}; a box is 8 lanes x 256 rows
+    cuuint64_t dims[3] = {(cuuint64_t)g.oshape[last], (cuuint64_t)g.axis_len, (cuuint64_t)(g.n_outer == 2 ? g.oshape[0] : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)g.axis_stride * sizeof(T),
+                             (cuuint64_t)(g.n_outer == 2 ? g.in_ostride[0] : g.axis_stride * (long long)g.axis_len) * sizeof(T)};
+    cuuint32_t box[3] = {CT_CW, CT_SLOT_ROWS, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap tmap;
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(c.data), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorNotSupported;
+    auto kernel = cols_tma_kernel<T>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_tma);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)std::min<unsigned long long>(p.n_strips, (unsigned long long)ctx->sm_count);
+    kernel<<<grid, CT_THREADS, p.smem_tma, ctx->stream>>>(tmap, (const T *)c.data, g, c.q, (T *)c.out, p.n_strips,
+                                                          p.strips_per_group, p.nslots);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
 template <typename T> cudaError_t launch_cols_typed(nds_ctx *ctx, const DeviceCall &c, const ColsPlan &p) {
     if constexpr (sizeof(T) == 4) {
-        if (p.v2 && p.ok && p.async) {  // experimental, opt-in
-            auto kernel = cols_pipelined_kernel<T>;
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_v2);
-            if (e != cudaSuccess) return e;
-            const unsigned grid = (unsigned)std::min<unsigned long long>(p.n_strips_v2 / 2, (unsigned long long)ctx->sm_count);
-            kernel<<<grid, C2_THREADS, p.smem_v2, ctx->stream>>>((const T *)c.data, c.geom, c.q, (T *)c.out, p.n_strips_v2,
-                                                                  p.strips_per_group_v2);
-            ctx->launches += 1;
-            ctx->last_path = "cols_pipelined";
-            return cudaGetLastError();
+        if (p.tma && p.ok && p.async && p.cw == 8) {
+            cudaError_t e = launch_cols_tma<T>(ctx, c, p);
+            if (e != cudaErrorNotSupported) return e;   // (no tensor map could be made: the cp.async kernel takes the call)
         }
         if (p.async && p.cw == 4) return launch_cols_typed2<T, true, 4>(ctx, c, p);
         if (p.async) return launch_cols_typed2<T, true, COLS_CW_ASYNC>(ctx, c, p);

@@ -497,9 +497,19 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
 constexpr int CT_CW = 8;
 constexpr int CT_SLOT_ROWS = 256;
 constexpr unsigned CT_SLOT_BYTES = CT_SLOT_ROWS * CT_CW * 4;   // 8192
-constexpr int CT_CONSUMERS = 256;                             // 8 warps = 4 pairs
+#ifndef NDS_CT_CONSUMERS
+#define NDS_CT_CONSUMERS 256  // (384 = six pairs with a ring of six slots: 0.84 ms on C3 against 0.76 ms)
+#endif
+constexpr int CT_CONSUMERS = NDS_CT_CONSUMERS;                // pairs of warps build; the first 8 warps walk a lane each
 constexpr int CT_THREADS = CT_CONSUMERS + 32;                 // + the producer warp
 constexpr int CT_MAX_SLOTS = 16;
+constexpr int CT_PAIRS = CT_CONSUMERS / 64;
+// lanes of the producer warp that issue boxes.  Slot q of the CTA's sequence is issued by lane q % CT_PRODUCERS, lives
+// in ring entry q % nslots and is read by pair q % CT_PAIRS; nslots is a multiple of both, so a ring entry is always
+// filled by the same lane and read by the same pair -- which keeps everybody within one barrier phase of everybody else
+// (a parity wait cannot tell two phases apart from none).
+constexpr int CT_PRODUCERS = (CT_PAIRS % 4 == 0) ? 4 : 3;
+constexpr int CT_SLOT_QUANTUM = (CT_PAIRS % CT_PRODUCERS == 0) ? CT_PAIRS : CT_PAIRS * CT_PRODUCERS;
 
 __device__ __forceinline__ uint32_t ct_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ct_mbar_init(uint64_t *bar, unsigned count) {
@@ -533,7 +543,17 @@ __device__ __forceinline__ void ct_tma_load_3d(void *dst_smem, const CUtensorMap
         : "memory");
 }
 
-template <typename T>
+// arrive on the mbarrier once all cp.async of this thread have landed (the barrier's count includes these arrivals)
+__device__ __forceinline__ void ct_cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ct_smem_u32(bar)) : "memory");
+}
+
+// USE_TMA: the producer is one thread issuing tensor-map boxes (UTMALDG); otherwise the 32 threads of the producer warp
+// issue the same slots as 16-byte cp.async copies (LDGSTS) that arrive on the same mbarriers.  A box of 256 rows x 32
+// bytes is 256 separate 32-byte requests either way, and that request rate is what bounds the kernel: measured on
+// B200, the TMA unit retires one such row every ~3.2 cycles per SM (2.8 TB/s over the chip), the load/store unit one
+// per cycle.
+template <typename T, bool USE_TMA>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ data, LaneGeom g, QuantArgs qa,
                 T *__restrict__ out, unsigned long long n_strips, unsigned strips_per_group, int nslots) {
@@ -574,8 +594,8 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
 
     if (tid == 0) {
         for (int s = 0; s < nslots; ++s) {
-            ct_mbar_init(full + s, 1);
-            ct_mbar_init(empty + s, 2);   // the two warps that read a slot
+            ct_mbar_init(full + s, USE_TMA ? 1 : 32);   // one expect_tx arrival / the 32 copying threads
+            ct_mbar_init(empty + s, 2);                  // the two warps that read a slot
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -585,19 +605,53 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
 
     if (warp == CT_CONSUMERS / 32) {
         // ================= producer: every slot of every strip of this CTA, in order =================
-        if (lane == 0) {
+        if constexpr (!USE_TMA) {
             unsigned long long q = 0;
+            const unsigned rl0 = (unsigned)lane >> 1, half = (unsigned)lane & 1u;  // chunk 32 i + lane: row rl0 + 16 i
             for (unsigned long long it = 0; it < my_strips; ++it) {
                 const unsigned long long strip = blockIdx.x + it * gridDim.x;
                 const unsigned long long grp = strip / strips_per_group;
-                const int col0 = (int)((strip - grp * strips_per_group) * CT_CW);
+                const unsigned long long col0 = (strip - grp * strips_per_group) * CT_CW;
+                long long io, oo;
+                lane_offsets(g, grp * ncols + col0, io, oo);
+                const T *src = data + io + (long long)rl0 * pitch + half * 4;
+                const long long step = 16ll * pitch;
                 for (unsigned j = 0; j < sps; ++j, ++q) {
                     const unsigned r = (unsigned)(q % (unsigned)nslots);
                     const unsigned long long turn = q / (unsigned)nslots;
-                    if (turn > 0) ct_mbar_wait(empty + r, (unsigned)((turn - 1) & 1ull));  // the readers are done with it
-                    ct_mbar_expect_tx(full + r, CT_SLOT_BYTES);
-                    ct_tma_load_3d(ring + (size_t)r * CT_SLOT_BYTES, &tmap, col0, (int)(j * CT_SLOT_ROWS), (int)grp, full + r);
+                    if (turn > 0) ct_mbar_wait(empty + r, (unsigned)((turn - 1) & 1ull));
+                    unsigned char *dst = ring + (size_t)r * CT_SLOT_BYTES + rl0 * 32u + half * 16u;
+                    const unsigned row0 = j * CT_SLOT_ROWS + rl0;
+                    if (row0 + CT_SLOT_ROWS - rl0 <= n) {  // a whole slot (uniform)
+#pragma unroll
+                        for (int i = 0; i < 16; ++i, src += step) cp_async16(dst + i * 512, src);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i, src += step)
+                            if (row0 + 16u * i < n) cp_async16(dst + i * 512, src);
+                    }
+                    ct_cp_async_arrive(full + r);
                 }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            return;
+        }
+        // Several lanes issue, each its own subsequence of the slots (q = lane, lane + CT_PRODUCERS, ...): one thread that
+        // waits for a free slot, arms the barrier and issues the box needs ~280 ns per box, i.e. 29 GB/s per SM -- the
+        // whole chip would stop at 4.3 TB/s (measured with the data thrown away).
+        if (lane < CT_PRODUCERS) {
+            const unsigned long long total = my_strips * sps;
+            for (unsigned long long q = (unsigned long long)lane; q < total; q += CT_PRODUCERS) {
+                const unsigned long long it = q / sps;
+                const unsigned j = (unsigned)(q - it * sps);
+                const unsigned long long strip = blockIdx.x + it * gridDim.x;
+                const unsigned long long grp = strip / strips_per_group;
+                const int col0 = (int)((strip - grp * strips_per_group) * CT_CW);
+                const unsigned r = (unsigned)(q % (unsigned)nslots);
+                const unsigned long long turn = q / (unsigned)nslots;
+                if (turn > 0) ct_mbar_wait(empty + r, (unsigned)((turn - 1) & 1ull));  // the readers are done with it
+                ct_mbar_expect_tx(full + r, CT_SLOT_BYTES);
+                ct_tma_load_3d(ring + (size_t)r * CT_SLOT_BYTES, &tmap, col0, (int)(j * CT_SLOT_ROWS), (int)grp, full + r);
             }
         }
         return;
@@ -618,8 +672,9 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
         {
             uint32_t *pdst = planes + (size_t)bc * col_pitch;
 #pragma unroll 1
-            for (unsigned j = (unsigned)pair; j < sps; j += 4u) {
-                const unsigned long long q = it * sps + j;
+            const unsigned long long q0 = it * sps;   // this strip's slots are q0 .. q0 + sps - 1; mine: q % CT_PAIRS == pair
+            for (unsigned j = (unsigned)(((unsigned long long)pair + CT_PAIRS - q0 % CT_PAIRS) % CT_PAIRS); j < sps; j += (unsigned)CT_PAIRS) {
+                const unsigned long long q = q0 + j;
                 const unsigned r = (unsigned)(q % (unsigned)nslots);
                 ct_mbar_wait(full + r, (unsigned)((q / (unsigned)nslots) & 1ull));
                 const uint32_t *st = reinterpret_cast<const uint32_t *>(ring + (size_t)r * CT_SLOT_BYTES) + (ph * 128 + bsub) * CT_CW + bc;
@@ -651,7 +706,7 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
         named_bar_sync(1, CT_CONSUMERS);   // the strip's planes are complete
 
         // ---- warp w selects the quantiles of lane w ---------------------------------------------------------
-        {
+        if (warp < CT_CW) {
             const T *lp = sp + warp;
             uint32_t *pl = planes + (size_t)warp * col_pitch + lane;  // word k of plane b: pl[b * nrbp + 32 * k]
             unsigned *mylist = clist + warp * COLS_CAND;
@@ -960,8 +1015,12 @@ ColsPlan plan_cols(const nds_ctx *ctx, const DeviceCall &c) {
             const size_t fixed = (size_t)CT_CW * pitch_w * 4 + (size_t)CT_CW * COLS_CAND * 4 + 2 * CT_MAX_SLOTS * 8 + 128;
             if ((size_t)ctx->max_smem_optin > fixed + 4 * CT_SLOT_BYTES) {
                 p.nslots = (int)std::min<size_t>(CT_MAX_SLOTS, ((size_t)ctx->max_smem_optin - fixed) / CT_SLOT_BYTES);
+                if (const char *e = getenv("NDS_COLS_SLOTS")) p.nslots = std::max(CT_SLOT_QUANTUM, std::min(p.nslots, atoi(e)));  // tuning
+                // a slot must always be filled by the same producer lane: lanes that alternated on a slot could run two
+                // barrier phases apart, and a parity wait cannot tell those from zero
+                p.nslots = p.nslots / CT_SLOT_QUANTUM * CT_SLOT_QUANTUM;
                 p.smem_tma = fixed + (size_t)p.nslots * CT_SLOT_BYTES;
-                p.tma = true;
+                p.tma = p.nslots > 0;
             }
         }
     }
@@ -1011,6 +1070,49 @@ template <typename T, bool ASYNC, int CW> cudaError_t launch_cols_typed2(nds_ctx
     return cudaGetLastError();
 }
 
+// Diagnostic (NDS_COLS_DRY=<box width in lanes>): stream the whole array through the slot ring with TMA boxes of the given
+// width and 2048 / width rows (8 KB each) and throw the data away -- the ceiling of the access pattern, nothing else.
+__global__ void __launch_bounds__(64, 1)
+cols_dry_kernel(const __grid_constant__ CUtensorMap tmap, unsigned long long nboxes_x, unsigned long long nboxes_y, int box_w,
+                int box_h, int nslots, unsigned *sink) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + CT_MAX_SLOTS;
+    const uint32_t base_addr = ct_smem_u32(smem_raw);
+    const uint32_t ring_addr = (ct_smem_u32(empty + CT_MAX_SLOTS) + 127u) & ~127u;
+    unsigned char *ring = smem_raw + (ring_addr - base_addr);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nslots; ++s) {
+            ct_mbar_init(full + s, 1);
+            ct_mbar_init(empty + s, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // macro-strip x of this CTA, all its boxes top to bottom, then the next macro-strip
+    const unsigned long long mine = blockIdx.x < nboxes_x ? (nboxes_x - blockIdx.x + gridDim.x - 1) / gridDim.x : 0ull;
+    const unsigned long long total = mine * nboxes_y;
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + CT_PRODUCERS) {
+        for (unsigned long long q = threadIdx.x - 32; q < total; q += CT_PRODUCERS) {
+            const unsigned r = (unsigned)(q % (unsigned)nslots);
+            const unsigned long long turn = q / (unsigned)nslots;
+            if (turn > 0) ct_mbar_wait(empty + r, (unsigned)((turn - 1) & 1ull));
+            const unsigned long long bx = blockIdx.x + (q / nboxes_y) * gridDim.x, by = q % nboxes_y;
+            ct_mbar_expect_tx(full + r, CT_SLOT_BYTES);
+            ct_tma_load_3d(ring + (size_t)r * CT_SLOT_BYTES, &tmap, (int)(bx * box_w), (int)(by * box_h), 0, full + r);
+        }
+    } else if (threadIdx.x == 0) {
+        unsigned acc = 0;
+        for (unsigned long long q = 0; q < total; ++q) {
+            const unsigned r = (unsigned)(q % (unsigned)nslots);
+            ct_mbar_wait(full + r, (unsigned)((q / (unsigned)nslots) & 1ull));
+            acc += *reinterpret_cast<volatile unsigned *>(ring + (size_t)r * CT_SLOT_BYTES);
+            ct_mbar_arrive(empty + r);
+        }
+        if (acc == 0x12345678u) *sink = acc;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1040,18 +1142,44 @@ template <typename T> cudaError_t launch_cols_tma(nds_ctx *ctx, const DeviceCall
     cuuint32_t box[3] = {CT_CW, CT_SLOT_ROWS, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUtensorMap tmap;
+    if (const char *dry = getenv("NDS_COLS_DRY")) {  // diagnostic: the access pattern alone (the result is NOT computed)
+        const int bw = atoi(dry);
+        if (bw >= 4 && bw <= 256 && 2048 % bw == 0 && g.oshape[last] % bw == 0) {
+            box[0] = (cuuint32_t)bw;
+            box[1] = (cuuint32_t)(2048 / bw);
+            int promo = getenv("NDS_COLS_PROMO") ? atoi(getenv("NDS_COLS_PROMO")) : 2;
+            if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(c.data), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)promo,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return cudaErrorNotSupported;
+            int ns = getenv("NDS_COLS_SLOTS") ? atoi(getenv("NDS_COLS_SLOTS")) : 10;
+            ns = std::max(CT_PRODUCERS, std::min(ns, CT_MAX_SLOTS)) / CT_PRODUCERS * CT_PRODUCERS;
+            const size_t smem = 2 * CT_MAX_SLOTS * 8 + 128 + (size_t)ns * CT_SLOT_BYTES;
+            cudaError_t e = cudaFuncSetAttribute(cols_dry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            const unsigned long long nbx = g.oshape[last] / bw, nby = (g.axis_len + box[1] - 1) / box[1];
+            const unsigned grid = (unsigned)std::min<unsigned long long>(nbx, (unsigned long long)ctx->sm_count);
+            cols_dry_kernel<<<grid, 64, smem, ctx->stream>>>(tmap, nbx, nby, bw, (int)box[1], ns, (unsigned *)c.out);
+            ctx->launches += 1;
+            return cudaGetLastError();
+        }
+    }
     const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(c.data), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorNotSupported;
-    auto kernel = cols_tma_kernel<T>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_tma);
-    if (e != cudaSuccess) return e;
+    static const bool ldgsts_producer = getenv("NDS_COLS_TMA") && atoi(getenv("NDS_COLS_TMA")) == 3;  // 3: cp.async producer (slower)
     const unsigned grid = (unsigned)std::min<unsigned long long>(p.n_strips, (unsigned long long)ctx->sm_count);
-    kernel<<<grid, CT_THREADS, p.smem_tma, ctx->stream>>>(tmap, (const T *)c.data, g, c.q, (T *)c.out, p.n_strips,
-                                                          p.strips_per_group, p.nslots);
-    ctx->launches += 1;
-    return cudaGetLastError();
+    auto launch = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_tma);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, CT_THREADS, p.smem_tma, ctx->stream>>>(tmap, (const T *)c.data, g, c.q, (T *)c.out, p.n_strips,
+                                                              p.strips_per_group, p.nslots);
+        ctx->launches += 1;
+        return cudaGetLastError();
+    };
+    if (ldgsts_producer) return launch(cols_tma_kernel<T, false>);
+    return launch(cols_tma_kernel<T, true>);
 }
 
 template <typename T> cudaError_t launch_cols_typed(nds_ctx *ctx, const DeviceCall &c, const ColsPlan &p) {

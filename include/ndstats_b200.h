@@ -120,8 +120,16 @@ nds_status nds_quantiles_axis(nds_ctx *ctx, nds_dtype dtype, const void *data, i
 /*
  * Same computation for device-resident `data` and `out`, enqueued on the ctx stream without a host
  * synchronisation.  Argument errors are returned immediately; data-dependent conditions
- * (NDS_NAN_IN_INPUT, NDS_CAST_OVERFLOW) are reported by the next nds_ctx_synchronize().  `data` and `out` must stay
- * valid until that call: a long lane whose sampled brackets missed a rank is re-run there on the radix passes.
+ * (NDS_NAN_IN_INPUT, NDS_CAST_OVERFLOW) are reported by the next nds_ctx_synchronize().
+ *
+ * Calls on short / column lanes (`nds_ctx_last_path`: "short_bitslice", "cols_bitslice", "generic_cta", "long_radix")
+ * are complete in stream order: a consumer on the same stream may read `out` right behind the call.  A LONG lane that
+ * takes the one-pass bracket select ("bracket") is complete in stream order unless a requested rank escaped its
+ * sampled bracket (~1e-4 per call for 99 quantiles at the default 5 sigma; always for lanes whose segments stay large
+ * after three refinement rounds): then `out` is PROVISIONAL -- it holds unspecified values -- until
+ * nds_ctx_synchronize() has re-run the call on the radix passes, which re-reads `data`.  So for long lanes: keep `data`
+ * unmodified and do not consume `out` before nds_ctx_synchronize() returns; a caller that needs strict stream order on
+ * long lanes forces the radix passes (nds_ctx_force_path(ctx, "long_radix")) or uses the synchronous entry point.
  */
 nds_status nds_quantiles_axis_enqueue(nds_ctx *ctx, nds_dtype dtype, const void *data, int ndim,
                                       const size_t *shape, const ptrdiff_t *strides_elems, int axis,
@@ -153,7 +161,9 @@ nds_status nds_get_many_from_sorted(nds_ctx *ctx, nds_dtype dtype, const void *d
  * QuantileExt::{argmin_skipnan, argmax_skipnan, min_skipnan, max_skipnan}   mod.rs:302-318, 335-345, 365-382, 399-409
  * over the WHOLE array (any shape / strides).  `out_value` (host, one element, optional) receives the extremum,
  * `out_index` (host, ndim entries, optional) its coordinates (`D::Pattern`).  Among equal extrema the first in logical
- * (C) order is reported, as the reference's strict comparisons do; -0.0 and +0.0 are equal.
+ * (C) order is reported, as the reference's strict comparisons do; -0.0 and +0.0 are equal.  One exception, as in the
+ * reference: max_skipnan (want_max, skipnan, out_index == NULL) folds with `acc.max(elem)` and Ord::max returns its second
+ * operand on a tie, so the LAST of equal maxima is returned (max_skipnan([+0.0, -0.0]) is -0.0).
  *   NDS_EMPTY_INPUT      the array has no element (MinMaxError::EmptyInput / EmptyInput), or -- skipnan -- none that is
  *                        not NaN (arg*_skipnan: EmptyInput; min/max_skipnan: `out_value` holds the quiet NaN they return)
  *   NDS_UNDEFINED_ORDER  skipnan == 0 and the array holds a NaN (MinMaxError::UndefinedOrder)

@@ -246,7 +246,13 @@ class Context:
     def quantiles_axis(self, a, axis, qs, interpolate, skipnan=False, enqueue=False, out=None):
         """``nds_quantiles_axis`` / ``nds_quantiles_axis_enqueue`` on a numpy array or CUDA tensor.
 
-        Returns the C-order result with shape[axis] = len(qs) (same container kind as the input)."""
+        Returns the C-order result with shape[axis] = len(qs) (same container kind as the input).
+
+        ``enqueue=True`` (CUDA tensors only) returns without a host synchronisation.  For short and column lanes the
+        result is complete in stream order.  For a long lane on the one-pass bracket path it is PROVISIONAL until
+        ``synchronize()``: in the rare case that a rank escaped its sampled bracket the call is re-run there on the
+        radix passes, which re-reads ``a`` -- keep ``a`` unmodified and read ``out`` only after ``synchronize()``
+        (or ``force_path("long_radix")`` for strict stream order)."""
         code, ptr, shape, strides, keep, is_torch = self._describe(a)
         ndim = len(shape)
         axis = int(axis)
@@ -340,8 +346,10 @@ class Context:
         self._raise(st)
         return out
 
-    def minmax(self, a, want_max, skipnan):
-        """``nds_minmax`` -> (status, value or None, index tuple or None); the callers map the status."""
+    def minmax(self, a, want_max, skipnan, want_index=True):
+        """``nds_minmax`` -> (status, value or None, index tuple or None); the callers map the status.
+        ``want_index=False`` asks for the value alone (max_skipnan then returns the LAST of equal maxima, as the
+        reference's ``acc.max(elem)`` fold does)."""
         code, ptr, shape, strides, keep, is_torch = self._describe(a)
         ndim = len(shape)
         np_dtype = keep.dtype if not is_torch else {v: k for k, v in _NP_DTYPES.items()}[code]
@@ -349,7 +357,8 @@ class Context:
         idx = (ctypes.c_size_t * (ndim or 1))()
         st = self._lib.nds_minmax(self._h, code, ctypes.c_void_p(ptr if a_size(shape) else 0), ndim,
                                   (ctypes.c_size_t * (ndim or 1))(*shape), (ctypes.c_ssize_t * (ndim or 1))(*strides),
-                                  int(bool(want_max)), int(bool(skipnan)), ctypes.c_void_p(val.ctypes.data), idx)
+                                  int(bool(want_max)), int(bool(skipnan)), ctypes.c_void_p(val.ctypes.data),
+                                  idx if want_index else None)
         if st not in (NDS_OK, NDS_EMPTY_INPUT, NDS_UNDEFINED_ORDER):
             self._raise(st)
         return st, val[0], tuple(int(idx[d]) for d in range(ndim))
@@ -513,8 +522,8 @@ def _pattern(idx):
     return idx[0] if len(idx) == 1 else idx
 
 
-def _minmax(a, want_max, skipnan, ctx):
-    return _ctx_for(a, ctx).minmax(a, want_max, skipnan)
+def _minmax(a, want_max, skipnan, ctx, want_index=True):
+    return _ctx_for(a, ctx).minmax(a, want_max, skipnan, want_index)
 
 
 def argmin(a, ctx=None):
@@ -580,7 +589,7 @@ def min_skipnan(a, ctx=None):
 
 def max_skipnan(a, ctx=None):
     """QuantileExt::max_skipnan (src/quantile/mod.rs:399-409)."""
-    return _minmax(a, True, True, ctx)[1]
+    return _minmax(a, True, True, ctx, want_index=False)[1]
 
 
 from .strategies import BinsBuildError, EquiSpaced, FreedmanDiaconis  # noqa: E402,F401  (SURVEY.md §8f row N3)

@@ -32,6 +32,9 @@ nds_status cuda_fail(nds_ctx *ctx, cudaError_t e, const char *where) {
 
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// clear some bits of the deferred status word in stream order (the other bits belong to calls still in flight)
+__global__ void status_clear_bits_kernel(int *status, int bits) { atomicAnd(status, ~bits); }
+
 bool is_device_pointer(const void *p) {
     cudaPointerAttributes attr;
     cudaError_t e = cudaPointerGetAttributes(&attr, p);
@@ -249,7 +252,9 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
         bracket_done = e == cudaSuccess && synchronous && !failed;
         if (e == cudaSuccess && synchronous && failed) {
             // a rank escaped its sampled bracket (or scratch ran out): the exact multi-pass radix select takes over
-            CUDA_TRY(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+            // (only the give-up bit: NaN / overflow bits of earlier, not yet synchronised enqueued calls must survive)
+            status_clear_bits_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_status, STATUS_BIT_FALLBACK);
+            ctx->launches += 1;
             e = launch_long_radix(ctx, c, arena + o_long_fb, sharded);
             ctx->last_path = "bracket->long_radix";
         } else if (e == cudaSuccess && !synchronous) {

@@ -942,11 +942,12 @@ __device__ __forceinline__ unsigned brk_tie1_entry(Key k, unsigned ent, const Ke
     return k < v ? b : (k == v ? t : b + 1u);
 }
 
-// HI32: 64-bit keys, tables indexed with the high word (see brk_plan_kernel); the kernel of the other mode returns.
+// HI32: 64-bit keys, tables indexed with the high word (see brk_plan_kernel).
 // COUNT: low-cardinality lanes (every bracket is one distinct key): classify and count only, nothing is compacted.
+// One kernel holds all variants: which one runs is the plan's decision, read from device memory (brk_stream_kernel).
 template <typename T, bool HI32, bool COUNT>
-__global__ void __launch_bounds__(STR_THREADS, 1)
-brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typename Traits<T>::Key> buf) {
+__device__ __forceinline__ void
+brk_stream_body(const T *__restrict__ data, unsigned long long n, const BrkBuf<typename Traits<T>::Key> &buf) {
     using Tr = Traits<T>;
     using Key = typename Tr::Key;
     constexpr bool IS_FLOAT = Tr::is_float;
@@ -973,10 +974,8 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
     Key *__restrict__ wkey = reinterpret_cast<Key *>(p); p += (size_t)STR_WARPS * STR_RING * sizeof(Key);  // per-warp candidate ring
     unsigned char *wbrk = p;
 
-    if (failed_any(buf.hdr)) return;  // the plan already gave up: the caller falls back
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const BrkLutConst<Key> lc = *buf.lutc;
-    if ((lc.hi32 != 0) != HI32 || (lc.count_only != 0) != COUNT) return;
 #ifdef NDS_STR_TIMING  // diagnostic build (make strvar TIMING=1): per-CTA cycle counts of the streaming pass
     const long long t_begin = clock64();
     long long t_loop = 0;
@@ -1269,6 +1268,22 @@ brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typen
         printf("strtime cta %d sm %u loop %lld total %lld\n", (int)blockIdx.x, smid, t_loop - t_begin, clock64() - t_begin);
     }
 #endif
+}
+
+template <typename T>
+__global__ void __launch_bounds__(STR_THREADS, 1)
+brk_stream_kernel(const T *__restrict__ data, unsigned long long n, BrkBuf<typename Traits<T>::Key> buf) {
+    if (failed_any(buf.hdr)) return;  // the plan already gave up: the caller falls back
+    const int hi32 = buf.lutc->hi32, count_only = buf.lutc->count_only;  // (uniform over the grid)
+    if constexpr (sizeof(T) == 8) {
+        if (hi32) {
+            if (count_only) brk_stream_body<T, true, true>(data, n, buf);
+            else brk_stream_body<T, true, false>(data, n, buf);
+            return;
+        }
+    }
+    if (count_only) brk_stream_body<T, false, true>(data, n, buf);
+    else brk_stream_body<T, false, false>(data, n, buf);
 }
 
 // in-counts of the non-tie brackets are their segment fills
@@ -2557,18 +2572,10 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     // 4. stream (the kernel of the table mode the plan did not choose returns at once)
     {
         const size_t smem = stream_smem_bytes<Key>();
-        auto launch_stream = [&](auto k) -> cudaError_t {
-            cudaError_t e2 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e2 != cudaSuccess) return e2;
-            k<<<sgrid, STR_THREADS, smem, st>>>(lane, n, buf);
-            return count();
-        };
-        if ((e = launch_stream(brk_stream_kernel<T, false, false>)) != cudaSuccess) return e;
-        if ((e = launch_stream(brk_stream_kernel<T, false, true>)) != cudaSuccess) return e;
-        if constexpr (sizeof(Key) == 8) {
-            if ((e = launch_stream(brk_stream_kernel<T, true, false>)) != cudaSuccess) return e;
-            if ((e = launch_stream(brk_stream_kernel<T, true, true>)) != cudaSuccess) return e;
-        }
+        auto k = brk_stream_kernel<T>;
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<sgrid, STR_THREADS, smem, st>>>(lane, n, buf);
+        if ((e = count()) != cudaSuccess) return e;
         brk_publish_fill_kernel<Key><<<1, 128, 0, st>>>(buf);
         if ((e = count()) != cudaSuccess) return e;
         timer.mark("stream");

@@ -47,16 +47,18 @@ template <typename T> __device__ __forceinline__ typename Traits<T>::Key mm_key(
     return Traits<T>::to_key(x);
 }
 
+// `tie_last`: among equal extrema the LAST in logical order wins (max_skipnan folds with `acc.max(elem)`, and Ord::max
+// returns its second operand on a tie, src/quantile/mod.rs:399-409); everywhere else the first one does.
 template <bool MAX> __device__ __forceinline__ bool mm_better(unsigned long long k, unsigned long long i, int f,
-                                                              unsigned long long bk, unsigned long long bi, int bf) {
+                                                              unsigned long long bk, unsigned long long bi, int bf, int tie_last) {
     if (!f) return false;
     if (!bf) return true;
     if (k != bk) return MAX ? k > bk : k < bk;
-    return i < bi;
+    return tie_last ? i > bi : i < bi;
 }
 
 template <typename T, bool MAX>
-__global__ void __launch_bounds__(MM_THREADS) minmax_partial_kernel(const T *__restrict__ data, MmGeom g, MmPartial *partial) {
+__global__ void __launch_bounds__(MM_THREADS) minmax_partial_kernel(const T *__restrict__ data, MmGeom g, MmPartial *partial, int tie_last) {
     using Tr = Traits<T>;
     constexpr int VEC = 16 / (int)sizeof(T);
     unsigned long long bk = 0, bi = 0, nans = 0;
@@ -67,8 +69,8 @@ __global__ void __launch_bounds__(MM_THREADS) minmax_partial_kernel(const T *__r
             return;
         }
         const unsigned long long k = (unsigned long long)mm_key<T>(x);
-        // a thread sees increasing i, so a tie never replaces
-        if (!bf || (MAX ? k > bk : k < bk)) {
+        // a thread sees increasing i, so a tie never replaces -- unless the last of equal extrema is wanted
+        if (!bf || (MAX ? k > bk : k < bk) || (tie_last && k == bk)) {
             bk = k;
             bi = i;
             bf = 1;
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(MM_THREADS) minmax_partial_kernel(const T *__r
         const unsigned long long ok = __shfl_down_sync(0xffffffffu, bk, d), oi = __shfl_down_sync(0xffffffffu, bi, d);
         const int of = __shfl_down_sync(0xffffffffu, bf, d);
         nans += __shfl_down_sync(0xffffffffu, nans, d);
-        if (mm_better<MAX>(ok, oi, of, bk, bi, bf)) { bk = ok; bi = oi; bf = of; }
+        if (mm_better<MAX>(ok, oi, of, bk, bi, bf, tie_last)) { bk = ok; bi = oi; bf = of; }
     }
     __shared__ MmPartial sp[MM_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(MM_THREADS) minmax_partial_kernel(const T *__r
         MmPartial r = sp[0];
         for (int w = 1; w < MM_THREADS / 32; ++w) {
             r.nan_count += sp[w].nan_count;
-            if (mm_better<MAX>(sp[w].key, sp[w].index, sp[w].found, r.key, r.index, r.found)) {
+            if (mm_better<MAX>(sp[w].key, sp[w].index, sp[w].found, r.key, r.index, r.found, tie_last)) {
                 r.key = sp[w].key; r.index = sp[w].index; r.found = sp[w].found;
             }
         }
@@ -122,7 +124,7 @@ struct MmResult {
 
 template <typename T, bool MAX>
 __global__ void __launch_bounds__(MM_THREADS) minmax_final_kernel(const T *__restrict__ data, MmGeom g, const MmPartial *partial,
-                                                                  int nparts, MmResult *res) {
+                                                                  int nparts, MmResult *res, int tie_last) {
     __shared__ MmPartial sp[MM_THREADS];
     MmPartial r;
     r.key = r.index = r.nan_count = 0;
@@ -130,14 +132,14 @@ __global__ void __launch_bounds__(MM_THREADS) minmax_final_kernel(const T *__res
     for (int p = threadIdx.x; p < nparts; p += MM_THREADS) {
         const MmPartial q = partial[p];
         r.nan_count += q.nan_count;
-        if (mm_better<MAX>(q.key, q.index, q.found, r.key, r.index, r.found)) { r.key = q.key; r.index = q.index; r.found = q.found; }
+        if (mm_better<MAX>(q.key, q.index, q.found, r.key, r.index, r.found, tie_last)) { r.key = q.key; r.index = q.index; r.found = q.found; }
     }
     sp[threadIdx.x] = r;
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int t = 1; t < MM_THREADS; ++t) {
             r.nan_count += sp[t].nan_count;
-            if (mm_better<MAX>(sp[t].key, sp[t].index, sp[t].found, r.key, r.index, r.found)) {
+            if (mm_better<MAX>(sp[t].key, sp[t].index, sp[t].found, r.key, r.index, r.found, tie_last)) {
                 r.key = sp[t].key; r.index = sp[t].index; r.found = sp[t].found;
             }
         }
@@ -156,13 +158,13 @@ __global__ void __launch_bounds__(MM_THREADS) minmax_final_kernel(const T *__res
 
 template <typename T>
 cudaError_t launch_minmax_typed(nds_ctx *ctx, const void *data, const MmGeom &g, bool want_max, MmPartial *partial, int nparts,
-                                MmResult *res) {
+                                MmResult *res, int tie_last) {
     if (want_max) {
-        minmax_partial_kernel<T, true><<<nparts, MM_THREADS, 0, ctx->stream>>>((const T *)data, g, partial);
-        minmax_final_kernel<T, true><<<1, MM_THREADS, 0, ctx->stream>>>((const T *)data, g, partial, nparts, res);
+        minmax_partial_kernel<T, true><<<nparts, MM_THREADS, 0, ctx->stream>>>((const T *)data, g, partial, tie_last);
+        minmax_final_kernel<T, true><<<1, MM_THREADS, 0, ctx->stream>>>((const T *)data, g, partial, nparts, res, tie_last);
     } else {
-        minmax_partial_kernel<T, false><<<nparts, MM_THREADS, 0, ctx->stream>>>((const T *)data, g, partial);
-        minmax_final_kernel<T, false><<<1, MM_THREADS, 0, ctx->stream>>>((const T *)data, g, partial, nparts, res);
+        minmax_partial_kernel<T, false><<<nparts, MM_THREADS, 0, ctx->stream>>>((const T *)data, g, partial, tie_last);
+        minmax_final_kernel<T, false><<<1, MM_THREADS, 0, ctx->stream>>>((const T *)data, g, partial, nparts, res, tie_last);
     }
     ctx->launches += 2;
     return cudaGetLastError();
@@ -234,20 +236,22 @@ extern "C" nds_status nds_minmax(nds_ctx *ctx, nds_dtype dtype, const void *data
             return fail(NDS_CUDA_ERROR, "H2D copy");
         dptr = arena + o_in - min_off * (long long)esize;
     }
+    // max_skipnan (the value alone is asked for): the last of equal maxima, see mm_better
+    const int tie_last = (want_max && skipnan && !out_index) ? 1 : 0;
     MmPartial *partial = (MmPartial *)(arena + o_part);
     MmResult *res = (MmResult *)(arena + o_res);
     cudaError_t e;
     switch (dtype) {
-    case NDS_I8: e = launch_minmax_typed<int8_t>(ctx, dptr, g, want_max, partial, nparts, res); break;
-    case NDS_I16: e = launch_minmax_typed<int16_t>(ctx, dptr, g, want_max, partial, nparts, res); break;
-    case NDS_I32: e = launch_minmax_typed<int32_t>(ctx, dptr, g, want_max, partial, nparts, res); break;
-    case NDS_I64: e = launch_minmax_typed<int64_t>(ctx, dptr, g, want_max, partial, nparts, res); break;
-    case NDS_U8: e = launch_minmax_typed<uint8_t>(ctx, dptr, g, want_max, partial, nparts, res); break;
-    case NDS_U16: e = launch_minmax_typed<uint16_t>(ctx, dptr, g, want_max, partial, nparts, res); break;
-    case NDS_U32: e = launch_minmax_typed<uint32_t>(ctx, dptr, g, want_max, partial, nparts, res); break;
-    case NDS_U64: e = launch_minmax_typed<uint64_t>(ctx, dptr, g, want_max, partial, nparts, res); break;
-    case NDS_F32: e = launch_minmax_typed<float>(ctx, dptr, g, want_max, partial, nparts, res); break;
-    default: e = launch_minmax_typed<double>(ctx, dptr, g, want_max, partial, nparts, res); break;
+    case NDS_I8: e = launch_minmax_typed<int8_t>(ctx, dptr, g, want_max, partial, nparts, res, tie_last); break;
+    case NDS_I16: e = launch_minmax_typed<int16_t>(ctx, dptr, g, want_max, partial, nparts, res, tie_last); break;
+    case NDS_I32: e = launch_minmax_typed<int32_t>(ctx, dptr, g, want_max, partial, nparts, res, tie_last); break;
+    case NDS_I64: e = launch_minmax_typed<int64_t>(ctx, dptr, g, want_max, partial, nparts, res, tie_last); break;
+    case NDS_U8: e = launch_minmax_typed<uint8_t>(ctx, dptr, g, want_max, partial, nparts, res, tie_last); break;
+    case NDS_U16: e = launch_minmax_typed<uint16_t>(ctx, dptr, g, want_max, partial, nparts, res, tie_last); break;
+    case NDS_U32: e = launch_minmax_typed<uint32_t>(ctx, dptr, g, want_max, partial, nparts, res, tie_last); break;
+    case NDS_U64: e = launch_minmax_typed<uint64_t>(ctx, dptr, g, want_max, partial, nparts, res, tie_last); break;
+    case NDS_F32: e = launch_minmax_typed<float>(ctx, dptr, g, want_max, partial, nparts, res, tie_last); break;
+    default: e = launch_minmax_typed<double>(ctx, dptr, g, want_max, partial, nparts, res, tie_last); break;
     }
     ctx->last_path = "minmax";
     if (e != cudaSuccess) return fail(NDS_CUDA_ERROR, cudaGetErrorString(e));

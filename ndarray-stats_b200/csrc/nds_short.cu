@@ -15,6 +15,7 @@
 //   4. as soon as <= 32 candidates remain they are gathered (from L2) and ranked directly.
 // Key bits beyond the first 16 are handled by further rounds that re-read the lane (L2-resident).
 // No key transform is applied: the walk interprets IEEE sign / two's-complement sign on the fly.
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -525,6 +526,11 @@ ShortPlan plan_short(const nds_ctx *ctx, const DeviceCall &c) {
         p.warps = (int)std::min<size_t>(16, budget / (p.stages * blk_bytes + fixed));
     }
     p.warps = p.warps / 4 * 4 > 0 ? p.warps / 4 * 4 : p.warps;  // whole warps per scheduler
+    // few lanes (BASELINE config 1: 1024 lanes): spread them over all SMs instead of filling 16 warps on a few
+    {
+        const unsigned long long per_sm = (g.nlanes + (unsigned long long)ctx->sm_count - 1) / (unsigned long long)ctx->sm_count;
+        if (per_sm < (unsigned long long)p.warps) p.warps = (int)std::max<unsigned long long>(1, per_sm);
+    }
     if (const char *e = getenv("NDS_SHORT_WARPS")) p.warps = std::min(p.warps, std::max(1, atoi(e)));
     if (p.warps < 1) return p;
     p.smem = (size_t)p.warps * (p.stages * blk_bytes + fixed);

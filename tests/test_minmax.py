@@ -140,10 +140,9 @@ def test_gpu_max_skipnan_tie_is_the_last(nds, gpu_ctx, oracle, dtype):
     v = nds.max_skipnan(a, ctx=gpu_ctx)
     assert v == 0.0 and np.signbit(v)                      # the last zero is -0.0
     assert nds.argmax_skipnan(a, ctx=gpu_ctx) == 5         # the first one
-    assert not np.signbit(nds.min_skipnan(-a, ctx=gpu_ctx)) or True
     st, want, _ = oracle.minmax(a, True, True)
-    assert np.array_equal(np.asarray(v).view(np.uint8), np.asarray(want).view(np.uint8))
+    assert np.asarray(v).tobytes() == np.asarray(want).tobytes()
     b = a.reshape(100, 1000)[:, ::-1]                       # a strided view: logical order is what counts
     v = nds.max_skipnan(b, ctx=gpu_ctx)
     st, want, _ = oracle.minmax(b, True, True)
-    assert np.array_equal(np.asarray(v).view(np.uint8), np.asarray(want).view(np.uint8))
+    assert np.asarray(v).tobytes() == np.asarray(want).tobytes()

@@ -218,8 +218,14 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
     c.q.interp = interp;
     c.q.skipnan = skipnan;
     c.q.status = ctx->d_status;
-    CUDA_TRY(cudaMemcpyAsync(arena + o_qs, ranks ? (const void *)ranks : (const void *)qs, nq * sizeof(double),
-                             cudaMemcpyHostToDevice, ctx->stream));
+    c.q.inline_q = 0;
+    if (!ranks && nq <= (size_t)NDS_Q_INLINE) {
+        c.q.inline_q = 1;
+        for (size_t t = 0; t < nq; ++t) c.q.qv[t] = qs[t];
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(arena + o_qs, ranks ? (const void *)ranks : (const void *)qs, nq * sizeof(double),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    }
     if (data_on_device) {
         c.data = data;
         c.valid = valid;

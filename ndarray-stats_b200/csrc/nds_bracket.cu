@@ -558,7 +558,7 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
     for (int t = tid; t < (low ? 0 : nq); t += nthreads) {
         double p;
         if (qa.ranks) p = n_total > 1 ? (double)qa.ranks[t] / (double)(n_total - 1) : 0.0;
-        else p = qa.qs[t];
+        else p = qa.inline_q ? qa.qv[t] : qa.qs[t];
         p = fmin(fmax(p, 0.0), 1.0);
         const double P = p * (double)(s1v - 1);
         const double sd = sqrt(fmax(p * (1.0 - p) * (double)s1v, 1.0));
@@ -1156,34 +1156,34 @@ brk_stream_body(const T *__restrict__ data, unsigned long long n, const BrkBuf<t
         }
         // phase 3: private counters (plain read-modify-write of this thread's own bytes, one after the other: two
         // keys of a thread may share a class), candidate mask
-        unsigned cflag[EPT], cnt = 0;
+        unsigned cflag[EPT];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             const unsigned a = myctr_a + (ent[e] & 0xffu) * (unsigned)STR_THREADS;
             sts_u8(a, lds_u8(a) + 1u);
             cflag[e] = (ent[e] >> 8) & 1u;
-            cnt += cflag[e];
         }
         if constexpr (COUNT) return;  // nothing is ever compacted in this mode
-        if (!__any_sync(0xffffffffu, cnt != 0)) return;  // a tile without candidates (common when brackets are few)
-        // phase 4: the ~10 % of keys inside a bracket are packed into the warp's ring (warp prefix sum); full groups
-        // of 32 are appended to the brackets' segments, the rest waits for the next tile
-        unsigned incl = cnt;
+        // phase 4: the ~10 % of keys inside a bracket are packed into the warp's ring; full groups of 32 are appended to
+        // the brackets' segments, the rest waits for the next tile.  Ring positions from one ballot per key slot (the
+        // ballots are independent of each other; a shuffle scan is a chain of five dependent shuffles): the candidates
+        // of slot e of all lanes come before those of slot e + 1 -- the order inside the ring does not matter.
+        const unsigned lt = (1u << lane) - 1u;
+        unsigned total = 0, mypos[EPT];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
+        for (int e = 0; e < EPT; ++e) {
+            const unsigned bal = __ballot_sync(0xffffffffu, cflag[e] != 0u);
+            mypos[e] = total + __popc(bal & lt);
+            total += __popc(bal);
         }
-        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) return;
+        if (total == 0) return;  // a tile without candidates (common when brackets are few)
         if (wpend + total > (unsigned)STR_RING) drain(true);  // rare: make room for a tile full of candidates
-        unsigned pos = whead + wpend + incl - cnt;
+        const unsigned pos0 = whead + wpend;
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {  // the ring keeps the class (= bracket + 1) of a candidate
-            const unsigned i = pos & (unsigned)(STR_RING - 1);
+            const unsigned i = (pos0 + mypos[e]) & (unsigned)(STR_RING - 1);
             if constexpr (sizeof(Key) == 8) sts_key64_if(cflag[e], mykey_a + i * 8u, (unsigned long long)k[e], mybrk_a + i, ent[e]);
             else sts_key32_if(cflag[e], mykey_a + i * 4u, (unsigned)k[e], mybrk_a + i, ent[e]);
-            pos += cflag[e];
         }
         wpend += total;
         __syncwarp();
@@ -1598,16 +1598,73 @@ __global__ void __launch_bounds__(BRK_THREADS, 2) brk_refine_round0_kernel(BrkBu
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int WARPS = BRK_THREADS / 32;
     constexpr int KPT = BRK_RCHUNK / BRK_THREADS;
-    const int groups = (int)gridDim.x / B > 0 ? B : (int)gridDim.x;      // brackets in flight at once
-    const int cpb = (int)gridDim.x / groups;                             // CTAs per bracket
-    if ((int)blockIdx.x >= groups * cpb) return;
-    const int part = blockIdx.x % cpb;
+    // The active brackets' candidates, bracket after bracket, are one long sequence of keys; CTA c takes the part
+    // [c K / G, (c + 1) K / G) of it, cut at piece boundaries (the pieces of one bracket have nearly equal fills, the
+    // brackets themselves differ by a factor of five between the median and the first percentile).  A CTA touches one or
+    // two brackets, so its private counters are spilled once or twice.
+    __shared__ unsigned char act[BRK_MAXB];
+    __shared__ unsigned long long acnt[BRK_MAXB], apre[BRK_MAXB + 1];
+    __shared__ unsigned actmask[4];
+    __shared__ int n_act;
+    if (tid < 4) actmask[tid] = 0;
+    __syncthreads();
+    unsigned long long my_cnt = 0;
+    if (tid < B) {
+        const BrkSeg<Key> &sgt = buf.seg[0][tid];
+        const int fl = sgt.flags;
+        if ((fl & SEG_USED) && !(fl & (SEG_FINAL | SEG_TIE))) {
+            atomicOr(&actmask[tid >> 5], 1u << (tid & 31));
+            my_cnt = sgt.cnt_local > 0 ? sgt.cnt_local : 1ull;
+        }
+    }
+    __syncthreads();
+    if (tid < B && (actmask[tid >> 5] >> (tid & 31) & 1u)) {
+        int pos = __popc(actmask[tid >> 5] & ((1u << (tid & 31)) - 1u));
+        for (int wd = 0; wd < (tid >> 5); ++wd) pos += __popc(actmask[wd]);
+        act[pos] = (unsigned char)tid;
+        acnt[pos] = my_cnt;
+    }
+    if (tid == 0) n_act = __popc(actmask[0]) + __popc(actmask[1]) + __popc(actmask[2]) + __popc(actmask[3]);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < n_act; ++i) {
+            apre[i] = run;
+            run += acnt[i];
+        }
+        apre[n_act] = run;
+    }
+    __syncthreads();
+    const int nact = n_act;
+    if (nact == 0) return;
+    const unsigned long long keys = apre[nact];
+    // position k of the sequence -> (active bracket, piece)
+    auto locate = [&](unsigned long long k, int &ai, unsigned &w) {
+        if (k >= keys) { ai = nact; w = 0; return; }
+        int lo = 0, hi = nact;  // last ai with apre[ai] <= k
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (apre[mid] <= k) lo = mid;
+            else hi = mid;
+        }
+        ai = lo;
+        const unsigned long long inb = k - apre[lo];
+        unsigned long long ww = inb * nw / acnt[lo];  // (inb < acnt <= 2^40, nw <= 148: no overflow)
+        w = (unsigned)(ww < nw ? ww : nw - 1);
+    };
+    int ai0, ai1;
+    unsigned w0, w1;
+    locate(keys * blockIdx.x / gridDim.x, ai0, w0);
+    locate(keys * (blockIdx.x + 1ull) / gridDim.x, ai1, w1);
     unsigned char *myctr = counters + (warp >> 2) * 128 + lane * 4 + (warp & 3);  // conflict-free (see the streaming pass)
     BrkSeg<Key> *nsegs = buf.seg[1];
     Key *dst = buf.cand[1];
-    for (int b = blockIdx.x / cpb; b < B; b += groups) {
+    for (int ai = ai0; ai <= ai1 && ai < nact; ++ai) {
+        const int b = (int)act[ai];
+        const unsigned w_begin = ai == ai0 ? w0 : 0u;
+        const unsigned w_end = ai == ai1 ? w1 : nw;
+        if (w_begin >= w_end) continue;
         const BrkSeg<Key> sg = buf.seg[0][b];
-        if (!(sg.flags & SEG_USED) || (sg.flags & (SEG_FINAL | SEG_TIE))) continue;  // CTA-uniform
         if (COMPACT) {
             __syncthreads();
             if (tid == 0) n_wanted = 0;
@@ -1661,13 +1718,13 @@ __global__ void __launch_bounds__(BRK_THREADS, 2) brk_refine_round0_kernel(BrkBu
                 wseg_cap[j] = nsegs[id].cnt_local;
             }
         __syncthreads();
-        unsigned cw = (unsigned)part, ce0 = 0;   // current chunk: piece cw, first key ce0
+        unsigned cw = w_begin, ce0 = 0;   // current chunk: piece cw, first key ce0
         auto seek = [&](unsigned &w, unsigned &e0) -> bool {  // move (w, e0) to the next non-empty chunk at or after it
-            while (w < nw && e0 >= sfill[w]) {
-                w += (unsigned)cpb;
+            while (w < w_end && e0 >= sfill[w]) {
+                w += 1u;
                 e0 = 0;
             }
-            return w < nw;
+            return w < w_end;
         };
         // keys of chunk (w, e0) into k[]; bit e of the result is set when k[e] is a real key
         auto load = [&](unsigned w, unsigned e0, Key (&k)[KPT]) -> unsigned {
@@ -2603,11 +2660,21 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         const size_t smem0 = (size_t)256 * BRK_THREADS;  // 8-bit counters
         if ((e = cudaFuncSetAttribute(kc0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0)) != cudaSuccess) return e;
         const int max_rounds = (int)sizeof(Key) + 1;
+        // whole waves: as many CTAs as are resident at once (3 per SM were launched where 2 fit: a second, half-empty wave)
+        int occ_c0 = 2, occ_p0 = 4;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c0, kc0, BRK_THREADS, smem0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p0, kp0, BRK_THREADS, 0);
+        // (measured on C4: count 547 us at 2 CTAs per SM = one resident wave; compact 629 us at 4 per SM against 660 at 2)
+        unsigned grid_c0 = (unsigned)(sm * std::max(1, occ_c0)), grid_p0 = (unsigned)(sm * 2 * std::max(1, occ_p0));
+        if (const char *e = getenv("NDS_BRK_R0GRID")) {  // tuning: CTAs per SM of the count / compact pass of round 0
+            int a = 0, b = 0;
+            if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0) { grid_c0 = (unsigned)(sm * a); grid_p0 = (unsigned)(sm * b); }
+        }
         if ((e = finish_small()) != cudaSuccess) return e;
         timer.mark("small-segments");
         auto one_round = [&](int round) -> cudaError_t {
             cudaError_t e2;
-            if (round == 0) kc0<<<sm * 3, BRK_THREADS, smem0, st>>>(buf);
+            if (round == 0) kc0<<<grid_c0, BRK_THREADS, smem0, st>>>(buf);
             else kc<<<sm, BRK_THREADS, smem, st>>>(buf);
             if ((e2 = count()) != cudaSuccess) return e2;
             timer.mark(round == 0 ? "r0:count" : "r:count");
@@ -2621,7 +2688,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
             brk_refine_decide_kernel<Key><<<1, 1024, 0, st>>>(buf);
             if ((e2 = count()) != cudaSuccess) return e2;
             timer.mark("decide");
-            if (round == 0) kp0<<<sm * 6, BRK_THREADS, 0, st>>>(buf);
+            if (round == 0) kp0<<<grid_p0, BRK_THREADS, 0, st>>>(buf);
             else brk_refine_compact_kernel<Key><<<sm * 2, BRK_THREADS, 0, st>>>(buf);
             if ((e2 = count()) != cudaSuccess) return e2;
             brk_refine_advance_kernel<Key><<<1, 32, 0, st>>>(buf);

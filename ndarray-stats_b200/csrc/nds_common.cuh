@@ -47,8 +47,11 @@ __host__ __device__ inline void lane_offsets(const LaneGeom &g, unsigned long lo
     }
 }
 
+constexpr int NDS_Q_INLINE = 8;
 struct QuantArgs {
-    const double *qs;  // device pointer, nq entries (already validated on the host)
+    const double *qs;  // device pointer, nq entries (already validated on the host); unused when `inline_q`
+    double qv[NDS_Q_INLINE];  // up to 8 quantiles travel inside the kernel arguments: no host-to-device copy per call
+    int inline_q;
     const unsigned long long *ranks;  // Sort1dExt mode: nq explicit ranks instead of qs (interp = LOWER)
     int nq;
     int interp;        // nds_interp
@@ -145,7 +148,7 @@ __device__ inline RankMath slot_rank_math(const QuantArgs &qa, int t, unsigned l
         r.frac = 0.0;
         return r;
     }
-    return rank_math(qa.qs[t], n_eff);
+    return rank_math(qa.inline_q ? qa.qv[t] : qa.qs[t], n_eff);
 }
 // Interpolate::needs_lower / needs_higher — interpolate.rs:65-70,78-83,91-96,111-116,130-135
 __host__ __device__ inline bool needs_lower(int interp, double frac) {

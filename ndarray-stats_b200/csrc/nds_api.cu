@@ -121,17 +121,24 @@ nds_status status_from_bits(nds_ctx *ctx, int bits) {
 
 // Grid-wide selection of ONE lane at a time (bracket select, else the radix passes: every requested rank per pass) against
 // the CTA-per-lane kernel (one rank at a time, one CTA per lane).  `fast_lanes`: a bit-sliced lane kernel takes the call.
-bool use_long_path(const nds_ctx *ctx, const LaneGeom &g, size_t nq, bool fast_lanes) {
+// Neither of the two general paths is right for every shape, so a rough cost model picks: the CTA kernel scans a lane
+// once per distinct rank and key byte at ~25 GB/s per CTA (shared-memory atomics) and at most ~3 TB/s over all CTAs;
+// the grid-wide paths pay ~150 us of launches per lane and then stream it at ~3 TB/s, 1.4 times (bracket select) or once
+// per key byte (radix passes).
+bool use_long_path(const nds_ctx *ctx, const LaneGeom &g, size_t nq, int interp, size_t esize, bool fast_lanes) {
     if (ctx->forced_path == "long_radix") return true;
     if (ctx->forced_path != "auto") return false;
-    if (g.axis_len >= (1ull << 32)) return true;
+    if (g.axis_len >= (1ull << 32)) return true;   // the lane kernels index with 32 bits
     if (fast_lanes) return false;
-    if (g.axis_len >= (1ull << 18) && g.nlanes * 4 <= (unsigned long long)ctx->sm_count) return true;
-    // mid-length lanes that no lane kernel takes: a handful of lanes, or many quantiles of a few lanes, are quicker one
-    // after the other over the whole grid (~0.1 ms each) than as one CTA each that selects rank after rank
-    if (g.axis_len >= 8192 && g.nlanes <= 8) return true;
-    if (g.axis_len >= 8192 && nq >= 8 && g.nlanes <= 32) return true;
-    return false;
+    if (g.axis_len < 8192) return false;
+    const double n = (double)g.axis_len, lanes = (double)g.nlanes, es = (double)esize;
+    const double ranks = (double)nq * ((interp == NDS_LOWER || interp == NDS_HIGHER) ? 1.0 : 2.0);
+    const double conc = std::min(lanes, (double)ctx->sm_count * 8.0);
+    const double bw_cta = std::min(25e9, 3e12 / conc);
+    const double t_cta = std::ceil(lanes / conc) * ranks * es * n * es / bw_cta;
+    const bool bracket_like = g.axis_stride == 1 && esize >= 4 && g.axis_len >= (1ull << 16) && nq <= 16;
+    const double t_long = lanes * (150e-6 + n * es * (bracket_like ? 1.4 : es) / 3e12);
+    return t_long < t_cta;
 }
 
 // Common body once everything is parsed. `host_io`: data/out (and masks) are host pointers to stage.
@@ -165,7 +172,7 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
         pre.q.nq = (int)nq;
         fast_lanes = short_bitslice_supported(ctx, pre) || cols_bitslice_supported(ctx, pre);
     }
-    const bool long_path = sharded || use_long_path(ctx, p.geom, nq, fast_lanes);
+    const bool long_path = sharded || use_long_path(ctx, p.geom, nq, interp, esize, fast_lanes);
     // ---- carve the arena ---------------------------------------------------------------------------
     size_t off = 0;
     auto carve = [&](size_t bytes) {

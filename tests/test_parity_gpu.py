@@ -640,8 +640,10 @@ def test_mid_length_lanes_dispatch(nds, gpu_ctx, oracle, dtype):
     check(gpu_ctx, oracle, a[0], 0, pct, "nearest", select_impl=1)          # the smoke shape
     assert gpu_ctx.last_path in ("long_radix", "bracket", "bracket->long_radix"), gpu_ctx.last_path
     b = a[:, :20001].T.copy()                                                 # 20001 x 3: strided lanes along axis 0
-    check(gpu_ctx, oracle, b, 0, [0.25, 0.5], "midpoint", select_impl=1)
-    assert gpu_ctx.last_path in ("long_radix", "bracket", "bracket->long_radix"), gpu_ctx.last_path
+    check(gpu_ctx, oracle, b, 0, [0.25, 0.5], "midpoint", select_impl=1)     # (either path may win the cost model)
+    check(gpu_ctx, oracle, b, 0, pct, "higher", select_impl=1)               # 99 ranks of strided lanes: grid-wide passes
+    if np.dtype(dtype).itemsize >= 4:
+        assert gpu_ctx.last_path in ("long_radix", "bracket", "bracket->long_radix"), gpu_ctx.last_path
     wide = np.tile(a[:, :9000], (20, 1))                                      # 60 lanes x 9000, 2 quantiles: one CTA per lane
     check(gpu_ctx, oracle, wide, 1, [0.5, 0.9], "higher", select_impl=1)
     assert gpu_ctx.last_path == "generic_cta", gpu_ctx.last_path

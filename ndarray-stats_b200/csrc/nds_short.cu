@@ -65,7 +65,7 @@ template <int NB> __host__ __device__ constexpr unsigned short_warp_fixed_bytes(
 constexpr unsigned SHORT_WARP_TAIL_BYTES = SHORT_MAX_STAGES * 8 + 128 + 256;
 
 template <typename T, int NB>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(NB == 8 ? 256 : 512, 1)
 short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__restrict__ out, int S) {
     using Tr = Traits<T>;
     using Key = typename Tr::Key;   // order-preserving key (only used to rank the final <= 32 candidates)
@@ -80,6 +80,14 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
     constexpr bool TOP_INVERTED = IS_FLOAT || std::is_signed<T>::value;  // sign bit set => smaller
     constexpr int EXP_LO = (ES == 4) ? 7 : 4;  // exponent bits inside the top 16-bit field: [EXP_LO, 14]
     constexpr unsigned FULL = 0xffffffffu;
+    // SMART (8-byte types, 4-byte integers): the 16-bit window of a round is not a fixed slice of the key.  Bits on which
+    // the whole lane agrees -- and, for signed integers, bits that merely repeat the sign -- tell no two elements apart, so
+    // round 0 takes the sign bit plus the 15 bits below the highest INFORMATIVE bit of the lane, and later rounds start at
+    // the next informative bit.  Small integers in a wide type, doubles of one binade, tie-heavy lanes: one round instead
+    // of up to four.  (f32 keeps the fixed top half: sign, exponent and 7 mantissa bits nearly always do.)
+    constexpr bool SMART = (ES == 8) || !IS_FLOAT;
+    constexpr bool SIGNED_INT = !IS_FLOAT && std::is_signed<T>::value;
+    constexpr Raw SIGN = (Raw)1 << (KEYBITS - 1);
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
@@ -176,6 +184,159 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
         }
     };
 
+    // ---- SMART windows ------------------------------------------------------------------------------------
+    // field of one element for the window that starts at bit `sh`: round 0 (`first`) = sign bit on top of 15 window bits,
+    // later rounds = 16 window bits (the upper half of the returned word is garbage, the byte permute drops it)
+    auto field64 = [&](uint32_t lo, uint32_t hi, int sh, bool first) -> uint32_t {
+        uint32_t v = sh >= 32 ? (hi >> (sh - 32)) : __funnelshift_r(lo, hi, sh);
+        if (first) v = bitsel(v, hi >> 16, 0x7fffu);
+        return v;
+    };
+    auto field32 = [&](uint32_t x, int sh, bool first) -> uint32_t {
+        uint32_t v = x >> sh;
+        if (first) v = bitsel(v, x >> 16, 0x7fffu);
+        return v;
+    };
+    auto pack_smart = [&](const uint4 &q, uint32_t (&w)[16], int j, int sh, bool first) {
+        if constexpr (ES == 4) {
+            w[2 * j] = __byte_perm(field32(q.x, sh, first), field32(q.y, sh, first), 0x5410u);
+            w[2 * j + 1] = __byte_perm(field32(q.z, sh, first), field32(q.w, sh, first), 0x5410u);
+        } else {
+            w[j] = __byte_perm(field64(q.x, q.y, sh, first), field64(q.z, q.w, sh, first), 0x5410u);
+        }
+    };
+    // lane statistics gathered while the lane streams through the registers: z = OR of (x ^ first element) -- the bits
+    // that differ somewhere in the lane; o = OR of (x ^ sign copies) -- the bits that are not a repetition of the sign
+    // (signed integers); am = largest |x| seen, high word (doubles: is an inf / NaN present?)
+    uint32_t st_zlo = 0, st_zhi = 0, st_olo = 0, st_ohi = 0, st_x0lo = 0, st_x0hi = 0;
+    auto stats = [&](const uint4 &q, uint32_t &am) {
+        if constexpr (ES == 4) {
+            const uint32_t e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                st_zlo |= e[u] ^ st_x0lo;
+                if constexpr (SIGNED_INT) st_olo |= e[u] ^ (uint32_t)((int32_t)e[u] >> 31);
+            }
+        } else {
+            st_zlo |= q.x ^ st_x0lo;
+            st_zhi |= q.y ^ st_x0hi;
+            st_zlo |= q.z ^ st_x0lo;
+            st_zhi |= q.w ^ st_x0hi;
+            if constexpr (SIGNED_INT) {
+                const uint32_t s0 = (uint32_t)((int32_t)q.y >> 31), s1 = (uint32_t)((int32_t)q.w >> 31);
+                st_olo |= q.x ^ s0;
+                st_ohi |= q.y ^ s0;
+                st_olo |= q.z ^ s1;
+                st_ohi |= q.w ^ s1;
+            }
+            if constexpr (IS_FLOAT) am = max(am, max(q.y & 0x7fffffffu, q.w & 0x7fffffffu));
+        }
+    };
+    // informative bits below the sign, over the whole warp
+    auto informative = [&]() -> Raw {
+        uint32_t lo = __reduce_or_sync(FULL, st_zlo), hi = 0;
+        if constexpr (SIGNED_INT) lo &= __reduce_or_sync(FULL, st_olo);
+        if constexpr (ES == 8) {
+            hi = __reduce_or_sync(FULL, st_zhi);
+            if constexpr (SIGNED_INT) hi &= __reduce_or_sync(FULL, st_ohi);
+            return (((Raw)hi << 32) | (Raw)lo) & ~SIGN;
+        } else {
+            return (Raw)lo & ~SIGN;
+        }
+    };
+    auto msb = [](Raw v) -> int { return ES == 8 ? 63 - __clzll((long long)v) : 31 - __clz((int)v); };
+    auto low_mask = [](int pos) -> Raw { return pos >= KEYBITS ? ~(Raw)0 : (((Raw)1 << pos) - (Raw)1); };
+    // shift of the round-0 window whose top informative bit is expected at msb(V) (+ margin when V covers only the
+    // first block of the lane and the rest may reach a little higher)
+    auto pick_shift = [&](Raw V, int margin) -> int {
+        if (V == 0) return KEYBITS - 16;
+        const int top = min(msb(V) + margin, KEYBITS - 2);
+        return max(top - 14, 0);
+    };
+    Raw V_lane = 0;   // informative bits of the current lane (sign excluded)
+    int sh0 = KEYBITS - 16;  // shift of the round-0 window the plane area holds (while !planes_dirty)
+    unsigned smart_nan = 0;  // this thread's NaN count of the current lane (doubles)
+
+    // Any round, from the lane in global memory (L2-resident), window at `sh`.
+    auto build_from_global_smart = [&](const unsigned char *gsrc, int sh, bool first) {
+#pragma unroll 1
+        for (int blk = 0; blk < nbn; ++blk) {
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < LD_PER_BLK; ++j) {
+                const unsigned chunk = min((unsigned)((blk * LD_PER_BLK + j) * 32 + lane), n_chunks - 1);
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(gsrc + (size_t)chunk * 16));
+                pack_smart(q, w, j, sh, first);
+            }
+            transpose16(w);
+#pragma unroll
+            for (int b = 0; b < 16; ++b) planes[(b * NB + blk) * 32] = w[b];
+        }
+    };
+    // Round 0 of a fresh lane from the ring.  The first block (already in registers) proposes the window, the whole lane
+    // confirms it; a lane whose later blocks reach above the proposal is built again from L2 with the right window.
+    auto build_from_ring_smart = [&](const unsigned char *gsrc) {
+        st_zlo = st_zhi = st_olo = st_ohi = 0;
+        smart_nan = 0;
+#pragma unroll 1
+        for (int blk = 0; blk < nbn; ++blk) {
+            const unsigned nchunks_blk = min(BLK_BYTES, lane_bytes - (unsigned)blk * BLK_BYTES) / 16;
+            const unsigned char *src = ring + (size_t)c_stage * BLK_BYTES;
+            mbar_wait(bars + c_stage, (c_parity >> c_stage) & 1u);
+            c_parity ^= 1u << c_stage;
+            c_stage = (c_stage + 1 == S) ? 0 : c_stage + 1;
+            uint4 q[LD_PER_BLK];
+            if (nchunks_blk == BLK_BYTES / 16) {
+#pragma unroll
+                for (int j = 0; j < LD_PER_BLK; ++j)
+                    q[j] = *reinterpret_cast<const uint4 *>(src + (size_t)(j * 32 + lane) * 16);
+            } else {
+#pragma unroll
+                for (int j = 0; j < LD_PER_BLK; ++j) {
+                    const unsigned chunk = min((unsigned)(j * 32 + lane), nchunks_blk - 1);
+                    q[j] = *reinterpret_cast<const uint4 *>(src + (size_t)chunk * 16);
+                }
+            }
+            __syncwarp();
+            produce();
+            if (blk == 0) {
+                st_x0lo = __shfl_sync(FULL, q[0].x, 0);
+                if constexpr (ES == 8) st_x0hi = __shfl_sync(FULL, q[0].y, 0);
+            }
+            uint32_t am = 0;
+#pragma unroll
+            for (int j = 0; j < LD_PER_BLK; ++j) stats(q[j], am);
+            if (blk == 0) sh0 = pick_shift(informative(), nbn > 1 ? 2 : 0);
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < LD_PER_BLK; ++j) pack_smart(q[j], w, j, sh0, true);
+            if constexpr (IS_FLOAT) {  // (doubles) NaN positions of the block, straight from the registers
+                const uint32_t valid = vm[blk * 32];
+                uint32_t nanm = 0;
+                if (__any_sync(FULL, am >= 0x7ff00000u)) {
+#pragma unroll
+                    for (int j = 0; j < LD_PER_BLK; ++j) {
+                        const double d0 = __hiloint2double((int)q[j].y, (int)q[j].x);
+                        const double d1 = __hiloint2double((int)q[j].w, (int)q[j].z);
+                        nanm |= (d0 != d0 ? 1u : 0u) << j;
+                        nanm |= (d1 != d1 ? 1u : 0u) << (j + 16);
+                    }
+                }
+                smart_nan += __popc(valid & nanm);
+                im[blk * 32] = valid & ~nanm;
+            }
+            transpose16(w);
+#pragma unroll
+            for (int b = 0; b < 16; ++b) planes[(b * NB + blk) * 32] = w[b];
+        }
+        V_lane = informative();
+        if ((V_lane >> (sh0 + 15)) != 0) {  // (rare) informative bits above the proposed window
+            sh0 = pick_shift(V_lane, 0);
+            __syncwarp();
+            build_from_global_smart(gsrc, sh0, true);
+        }
+    };
+
     // Round 0 of a fresh lane: consume its blocks from the ring (refilling each stage as soon as it has
     // been read).  Returns (floats) the OR of the "exponent all ones" masks: is an inf/NaN present?
     auto build_from_ring = [&]() -> uint32_t {
@@ -230,12 +391,22 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
         lane_offsets(g, L, in_off, out_off);
         const T *lp = data + in_off;
 
-        const uint32_t special_any = build_from_ring();
+        uint32_t special_any = 0;
+        if constexpr (SMART) build_from_ring_smart(reinterpret_cast<const unsigned char *>(lp));
+        else special_any = build_from_ring();
 
         // ---- NaN handling (floats): elements with an all-ones exponent are inspected individually ----
         const uint32_t *init = vm;
         unsigned n_eff = n;
-        if (IS_FLOAT && __any_sync(FULL, special_any != 0)) {
+        if constexpr (SMART && IS_FLOAT) {  // (doubles) the build already wrote the NaN-free masks
+            const unsigned nan_total = __reduce_add_sync(FULL, smart_nan);
+            if (nan_total) {
+                if (!qa.skipnan && lane == 0) atomicOr(qa.status, STATUS_BIT_NAN);
+                n_eff = n - nan_total;
+            }
+            init = im;
+        }
+        if (!SMART && IS_FLOAT && __any_sync(FULL, special_any != 0)) {
             unsigned my_nan = 0;
 #pragma unroll 1
             for (int blk = 0; blk < nbn; ++blk) {
@@ -442,6 +613,177 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
             }
         };
 
+        // ---- SMART variant of select: informative-bit windows (see the top of the kernel) ------------------
+        auto select_smart = [&](unsigned r, bool want_next, Raw &raw_r, Raw &raw_next) {
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                if (planes_dirty) {
+                    __syncwarp();
+                    build_from_global_smart(reinterpret_cast<const unsigned char *>(lp), sh0, true);
+                    __syncwarp();
+                    planes_dirty = false;
+                }
+                uint32_t m[NB];
+#pragma unroll
+                for (int blk = 0; blk < NB; ++blk) m[blk] = (blk < nbn) ? init[blk * 32] : 0u;
+                unsigned total = n_eff, rem = r + (unsigned)pass;
+                bool neg = false;
+                bool small = total <= 32, alleq = false;
+                int sh = sh0, topb = 15;
+                bool first = true;
+#pragma unroll 1
+                while (!small) {
+                    const uint32_t *pp = planes + topb * NB * 32;
+                    uint32_t inv = first ? (TOP_INVERTED ? 0xffffffffu : 0u) : ((IS_FLOAT && neg) ? 0xffffffffu : 0u);
+#pragma unroll 1
+                    for (int b = topb; b >= 0; --b, pp -= NB * 32) {
+                        uint32_t x[NB];
+                        unsigned ones = 0;
+#pragma unroll
+                        for (int blk = 0; blk < NB; ++blk) {
+                            x[blk] = pp[blk * 32];
+                            ones += __popc(m[blk] & (x[blk] ^ inv));
+                        }
+                        ones = __reduce_add_sync(FULL, ones);
+                        const unsigned small_cnt = total - ones;
+                        const bool take_small = rem < small_cnt;
+                        total = take_small ? small_cnt : ones;
+                        rem = take_small ? rem : rem - small_cnt;
+                        const uint32_t keep = take_small ? inv : ~inv;
+#pragma unroll
+                        for (int blk = 0; blk < NB; ++blk) m[blk] &= ~(x[blk] ^ keep);
+                        if (first && b == 15) {
+                            neg = IS_FLOAT && (keep & 1u);
+                            inv = neg ? 0xffffffffu : 0u;
+                        }
+                        if (total <= 32) {
+                            small = true;
+                            break;
+                        }
+                        // no informative bit below this one: the candidates are all one value
+                        if ((V_lane & low_mask(sh + ((first && b == 15) ? 15 : b))) == 0) {
+                            alleq = true;
+                            break;
+                        }
+                    }
+                    if (small || alleq) break;
+                    // More than 32 candidates survived the window.  Before the lane is read and transposed again: are they
+                    // all one value already?  (Tie-heavy lanes: usually yes once the few distinct values are told apart.)
+                    {
+                        Raw mine = 0;
+                        bool have = false;
+#pragma unroll
+                        for (int blk = 0; blk < NB; ++blk)
+                            if (!have && m[blk]) {
+                                mine = to_raw<T>(lp[elem_index(blk, slot_of_pos(__ffs(m[blk]) - 1))]);
+                                have = true;
+                            }
+                        const unsigned owners = __ballot_sync(FULL, have);
+                        const Raw ref = __shfl_sync(FULL, mine, __ffs(owners) - 1);
+                        bool same = true, go = true;
+#pragma unroll
+                        for (int blk = 0; blk < NB; ++blk) {
+                            if (go) {
+                                uint32_t bits = m[blk];
+                                while (bits) {
+                                    const int p = __ffs(bits) - 1;
+                                    bits &= bits - 1;
+                                    same = same && (to_raw<T>(lp[elem_index(blk, slot_of_pos(p))]) == ref);
+                                }
+                                go = __all_sync(FULL, same);
+                            }
+                        }
+                        if (go) {
+                            alleq = true;
+                            break;
+                        }
+                    }
+                    const int top = msb(V_lane & low_mask(sh));  // (non-zero: the walk would have stopped at b == 0)
+                    const int nsh = max(top - 15, 0);
+                    __syncwarp();
+                    build_from_global_smart(reinterpret_cast<const unsigned char *>(lp), nsh, false);
+                    __syncwarp();
+                    planes_dirty = true;
+                    sh = nsh;
+                    topb = top - nsh;
+                    first = false;
+                }
+                Raw found, found_next = 0;
+                bool have_next = false;
+                if (!small) {
+                    // every remaining candidate is the same value: take the first one
+                    Raw mine = 0;
+                    bool have = false;
+#pragma unroll
+                    for (int blk = 0; blk < NB; ++blk)
+                        if (!have && m[blk]) {
+                            mine = to_raw<T>(lp[elem_index(blk, slot_of_pos(__ffs(m[blk]) - 1))]);
+                            have = true;
+                        }
+                    const unsigned owners = __ballot_sync(FULL, have);
+                    found = __shfl_sync(FULL, mine, __ffs(owners) - 1);
+                    if (rem + 1 < total) {
+                        found_next = found;
+                        have_next = true;
+                    }
+                } else {
+                    unsigned mycnt = 0;
+#pragma unroll
+                    for (int blk = 0; blk < NB; ++blk) mycnt += __popc(m[blk]);
+                    unsigned incl = mycnt;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        unsigned tt = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= d) incl += tt;
+                    }
+                    unsigned base = incl - mycnt;
+#pragma unroll
+                    for (int blk = 0; blk < NB; ++blk) {
+                        uint32_t bits = m[blk];
+                        while (bits) {
+                            int p = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            clist[base++] = elem_index(blk, slot_of_pos(p));
+                        }
+                    }
+                    __syncwarp();
+                    Raw myraw = 0;
+                    Key mykey = (Key) ~(Key)0;
+                    if ((unsigned)lane < total) {
+                        T x = lp[clist[lane]];
+                        myraw = to_raw<T>(x);
+                        mykey = Tr::to_key(x);
+                    }
+                    ckeys[lane] = mykey;
+                    __syncwarp();
+                    unsigned less = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const Key kj = ckeys[j];
+                        less += (kj < mykey || (kj == mykey && j < lane)) ? 1u : 0u;
+                    }
+                    __syncwarp();
+                    unsigned hit = __ballot_sync(FULL, (unsigned)lane < total && less == rem);
+                    found = __shfl_sync(FULL, myraw, __ffs(hit) - 1);
+                    if (rem + 1 < total) {
+                        unsigned hit2 = __ballot_sync(FULL, (unsigned)lane < total && less == rem + 1);
+                        found_next = __shfl_sync(FULL, myraw, __ffs(hit2) - 1);
+                        have_next = true;
+                    }
+                }
+                if (pass == 0) {
+                    raw_r = found;
+                    if (!want_next) return;
+                    if (have_next) {
+                        raw_next = found_next;
+                        return;
+                    }
+                } else {
+                    raw_next = found;
+                }
+            }
+        };
+
         // ---- every requested quantile of the lane (src/quantile/mod.rs:475-487) ------------------------
         unsigned cache_rank[2] = {0xffffffffu, 0xffffffffu};
         Raw cache_raw[2] = {0, 0};
@@ -470,7 +812,8 @@ short_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *_
                 const unsigned r = !have_l ? rl : rh;
                 const bool want_next = !have_l && !have_h && rh == rl + 1;
                 Raw a = 0, b = 0;
-                select(r, want_next, a, b);
+                if constexpr (SMART) select_smart(r, want_next, a, b);
+                else select(r, want_next, a, b);
                 remember(r, a);
                 if (want_next) remember(r + 1, b);
             }

@@ -330,6 +330,67 @@ def test_short_bitslice_nan(nds, gpu_ctx, oracle, dtype):
         gpu_ctx.force_path("auto")
 
 
+@pytest.mark.parametrize("dtype", [np.int64, np.uint64, np.int32, np.uint32, np.float64], ids=lambda d: np.dtype(d).name)
+def test_short_bitslice_informative_windows(gpu_ctx, oracle, dtype):
+    """The 8-byte types and the 4-byte integers pick the 16-bit window of a round from the bits that tell the lane's
+    elements apart (nds_short.cu, SMART): small magnitudes in a wide type, sign-extended negatives, constant leading
+    bits, values that differ only far down, a first block that under-states the lane (window re-proposed), NaNs that
+    appear only in later blocks, many distinct tie values (several rounds)."""
+    dtype = np.dtype(dtype)
+    rng = np.random.default_rng(zlib.crc32(repr(("smart", dtype.name)).encode()))
+    lanes = 96
+    cases = []
+    for n in (8192, 4096, 3000 // (16 // dtype.itemsize) * (16 // dtype.itemsize), 1024, 256):
+        if dtype.kind == "f":
+            base = rng.random((lanes, n))
+            cases += [
+                ("binade", 1.0 + base * 0.5),
+                ("tiny-spread", 1e-300 * (1 + base)),
+                ("mixed-sign-small", (base - 0.5) * 1e-3),
+                ("few-values-random-mantissa", rng.choice(rng.standard_normal(100), size=(lanes, n))),
+                ("two-values-low-bits", np.where(base < 0.5, 1.0, np.nextafter(1.0, 2.0))),
+                ("signed-zeros", np.where(base < 0.3, -0.0, np.where(base < 0.6, 0.0, base))),
+            ]
+            late = 1.0 + base
+            late[:, n // 2:] *= 1e200     # the first block under-states the range
+            cases.append(("late-large", late))
+            late_nan = base.copy()
+            late_nan[:, n - n // 4:][rng.random((lanes, n // 4)) < 0.2] = np.nan   # NaNs only at the end of the lane
+            cases.append(("late-nan", late_nan))
+        else:
+            info = np.iinfo(dtype)
+            signed = info.min < 0
+            lo16 = -8 if signed else 0
+            sh = 40 if dtype.itemsize == 8 else 20
+            small = rng.integers(lo16, lo16 + 16, size=(lanes, n)).astype(np.int64)
+            cases += [
+                ("16-values-shifted", (small * (1 << sh)).astype(dtype)),
+                ("small", rng.integers(-1000 if signed else 0, 1000, size=(lanes, n)).astype(dtype)),
+                ("low-bits-only", rng.integers(0, 3, size=(lanes, n)).astype(dtype) + dtype.type(info.max - 5)),
+                ("high-constant", rng.integers(0, 1 << 20, size=(lanes, n)).astype(dtype) + dtype.type(info.max // 2 + 12345)),
+                ("full-range", rng.integers(info.min, info.max, size=(lanes, n), dtype=dtype, endpoint=True)),
+                ("100-values", rng.choice(rng.integers(info.min, info.max, size=100, dtype=dtype), size=(lanes, n))),
+            ]
+            late = rng.integers(0, 100, size=(lanes, n)).astype(dtype)
+            late[:, n // 2:] = rng.integers(info.max // 4, info.max // 2, size=(lanes, n - n // 2), dtype=dtype)
+            cases.append(("late-large", late))
+            if signed:
+                late = rng.integers(0, 100, size=(lanes, n)).astype(dtype)
+                late[:, n - 3:] = -1
+                cases.append(("late-negative", late))
+                cases.append(("min-max", rng.choice(np.array([info.min, info.max, -1, 0], dtype=dtype), size=(lanes, n))))
+    try:
+        gpu_ctx.force_path("short_bitslice")
+        for name, a in cases:
+            a = np.ascontiguousarray(a.astype(dtype))
+            skip = bool(dtype.kind == "f" and np.isnan(a).any())
+            for interp, qs in (("lower", [0.1, 0.5, 0.9]), ("higher", [0.0, 0.5, 1.0]), ("midpoint", [0.5]), ("nearest", [0.25, 0.999])):
+                check(gpu_ctx, oracle, a, 1, qs, interp, skipnan=skip, select_impl=1)
+                assert gpu_ctx.last_path == "short_bitslice", (name, gpu_ctx.last_path)
+    finally:
+        gpu_ctx.force_path("auto")
+
+
 # NDS_COLS_V2=1 routes the qualifying calls to the experimental pipelined strip kernel (nds_cols.cu); the same cases apply
 COLS_PATHS = ("cols_bitslice", "cols_pipelined") if os.environ.get("NDS_COLS_V2") else ("cols_bitslice",)
 

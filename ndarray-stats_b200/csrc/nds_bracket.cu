@@ -73,6 +73,13 @@ constexpr unsigned ENT_COMPACT = 0x100u, ENT_MIXED = 0x200u;
 // over the bracket edges.  Tie-heavy lanes send most of their keys through such cells.
 constexpr unsigned ENT_TIE1 = 0x400u;
 constexpr int BRK_LOWCARD_MAX = 63;       // distinct sample keys up to which a lane is counted per key (2 K + 1 classes)
+// low-cardinality lanes: the streaming pass finds a key's class with ONE probe of a perfect hash table {key, class} in
+// shared memory (4096 slots of 8 bytes for 4-byte keys, 2048 slots of 16 bytes for 8-byte keys: 32 KB either way)
+template <typename Key> __host__ __device__ constexpr int brk_hash_bits() { return sizeof(Key) == 8 ? 11 : 12; }
+template <typename Key> __device__ __forceinline__ unsigned brk_hash_fold(Key k) {
+    if constexpr (sizeof(Key) == 8) return (unsigned)(k >> 32) ^ ((unsigned)k * 0x9E3779B1u);
+    else return (unsigned)k;
+}
 
 enum : int {
     H_NTOTAL = 0, H_NINVALID, H_NEFF, H_FAIL, H_B, H_NSEG, H_NTASK, H_NACTIVE, H_S1VALID, H_EMPTY, H_NCHUNK_COUNT,
@@ -106,6 +113,8 @@ template <typename Key> struct BrkLutConst {
     int B, ncls_used;
     int hi32;          // 64-bit keys: the tables are indexed with the high word only (shift1, subshift >= 32)
     int count_only;    // low-cardinality lane: every bracket is one distinct key, nothing is compacted (tie class = B + 1 + b)
+    int hashed;        // count_only: `hmul` maps the distinct keys one-to-one onto the slots of a small hash table
+    unsigned hmul;     // slot = (fold(key) * hmul) >> (32 - BRK_HASH_BITS)
 };
 
 template <typename Key> struct BrkBuf {
@@ -520,6 +529,8 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
             buf.lutc->submask = 0;
             buf.lutc->ncls_used = 1;
             buf.lutc->count_only = 0;
+            buf.lutc->hashed = 0;
+            buf.lutc->hmul = 1u;
         }
         for (int c = tid; c < BRK_NC1; c += nthreads) buf.lut1[c] = 0u;  // every number is class 0 (NaNs: invalid class)
         for (int i = tid; i < BRK_L2_PURE; i += nthreads) buf.lut2[i] = (unsigned short)0;
@@ -725,6 +736,44 @@ brk_plan_kernel(BrkBuf<Key> buf, QuantArgs qa, double csigma, unsigned long long
     }
     __syncthreads();
     const int B = sB, shift1 = sShift1;
+    // ---- low-cardinality lanes: a multiplier that hashes the distinct keys onto different slots (and, among those,
+    //      one that spreads them over the shared-memory banks).  One candidate per warp and turn: lane i holds keys i and
+    //      i + 32, duplicates show up in match.any and in one round of shuffles. -----------------------------------
+    __shared__ unsigned hbest[32];
+    if (low && !sFail) {
+        constexpr int HB = brk_hash_bits<Key>();
+        constexpr unsigned GROUPS = sizeof(Key) == 8 ? 8u : 16u;   // table entries per 128 bytes of shared memory
+        const int lane = tid & 31, warp = tid >> 5;
+        const bool va = lane < B, vb = lane + 32 < B;
+        const unsigned fa = va ? brk_hash_fold<Key>(blo[lane]) : 0u, fb = vb ? brk_hash_fold<Key>(blo[lane + 32]) : 0u;
+        unsigned best = 0xffffffffu;  // (score << 24 | candidate): smaller is better
+        for (int turn = 0; turn < 16; ++turn) {
+            const unsigned cand = (unsigned)(turn * 32 + warp);
+            const unsigned mul = mix32(cand * 2654435761u + 12345u) | 1u;
+            const unsigned sa = va ? (fa * mul) >> (32 - HB) : 0xffff0000u + (unsigned)lane;   // (idle lanes: unique dummies)
+            const unsigned sb = vb ? (fb * mul) >> (32 - HB) : 0xfffe0000u + (unsigned)lane;
+            const unsigned pa = __match_any_sync(0xffffffffu, sa), pb = __match_any_sync(0xffffffffu, sb);
+            bool dup = (pa & (pa - 1)) != 0 || (pb & (pb - 1)) != 0;
+            unsigned load = __popc(__match_any_sync(0xffffffffu, va ? (sa & (GROUPS - 1)) : 0x100u + (unsigned)lane));
+            for (int j = 0; j < 32; ++j) {
+                const unsigned o = __shfl_sync(0xffffffffu, sb, j);
+                dup = dup || o == sa;
+                load += (va && o < 0xfffe0000u && ((o ^ sa) & (GROUPS - 1)) == 0) ? 1u : 0u;
+            }
+            const bool bad = __any_sync(0xffffffffu, dup);
+            const unsigned score = __reduce_max_sync(0xffffffffu, load);
+            if (!bad) best = min(best, (score << 24) | cand);
+        }
+        if (lane == 0) hbest[warp] = best;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned best = 0xffffffffu;
+        if (low && !sFail)
+            for (int w = 0; w < 32; ++w) best = min(best, hbest[w]);
+        buf.lutc->hashed = best != 0xffffffffu ? 1 : 0;
+        buf.lutc->hmul = mix32((best & 0xffffffu) * 2654435761u + 12345u) | 1u;
+    }
     // candidate segments: predicted size from the sample, with head room (one bracket per thread)
     {
         const double scale = (double)n_total / (double)s1v;
@@ -987,8 +1036,12 @@ brk_stream_body(const T *__restrict__ data, unsigned long long n, const BrkBuf<t
     const int ncls_used = lc.ncls_used;
     const unsigned nw = (unsigned)buf.hdr[H_NW];        // pieces per bracket segment = streaming CTAs
 
-    for (int i = tid; i < BRK_NC1; i += STR_THREADS) const_cast<unsigned *>(lut1)[i] = buf.lut1[i];
-    for (int i = tid; i < BRK_L2N; i += STR_THREADS) const_cast<unsigned short *>(lut2)[i] = buf.lut2[i];
+    bool hashed = false;   // low-cardinality lanes with a perfect hash of their distinct keys: no lookup tables at all
+    if constexpr (COUNT) hashed = lc.hashed != 0;
+    if (!hashed) {
+        for (int i = tid; i < BRK_NC1; i += STR_THREADS) const_cast<unsigned *>(lut1)[i] = buf.lut1[i];
+        for (int i = tid; i < BRK_L2N; i += STR_THREADS) const_cast<unsigned short *>(lut2)[i] = buf.lut2[i];
+    }
     for (int i = tid; i < BRK_MAXB; i += STR_THREADS) {
         blo[i] = i < B ? buf.blo[i] : (Key)0;
         bhi[i] = i < B ? buf.bhi[i] : (Key)0;
@@ -1004,6 +1057,37 @@ brk_stream_body(const T *__restrict__ data, unsigned long long n, const BrkBuf<t
     for (int i = tid; i < BRK_NCLS; i += STR_THREADS) cta_cnt[i] = 0;
     for (int i = tid; i < BRK_NCLS * STR_THREADS / 4; i += STR_THREADS) reinterpret_cast<unsigned *>(counters)[i] = 0;
     __syncthreads();
+    // the hash table {key, class} lives where the lookup tables would be.  Empty slots repeat the entry of key 0: a key
+    // equal to it probes its own slot, so a copy elsewhere can never be hit by mistake.
+    constexpr int HB = brk_hash_bits<Key>();
+    constexpr int HENT = sizeof(Key) == 8 ? 16 : 8;   // bytes per entry
+    static_assert(((size_t)HENT << HB) <= (size_t)BRK_NC1 * 4 + (size_t)BRK_L2N * 2, "hash table fits the lookup tables' room");
+    const unsigned htab_a = sm_addr(lut1);
+    const unsigned hmul = lc.hmul;
+    auto hash_store = [&](unsigned slot, Key key, unsigned cls) {
+        if constexpr (sizeof(Key) == 8)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(htab_a + slot * 16u), "r"((unsigned)key),
+                         "r"((unsigned)((unsigned long long)key >> 32)), "r"(cls), "r"(0u) : "memory");
+        else
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(htab_a + slot * 8u), "r"((unsigned)key), "r"(cls) : "memory");
+    };
+    if (hashed) {
+        for (unsigned i = tid; i < (1u << HB); i += STR_THREADS) hash_store(i, blo[0], (unsigned)btie[0]);
+        __syncthreads();
+        if (tid < B) hash_store((brk_hash_fold<Key>(blo[tid]) * hmul) >> (32 - HB), blo[tid], (unsigned)btie[tid]);
+        __syncthreads();
+    }
+    // class of a key without any table (count-only lanes: every bracket is a single key): binary search over the keys
+    auto classify_slow = [&](Key k) -> unsigned {
+        if (key_is_nan<T>(k)) return (unsigned)BRK_INVALID_CLS;
+        int a = 0, e = B;   // number of brackets with blo <= k
+        while (a < e) {
+            const int mid = (a + e) >> 1;
+            if (blo[mid] <= k) a = mid + 1;
+            else e = mid;
+        }
+        return (a > 0 && blo[a - 1] == k && btie[a - 1] != 0xffu) ? (unsigned)btie[a - 1] : (unsigned)a;
+    };
 
     // conflict-free private counter of this thread in a class row of 512 bytes: the 32 lanes of a warp hit 32
     // different banks, four warps share a 128-byte line (byte 0..3 of each word)
@@ -1190,17 +1274,66 @@ brk_stream_body(const T *__restrict__ data, unsigned long long n, const BrkBuf<t
         if (wpend >= 32u) drain(false);
     };
 
+    // low-cardinality lanes with a perfect hash: one multiply, one probe, one compare per key; a key the table does not
+    // hold (unseen by the sample, or a NaN) is classified by the binary search
+    auto process_tile_hashed = [&](const uint4 (&q)[NLD]) {
+        unsigned cls[EPT];
+        Key k[EPT];
+        bool miss = false;
+#pragma unroll
+        for (int j = 0; j < NLD; ++j) {
+            if constexpr (ES == 4) {
+                const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const Key kk = Tr::to_key(from_raw<T>(w[u]));
+                    k[j * 4 + u] = kk;
+                    const unsigned slot = ((unsigned)kk * hmul) >> (32 - HB);
+                    unsigned tk, tc;
+                    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tk), "=r"(tc) : "r"(htab_a + slot * 8u));
+                    const bool hit = tk == (unsigned)kk;
+                    cls[j * 4 + u] = hit ? tc : 0xffffffffu;
+                    miss |= !hit;
+                }
+            } else {
+                const uint64_t w0 = (uint64_t)q[j].x | ((uint64_t)q[j].y << 32);
+                const uint64_t w1 = (uint64_t)q[j].z | ((uint64_t)q[j].w << 32);
+                const Key kk[2] = {Tr::to_key(from_raw<T>(w0)), Tr::to_key(from_raw<T>(w1))};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    k[j * 2 + u] = kk[u];
+                    const unsigned slot = (brk_hash_fold<Key>(kk[u]) * hmul) >> (32 - HB);
+                    unsigned t0, t1, tc, tp;
+                    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(tc), "=r"(tp) : "r"(htab_a + slot * 16u));
+                    const bool hit = t0 == (unsigned)kk[u] && t1 == (unsigned)((unsigned long long)kk[u] >> 32);
+                    cls[j * 2 + u] = hit ? tc : 0xffffffffu;
+                    miss |= !hit;
+                }
+            }
+        }
+        if (miss) {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e)
+                if (cls[e] == 0xffffffffu) cls[e] = classify_slow(k[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const unsigned a = myctr_a + cls[e] * (unsigned)STR_THREADS;
+            sts_u8(a, lds_u8(a) + 1u);
+        }
+    };
+
     // (Measured and dropped: rotating the tile assignment per round, evict-first loads, L2 bulk prefetch two to eight
     // rounds ahead -- none of them moves the pass; what did was the CTA-major layout of the candidate pieces.)
     unsigned tiles_since_spill = 0;
-    {
+    auto run_tiles = [&](auto &&process) {
         uint4 qa[NLD], qb[NLD];
         unsigned long long tile = blockIdx.x;
         if (tile < n_tiles) load_tile(tile, qa);
         while (tile < n_tiles) {
             const unsigned long long next = tile + gridDim.x;
             if (next < n_tiles) load_tile(next, qb);
-            process_tile(qa);
+            process(qa);
             if (++tiles_since_spill >= SPILL_TILES) {
                 spill_counters();
                 tiles_since_spill = 0;
@@ -1209,13 +1342,19 @@ brk_stream_body(const T *__restrict__ data, unsigned long long n, const BrkBuf<t
             if (tile >= n_tiles) break;
             const unsigned long long next2 = tile + gridDim.x;
             if (next2 < n_tiles) load_tile(next2, qa);
-            process_tile(qb);
+            process(qb);
             if (++tiles_since_spill >= SPILL_TILES) {
                 spill_counters();
                 tiles_since_spill = 0;
             }
             tile = next2;
         }
+    };
+    if constexpr (COUNT) {
+        if (hashed) run_tiles(process_tile_hashed);
+        else run_tiles(process_tile);
+    } else {
+        run_tiles(process_tile);
     }
 #ifdef NDS_STR_TIMING
     t_loop = clock64();
@@ -1235,7 +1374,9 @@ brk_stream_body(const T *__restrict__ data, unsigned long long n, const BrkBuf<t
             if (have) {
                 const unsigned long long idx = i < head ? i : tail0 + (i - head);
                 k = Tr::to_key(data[idx]);
-                if (key_is_nan<T>(k)) {
+                if (hashed) {
+                    ent = classify_slow(k);
+                } else if (key_is_nan<T>(k)) {
                     ent = (unsigned)BRK_INVALID_CLS;
                 } else {
                     ent = lookup(k);

@@ -664,6 +664,10 @@ def test_bracket_low_cardinality(nds, gpu_ctx, oracle, dtype):
     a[n // 3] = 9
     check(gpu_ctx, oracle, a, 0, [0.5, 1.0], "lower", select_impl=1)
     assert gpu_ctx.last_path == "bracket->long_radix", gpu_ctx.last_path
+    # ... and the same lane asked for ranks far from the unseen key: it is counted in the gap above 7 (the table misses
+    # it), the requested ranks resolve from the counts
+    check(gpu_ctx, oracle, a, 0, [0.2, 0.5], "higher", select_impl=1)
+    assert gpu_ctx.last_path == "bracket", gpu_ctx.last_path
     if np.dtype(dtype).kind == "f":  # NaNs beside few values, skipnan and not
         b = a.copy()
         b[rng.random(n) < 0.05] = np.nan

@@ -534,6 +534,12 @@ __device__ __forceinline__ void ct_mbar_wait(uint64_t *bar, unsigned parity) {
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ bool ct_mbar_test(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred P1;\nmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
+                 : "=r"(ok) : "r"(ct_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 // one box of the tensor map -> shared memory, completion on the mbarrier (SASS: UTMALDG)
 __device__ __forceinline__ void ct_tma_load_3d(void *dst_smem, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
     asm volatile(
@@ -660,6 +666,29 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
     // ================= consumers =================
     const int pair = warp >> 1, ph = warp & 1;     // build role: which slots (j % 4 == pair), which 128 rows of the slot
     const int bc = lane & 7, bsub = lane >> 3;     // lane (column) and row phase: rows bsub, bsub + 4, ... of the 128
+    // this warp's position in the CTA's slot sequence (slots q with q % CT_PAIRS == pair), ring entry and phase of slot cq
+    const unsigned long long total_q = my_strips * sps;
+    unsigned long long cq = (unsigned long long)pair;
+    unsigned cr = (unsigned)pair % (unsigned)nslots, cpar = ((unsigned)pair / (unsigned)nslots) & 1u;
+    uint32_t xn[32];          // the rows of slot cq, once `have_next`
+    bool have_next = false;
+    // pull slot cq into xn and hand the ring entry back; non-blocking calls return false if the slot has not landed
+    auto fetch = [&](bool blocking) -> bool {
+        if (blocking) ct_mbar_wait(full + cr, cpar);
+        else if (!__all_sync(FULLMASK, ct_mbar_test(full + cr, cpar))) return false;
+        const uint32_t *st = reinterpret_cast<const uint32_t *>(ring + (size_t)cr * CT_SLOT_BYTES) + (ph * 128 + bsub) * CT_CW + bc;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xn[i] = st[i * 4 * CT_CW];   // a warp reads 32 consecutive words per step
+        __syncwarp();
+        if (lane == 0) ct_mbar_arrive(empty + cr);   // this warp has read its half of the slot
+        cr += CT_PAIRS;                              // (nslots is a multiple of CT_PAIRS)
+        if (cr >= (unsigned)nslots) {
+            cr -= (unsigned)nslots;
+            cpar ^= 1u;
+        }
+        return true;
+    };
+    if (cq < total_q) have_next = fetch(true);
     for (unsigned long long it = 0; it < my_strips; ++it) {
         const unsigned long long strip = blockIdx.x + it * gridDim.x;
         const unsigned long long grp = strip / strips_per_group;
@@ -669,25 +698,21 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
         const T *sp = data + in_off;
 
         // ---- build: this pair's slots of the strip ---------------------------------------------------------
+        // Software pipeline: the rows of the pair's NEXT slot are pulled into registers (and the slot handed back to the
+        // producer) before the current one is transposed, so a landed slot never waits for a transposition -- the ring's
+        // entries spend their time in flight, not parked.  The first slot of the next strip is pulled before the walk.
         {
             uint32_t *pdst = planes + (size_t)bc * col_pitch;
+            const unsigned long long q_end = (it + 1) * sps;   // one past this strip's last slot
 #pragma unroll 1
-            const unsigned long long q0 = it * sps;   // this strip's slots are q0 .. q0 + sps - 1; mine: q % CT_PAIRS == pair
-            for (unsigned j = (unsigned)(((unsigned long long)pair + CT_PAIRS - q0 % CT_PAIRS) % CT_PAIRS); j < sps; j += (unsigned)CT_PAIRS) {
-                const unsigned long long q = q0 + j;
-                const unsigned r = (unsigned)(q % (unsigned)nslots);
-                ct_mbar_wait(full + r, (unsigned)((q / (unsigned)nslots) & 1ull));
-                const uint32_t *st = reinterpret_cast<const uint32_t *>(ring + (size_t)r * CT_SLOT_BYTES) + (ph * 128 + bsub) * CT_CW + bc;
+            while (cq < q_end) {
                 uint32_t w[16];
-                {
-                    uint32_t x[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) x[i] = st[i * 4 * CT_CW];   // a warp reads 32 consecutive words per step
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) w[k] = __byte_perm(x[2 * k], x[2 * k + 1], 0x7632);
-                }
-                __syncwarp();
-                if (lane == 0) ct_mbar_arrive(empty + r);   // this warp has read its half of the slot
+                for (int k = 0; k < 16; ++k) w[k] = __byte_perm(xn[2 * k], xn[2 * k + 1], 0x7632);
+                const unsigned j = (unsigned)(cq - it * sps);
+                cq += CT_PAIRS;
+                have_next = false;
+                if (cq < total_q) have_next = fetch(false);   // (may belong to the next strip)
                 const unsigned W = (j * 2u + (unsigned)ph) * 4u + (unsigned)bsub;
                 transpose16(w);
 #pragma unroll
@@ -701,6 +726,7 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
                     pdst[16 * nrbp + W] = e & mhi;
                     pdst[17 * nrbp + W] = e & ~mhi;
                 }
+                if (!have_next && cq < q_end) have_next = fetch(true);   // still this strip's: wait for it now
             }
         }
         named_bar_sync(1, CT_CONSUMERS);   // the strip's planes are complete
@@ -959,6 +985,7 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
                 }
             }
         }
+        if (!have_next && cq < total_q) have_next = fetch(true);
         named_bar_sync(1, CT_CONSUMERS);  // the planes are rewritten by the next strip
     }
 }

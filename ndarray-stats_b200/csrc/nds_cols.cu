@@ -420,7 +420,7 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                                 return __shfl_sync(FULLMASK, v, __ffs(hit) - 1);
                             };
                             found = fetch_rank(rem);
-                            if (rem + 1 < total) {
+                            if (want_next && pass == 0 && rem + 1 < total) {  // (a second ballot walk: only when asked for)
                                 found_next = fetch_rank(rem + 1);
                                 have_next = true;
                             }
@@ -571,7 +571,7 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
     constexpr bool IS_FLOAT = Tr::is_float;
     constexpr bool TOP_INVERTED = IS_FLOAT || std::is_signed<T>::value;
     constexpr int EXP_LO = 7;
-    constexpr int NPL = IS_FLOAT ? 18 : 16;
+    constexpr int NPL = 16;   // (no NaN planes here: 16 KB more for the ring; the walk derives the NaN masks from the exponent planes)
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const unsigned n = (unsigned)g.axis_len;
@@ -651,7 +651,7 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
                 const unsigned long long it = q / sps;
                 const unsigned j = (unsigned)(q - it * sps);
                 const unsigned long long strip = blockIdx.x + it * gridDim.x;
-                const unsigned long long grp = strip / strips_per_group;
+                const unsigned long long grp = (strip >> 32) ? strip / strips_per_group : (unsigned long long)((unsigned)strip / strips_per_group);
                 const int col0 = (int)((strip - grp * strips_per_group) * CT_CW);
                 const unsigned r = (unsigned)(q % (unsigned)nslots);
                 const unsigned long long turn = q / (unsigned)nslots;
@@ -691,7 +691,7 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
     if (cq < total_q) have_next = fetch(true);
     for (unsigned long long it = 0; it < my_strips; ++it) {
         const unsigned long long strip = blockIdx.x + it * gridDim.x;
-        const unsigned long long grp = strip / strips_per_group;
+        const unsigned long long grp = (strip >> 32) ? strip / strips_per_group : (unsigned long long)((unsigned)strip / strips_per_group);
         const unsigned long long col0 = (strip - grp * strips_per_group) * CT_CW;
         long long in_off, out_off;
         lane_offsets(g, grp * ncols + col0, in_off, out_off);
@@ -717,15 +717,6 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
                 transpose16(w);
 #pragma unroll
                 for (int b = 0; b < 16; ++b) pdst[b * nrbp + W] = w[b];
-                if constexpr (IS_FLOAT) {
-                    uint32_t e = 0xffffffffu, mhi = 0;
-#pragma unroll
-                    for (int b = EXP_LO; b <= 14; ++b) e &= w[b];
-#pragma unroll
-                    for (int b = 0; b < EXP_LO; ++b) mhi |= w[b];
-                    pdst[16 * nrbp + W] = e & mhi;
-                    pdst[17 * nrbp + W] = e & ~mhi;
-                }
                 if (!have_next && cq < q_end) have_next = fetch(true);   // still this strip's: wait for it now
             }
         }
@@ -750,8 +741,15 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
                         for (int p = 0; p < 32; ++p)
                             if (row_of(W, p) < n) v |= 1u << p;
                     if (IS_FLOAT && v) {
-                        uint32_t nanm = pl[16 * nrbp + 32 * k] & v;
-                        uint32_t amb = pl[17 * nrbp + 32 * k] & v;
+                        // exponent all ones: a NaN for sure if one of the top mantissa bits is set, otherwise (inf, or a NaN
+                        // whose payload sits in the low mantissa bits) the element itself is inspected
+                        uint32_t e = v, mhi = 0;
+#pragma unroll
+                        for (int b = EXP_LO; b <= 14; ++b) e &= pl[b * nrbp + 32 * k];
+#pragma unroll
+                        for (int b = 0; b < EXP_LO; ++b) mhi |= pl[b * nrbp + 32 * k];
+                        uint32_t nanm = e & mhi;
+                        uint32_t amb = e & ~mhi;
                         while (amb) {
                             int p = __ffs(amb) - 1;
                             amb &= amb - 1;
@@ -930,7 +928,7 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
                                 return __shfl_sync(FULLMASK, v, __ffs(hit) - 1);
                             };
                             found = fetch_rank(rem);
-                            if (rem + 1 < total) {
+                            if (want_next && pass == 0 && rem + 1 < total) {  // (a second ballot walk: only when asked for)
                                 found_next = fetch_rank(rem + 1);
                                 have_next = true;
                             }
@@ -1037,11 +1035,14 @@ ColsPlan plan_cols(const nds_ctx *ctx, const DeviceCall &c) {
     if (tma_knob && aligned && cwa == 8 && g.n_outer <= 2 && g.axis_stride > 0 && (g.n_outer == 1 || g.in_ostride[0] > 0) &&
         g.axis_len <= 0x7fffffffull && g.oshape[last] <= 0x7fffffffull && (g.n_outer == 1 || g.oshape[0] <= 0x7fffffffull)) {
         const unsigned sps = (unsigned)((g.axis_len + CT_SLOT_ROWS - 1) / CT_SLOT_ROWS);
-        const unsigned kw = (sps * 8 + 31) / 32, pitch_w = npl * kw * 32 + 4;
+        const unsigned kw = (sps * 8 + 31) / 32, pitch_w = 16 * kw * 32 + 4;   // (16 planes: cols_tma_kernel keeps no NaN planes)
         if (kw <= COLS_KMAX) {
             const size_t fixed = (size_t)CT_CW * pitch_w * 4 + (size_t)CT_CW * COLS_CAND * 4 + 2 * CT_MAX_SLOTS * 8 + 128;
             if ((size_t)ctx->max_smem_optin > fixed + 4 * CT_SLOT_BYTES) {
-                p.nslots = (int)std::min<size_t>(CT_MAX_SLOTS, ((size_t)ctx->max_smem_optin - fixed) / CT_SLOT_BYTES);
+                // eight slots (64 KB in flight per SM) are the optimum on B200: measured 0.726 ms on BASELINE config 3
+                // against 0.80 ms with twelve -- with more rows in flight the SMs drift apart and the 32-byte row pieces of
+                // neighbouring strips stop meeting in the same DRAM pages (the dry streaming kernel shows the same)
+                p.nslots = (int)std::min<size_t>(8, ((size_t)ctx->max_smem_optin - fixed) / CT_SLOT_BYTES);
                 if (const char *e = getenv("NDS_COLS_SLOTS")) p.nslots = std::max(CT_SLOT_QUANTUM, std::min(p.nslots, atoi(e)));  // tuning
                 // a slot must always be filled by the same producer lane: lanes that alternated on a slot could run two
                 // barrier phases apart, and a parity wait cannot tell those from zero

@@ -700,10 +700,13 @@ def test_mid_length_lanes_dispatch(nds, gpu_ctx, oracle, dtype):
     else:
         info = np.iinfo(dtype)
         a = rng.integers(info.min, info.max, size=(3, 65536), dtype=dtype, endpoint=True)
+    grid_wide = ("long_radix", "bracket", "bracket->long_radix")
+    # (one-byte keys need a single digit pass per rank: there the cost model may rightly keep the CTA kernel)
+    ok_paths = grid_wide if np.dtype(dtype).itemsize >= 2 else grid_wide + ("generic_cta",)
     check(gpu_ctx, oracle, a, 1, pct, "linear" if np.dtype(dtype).kind == "f" else "lower", select_impl=1)
-    assert gpu_ctx.last_path in ("long_radix", "bracket", "bracket->long_radix"), gpu_ctx.last_path
+    assert gpu_ctx.last_path in ok_paths, gpu_ctx.last_path
     check(gpu_ctx, oracle, a[0], 0, pct, "nearest", select_impl=1)          # the smoke shape
-    assert gpu_ctx.last_path in ("long_radix", "bracket", "bracket->long_radix"), gpu_ctx.last_path
+    assert gpu_ctx.last_path in ok_paths, gpu_ctx.last_path
     b = a[:, :20001].T.copy()                                                 # 20001 x 3: strided lanes along axis 0
     check(gpu_ctx, oracle, b, 0, [0.25, 0.5], "midpoint", select_impl=1)     # (either path may win the cost model)
     check(gpu_ctx, oracle, b, 0, pct, "higher", select_impl=1)               # 99 ranks of strided lanes: grid-wide passes

@@ -82,11 +82,11 @@ nds_status nds_ctx_synchronize(nds_ctx *ctx);
 const char *nds_ctx_last_error(nds_ctx *ctx);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches is a difference of these). */
 uint64_t nds_ctx_kernel_launches(nds_ctx *ctx);
-/* Name of the selection path the last call dispatched to: "short_bitslice", "cols_bitslice", "bracket",
+/* Name of the selection path the last call dispatched to: "short_bitslice", "mid_bitslice", "cols_bitslice", "bracket",
  * "bracket_sharded", "bracket->long_radix" (a rank escaped its sampled bracket and the radix passes re-ran the call),
  * "long_radix", "long_radix_sharded", "generic_cta", "minmax". */
 const char *nds_ctx_last_path(nds_ctx *ctx);
-/* Force a selection path for testing: "short_bitslice", "cols_bitslice", "bracket", "long_radix", "generic_cta"
+/* Force a selection path for testing: "short_bitslice", "mid_bitslice", "cols_bitslice", "bracket", "long_radix", "generic_cta"
  * (NULL or "auto" = default dispatch).  Returns NDS_BAD_ARGUMENT for unknown names. */
 nds_status nds_ctx_force_path(nds_ctx *ctx, const char *name);
 

@@ -125,7 +125,7 @@ nds_status status_from_bits(nds_ctx *ctx, int bits) {
 // once per distinct rank and key byte at ~25 GB/s per CTA (shared-memory atomics) and at most ~3 TB/s over all CTAs;
 // the grid-wide paths pay ~150 us of launches per lane and then stream it at ~3 TB/s, 1.4 times (bracket select) or once
 // per key byte (radix passes).
-bool use_long_path(const nds_ctx *ctx, const LaneGeom &g, size_t nq, int interp, size_t esize, bool fast_lanes) {
+bool use_long_path(const nds_ctx *ctx, const LaneGeom &g, size_t nq, int interp, size_t esize, bool fast_lanes, bool mid_ok) {
     if (ctx->forced_path == "long_radix") return true;
     if (ctx->forced_path != "auto") return false;
     if (g.axis_len >= (1ull << 32)) return true;   // the lane kernels index with 32 bits
@@ -133,6 +133,15 @@ bool use_long_path(const nds_ctx *ctx, const LaneGeom &g, size_t nq, int interp,
     if (g.axis_len < 8192) return false;
     const double n = (double)g.axis_len, lanes = (double)g.nlanes, es = (double)esize;
     const double ranks = (double)nq * ((interp == NDS_LOWER || interp == NDS_HIGHER) ? 1.0 : 2.0);
+    if (mid_ok) {
+        // the CTA-per-lane bit-sliced kernel reads a lane once at ~40 GB/s per SM and then walks ~2.5 us per rank; only
+        // a few lanes with many ranks are quicker one after the other over the whole grid
+        const double rounds = std::ceil(lanes / (double)ctx->sm_count);
+        const double t_mid = rounds * (5e-6 + n * es / 40e9 + (double)nq * 2.5e-6);
+        const bool bracket_like = esize >= 4 && g.axis_len >= (1ull << 16) && nq <= 16;
+        const double t_grid = lanes * (150e-6 + n * es * (bracket_like ? 1.4 : es) / 3e12);
+        return t_grid < t_mid;
+    }
     const double conc = std::min(lanes, (double)ctx->sm_count * 8.0);
     const double bw_cta = std::min(25e9, 3e12 / conc);
     const double t_cta = std::ceil(lanes / conc) * ranks * es * n * es / bw_cta;
@@ -161,7 +170,7 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
     view_span(ndim, shape, strides, min_off, max_off);
     const size_t span_elems = (size_t)(max_off - min_off + 1);
 
-    bool fast_lanes = false;
+    bool fast_lanes = false, mid_ok = false;
     if (!sharded && ctx->forced_path == "auto") {
         DeviceCall pre;
         pre.dtype = dtype;
@@ -171,8 +180,9 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
         pre.geom = p.geom;
         pre.q.nq = (int)nq;
         fast_lanes = short_bitslice_supported(ctx, pre) || cols_bitslice_supported(ctx, pre);
+        mid_ok = !fast_lanes && mid_bitslice_supported(ctx, pre);
     }
-    const bool long_path = sharded || use_long_path(ctx, p.geom, nq, interp, esize, fast_lanes);
+    const bool long_path = sharded || use_long_path(ctx, p.geom, nq, interp, esize, fast_lanes, mid_ok);
     // ---- carve the arena ---------------------------------------------------------------------------
     size_t off = 0;
     auto carve = [&](size_t bytes) {
@@ -259,6 +269,9 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
         return fail(ctx, NDS_UNSUPPORTED, "forced path short_bitslice does not support this call");
     if (ctx->forced_path == "cols_bitslice" && !cols_bitslice_supported(ctx, c))
         return fail(ctx, NDS_UNSUPPORTED, "forced path cols_bitslice does not support this call");
+    const bool want_mid = ctx->forced_path == "auto" || ctx->forced_path == "mid_bitslice";
+    if (ctx->forced_path == "mid_bitslice" && !mid_bitslice_supported(ctx, c))
+        return fail(ctx, NDS_UNSUPPORTED, "forced path mid_bitslice does not support this call");
     if (use_bracket) {
         int failed = 0;
         e = launch_bracket(ctx, c, arena + o_brk, sharded, synchronous, &failed, &bracket_n_total);
@@ -285,6 +298,8 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
         e = launch_short_bitslice(ctx, c);
     } else if (want_cols && cols_bitslice_supported(ctx, c)) {
         e = launch_cols_bitslice(ctx, c);
+    } else if (want_mid && mid_bitslice_supported(ctx, c)) {
+        e = launch_mid_bitslice(ctx, c);
     } else {
         e = launch_generic_cta(ctx, c);
     }
@@ -476,7 +491,7 @@ nds_status nds_ctx_force_path(nds_ctx *ctx, const char *name) {
     if (!ctx) return NDS_BAD_ARGUMENT;
     std::string n = name ? name : "auto";
     if (n != "auto" && n != "generic_cta" && n != "long_radix" && n != "short_bitslice" && n != "cols_bitslice" &&
-        n != "bracket")
+        n != "mid_bitslice" && n != "bracket")
         return fail(ctx, NDS_BAD_ARGUMENT, "unknown path name");
     ctx->forced_path = n;
     return NDS_OK;

@@ -105,6 +105,11 @@ cudaError_t launch_short_bitslice(nds_ctx *ctx, const DeviceCall &c);
 bool cols_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c);
 cudaError_t launch_cols_bitslice(nds_ctx *ctx, const DeviceCall &c);
 
+// Contiguous lanes of up to 98304 elements that the warp-per-lane kernel does not take (longer than 8192, or too few
+// lanes): CTA per lane, bit-sliced (nds_mid.cu).
+bool mid_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c);
+cudaError_t launch_mid_bitslice(nds_ctx *ctx, const DeviceCall &c);
+
 // Peer-memory exchange (nds_xchg.cu).  `dev_words` (optional, device): the number of 8-byte words to exchange, `gate`
 // (optional, device): skip the step when the word is 0 -- both must hold the same value on every rank.
 bool xchg_setup(nds_ctx *ctx);                      // collective; false = stay on NCCL

@@ -703,6 +703,8 @@ def test_mid_length_lanes_dispatch(nds, gpu_ctx, oracle, dtype):
     grid_wide = ("long_radix", "bracket", "bracket->long_radix")
     # (one-byte keys need a single digit pass per rank: there the cost model may rightly keep the CTA kernel)
     ok_paths = grid_wide if np.dtype(dtype).itemsize >= 2 else grid_wide + ("generic_cta",)
+    if np.dtype(dtype).itemsize >= 4:
+        ok_paths = ok_paths + ("mid_bitslice",)   # contiguous lanes of up to 98304 elements: the CTA-per-lane bit-sliced kernel
     check(gpu_ctx, oracle, a, 1, pct, "linear" if np.dtype(dtype).kind == "f" else "lower", select_impl=1)
     assert gpu_ctx.last_path in ok_paths, gpu_ctx.last_path
     check(gpu_ctx, oracle, a[0], 0, pct, "nearest", select_impl=1)          # the smoke shape
@@ -714,4 +716,93 @@ def test_mid_length_lanes_dispatch(nds, gpu_ctx, oracle, dtype):
         assert gpu_ctx.last_path in ("long_radix", "bracket", "bracket->long_radix"), gpu_ctx.last_path
     wide = np.tile(a[:, :9000], (20, 1))                                      # 60 lanes x 9000, 2 quantiles: one CTA per lane
     check(gpu_ctx, oracle, wide, 1, [0.5, 0.9], "higher", select_impl=1)
-    assert gpu_ctx.last_path == "generic_cta", gpu_ctx.last_path
+    assert gpu_ctx.last_path == ("mid_bitslice" if np.dtype(dtype).itemsize >= 4 else "generic_cta"), gpu_ctx.last_path
+
+
+@pytest.mark.parametrize("dtype", SHORT_DTYPES, ids=lambda d: np.dtype(d).name)
+def test_mid_bitslice_path(nds, gpu_ctx, oracle, dtype):
+    """Contiguous lanes between the warp-per-lane kernel and the grid-wide passes (8193 ... 98304 elements), and calls with
+    too few lanes for warp-per-lane: one CTA per lane, bit-sliced with informative-bit windows (nds_mid.cu).  Lengths up
+    to the limit, ragged last blocks, fewer blocks than warps, every data kind of the short-lane tests plus the window
+    cases (small magnitudes, late large values, late NaNs, many tie values)."""
+    dtype = np.dtype(dtype)
+    rng = np.random.default_rng(zlib.crc32(repr(("mid", dtype.name)).encode()))
+    vec = 16 // dtype.itemsize
+    qs_sets = {"midpoint": [0.5], "linear": [0.25, 0.5, 0.75], "lower": [0.0, 0.1, 0.9, 1.0], "higher": [0.999, 0.5, 0.5],
+               "nearest": [0.3, 0.7]}
+    try:
+        gpu_ctx.force_path("mid_bitslice")
+        for n, lanes in ((98304, 3), (98304 - vec, 2), (65536, 5), (20000 // vec * vec, 160), (9000 // vec * vec, 7), (1024, 9), (64, 3), (300 // vec * vec, 4)):
+            kinds = ["normal", "uniform", "ties", "equal", "small", "late-large", "100-values"]
+            if dtype.kind == "f":
+                kinds += ["extremes", "late-nan"]
+            for kind in kinds:
+                skip = False
+                if dtype.kind == "f":
+                    if kind == "normal":
+                        a = rng.standard_normal((lanes, n))
+                    elif kind == "uniform":
+                        a = rng.random((lanes, n))
+                    elif kind == "ties":
+                        a = rng.integers(-8, 8, size=(lanes, n)).astype(np.float64)
+                    elif kind == "equal":
+                        a = np.full((lanes, n), -3.25)
+                    elif kind == "small":
+                        a = (rng.random((lanes, n)) - 0.5) * 1e-30
+                    elif kind == "late-large":
+                        a = 1.0 + rng.random((lanes, n))
+                        a[:, n - n // 3:] *= 1e30
+                    elif kind == "100-values":
+                        a = rng.choice(rng.standard_normal(100), size=(lanes, n))
+                    elif kind == "extremes":
+                        a = rng.standard_normal((lanes, n))
+                        a[:, ::7] = np.inf
+                        a[:, 1::13] = -np.inf
+                        a[:, 2::17] = 0.0
+                        a[:, 3::19] = -0.0
+                        a[:, 5::23] = np.finfo(dtype).tiny / 4
+                    else:
+                        a = rng.random((lanes, n))
+                        a[:, n - n // 4:][rng.random((lanes, n // 4)) < 0.2] = np.nan
+                        a[0, :] = np.nan
+                        skip = True
+                    a = a.astype(dtype)
+                else:
+                    info = np.iinfo(dtype)
+                    if kind in ("normal", "uniform"):
+                        a = rng.integers(info.min // 2, info.max // 2, size=(lanes, n), dtype=dtype, endpoint=True)
+                    elif kind == "ties":
+                        a = rng.integers(0, 16, size=(lanes, n)).astype(dtype)
+                    elif kind == "equal":
+                        a = np.full((lanes, n), 7, dtype=dtype)
+                    elif kind == "small":
+                        a = rng.integers(-1000 if info.min < 0 else 0, 1000, size=(lanes, n)).astype(dtype)
+                    elif kind == "late-large":
+                        a = rng.integers(0, 100, size=(lanes, n)).astype(dtype)
+                        a[:, n - n // 3:] = rng.integers(info.max // 4, info.max // 2, size=(lanes, n // 3), dtype=dtype)
+                    else:
+                        a = rng.choice(rng.integers(info.min, info.max, size=100, dtype=dtype), size=(lanes, n))
+                for interp, qs in qs_sets.items():
+                    if n > 30000 and interp in ("nearest", "higher") and kind not in ("uniform", "ties"):
+                        continue  # (keeps the oracle's share of the run time down)
+                    check(gpu_ctx, oracle, a, 1, qs, interp, skipnan=skip, select_impl=1)
+                    assert gpu_ctx.last_path == "mid_bitslice", gpu_ctx.last_path
+        # a 3-d array whose last axis is the lane, and a pitched 2-d view
+        a = rng.standard_normal((3, 4, 12000)).astype(dtype) if dtype.kind == "f" else rng.integers(0, 10**6, size=(3, 4, 12000)).astype(dtype)
+        check(gpu_ctx, oracle, a, 2, [0.5, 0.9], "lower")
+        assert gpu_ctx.last_path == "mid_bitslice"
+        check(gpu_ctx, oracle, a[:, :, :10000], 2, [0.5], "midpoint")
+        assert gpu_ctx.last_path == "mid_bitslice"
+        with pytest.raises(nds.NdsError):
+            gpu_ctx.quantiles_axis(a[:, :, ::2], 2, [0.5], "lower")   # strided lanes: not this kernel
+    finally:
+        gpu_ctx.force_path("auto")
+    # default dispatch: a few short lanes (fewer than the warp-per-lane kernel wants) and many mid-length lanes
+    a = rng.standard_normal((5, 2048)).astype(dtype) if dtype.kind == "f" else rng.integers(0, 10**6, size=(5, 2048)).astype(dtype)
+    check(gpu_ctx, oracle, a, 1, [0.25, 0.5], "higher")
+    assert gpu_ctx.last_path == "mid_bitslice", gpu_ctx.last_path
+    if dtype.kind == "f":
+        b = a.copy()
+        b[1, 5] = np.nan
+        with pytest.raises(nds.NanInInput):
+            gpu_ctx.quantiles_axis(b, 1, [0.5], "lower")

@@ -35,7 +35,7 @@ __all__ = [
     "NanInInput", "CastOverflow", "Context", "default_context", "quantile_axis_mut", "quantiles_axis_mut",
     "quantile_axis_skipnan_mut", "quantile_mut", "quantiles_mut", "get_from_sorted_mut", "get_many_from_sorted_mut",
     "shard_lanes", "MinMaxError", "MinMaxEmptyInput", "UndefinedOrder", "argmin", "argmax", "min", "max",
-    "argmin_skipnan", "argmax_skipnan", "min_skipnan", "max_skipnan", "FreedmanDiaconis", "BinsBuildError",
+    "argmin_skipnan", "argmax_skipnan", "min_skipnan", "max_skipnan", "FreedmanDiaconis", "Sqrt", "Rice", "Sturges", "Auto", "EquiSpaced", "BinsBuildError",
 ]
 
 
@@ -592,5 +592,5 @@ def max_skipnan(a, ctx=None):
     return _minmax(a, True, True, ctx, want_index=False)[1]
 
 
-from .strategies import BinsBuildError, EquiSpaced, FreedmanDiaconis  # noqa: E402,F401  
+from .strategies import Auto, BinsBuildError, EquiSpaced, FreedmanDiaconis, Rice, Sqrt, Sturges  # noqa: E402,F401  
 from . import synth  # noqa: E402,F401  (synthetic benchmark inputs)

@@ -215,3 +215,42 @@ def freedman_diaconis(a):
         edge = edge + bw
         nb += 1
     return ("ok", bw, lo, hi, nb)
+
+
+# ---- Sqrt / Rice / Sturges / Auto (src/histogram/strategies.rs:256-371, 439-503).  TEST INFRASTRUCTURE. ----
+def _rust_round_usize(x):
+    import math
+    return int(math.floor(x + 0.5)) if x >= 0 else 0
+
+
+def count_rule(a, rule):
+    """("ok", bin_width, min, max, n_bins) or ("EmptyInput"|"Strategy",) for rule in {"sqrt", "rice", "sturges"}."""
+    import math
+    a = np.asarray(a)
+    n = a.size
+    if n == 0:
+        return ("EmptyInput",)                                    # a.min()? on an empty array
+    nb = {"sqrt": lambda: _rust_round_usize(math.sqrt(n)), "rice": lambda: _rust_round_usize(2.0 * n ** (1.0 / 3.0)),
+          "sturges": lambda: _rust_round_usize(math.log2(n)) + 1}[rule]()
+    lo, hi = a.min(), a.max()
+    with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+        rng = hi - lo
+        bw = a.dtype.type(int(rng) // nb) if a.dtype.kind in "iu" else rng / a.dtype.type(nb)
+    if bw <= 0 or lo >= hi:
+        return ("Strategy",)
+    edge, k = lo, 0
+    while edge <= hi:
+        edge = edge + bw
+        k += 1
+    return ("ok", bw, lo, hi, k)
+
+
+def auto_rule(a):
+    fd, st = freedman_diaconis(a), count_rule(a, "sturges")
+    if fd[0] != "ok" and st[0] != "ok":
+        return fd
+    if fd[0] != "ok":
+        return ("sturges",) + st[1:]
+    if st[0] != "ok":
+        return ("fd",) + fd[1:]
+    return (("sturges",) + st[1:]) if fd[1] > st[1] else (("fd",) + fd[1:])

@@ -125,7 +125,8 @@ nds_status status_from_bits(nds_ctx *ctx, int bits) {
 // once per distinct rank and key byte at ~25 GB/s per CTA (shared-memory atomics) and at most ~3 TB/s over all CTAs;
 // the grid-wide paths pay ~150 us of launches per lane and then stream it at ~3 TB/s, 1.4 times (bracket select) or once
 // per key byte (radix passes).
-bool use_long_path(const nds_ctx *ctx, const LaneGeom &g, size_t nq, int interp, size_t esize, bool fast_lanes, bool mid_ok) {
+bool use_long_path(const nds_ctx *ctx, const LaneGeom &g, size_t nq, int interp, size_t esize, bool fast_lanes, bool mid_ok,
+                   int mid_cluster) {
     if (ctx->forced_path == "long_radix") return true;
     if (ctx->forced_path != "auto") return false;
     if (g.axis_len >= (1ull << 32)) return true;   // the lane kernels index with 32 bits
@@ -136,8 +137,9 @@ bool use_long_path(const nds_ctx *ctx, const LaneGeom &g, size_t nq, int interp,
     if (mid_ok) {
         // the CTA-per-lane bit-sliced kernel reads a lane once at ~40 GB/s per SM and then walks ~2.5 us per rank; only
         // a few lanes with many ranks are quicker one after the other over the whole grid
-        const double rounds = std::ceil(lanes / (double)ctx->sm_count);
-        const double t_mid = rounds * (5e-6 + n * es / 40e9 + (double)nq * 2.5e-6);
+        const double cl = (double)mid_cluster;   // CTAs that share a lane
+        const double rounds = std::ceil(lanes / std::floor((double)ctx->sm_count / cl));
+        const double t_mid = rounds * (5e-6 + n * es / (40e9 * cl) + (double)nq * (cl > 1 ? 5e-6 : 2.5e-6));
         const bool bracket_like = esize >= 4 && g.axis_len >= (1ull << 16) && nq <= 16;
         const double t_grid = lanes * (150e-6 + n * es * (bracket_like ? 1.4 : es) / 3e12);
         return t_grid < t_mid;
@@ -171,6 +173,7 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
     const size_t span_elems = (size_t)(max_off - min_off + 1);
 
     bool fast_lanes = false, mid_ok = false;
+    int mid_cluster = 1;
     if (!sharded && ctx->forced_path == "auto") {
         DeviceCall pre;
         pre.dtype = dtype;
@@ -181,8 +184,9 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
         pre.q.nq = (int)nq;
         fast_lanes = short_bitslice_supported(ctx, pre) || cols_bitslice_supported(ctx, pre);
         mid_ok = !fast_lanes && mid_bitslice_supported(ctx, pre);
+        if (mid_ok) mid_cluster = mid_bitslice_cluster(ctx, pre);
     }
-    const bool long_path = sharded || use_long_path(ctx, p.geom, nq, interp, esize, fast_lanes, mid_ok);
+    const bool long_path = sharded || use_long_path(ctx, p.geom, nq, interp, esize, fast_lanes, mid_ok, mid_cluster);
     // ---- carve the arena ---------------------------------------------------------------------------
     size_t off = 0;
     auto carve = [&](size_t bytes) {

@@ -105,9 +105,10 @@ cudaError_t launch_short_bitslice(nds_ctx *ctx, const DeviceCall &c);
 bool cols_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c);
 cudaError_t launch_cols_bitslice(nds_ctx *ctx, const DeviceCall &c);
 
-// Contiguous lanes of up to 98304 elements that the warp-per-lane kernel does not take (longer than 8192, or too few
-// lanes): CTA per lane, bit-sliced (nds_mid.cu).
+// Contiguous lanes of up to 786432 elements that the warp-per-lane kernel does not take (longer than 8192, or too few
+// lanes): CTA -- or cluster of CTAs -- per lane, bit-sliced (nds_mid.cu).
 bool mid_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c);
+int mid_bitslice_cluster(const nds_ctx *ctx, const DeviceCall &c);   // CTAs that share one lane (1, 2, 4 or 8)
 cudaError_t launch_mid_bitslice(nds_ctx *ctx, const DeviceCall &c);
 
 // Peer-memory exchange (nds_xchg.cu).  `dev_words` (optional, device): the number of 8-byte words to exchange, `gate`

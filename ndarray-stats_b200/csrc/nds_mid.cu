@@ -1,22 +1,30 @@
-// Contiguous lanes that are too long for one warp (8193 ... 98304 elements) -- and calls with too few lanes for the
-// warp-per-lane kernel to fill the machine: one CTA of 16 warps per lane, bit-sliced MSB-first selection.
+// Contiguous lanes that are too long for one warp (8193 ... 786432 elements) -- and calls with too few lanes for the
+// warp-per-lane kernel to fill the machine: one CTA of 12 warps per lane, or a thread-block CLUSTER of 2, 4 or 8 CTAs
+// per lane beyond 98304 elements; bit-sliced MSB-first selection.
 //
-// The lane is read ONCE from HBM, straight into registers (16-byte loads, a warp takes every 16th block of 1024
-// elements: 16 x 8 KB in flight per SM without any staging buffer), transposed into 16 bit planes in shared memory
-// (2 bytes per element: 192 KB for the longest lane) and the planes are then walked by all 512 threads: one popc per
-// plane word and thread, REDUX per warp, one CTA barrier per key bit.  The 16-bit window of a round is chosen from the
-// bits that tell the lane's elements apart (see nds_short.cu, SMART): the first block of every warp proposes it, the
-// whole lane confirms it.  At most 128 survivors are ranked by full key.  Later windows (rare: more than 128 elements
-// agree on 15 informative bits) re-read the lane from L2.
+// The lane is read ONCE from HBM, straight into registers (16-byte loads, a warp takes every 12th block of 1024
+// elements: 12 x 8 KB in flight per SM without any staging buffer), transposed into 16 bit planes in shared memory
+// (2 bytes per element: 192 KB for 98304 elements; a cluster splits the lane's blocks over its CTAs) and the planes are
+// then walked by all threads: one popc per plane word and thread, REDUX per warp, one barrier per key bit -- a CTA
+// barrier, or a cluster barrier with the per-warp counts read from the other CTAs' shared memory (DSMEM).  Up to three
+// ranks are walked together (one read of the plane words, one barrier per bit for all of them).  The 16-bit window of
+// a round is chosen from the bits that tell the lane's elements apart (see nds_short.cu, SMART; here with a 16-bit
+// no-sign mode when the whole lane has one sign): the first block of every warp proposes it, the whole lane confirms
+// it.  At most 128 survivors per rank are collected in the first CTA and ranked by full key.  Later windows (rare: more
+// than 128 elements agree on the window's informative bits) re-read the lane from L2.
 //
 // Replaces generic_lanes_kernel (one digit pass per rank and key byte, one shared atomic per element) for these shapes:
 // src/quantile/mod.rs:470-488 treats every lane alike, so must we.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
 #include "nds_bitslice.cuh"
 #include "nds_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace nds {
 
@@ -25,24 +33,28 @@ namespace {
 constexpr int MID_THREADS = 384;
 constexpr int MID_WARPS = MID_THREADS / 32;
 constexpr int MID_MAXW = 8;                       // plane words per thread
-constexpr unsigned MID_MAX_N = MID_MAXW * MID_THREADS * 32;   // 98304 elements
+constexpr unsigned MID_CTA_N = MID_MAXW * MID_THREADS * 32;   // 98304 elements per CTA
+constexpr int MID_MAX_CLUSTER = 8;
+constexpr unsigned MID_MAX_N = MID_CTA_N * MID_MAX_CLUSTER;
 constexpr int MID_CAND = 128;                     // survivors ranked directly
-
 constexpr int MID_K = 3;                          // ranks walked together (MID_K * MID_CAND == MID_THREADS)
+
 struct MidShared {          // small fixed part in front of the planes
     unsigned partial[2][MID_K][MID_WARPS];
-    unsigned stat[2][6];    // [stage][zlo, zhi, olo, ohi, special, nan count]
+    unsigned stat[2][6];    // [stage][zlo, zhi, olo, ohi, (unused), nan count]
     unsigned ncand[MID_K];
     unsigned sel[MID_K][2];
+    unsigned long long res[MID_K][2];   // first CTA: the raw values at ranks r and r + 1 of every rank of the group
     unsigned clist[MID_K][MID_CAND];
     unsigned long long ckeys[MID_K][MID_CAND];
     unsigned long long craw[MID_K][MID_CAND];
 };
 static_assert(MID_K * MID_CAND == MID_THREADS, "one thread per survivor of a group");
 
-template <typename T>
+// CL: the lane is shared by the CTAs of a cluster (CTA c owns blocks [c * bpc, (c + 1) * bpc) of 1024 elements)
+template <typename T, bool CL>
 __global__ void __launch_bounds__(MID_THREADS, 1)
-mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__restrict__ out, unsigned nwords) {
+mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__restrict__ out, unsigned nwords, unsigned bpc) {
     using Tr = Traits<T>;
     using Key = typename Tr::Key;
     using Raw = typename RawBits<T>::U;
@@ -61,10 +73,25 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
     uint32_t *planes = reinterpret_cast<uint32_t *>(smem_raw + sizeof(MidShared));   // [16][nwords]
     uint32_t *im = planes + 16u * nwords;                                              // [nwords] valid and not NaN
 
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned csize = CL ? cluster.num_blocks() : 1u;
+    const unsigned crank = CL ? cluster.block_rank() : 0u;
+    auto sync_all = [&]() {
+        if constexpr (CL) cluster.sync();
+        else __syncthreads();
+    };
+    auto peer = [&](unsigned r) -> MidShared * {   // the fixed part of CTA r's shared memory
+        if constexpr (CL) return cluster.map_shared_rank(&sh, r);
+        else return &sh;
+    };
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned n = (unsigned)g.axis_len;
     const unsigned n_chunks = n * ES / 16;
     const int nb = (int)((n + 1023u) / 1024u);
+    const int blk0 = (int)(crank * bpc);                                    // first block of this CTA
+    const int nbl = max(0, min((int)bpc, nb - blk0));                       // its number of blocks
+    const unsigned long long n_groups = gridDim.x / csize, my_group = blockIdx.x / csize;
 
     auto slot_of_pos = [](int p) -> int { return 2 * (p & 15) + (p >> 4); };
     // element index of slot s of the block-thread (blk, ln)
@@ -72,6 +99,8 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
         if (ES == 4) return (unsigned)(((blk * LD_PER_BLK + (s >> 2)) * 32 + ln) * 4 + (s & 3));
         return (unsigned)(((blk * LD_PER_BLK + (s >> 1)) * 32 + ln) * 2 + (s & 1));
     };
+    // element index of bit p of this CTA's plane word w
+    auto elem_of = [&](unsigned w, int p) -> unsigned { return elem_index(blk0 + (int)(w >> 5), (int)(w & 31u), slot_of_pos(p)); };
     auto valid_mask = [&](int blk, int ln) -> uint32_t {
         if ((unsigned)(blk + 1) * 1024u <= n) return FULL;
         uint32_t v = 0;
@@ -107,7 +136,7 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
         return max(top - (no_sign ? 15 : 14), 0);
     };
 
-    for (unsigned long long L = blockIdx.x; L < g.nlanes; L += gridDim.x) {
+    for (unsigned long long L = my_group; L < g.nlanes; L += n_groups) {
         long long in_off, out_off;
         lane_offsets(g, L, in_off, out_off);
         const T *lp = data + in_off;
@@ -143,7 +172,7 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
             }
         };
         constexpr uint32_t SPECIAL = ES == 8 ? 0x7ff00000u : 0x7f800000u;   // |x| (high word) with an all-ones exponent
-        auto publish_stats = [&](int stage) {  // warp OR -> shared OR
+        auto publish_stats = [&](int stage) {  // warp OR -> shared OR (this CTA's share)
             const uint32_t a = __reduce_or_sync(FULL, zlo), b = __reduce_or_sync(FULL, zhi);
             const uint32_t c = __reduce_or_sync(FULL, olo), d = __reduce_or_sync(FULL, ohi);
             if (lane == 0) {
@@ -153,18 +182,28 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
                 atomicOr(&sh.stat[stage][3], d);
             }
         };
-        auto informative = [&](int stage) -> Raw {
-            uint32_t lo = sh.stat[stage][0], hi = sh.stat[stage][1];
+        // the statistics of the whole lane: OR (sum for the NaN count) over the CTAs of the cluster
+        uint32_t cs[6];
+        auto combine_stats = [&](int stage) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) cs[i] = 0;
+            for (unsigned r = 0; r < csize; ++r) {
+                const MidShared *p = peer(r);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cs[i] |= p->stat[stage][i];
+                cs[5] += p->stat[stage][5];
+            }
+        };
+        auto informative = [&]() -> Raw {
+            uint32_t lo = cs[0], hi = cs[1];
             if constexpr (SIGNED_INT) {
-                lo &= sh.stat[stage][2];
-                hi &= sh.stat[stage][3];
+                lo &= cs[2];
+                hi &= cs[3];
             }
             if constexpr (ES == 8) return (((Raw)hi << 32) | (Raw)lo) & ~SIGN;
             else return (Raw)lo & ~SIGN;
         };
-        auto sign_constant = [&](int stage) -> bool {
-            return ((ES == 8 ? sh.stat[stage][1] : sh.stat[stage][0]) & 0x80000000u) == 0u;
-        };
+        auto sign_constant = [&]() -> bool { return ((ES == 8 ? cs[1] : cs[0]) & 0x80000000u) == 0u; };
         auto load_block = [&](int blk, uint4 (&q)[LD_PER_BLK]) {
 #pragma unroll
             for (int j = 0; j < LD_PER_BLK; ++j) {
@@ -172,20 +211,20 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
                 q[j] = __ldg(reinterpret_cast<const uint4 *>(gsrc + (size_t)chunk * 16));
             }
         };
-        auto store_block = [&](uint32_t (&w)[16], int blk) {
+        auto store_block = [&](uint32_t (&w)[16], int lb) {
             transpose16(w);
 #pragma unroll
-            for (int b = 0; b < 16; ++b) planes[(size_t)b * nwords + blk * 32 + lane] = w[b];
+            for (int b = 0; b < 16; ++b) planes[(size_t)b * nwords + lb * 32 + lane] = w[b];
         };
-        // planes of one window from global memory (the lane is L2-resident after the first pass)
+        // this CTA's planes of one window from global memory (the lane is L2-resident after the first pass)
         auto rebuild = [&](int s, bool first) {
-            for (int blk = warp; blk < nb; blk += MID_WARPS) {
+            for (int lb = warp; lb < nbl; lb += MID_WARPS) {
                 uint4 q[LD_PER_BLK];
-                load_block(blk, q);
+                load_block(blk0 + lb, q);
                 uint32_t w[16];
 #pragma unroll
                 for (int j = 0; j < LD_PER_BLK; ++j) pack(q[j], w, j, s, first);
-                store_block(w, blk);
+                store_block(w, lb);
             }
             __syncthreads();
         };
@@ -200,19 +239,19 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
         {
             uint4 q[LD_PER_BLK];
             uint32_t am = 0;
-            const bool have_first = warp < nb;
-            if (have_first) {
-                load_block(warp, q);
+            if (warp < nbl) {
+                load_block(blk0 + warp, q);
 #pragma unroll
                 for (int j = 0; j < LD_PER_BLK; ++j) stats(q[j], am);
             }
             publish_stats(0);
-            __syncthreads();
-            signless = sign_constant(0);
-            sh0 = pick_shift(informative(0), nb > MID_WARPS ? 1 : 0, signless);
-            for (int blk = warp; blk < nb; blk += MID_WARPS) {
-                if (blk != warp) {
-                    load_block(blk, q);
+            sync_all();
+            combine_stats(0);
+            signless = sign_constant();
+            sh0 = pick_shift(informative(), bpc > (unsigned)MID_WARPS ? 1 : 0, signless);
+            for (int lb = warp; lb < nbl; lb += MID_WARPS) {
+                if (lb != warp) {
+                    load_block(blk0 + lb, q);
                     am = 0;
 #pragma unroll
                     for (int j = 0; j < LD_PER_BLK; ++j) stats(q[j], am);
@@ -220,7 +259,7 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
                 uint32_t w[16];
 #pragma unroll
                 for (int j = 0; j < LD_PER_BLK; ++j) pack(q[j], w, j, sh0, !signless);
-                uint32_t keep = valid_mask(blk, lane);
+                uint32_t keep = valid_mask(blk0 + lb, lane);
                 if constexpr (IS_FLOAT) {
                     uint32_t nanm = 0;
                     if (__any_sync(FULL, am >= SPECIAL)) {
@@ -244,192 +283,42 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
                     my_nan += __popc(keep & nanm);
                     keep &= ~nanm;
                 }
-                im[blk * 32 + lane] = keep;
-                store_block(w, blk);
+                im[lb * 32 + lane] = keep;
+                store_block(w, lb);
             }
             publish_stats(1);
             if constexpr (IS_FLOAT) {
                 const unsigned wn = __reduce_add_sync(FULL, my_nan);
                 if (lane == 0 && wn) atomicAdd(&sh.stat[1][5], wn);
             }
-            __syncthreads();
+            sync_all();
+            combine_stats(1);
         }
-        const Raw V = informative(1);
-        const unsigned nan_total = IS_FLOAT ? sh.stat[1][5] : 0u;
-        if ((V & ~low_mask(sh0 + (signless ? 16 : 15))) != 0 || (signless && !sign_constant(1))) {
+        const Raw V = informative();
+        const unsigned nan_total = IS_FLOAT ? cs[5] : 0u;
+        if ((V & ~low_mask(sh0 + (signless ? 16 : 15))) != 0 || (signless && !sign_constant())) {
             // (rare) informative bits above the proposed window, or a sign the first blocks did not show
-            signless = sign_constant(1);
+            signless = sign_constant();
             sh0 = pick_shift(V, 0, signless);
             rebuild(sh0, !signless);
         }
         const bool lane_neg = IS_FLOAT && (((ES == 8 ? x0hi : x0lo) & 0x80000000u) != 0u);   // (meaningful when signless)
-        if (nan_total && !qa.skipnan && tid == 0) atomicOr(qa.status, STATUS_BIT_NAN);
+        if (nan_total && !qa.skipnan && tid == 0 && crank == 0) atomicOr(qa.status, STATUS_BIT_NAN);
         const unsigned n_eff = n - nan_total;   // (non-skipnan with NaNs: status raised, result meaningless but in bounds)
 
         if (n_eff == 0) {
-            for (int t = tid; t < qa.nq; t += MID_THREADS) out[out_off + (long long)t * g.out_axis_stride] = canonical_nan<T>();
-            __syncthreads();
+            if (crank == 0)
+                for (int t = tid; t < qa.nq; t += MID_THREADS) out[out_off + (long long)t * g.out_axis_stride] = canonical_nan<T>();
+            sync_all();
             continue;
         }
 
         bool planes_dirty = false;
-        unsigned step_no = 0;   // parity of the partial-sum buffer (identical in every thread)
+        unsigned step_no = 0;   // parity of the partial-sum buffer (identical in every thread of the cluster)
 
-        // ---- rank r (and r + 1 when want_next): raw bit patterns, in every thread ----------------------------
-        auto select = [&](unsigned r, bool want_next, Raw &raw_r, Raw &raw_next) {
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                if (planes_dirty) {
-                    __syncthreads();
-                    rebuild(sh0, !signless);
-                    planes_dirty = false;
-                }
-                uint32_t m[MID_MAXW];
-#pragma unroll
-                for (int i = 0; i < MID_MAXW; ++i) {
-                    const unsigned w = (unsigned)tid + (unsigned)MID_THREADS * i;
-                    m[i] = w < nwords ? im[w] : 0u;
-                }
-                unsigned total = n_eff, rem = r + (unsigned)pass;
-                bool neg = signless && lane_neg, small = total <= (unsigned)MID_CAND, alleq = false;
-                int s = sh0, topb = 15;
-                bool first = !signless;
-#pragma unroll 1
-                while (!small) {
-                    uint32_t inv = first ? (TOP_INVERTED ? FULL : 0u) : ((IS_FLOAT && neg) ? FULL : 0u);
-#pragma unroll 1
-                    for (int b = topb; b >= 0; --b) {
-                        const uint32_t *pp = planes + (size_t)b * nwords + tid;
-                        uint32_t x[MID_MAXW];
-                        unsigned ones = 0;
-#pragma unroll
-                        for (int i = 0; i < MID_MAXW; ++i) {
-                            x[i] = ((unsigned)tid + (unsigned)MID_THREADS * i < nwords) ? pp[MID_THREADS * i] : 0u;
-                            ones += __popc(m[i] & (x[i] ^ inv));
-                        }
-                        ones = __reduce_add_sync(FULL, ones);
-                        unsigned *part = sh.partial[step_no & 1u][0];
-                        step_no += 1;
-                        if (lane == 0) part[warp] = ones;
-                        __syncthreads();
-                        {
-                            const uint4 *p4 = reinterpret_cast<const uint4 *>(part);
-                            ones = 0;
-#pragma unroll
-                            for (int u = 0; u < MID_WARPS / 4; ++u) {
-                                const uint4 v = p4[u];
-                                ones += v.x + v.y + v.z + v.w;
-                            }
-                        }
-                        const unsigned small_cnt = total - ones;
-                        const bool take_small = rem < small_cnt;
-                        total = take_small ? small_cnt : ones;
-                        rem = take_small ? rem : rem - small_cnt;
-                        const uint32_t keep = take_small ? inv : ~inv;
-#pragma unroll
-                        for (int i = 0; i < MID_MAXW; ++i) m[i] &= ~(x[i] ^ keep);
-                        if (first && b == 15) {
-                            neg = IS_FLOAT && (keep & 1u);
-                            inv = neg ? FULL : 0u;
-                        }
-                        if (total <= (unsigned)MID_CAND) {
-                            small = true;
-                            break;
-                        }
-                        if ((V & low_mask(s + ((first && b == 15) ? 15 : b))) == 0) {  // no informative bit left
-                            alleq = true;
-                            break;
-                        }
-                    }
-                    if (small || alleq) break;
-                    const int top = msb(V & low_mask(s));   // (non-zero: the walk would have stopped at b == 0)
-                    const int ns = max(top - 15, 0);
-                    __syncthreads();
-                    rebuild(ns, false);
-                    planes_dirty = true;
-                    s = ns;
-                    topb = top - ns;
-                    first = false;
-                }
-                // ---- the survivors: their element indexes into the shared list --------------------------------
-                __syncthreads();
-                if (tid == 0) sh.ncand[0] = 0;
-                __syncthreads();
-                Raw found = 0, found_next = 0;
-                bool have_next = false;
-                if (!small) {
-                    // all candidates are one value: any of them
-                    bool have = false;
-#pragma unroll
-                    for (int i = 0; i < MID_MAXW; ++i)
-                        if (!have && m[i]) {
-                            const unsigned w = (unsigned)tid + (unsigned)MID_THREADS * i;
-                            if (atomicAdd(&sh.ncand[0], 1u) == 0u) sh.clist[0][0] = elem_index((int)(w >> 5), (int)(w & 31u), slot_of_pos(__ffs(m[i]) - 1));
-                            have = true;
-                        }
-                    __syncthreads();
-                    found = to_raw<T>(lp[sh.clist[0][0]]);
-                    if (rem + 1 < total) {
-                        found_next = found;
-                        have_next = true;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < MID_MAXW; ++i) {
-                        uint32_t bits = m[i];
-                        if (bits) {
-                            const unsigned w = (unsigned)tid + (unsigned)MID_THREADS * i;
-                            unsigned base = atomicAdd(&sh.ncand[0], (unsigned)__popc(bits));
-                            while (bits) {
-                                const int p = __ffs(bits) - 1;
-                                bits &= bits - 1;
-                                sh.clist[0][base++] = elem_index((int)(w >> 5), (int)(w & 31u), slot_of_pos(p));
-                            }
-                        }
-                    }
-                    __syncthreads();
-                    Key mykey = 0;
-                    if ((unsigned)tid < total) {
-                        const T xv = lp[sh.clist[0][tid]];
-                        mykey = Tr::to_key(xv);
-                        sh.ckeys[0][tid] = (unsigned long long)mykey;
-                        sh.craw[0][tid] = (unsigned long long)to_raw<T>(xv);
-                    }
-                    __syncthreads();
-                    if ((unsigned)tid < total) {
-                        unsigned less = 0;
-                        for (unsigned j = 0; j < total; ++j) {
-                            const Key kj = (Key)sh.ckeys[0][j];
-                            less += (kj < mykey || (kj == mykey && j < (unsigned)tid)) ? 1u : 0u;
-                        }
-                        if (less == rem) sh.sel[0][0] = (unsigned)tid;
-                        if (less == rem + 1) sh.sel[0][1] = (unsigned)tid;
-                    }
-                    __syncthreads();
-                    found = (Raw)sh.craw[0][sh.sel[0][0]];
-                    if (rem + 1 < total) {
-                        found_next = (Raw)sh.craw[0][sh.sel[0][1]];
-                        have_next = true;
-                    }
-                }
-                __syncthreads();   // the shared lists are reused by the next selection
-                if (pass == 0) {
-                    raw_r = found;
-                    if (!want_next) return;
-                    if (have_next) {
-                        raw_next = found_next;
-                        return;
-                    }
-                } else {
-                    raw_next = found;
-                }
-            }
-        };
-
-        // ---- up to MID_K ranks walked TOGETHER through the round-0 planes: one read of the plane words and one CTA barrier
+        // ---- up to MID_K ranks walked TOGETHER through the round-0 planes: one read of the plane words and one barrier
         //      per key bit serve all of them (get_many_from_sorted_mut's point, src/sort.rs:184-283).  hb[k]: rank r + 1
-        //      was among r's survivors and is returned in b[k].  A rank that needs a further window (rare) is finished by
-        //      the one-rank routine above. ------------------------------------------------------------------------
+        //      was among r's survivors and is returned in b[k]. ---------------------------------------------------
         auto run_group = [&](const unsigned (&rk)[MID_K], int K, Raw (&a)[MID_K], Raw (&b)[MID_K], bool (&hb)[MID_K]) {
             if (planes_dirty) {
                 __syncthreads();
@@ -445,7 +334,7 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
 #pragma unroll
                 for (int i = 0; i < MID_MAXW; ++i) {
                     const unsigned w = (unsigned)tid + (unsigned)MID_THREADS * i;
-                    m[k][i] = (k < K && w < nwords) ? im[w] : 0u;
+                    m[k][i] = (k < K && w < (unsigned)nbl * 32u) ? im[w] : 0u;
                 }
                 total[k] = n_eff;
                 rem[k] = k < K ? rk[k] : 0u;
@@ -455,32 +344,33 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
                 open[k] = k < K && !small[k];
                 hb[k] = false;
             }
-#pragma unroll 1
-            for (int bit = 15; bit >= 0; --bit) {
-                bool any_open = false;
-#pragma unroll
-                for (int k = 0; k < MID_K; ++k) any_open = any_open || open[k];
-                if (!any_open) break;
+            // one key bit for the ranks in `act`: counts of this CTA, exchange, decision
+            auto step = [&](int bit, int s, bool sign_step, const bool (&act)[MID_K]) {
                 const uint32_t *pp = planes + (size_t)bit * nwords + tid;
                 uint32_t x[MID_MAXW];
 #pragma unroll
-                for (int i = 0; i < MID_MAXW; ++i) x[i] = ((unsigned)tid + (unsigned)MID_THREADS * i < nwords) ? pp[MID_THREADS * i] : 0u;
-                unsigned(*part)[MID_WARPS] = sh.partial[step_no & 1u];
+                for (int i = 0; i < MID_MAXW; ++i) x[i] = ((unsigned)tid + (unsigned)MID_THREADS * i < (unsigned)nbl * 32u) ? pp[MID_THREADS * i] : 0u;
+                const unsigned par = step_no & 1u;
                 step_no += 1;
 #pragma unroll
                 for (int k = 0; k < MID_K; ++k) {
-                    if (!open[k]) continue;   // (uniform over the CTA)
+                    if (!act[k]) continue;   // (uniform over the cluster)
                     unsigned ones = 0;
 #pragma unroll
                     for (int i = 0; i < MID_MAXW; ++i) ones += __popc(m[k][i] & (x[i] ^ inv[k]));
                     ones = __reduce_add_sync(FULL, ones);
-                    if (lane == 0) part[k][warp] = ones;
+                    if (lane == 0) sh.partial[par][k][warp] = ones;
                 }
-                __syncthreads();
+                sync_all();
 #pragma unroll
                 for (int k = 0; k < MID_K; ++k) {
-                    if (!open[k]) continue;
-                    const unsigned ones = __reduce_add_sync(FULL, lane < MID_WARPS ? part[k][lane] : 0u);
+                    if (!act[k]) continue;
+                    unsigned v = 0;
+                    for (unsigned i = (unsigned)lane; i < csize * (unsigned)MID_WARPS; i += 32u) {
+                        const unsigned r = i / (unsigned)MID_WARPS;
+                        v += peer(r)->partial[par][k][i - r * (unsigned)MID_WARPS];
+                    }
+                    const unsigned ones = __reduce_add_sync(FULL, v);
                     const unsigned small_cnt = total[k] - ones;
                     const bool take_small = rem[k] < small_cnt;
                     total[k] = take_small ? small_cnt : ones;
@@ -488,20 +378,49 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
                     const uint32_t keep = take_small ? inv[k] : ~inv[k];
 #pragma unroll
                     for (int i = 0; i < MID_MAXW; ++i) m[k][i] &= ~(x[i] ^ keep);
-                    if (bit == 15 && !signless) inv[k] = (IS_FLOAT && (keep & 1u)) ? FULL : 0u;
+                    if (sign_step) inv[k] = (IS_FLOAT && (keep & 1u)) ? FULL : 0u;
                     if (total[k] <= (unsigned)MID_CAND) {
                         small[k] = true;
                         open[k] = false;
-                    } else if ((V & low_mask(sh0 + ((bit == 15 && !signless) ? 15 : bit))) == 0) {
+                    } else if ((V & low_mask(s + (sign_step ? 15 : bit))) == 0) {   // no informative bit below this one
                         alleq[k] = true;
                         open[k] = false;
                     }
                 }
+            };
+            // round 0: all ranks of the group
+#pragma unroll 1
+            for (int bit = 15; bit >= 0; --bit) {
+                bool any_open = false;
+#pragma unroll
+                for (int k = 0; k < MID_K; ++k) any_open = any_open || open[k];
+                if (!any_open) break;
+                step(bit, sh0, bit == 15 && !signless, open);
             }
-            // ---- survivors of all ranks at once: thread (k, j) owns survivor j of rank k ------------------------
-            __syncthreads();
-            if (tid < MID_K) sh.ncand[tid] = 0;
-            __syncthreads();
+            // (rare) a rank that more than MID_CAND elements still share: further windows, that rank alone
+#pragma unroll
+            for (int k = 0; k < MID_K; ++k) {
+                int s = sh0;
+#pragma unroll 1
+                while (open[k]) {
+                    const int top = msb(V & low_mask(s));   // (non-zero: the rank would have been closed as all-equal)
+                    const int ns = max(top - 15, 0);
+                    bool act[MID_K];
+#pragma unroll
+                    for (int kk = 0; kk < MID_K; ++kk) act[kk] = kk == k;
+                    sync_all();                               // every CTA has finished reading the old planes' partials
+                    rebuild(ns, false);
+                    planes_dirty = true;
+                    s = ns;
+#pragma unroll 1
+                    for (int bit = top - ns; bit >= 0 && open[k]; --bit) step(bit, s, false, act);
+                }
+            }
+            // ---- survivors of all ranks at once, collected in the first CTA: thread (k, j) owns survivor j of rank k ----
+            sync_all();
+            if (crank == 0 && tid < MID_K) sh.ncand[tid] = 0;
+            sync_all();
+            MidShared *s0 = peer(0);
 #pragma unroll
             for (int k = 0; k < MID_K; ++k) {
                 if (small[k]) {
@@ -510,11 +429,11 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
                         uint32_t bits = m[k][i];
                         if (bits) {
                             const unsigned w = (unsigned)tid + (unsigned)MID_THREADS * i;
-                            unsigned base = atomicAdd(&sh.ncand[k], (unsigned)__popc(bits));
+                            unsigned base = atomicAdd(&s0->ncand[k], (unsigned)__popc(bits));
                             while (bits) {
                                 const int p = __ffs(bits) - 1;
                                 bits &= bits - 1;
-                                sh.clist[k][base++] = elem_index((int)(w >> 5), (int)(w & 31u), slot_of_pos(p));
+                                s0->clist[k][base++] = elem_of(w, p);
                             }
                         }
                     }
@@ -524,67 +443,56 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
                     for (int i = 0; i < MID_MAXW; ++i)
                         if (!have && m[k][i]) {
                             const unsigned w = (unsigned)tid + (unsigned)MID_THREADS * i;
-                            if (atomicAdd(&sh.ncand[k], 1u) == 0u)
-                                sh.clist[k][0] = elem_index((int)(w >> 5), (int)(w & 31u), slot_of_pos(__ffs(m[k][i]) - 1));
+                            if (atomicAdd(&s0->ncand[k], 1u) == 0u) s0->clist[k][0] = elem_of(w, __ffs(m[k][i]) - 1);
                             have = true;
                         }
                 }
             }
-            __syncthreads();
-            const int mk = tid / MID_CAND;
-            const unsigned mj = (unsigned)(tid % MID_CAND);
-            unsigned tot_mine = 0, rem_mine = 0;
-            bool small_mine = false, alleq_mine = false;
+            sync_all();
+            if (crank == 0) {
+                const int mk = tid / MID_CAND;
+                const unsigned mj = (unsigned)(tid % MID_CAND);
+                unsigned tot_mine = 0, rem_mine = 0;
+                bool small_mine = false, alleq_mine = false;
+#pragma unroll
+                for (int k = 0; k < MID_K; ++k)
+                    if (k == mk) {
+                        tot_mine = total[k];
+                        rem_mine = rem[k];
+                        small_mine = small[k];
+                        alleq_mine = alleq[k];
+                    }
+                Key mykey = 0;
+                if ((small_mine && mj < tot_mine) || (alleq_mine && mj == 0)) {
+                    const T xv = lp[sh.clist[mk][mj]];
+                    mykey = Tr::to_key(xv);
+                    sh.ckeys[mk][mj] = (unsigned long long)mykey;
+                    sh.craw[mk][mj] = (unsigned long long)to_raw<T>(xv);
+                }
+                __syncthreads();
+                if (small_mine && mj < tot_mine) {
+                    unsigned less = 0;
+                    for (unsigned j = 0; j < tot_mine; ++j) {
+                        const Key kj = (Key)sh.ckeys[mk][j];
+                        less += (kj < mykey || (kj == mykey && j < mj)) ? 1u : 0u;
+                    }
+                    if (less == rem_mine) sh.res[mk][0] = sh.craw[mk][mj];
+                    if (less == rem_mine + 1) sh.res[mk][1] = sh.craw[mk][mj];
+                } else if (alleq_mine && mj == 0) {
+                    sh.res[mk][0] = sh.res[mk][1] = sh.craw[mk][0];
+                }
+            }
+            sync_all();
 #pragma unroll
             for (int k = 0; k < MID_K; ++k)
-                if (k == mk) {
-                    tot_mine = total[k];
-                    rem_mine = rem[k];
-                    small_mine = small[k];
-                    alleq_mine = alleq[k];
-                }
-            Key mykey = 0;
-            if ((small_mine && mj < tot_mine) || (alleq_mine && mj == 0)) {
-                const T xv = lp[sh.clist[mk][mj]];
-                mykey = Tr::to_key(xv);
-                sh.ckeys[mk][mj] = (unsigned long long)mykey;
-                sh.craw[mk][mj] = (unsigned long long)to_raw<T>(xv);
-            }
-            __syncthreads();
-            if (small_mine && mj < tot_mine) {
-                unsigned less = 0;
-                for (unsigned j = 0; j < tot_mine; ++j) {
-                    const Key kj = (Key)sh.ckeys[mk][j];
-                    less += (kj < mykey || (kj == mykey && j < mj)) ? 1u : 0u;
-                }
-                if (less == rem_mine) sh.sel[mk][0] = mj;
-                if (less == rem_mine + 1) sh.sel[mk][1] = mj;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < MID_K; ++k) {
-                if (small[k]) {
-                    a[k] = (Raw)sh.craw[k][sh.sel[k][0]];
+                if (k < K) {
+                    a[k] = (Raw)s0->res[k][0];
                     if (rem[k] + 1 < total[k]) {
-                        b[k] = (Raw)sh.craw[k][sh.sel[k][1]];
-                        hb[k] = true;
-                    }
-                } else if (alleq[k]) {
-                    a[k] = (Raw)sh.craw[k][0];
-                    if (rem[k] + 1 < total[k]) {
-                        b[k] = a[k];
+                        b[k] = (Raw)s0->res[k][1];
                         hb[k] = true;
                     }
                 }
-            }
-            __syncthreads();   // the shared lists are reused
-#pragma unroll
-            for (int k = 0; k < MID_K; ++k)
-                if (k < K && !small[k] && !alleq[k]) {   // needs another window: the one-rank routine (uniform over the CTA)
-                    Raw ra = 0, rb = 0;
-                    select(rk[k], false, ra, rb);
-                    a[k] = ra;
-                }
+            // (the next use of the shared lists starts with a barrier of its own)
         };
 
         // ---- every requested quantile of the lane (src/quantile/mod.rs:475-487), MID_K at a time ----------------
@@ -618,13 +526,13 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
                 rk2[k] = (both && !hb[k]) ? (unsigned)rm[k].higher : rk[k];
                 need2 = need2 || (both && !hb[k]);
             }
-            if (need2) {  // (uniform over the CTA)
+            if (need2) {  // (uniform over the cluster)
                 run_group(rk2, K, va2, vb2, hb2);
 #pragma unroll
                 for (int k = 0; k < MID_K; ++k)
                     if (k < K && nl[k] && nh[k] && !hb[k]) vb[k] = va2[k];
             }
-            if (tid == 0) {
+            if (tid == 0 && crank == 0) {
 #pragma unroll
                 for (int k = 0; k < MID_K; ++k)
                     if (k < K) {
@@ -634,13 +542,14 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
                     }
             }
         }
-        __syncthreads();   // planes and masks are rewritten by the next lane
+        sync_all();   // planes, masks and statistics are rewritten by the next lane
     }
 }
 
 struct MidPlan {
     bool ok = false;
-    unsigned nwords = 0;
+    unsigned nwords = 0, bpc = 0;
+    int csize = 1;
     size_t smem = 0;
 };
 
@@ -659,7 +568,17 @@ MidPlan plan_mid(const nds_ctx *ctx, const DeviceCall &c) {
     if (((uintptr_t)c.data) % 16 != 0) return p;
     for (int d = 0; d < g.n_outer; ++d)
         if (g.oshape[d] > 1 && ((g.in_ostride[d] * (long long)es) % 16) != 0) return p;
-    p.nwords = (unsigned)((g.axis_len + 1023) / 1024) * 32u;
+    const unsigned nb = (unsigned)((g.axis_len + 1023) / 1024);
+    p.csize = 1;
+    while ((unsigned long long)p.csize * MID_CTA_N < g.axis_len) p.csize *= 2;
+    static const int max_cluster = getenv("NDS_MID_MAX_CLUSTER") ? atoi(getenv("NDS_MID_MAX_CLUSTER")) : MID_MAX_CLUSTER;
+    if (p.csize > max_cluster) return p;
+    if (const char *e = getenv("NDS_MID_CLUSTER")) {   // testing: a cluster for lanes that one CTA could hold
+        const int want = atoi(e);
+        if ((want == 2 || want == 4 || want == 8) && want > p.csize && nb >= (unsigned)want) p.csize = want;
+    }
+    p.bpc = (nb + p.csize - 1) / p.csize;
+    p.nwords = p.bpc * 32u;
     p.smem = sizeof(MidShared) + (size_t)17 * p.nwords * 4;
     if (p.smem > (size_t)ctx->max_smem_optin) return p;
     p.ok = true;
@@ -667,18 +586,40 @@ MidPlan plan_mid(const nds_ctx *ctx, const DeviceCall &c) {
 }
 
 template <typename T> cudaError_t launch_mid_typed(nds_ctx *ctx, const DeviceCall &c, const MidPlan &p) {
-    auto kernel = mid_bitslice_kernel<T>;
+    if (p.csize == 1) {
+        auto kernel = mid_bitslice_kernel<T, false>;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        if (e != cudaSuccess) return e;
+        const unsigned grid = (unsigned)std::min<unsigned long long>(c.geom.nlanes, (unsigned long long)ctx->sm_count);
+        kernel<<<grid, MID_THREADS, p.smem, ctx->stream>>>((const T *)c.data, c.geom, c.q, (T *)c.out, p.nwords, p.bpc);
+        ctx->launches += 1;
+        return cudaGetLastError();
+    }
+    auto kernel = mid_bitslice_kernel<T, true>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)std::min<unsigned long long>(c.geom.nlanes, (unsigned long long)ctx->sm_count);
-    kernel<<<grid, MID_THREADS, p.smem, ctx->stream>>>((const T *)c.data, c.geom, c.q, (T *)c.out, p.nwords);
+    const unsigned long long groups = std::min<unsigned long long>(c.geom.nlanes, (unsigned long long)(ctx->sm_count / p.csize));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(groups * p.csize));
+    cfg.blockDim = dim3(MID_THREADS);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)p.csize;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kernel, (const T *)c.data, c.geom, c.q, (T *)c.out, p.nwords, p.bpc);
     ctx->launches += 1;
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace
 
 bool mid_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c) { return plan_mid(ctx, c).ok; }
+int mid_bitslice_cluster(const nds_ctx *ctx, const DeviceCall &c) { return plan_mid(ctx, c).csize; }
 
 cudaError_t launch_mid_bitslice(nds_ctx *ctx, const DeviceCall &c) {
     const MidPlan p = plan_mid(ctx, c);

@@ -797,6 +797,43 @@ def test_mid_bitslice_path(nds, gpu_ctx, oracle, dtype):
             gpu_ctx.quantiles_axis(a[:, :, ::2], 2, [0.5], "lower")   # strided lanes: not this kernel
     finally:
         gpu_ctx.force_path("auto")
+    # lanes shared by a thread-block cluster (2, 4, 8 CTAs): beyond 98304 elements, and forced on shorter lanes
+    try:
+        gpu_ctx.force_path("mid_bitslice")
+        for n, lanes in ((131072, 3), (200000 // vec * vec, 2), (786432, 2), (786432 - vec, 1), (300000 // vec * vec, 40)):
+            for kind in ("uniform", "ties", "late-large") + (("late-nan",) if dtype.kind == "f" else ()):
+                skip = False
+                if kind == "uniform":
+                    a = rng.random((lanes, n)) if dtype.kind == "f" else rng.integers(-10**6, 10**6, size=(lanes, n))
+                    if dtype.kind == "u":
+                        a = np.abs(a)
+                elif kind == "ties":
+                    a = rng.integers(0, 16, size=(lanes, n))
+                elif kind == "late-large":
+                    a = rng.integers(0, 100, size=(lanes, n)).astype(np.float64)
+                    a[:, n - n // 5:] += 2.0 ** 30
+                else:
+                    a = rng.random((lanes, n))
+                    a[:, n - n // 4:][rng.random((lanes, n // 4)) < 0.2] = np.nan
+                    skip = True
+                a = a.astype(dtype)
+                for interp, qs in (("linear", [0.25, 0.5, 0.75]), ("lower", [0.0, 0.001, 0.5, 1.0])):
+                    if lanes == 40 and (interp != "linear" or kind != "uniform"):
+                        continue
+                    if dtype.kind != "f" and interp == "linear" and kind == "late-large":
+                        pass
+                    check(gpu_ctx, oracle, a, 1, qs, interp, skipnan=skip, select_impl=1)
+                    assert gpu_ctx.last_path == "mid_bitslice", gpu_ctx.last_path
+        for force in ("2", "4", "8"):
+            os.environ["NDS_MID_CLUSTER"] = force
+            for n in (20000 // vec * vec, 9000 // vec * vec, 65536):
+                a = (rng.standard_normal((5, n)) * 1000).astype(dtype) if dtype.kind != "u" else rng.integers(0, 10**6, size=(5, n)).astype(dtype)
+                check(gpu_ctx, oracle, a, 1, [0.1, 0.5, 0.9, 0.99], "midpoint", select_impl=1)
+                b = rng.integers(0, 3, size=(4, n)).astype(dtype)
+                check(gpu_ctx, oracle, b, 1, [0.0, 0.4, 1.0], "higher", select_impl=1)
+    finally:
+        os.environ.pop("NDS_MID_CLUSTER", None)
+        gpu_ctx.force_path("auto")
     # default dispatch: a few short lanes (fewer than the warp-per-lane kernel wants) and many mid-length lanes
     a = rng.standard_normal((5, 2048)).astype(dtype) if dtype.kind == "f" else rng.integers(0, 10**6, size=(5, 2048)).astype(dtype)
     check(gpu_ctx, oracle, a, 1, [0.25, 0.5], "higher")

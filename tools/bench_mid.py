@@ -24,3 +24,5 @@ bench((2048, 65536), torch.float64, [0.5], "midpoint", "2048x65536 f64 median (1
 bench((16, 4096), torch.float32, [0.5], "midpoint", "16x4096 f32 median")
 bench((16384, 16384), torch.int64, [0.1, 0.5, 0.9], "lower", "16384x16384 i64 (2 GiB)")
 bench((8192, 32768), torch.float32, [0.5], "nearest", "8192x32768 f32 median (1 GiB)")
+bench((512, 524288), torch.float32, [0.5], "midpoint", "512x524288 f32 median (1 GiB, clusters of 8)")
+bench((1024, 131072), torch.float64, [0.25, 0.5, 0.75], "linear", "1024x131072 f64 quartiles (1 GiB, clusters of 2)")

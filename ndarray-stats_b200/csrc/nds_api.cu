@@ -119,6 +119,21 @@ nds_status status_from_bits(nds_ctx *ctx, int bits) {
     return NDS_OK;
 }
 
+// Geometry of the layout stage's scratch copy of the lanes of `g`: lane l (C order over the outer dims) starts at
+// l * pitch, elements are contiguous; the result's geometry is unchanged.
+LaneGeom gathered_geom(const LaneGeom &g, size_t esize, unsigned long long &pitch) {
+    LaneGeom o = g;
+    const unsigned long long vec = esize ? 16 / esize : 1;
+    pitch = vec ? (g.axis_len + vec - 1) / vec * vec : g.axis_len;
+    o.axis_stride = 1;
+    long long acc = (long long)pitch;
+    for (int d = g.n_outer - 1; d >= 0; --d) {
+        o.in_ostride[d] = acc;
+        acc *= (long long)g.oshape[d];
+    }
+    return o;
+}
+
 // Grid-wide selection of ONE lane at a time (bracket select, else the radix passes: every requested rank per pass) against
 // the CTA-per-lane kernel (one rank at a time, one CTA per lane).  `fast_lanes`: a bit-sliced lane kernel takes the call.
 // Neither of the two general paths is right for every shape, so a rough cost model picks: the CTA kernel scans a lane
@@ -126,7 +141,7 @@ nds_status status_from_bits(nds_ctx *ctx, int bits) {
 // the grid-wide paths pay ~150 us of launches per lane and then stream it at ~3 TB/s, 1.4 times (bracket select) or once
 // per key byte (radix passes).
 bool use_long_path(const nds_ctx *ctx, const LaneGeom &g, size_t nq, int interp, size_t esize, bool fast_lanes, bool mid_ok,
-                   int mid_cluster) {
+                   int mid_cluster, bool mid_gather) {
     if (ctx->forced_path == "long_radix") return true;
     if (ctx->forced_path != "auto") return false;
     if (g.axis_len >= (1ull << 32)) return true;   // the lane kernels index with 32 bits
@@ -139,8 +154,9 @@ bool use_long_path(const nds_ctx *ctx, const LaneGeom &g, size_t nq, int interp,
         // a few lanes with many ranks are quicker one after the other over the whole grid
         const double cl = (double)mid_cluster;   // CTAs that share a lane
         const double rounds = std::ceil(lanes / std::floor((double)ctx->sm_count / cl));
-        const double t_mid = rounds * (5e-6 + n * es / (40e9 * cl) + (double)nq * (cl > 1 ? 5e-6 : 2.5e-6));
-        const bool bracket_like = esize >= 4 && g.axis_len >= (1ull << 16) && nq <= 16;
+        double t_mid = rounds * (5e-6 + n * es / (40e9 * cl) + (double)nq * (cl > 1 ? 5e-6 : 2.5e-6));
+        if (mid_gather) t_mid += 5e-6 + 2.0 * lanes * n * es / 2e12;   // the layout stage: one more read and one write
+        const bool bracket_like = g.axis_stride == 1 && esize >= 4 && g.axis_len >= (1ull << 16) && nq <= 16;
         const double t_grid = lanes * (150e-6 + n * es * (bracket_like ? 1.4 : es) / 3e12);
         return t_grid < t_mid;
     }
@@ -172,8 +188,9 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
     view_span(ndim, shape, strides, min_off, max_off);
     const size_t span_elems = (size_t)(max_off - min_off + 1);
 
-    bool fast_lanes = false, mid_ok = false;
+    bool fast_lanes = false, mid_ok = false, mid_gather = false;
     int mid_cluster = 1;
+    unsigned long long gather_pitch = 0;
     if (!sharded && ctx->forced_path == "auto") {
         DeviceCall pre;
         pre.dtype = dtype;
@@ -184,9 +201,26 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
         pre.q.nq = (int)nq;
         fast_lanes = short_bitslice_supported(ctx, pre) || cols_bitslice_supported(ctx, pre);
         mid_ok = !fast_lanes && mid_bitslice_supported(ctx, pre);
+        if (!fast_lanes && !mid_ok) {   // through the layout stage?
+            pre.geom = gathered_geom(p.geom, esize, gather_pitch);
+            pre.lanes_padded = true;
+            mid_gather = mid_ok = (esize == 4 || esize == 8) && mid_bitslice_supported(ctx, pre);
+        }
         if (mid_ok) mid_cluster = mid_bitslice_cluster(ctx, pre);
+    } else if (!sharded && ctx->forced_path == "gather") {
+        DeviceCall pre;
+        pre.dtype = dtype;
+        pre.data = nullptr;
+        pre.valid = valid;
+        pre.out_valid = out_valid;
+        pre.geom = gathered_geom(p.geom, esize, gather_pitch);
+        pre.lanes_padded = true;
+        pre.q.nq = (int)nq;
+        mid_gather = (esize == 4 || esize == 8) && mid_bitslice_supported(ctx, pre);
+        if (!mid_gather) return fail(ctx, NDS_UNSUPPORTED, "forced path gather does not support this call");
     }
-    const bool long_path = sharded || use_long_path(ctx, p.geom, nq, interp, esize, fast_lanes, mid_ok, mid_cluster);
+    const bool long_path = sharded || use_long_path(ctx, p.geom, nq, interp, esize, fast_lanes, mid_ok, mid_cluster, mid_gather);
+    if (long_path) mid_gather = false;
     // ---- carve the arena ---------------------------------------------------------------------------
     size_t off = 0;
     auto carve = [&](size_t bytes) {
@@ -200,6 +234,7 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
     const size_t o_out = out_on_device ? 0 : carve(p.out_elems * esize);
     const size_t o_outv = (out_valid && !out_on_device) ? carve(p.out_elems) : 0;
     const size_t o_long = long_path ? carve(long_scratch_bytes((int)nq)) : 0;
+    const size_t o_gather = mid_gather ? carve((size_t)p.geom.nlanes * gather_pitch * esize) : 0;
     // bracket select (one streaming pass) is tried first on long lanes it supports
     DeviceCall probe;
     probe.dtype = dtype;
@@ -304,6 +339,17 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
         e = launch_cols_bitslice(ctx, c);
     } else if (want_mid && mid_bitslice_supported(ctx, c)) {
         e = launch_mid_bitslice(ctx, c);
+    } else if (mid_gather) {
+        // layout stage: the lanes gathered into aligned, padded, contiguous scratch, then the CTA-per-lane kernel
+        e = launch_gather_lanes(ctx, c, esize, arena + o_gather, gather_pitch);
+        if (e == cudaSuccess) {
+            DeviceCall c2 = c;
+            c2.data = arena + o_gather;
+            c2.geom = gathered_geom(c.geom, esize, gather_pitch);
+            c2.lanes_padded = true;
+            e = launch_mid_bitslice(ctx, c2);
+            ctx->last_path = "gather->mid_bitslice";
+        }
     } else {
         e = launch_generic_cta(ctx, c);
     }
@@ -495,7 +541,7 @@ nds_status nds_ctx_force_path(nds_ctx *ctx, const char *name) {
     if (!ctx) return NDS_BAD_ARGUMENT;
     std::string n = name ? name : "auto";
     if (n != "auto" && n != "generic_cta" && n != "long_radix" && n != "short_bitslice" && n != "cols_bitslice" &&
-        n != "mid_bitslice" && n != "bracket")
+        n != "mid_bitslice" && n != "gather" && n != "bracket")
         return fail(ctx, NDS_BAD_ARGUMENT, "unknown path name");
     ctx->forced_path = n;
     return NDS_OK;

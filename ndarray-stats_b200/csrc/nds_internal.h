@@ -66,6 +66,8 @@ struct DeviceCall {
     void *out;               // device, C-order result
     uint8_t *out_valid;      // optional, C-order result shape
     double brk_wsum = 0.0;   // bracket select: sum over quantiles of 2 c sqrt(p (1 - p)), see nds_bracket.cu
+    bool lanes_padded = false;  // `data` is the layout stage's scratch: every lane is followed by readable padding up
+                                // to a multiple of 16 bytes (the lane length itself need not be one)
 };
 
 // An enqueued long-lane call that may still need the radix fallback (decided at nds_ctx_synchronize)
@@ -110,6 +112,9 @@ cudaError_t launch_cols_bitslice(nds_ctx *ctx, const DeviceCall &c);
 bool mid_bitslice_supported(const nds_ctx *ctx, const DeviceCall &c);
 int mid_bitslice_cluster(const nds_ctx *ctx, const DeviceCall &c);   // CTAs that share one lane (1, 2, 4 or 8)
 cudaError_t launch_mid_bitslice(nds_ctx *ctx, const DeviceCall &c);
+
+// Layout stage (nds_layout.cu): the lanes of `c` gathered into dst[lane * pitch + r] (elements of 4 or 8 bytes).
+cudaError_t launch_gather_lanes(nds_ctx *ctx, const DeviceCall &c, size_t esize, void *dst, unsigned long long pitch);
 
 // Peer-memory exchange (nds_xchg.cu).  `dev_words` (optional, device): the number of 8-byte words to exchange, `gate`
 // (optional, device): skip the step when the word is 0 -- both must hold the same value on every rank.

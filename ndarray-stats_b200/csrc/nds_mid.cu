@@ -87,7 +87,7 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned n = (unsigned)g.axis_len;
-    const unsigned n_chunks = n * ES / 16;
+    const unsigned n_chunks = (n * ES + 15) / 16;   // (a ragged last chunk only with padded lanes, see plan_mid)
     const int nb = (int)((n + 1023u) / 1024u);
     const int blk0 = (int)(crank * bpc);                                    // first block of this CTA
     const int nbl = max(0, min((int)bpc, nb - blk0));                       // its number of blocks
@@ -564,7 +564,7 @@ MidPlan plan_mid(const nds_ctx *ctx, const DeviceCall &c) {
     const LaneGeom &g = c.geom;
     if (c.valid || c.out_valid) return p;
     if (g.axis_stride != 1 || g.axis_len < 64 || g.axis_len > MID_MAX_N) return p;
-    if ((g.axis_len * es) % 16 != 0) return p;      // whole 16-byte chunks from 16-byte aligned lanes
+    if ((g.axis_len * es) % 16 != 0 && !c.lanes_padded) return p;   // whole 16-byte chunks from 16-byte aligned lanes
     if (((uintptr_t)c.data) % 16 != 0) return p;
     for (int d = 0; d < g.n_outer; ++d)
         if (g.oshape[d] > 1 && ((g.in_ostride[d] * (long long)es) % 16) != 0) return p;

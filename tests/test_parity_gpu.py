@@ -843,3 +843,47 @@ def test_mid_bitslice_path(nds, gpu_ctx, oracle, dtype):
         b[1, 5] = np.nan
         with pytest.raises(nds.NanInInput):
             gpu_ctx.quantiles_axis(b, 1, [0.5], "lower")
+
+
+@pytest.mark.parametrize("dtype", SHORT_DTYPES, ids=lambda d: np.dtype(d).name)
+def test_gather_layout_stage(nds, gpu_ctx, oracle, dtype):
+    """Lanes the bit-sliced kernels cannot read in place (strided beyond the column kernel's reach, negative strides,
+    contiguous but not 16-byte aligned, odd lengths) are gathered into aligned, padded scratch (nds_layout.cu) and
+    selected by the CTA-per-lane kernel: transpose mode (lanes closer than elements) and direct mode."""
+    dtype = np.dtype(dtype)
+    rng = np.random.default_rng(zlib.crc32(repr(("gather", dtype.name)).encode()))
+
+    def data(shape):
+        if dtype.kind == "f":
+            return rng.standard_normal(shape).astype(dtype)
+        return rng.integers(-10**6 if dtype.kind == "i" else 0, 10**6, size=shape).astype(dtype)
+
+    cases = [
+        (data((10001, 70)), 0),                 # tall matrix, columns: transpose mode, odd lane length
+        (data((300000, 5)), 0),                 # very tall, few columns: clusters behind the layout stage
+        (data((40, 10001)), 1),                 # contiguous lanes whose rows are not 16-byte aligned: direct mode
+        (data((33, 9000))[:, ::3], 1),          # strided elements inside a lane
+        (data((50, 4000))[:, ::-1], 1),         # negative stride
+        (data((12000, 6, 7)), 0),               # 3-d, lanes along the slowest axis
+        (data((5, 12001, 3)), 1),               # 3-d, lanes along the middle axis
+        (np.asfortranarray(data((31, 700))), 1),  # Fortran order: lanes along the strided axis
+    ]
+    try:
+        gpu_ctx.force_path("gather")
+        for a, axis in cases:
+            for interp, qs in (("linear", [0.25, 0.5, 0.75]), ("lower", [0.0, 0.37, 1.0]), ("midpoint", [0.5])):
+                check(gpu_ctx, oracle, a, axis, qs, interp, select_impl=1)
+                assert gpu_ctx.last_path == "gather->mid_bitslice", gpu_ctx.last_path
+        if dtype.kind == "f":
+            a = data((9001, 40))
+            a[rng.random(a.shape) < 0.1] = np.nan
+            a[:, 3] = np.nan
+            check(gpu_ctx, oracle, a, 0, [0.1, 0.5], "nearest", skipnan=True, select_impl=1)
+            with pytest.raises(nds.NanInInput):
+                gpu_ctx.quantiles_axis(a, 0, [0.5], "lower")
+    finally:
+        gpu_ctx.force_path("auto")
+    # default dispatch: the tall matrix goes through the layout stage by itself
+    a = data((20000, 48))
+    check(gpu_ctx, oracle, a, 0, [0.5, 0.9], "higher", select_impl=1)
+    assert gpu_ctx.last_path == "gather->mid_bitslice", gpu_ctx.last_path

@@ -40,7 +40,7 @@ constexpr int MID_CAND = 128;                     // survivors ranked directly
 constexpr int MID_K = 3;                          // ranks walked together (MID_K * MID_CAND == MID_THREADS)
 
 struct MidShared {          // small fixed part in front of the planes
-    unsigned partial[2][MID_K][MID_WARPS];
+    unsigned partial[2][MID_K][MID_MAX_CLUSTER * MID_WARPS];   // per-warp counts of one key bit, of EVERY CTA of the cluster
     unsigned stat[2][6];    // [stage][zlo, zhi, olo, ohi, (unused), nan count]
     unsigned ncand[MID_K];
     unsigned sel[MID_K][2];
@@ -359,17 +359,15 @@ mid_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__r
 #pragma unroll
                     for (int i = 0; i < MID_MAXW; ++i) ones += __popc(m[k][i] & (x[i] ^ inv[k]));
                     ones = __reduce_add_sync(FULL, ones);
-                    if (lane == 0) sh.partial[par][k][warp] = ones;
+                    // pushed into every CTA's table (lane r stores to CTA r): after the barrier everybody sums locally
+                    if ((unsigned)lane < csize) peer((unsigned)lane)->partial[par][k][crank * (unsigned)MID_WARPS + (unsigned)warp] = ones;
                 }
                 sync_all();
 #pragma unroll
                 for (int k = 0; k < MID_K; ++k) {
                     if (!act[k]) continue;
                     unsigned v = 0;
-                    for (unsigned i = (unsigned)lane; i < csize * (unsigned)MID_WARPS; i += 32u) {
-                        const unsigned r = i / (unsigned)MID_WARPS;
-                        v += peer(r)->partial[par][k][i - r * (unsigned)MID_WARPS];
-                    }
+                    for (unsigned i = (unsigned)lane; i < csize * (unsigned)MID_WARPS; i += 32u) v += sh.partial[par][k][i];
                     const unsigned ones = __reduce_add_sync(FULL, v);
                     const unsigned small_cnt = total[k] - ones;
                     const bool take_small = rem[k] < small_cnt;

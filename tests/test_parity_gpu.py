@@ -554,9 +554,16 @@ def test_bracket_sort1d_and_enqueue(nds, gpu_ctx, oracle):
     assert all(got[i] == srt[i] for i in got)
     t = torch.from_numpy(a).cuda()
     dec = np.arange(1, 10) / 10.0
-    out = gpu_ctx.quantiles_axis(t, 0, dec, "linear", enqueue=True)
-    gpu_ctx.synchronize()
     st, want, _ = oracle.quantiles_axis(a, 0, dec, "linear", select_impl=1)
+    out = gpu_ctx.quantiles_axis(t, 0, dec, "linear", enqueue=True)   # (a lane this short: a cluster of CTAs takes it)
+    gpu_ctx.synchronize()
+    assert ulp_distance(out.cpu().numpy(), want) == 0 and gpu_ctx.last_path in ("mid_bitslice", "bracket")
+    try:
+        gpu_ctx.force_path("bracket")
+        out = gpu_ctx.quantiles_axis(t, 0, dec, "linear", enqueue=True)
+        gpu_ctx.synchronize()
+    finally:
+        gpu_ctx.force_path("auto")
     assert ulp_distance(out.cpu().numpy(), want) == 0
     assert gpu_ctx.last_path == "bracket"
     # 99 percentiles of a lane this short: the brackets would hold most of the lane, automatic dispatch goes
@@ -712,8 +719,8 @@ def test_mid_length_lanes_dispatch(nds, gpu_ctx, oracle, dtype):
     b = a[:, :20001].T.copy()                                                 # 20001 x 3: strided lanes along axis 0
     check(gpu_ctx, oracle, b, 0, [0.25, 0.5], "midpoint", select_impl=1)     # (either path may win the cost model)
     check(gpu_ctx, oracle, b, 0, pct, "higher", select_impl=1)               # 99 ranks of strided lanes: grid-wide passes
-    if np.dtype(dtype).itemsize >= 4:
-        assert gpu_ctx.last_path in ("long_radix", "bracket", "bracket->long_radix"), gpu_ctx.last_path
+    if np.dtype(dtype).itemsize >= 4:   # (or the layout stage + the CTA-per-lane kernel: three lanes run side by side)
+        assert gpu_ctx.last_path in ("long_radix", "bracket", "bracket->long_radix", "gather->mid_bitslice"), gpu_ctx.last_path
     wide = np.tile(a[:, :9000], (20, 1))                                      # 60 lanes x 9000, 2 quantiles: one CTA per lane
     check(gpu_ctx, oracle, wide, 1, [0.5, 0.9], "higher", select_impl=1)
     assert gpu_ctx.last_path == ("mid_bitslice" if np.dtype(dtype).itemsize >= 4 else "generic_cta"), gpu_ctx.last_path

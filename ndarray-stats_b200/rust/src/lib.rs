@@ -6,8 +6,9 @@
 //! reference crate; there is no CPU fallback inside this crate.
 mod ffi;
 
-use ndarray::{Array, ArrayBase, Axis, Data, DataMut, Dimension, Ix1, RemoveAxis};
-use ndarray_stats::errors::QuantileError;
+use indexmap::IndexMap;
+use ndarray::{Array, Array1, ArrayRef, Axis, Dimension, Ix1, RemoveAxis};
+use ndarray_stats::errors::{MinMaxError, QuantileError};
 use noisy_float::types::{n64, N32, N64};
 use std::ptr;
 
@@ -21,6 +22,7 @@ interp!(Lower = 0, Higher = 1, Nearest = 2, Midpoint = 3, Linear = 4);
 
 mod private {
     pub trait Sealed {}
+    pub trait SealedArray {}
 }
 /// Element types with a device representation.  N32/N64 have the layout of f32/f64
 /// (the reference pointer-casts between them itself, `src/maybe_nan/mod.rs:82-107`).
@@ -40,8 +42,8 @@ thread_local! {
     };
 }
 
-fn call<A: DeviceElem, S: Data<Elem = A>, D: Dimension>(
-    a: &ArrayBase<S, D>, axis: Axis, qs: &[f64], interp: i32, skipnan: bool, out: &mut [A],
+fn call<A: DeviceElem, D: Dimension>(
+    a: &ArrayRef<A, D>, axis: Axis, qs: &[f64], interp: i32, skipnan: bool, out: &mut [A],
 ) -> Result<(), QuantileError> {
     // ndarray's `len_of` panics on an out-of-bounds axis before anything else (as the reference does)
     let _ = a.len_of(axis);
@@ -64,34 +66,55 @@ fn call<A: DeviceElem, S: Data<Elem = A>, D: Dimension>(
     }
 }
 
-/// Same names and signatures as `ndarray_stats::QuantileExt` for the quantile methods
-/// (`src/quantile/mod.rs:186-277`); `&mut self` is kept for source compatibility, the data is not reordered.
-pub trait QuantileExtB200<A, S, D>: private::Sealed
+/// Same names and signatures as the quantile methods of `ndarray_stats::QuantileExt<A, D>`, which v0.7 implements for
+/// `ArrayRef<A, D>` and whose `qs` are `&ArrayRef<N64, Ix1>` (`src/quantile/mod.rs:12-15, 186-277, 279`).  `&mut self`
+/// is kept for source compatibility; the data is not reordered.
+pub trait QuantileExtB200<A, D>: private::SealedArray
 where
-    S: Data<Elem = A>,
     D: Dimension,
 {
-    fn quantiles_axis_mut<S2, I>(&mut self, axis: Axis, qs: &ArrayBase<S2, Ix1>, interpolate: &I) -> Result<Array<A, D>, QuantileError>
+    fn quantiles_axis_mut<I>(&mut self, axis: Axis, qs: &ArrayRef<N64, Ix1>, interpolate: &I) -> Result<Array<A, D>, QuantileError>
     where
-        D: RemoveAxis, A: DeviceElem, S: DataMut, S2: Data<Elem = N64>, I: DeviceInterpolate;
+        D: RemoveAxis, A: DeviceElem, I: DeviceInterpolate;
     fn quantile_axis_mut<I>(&mut self, axis: Axis, q: N64, interpolate: &I) -> Result<Array<A, D::Smaller>, QuantileError>
     where
-        D: RemoveAxis, A: DeviceElem, S: DataMut, I: DeviceInterpolate;
+        D: RemoveAxis, A: DeviceElem, I: DeviceInterpolate;
     fn quantile_axis_skipnan_mut<I>(&mut self, axis: Axis, q: N64, interpolate: &I) -> Result<Array<A, D::Smaller>, QuantileError>
     where
-        D: RemoveAxis, A: DeviceElem, S: DataMut, I: DeviceInterpolate;
+        D: RemoveAxis, A: DeviceElem, I: DeviceInterpolate;
+    /// `src/quantile/mod.rs:283-409`: the eight min / max methods are one device reduction each.
+    fn argmin(&self) -> Result<D::Pattern, MinMaxError> where A: DeviceElem;
+    fn argmax(&self) -> Result<D::Pattern, MinMaxError> where A: DeviceElem;
+    fn min(&self) -> Result<A, MinMaxError> where A: DeviceElem;
+    fn max(&self) -> Result<A, MinMaxError> where A: DeviceElem;
 }
 
-impl<A, S: Data<Elem = A>, D: Dimension> private::Sealed for ArrayBase<S, D> {}
+impl<A, D: Dimension> private::SealedArray for ArrayRef<A, D> {}
 
-impl<A, S, D> QuantileExtB200<A, S, D> for ArrayBase<S, D>
+fn minmax<A: DeviceElem, D: Dimension>(a: &ArrayRef<A, D>, want_max: bool, skipnan: bool) -> Result<(A, Vec<usize>), MinMaxError> {
+    let shape: Vec<usize> = a.shape().to_vec();
+    let strides: Vec<isize> = a.strides().to_vec();
+    let mut value = std::mem::MaybeUninit::<A>::uninit();
+    let mut index = vec![0usize; shape.len().max(1)];
+    let st = CTX.with(|&ctx| unsafe {
+        ffi::nds_minmax(ctx, A::DTYPE, a.as_ptr() as *const _, shape.len() as i32, shape.as_ptr(), strides.as_ptr(),
+                        want_max as i32, skipnan as i32, value.as_mut_ptr() as *mut _, index.as_mut_ptr())
+    });
+    match st {
+        ffi::NDS_OK => Ok((unsafe { value.assume_init() }, index)),
+        ffi::NDS_EMPTY_INPUT => Err(MinMaxError::EmptyInput),
+        ffi::NDS_UNDEFINED_ORDER => Err(MinMaxError::UndefinedOrder),
+        other => panic!("ndstats_b200 status {}", other),
+    }
+}
+
+impl<A, D> QuantileExtB200<A, D> for ArrayRef<A, D>
 where
-    S: Data<Elem = A>,
     D: Dimension,
 {
-    fn quantiles_axis_mut<S2, I>(&mut self, axis: Axis, qs: &ArrayBase<S2, Ix1>, _i: &I) -> Result<Array<A, D>, QuantileError>
+    fn quantiles_axis_mut<I>(&mut self, axis: Axis, qs: &ArrayRef<N64, Ix1>, _i: &I) -> Result<Array<A, D>, QuantileError>
     where
-        D: RemoveAxis, A: DeviceElem, S: DataMut, S2: Data<Elem = N64>, I: DeviceInterpolate,
+        D: RemoveAxis, A: DeviceElem, I: DeviceInterpolate,
     {
         let qv: Vec<f64> = qs.iter().map(|q| q.raw()).collect();
         let mut shape = self.raw_dim();
@@ -103,13 +126,13 @@ where
     }
     fn quantile_axis_mut<I>(&mut self, axis: Axis, q: N64, i: &I) -> Result<Array<A, D::Smaller>, QuantileError>
     where
-        D: RemoveAxis, A: DeviceElem, S: DataMut, I: DeviceInterpolate,
+        D: RemoveAxis, A: DeviceElem, I: DeviceInterpolate,
     {
         self.quantiles_axis_mut(axis, &ndarray::aview1(&[q]), i).map(|a| a.index_axis_move(axis, 0)) // mod.rs:507
     }
     fn quantile_axis_skipnan_mut<I>(&mut self, axis: Axis, q: N64, _i: &I) -> Result<Array<A, D::Smaller>, QuantileError>
     where
-        D: RemoveAxis, A: DeviceElem, S: DataMut, I: DeviceInterpolate,
+        D: RemoveAxis, A: DeviceElem, I: DeviceInterpolate,
     {
         let mut shape = self.raw_dim();
         shape[axis.index()] = 1;
@@ -117,5 +140,60 @@ where
         unsafe { out.set_len(shape.size()) };
         call(self, axis, &[q.raw()], I::CODE, true, &mut out)?;
         Ok(Array::from_shape_vec(shape, out).unwrap().index_axis_move(axis, 0))
+    }
+    fn argmin(&self) -> Result<D::Pattern, MinMaxError> where A: DeviceElem {
+        let (_, idx) = minmax(self, false, false)?;
+        let mut d = D::zeros(idx.len());                      // the index as the dimension's pattern (mod.rs:283-300)
+        d.slice_mut().copy_from_slice(&idx);
+        Ok(d.into_pattern())
+    }
+    fn argmax(&self) -> Result<D::Pattern, MinMaxError> where A: DeviceElem {
+        let (_, idx) = minmax(self, true, false)?;
+        let mut d = D::zeros(idx.len());
+        d.slice_mut().copy_from_slice(&idx);
+        Ok(d.into_pattern())
+    }
+    fn min(&self) -> Result<A, MinMaxError> where A: DeviceElem { minmax(self, false, false).map(|(v, _)| v) }
+    fn max(&self) -> Result<A, MinMaxError> where A: DeviceElem { minmax(self, true, false).map(|(v, _)| v) }
+}
+
+/// `Quantile1dExt<A>` for `ArrayRef<A, Ix1>` (`src/quantile/mod.rs:550-633`).
+pub trait Quantile1dExtB200<A>: private::SealedArray {
+    fn quantile_mut<I>(&mut self, q: N64, interpolate: &I) -> Result<A, QuantileError> where A: DeviceElem, I: DeviceInterpolate;
+    fn quantiles_mut<I>(&mut self, qs: &ArrayRef<N64, Ix1>, interpolate: &I) -> Result<Array1<A>, QuantileError>
+    where A: DeviceElem, I: DeviceInterpolate;
+}
+impl<A> Quantile1dExtB200<A> for ArrayRef<A, Ix1> {
+    fn quantile_mut<I>(&mut self, q: N64, i: &I) -> Result<A, QuantileError> where A: DeviceElem, I: DeviceInterpolate {
+        Ok(QuantileExtB200::quantile_axis_mut(self, Axis(0), q, i)?.into_scalar())              // mod.rs:613-621
+    }
+    fn quantiles_mut<I>(&mut self, qs: &ArrayRef<N64, Ix1>, i: &I) -> Result<Array1<A>, QuantileError>
+    where A: DeviceElem, I: DeviceInterpolate {
+        QuantileExtB200::quantiles_axis_mut(self, Axis(0), qs, i)                                // mod.rs:623-633
+    }
+}
+
+/// `Sort1dExt::{get_from_sorted_mut, get_many_from_sorted_mut}` (`src/sort.rs:99-131`): the values at the given sorted
+/// positions; the array is left as it is.
+pub trait Sort1dExtB200<A>: private::SealedArray {
+    fn get_from_sorted_mut(&mut self, i: usize) -> A where A: DeviceElem;
+    fn get_many_from_sorted_mut(&mut self, indexes: &ArrayRef<usize, Ix1>) -> IndexMap<usize, A> where A: DeviceElem;
+}
+impl<A> Sort1dExtB200<A> for ArrayRef<A, Ix1> {
+    fn get_from_sorted_mut(&mut self, i: usize) -> A where A: DeviceElem {
+        self.get_many_from_sorted_mut(&ndarray::aview1(&[i]))[&i]
+    }
+    fn get_many_from_sorted_mut(&mut self, indexes: &ArrayRef<usize, Ix1>) -> IndexMap<usize, A> where A: DeviceElem {
+        let mut idx: Vec<usize> = indexes.iter().copied().collect();
+        idx.sort_unstable();
+        idx.dedup();                                           // sort.rs:113-116
+        let mut out = Vec::<A>::with_capacity(idx.len());
+        unsafe { out.set_len(idx.len()) };
+        let st = CTX.with(|&ctx| unsafe {
+            ffi::nds_get_many_from_sorted(ctx, A::DTYPE, self.as_ptr() as *const _, self.len(), self.strides()[0],
+                                          idx.as_ptr(), idx.len(), out.as_mut_ptr() as *mut _)
+        });
+        assert_eq!(st, ffi::NDS_OK, "index out of bounds (the reference panics, sort.rs:27,38)");
+        idx.into_iter().zip(out).collect()
     }
 }

@@ -64,11 +64,18 @@ WORKLOADS = {
     "c5_i64_lanes_higher": dict(desc="16384x8192 i64 lanes ((z&15)-8)*2^40, quantiles_axis_mut(Axis(1), [.1,.5,.9], Higher)",
                                 dtype="int64", shape=(16384, 8192), axis=1, qs=[0.1, 0.5, 0.9], interp="higher",
                                 skipnan=False, stream="i64_16values", seed=1005),
+    # beyond BASELINE.json (the shapes between its configs): mid-length lanes and a tall matrix's columns
+    "x_mid_f64_rows": dict(desc="2048x65536 f64 row medians (quantile_axis_mut Axis(1), Midpoint): CTA per lane",
+                           dtype="float64", shape=(2048, 65536), axis=1, qs=[0.5], interp="midpoint", skipnan=False,
+                           stream="f64_uniform", seed=1006),
+    "x_tall_f32_cols": dict(desc="65536x4096 f32 column quartiles (quantiles_axis_mut Axis(0), [.25,.5,.75], Linear): "
+                                 "layout stage + CTA per lane", dtype="float32", shape=(65536, 4096), axis=0,
+                            qs=[0.25, 0.5, 0.75], interp="linear", skipnan=False, stream="f32_uniform", seed=1007),
 }
 ALIASES = {"c5": "c5_u32_lower"}
 HEADLINE = "c2"
 SUB_WORKLOADS_1GPU = ["c1", "c3", "c4", "c5_u32_lower", "c5_u32_higher", "c5_u32_adv", "c5_i64_lanes_lower",
-                      "c5_i64_lanes_higher"]
+                      "c5_i64_lanes_higher", "x_mid_f64_rows", "x_tall_f32_cols"]
 SUB_WORKLOADS_MULTI = ["c3"]  # lanes shard with no collective (weak scaling); c4 runs as `sharded_1d`
 DTYPE_TAG = {"float32": "f32", "float64": "f64", "uint32": "u32", "int64": "i64"}
 

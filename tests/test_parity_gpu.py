@@ -391,8 +391,7 @@ def test_short_bitslice_informative_windows(gpu_ctx, oracle, dtype):
         gpu_ctx.force_path("auto")
 
 
-# NDS_COLS_V2=1 routes the qualifying calls to the experimental pipelined strip kernel (nds_cols.cu); the same cases apply
-COLS_PATHS = ("cols_bitslice", "cols_pipelined") if os.environ.get("NDS_COLS_V2") else ("cols_bitslice",)
+COLS_PATHS = ("cols_bitslice",)
 
 
 @pytest.mark.parametrize("dtype", SHORT_DTYPES, ids=lambda d: np.dtype(d).name)

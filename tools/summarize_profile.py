@@ -53,8 +53,10 @@ def main():
             f.write("# totals_ns: " + json.dumps(tot) + "\n")
         print("wrote", out, tot)
     rep = os.path.join(src, f"prof_{wl}.ncu-rep")
-    if os.path.exists(rep):
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    raw = os.path.join(src, f"prof_{wl}.raw.csv")   # `ncu -i X.ncu-rep --page raw --csv` taken on the GPU box
+    if os.path.exists(rep) or os.path.exists(raw):
+        txt = open(raw).read() if os.path.exists(raw) else \
+            subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(txt)))
         hdr, units = rows[0], rows[1]
         out = os.path.join(ROOT, "profiles", f"{rnd}_{wl}_ncu.md")

@@ -47,8 +47,9 @@ def main():
                 short = name.split("(")[0].replace("void ", "")
                 if len(short) > 90:
                     short = short[:87] + "..."
+                short = short.replace(",", ";")
                 f.write(f"{r[0]},{short},{r[gi].replace(',', 'x')},{r[bi].replace(',', 'x')},{r[vi]}\n")
-                key = "nds" if "nds::" in name else "other"
+                key = "nds" if ("nds::" in name or "unnamed>::" in name) else "other"
                 tot[key] = tot.get(key, 0) + float(r[vi].replace(",", ""))
             f.write("# totals_ns: " + json.dumps(tot) + "\n")
         print("wrote", out, tot)

@@ -172,6 +172,17 @@ nds_status nds_get_many_from_sorted(nds_ctx *ctx, nds_dtype dtype, const void *d
 nds_status nds_minmax(nds_ctx *ctx, nds_dtype dtype, const void *data, int ndim, const size_t *shape,
                       const ptrdiff_t *strides_elems, int want_max, int skipnan, void *out_value, size_t *out_index);
 
+/* HistogramExt::histogram (src/histogram/histograms.rs:137-147; Grid::index_of, src/histogram/grid.rs:203-218;
+ * Edges::indices_of, src/histogram/bins.rs:217-229): the n-dimensional histogram of the rows of an
+ * (n_obs x n_dims) matrix -- element strides stride_obs between observations, stride_dim between the coordinates of one
+ * -- over a grid given by per-dimension SORTED edges (`edges`: the n_dims edge arrays one after the other, n_edges[d]
+ * of them for dimension d; bins are left-closed and right-open, dimension d has n_edges[d] - 1 of them).  An observation
+ * outside any projection is skipped, as the reference does (add_observation's BinNotFound is dropped, histograms.rs:141).
+ * `counts` (host or device) receives the C-order array of prod(n_edges[d] - 1) 64-bit counts.  Synchronous. */
+nds_status nds_histogram(nds_ctx *ctx, nds_dtype dtype, const void *data, size_t n_obs, size_t n_dims,
+                         ptrdiff_t stride_obs, ptrdiff_t stride_dim, const void *edges, const size_t *n_edges,
+                         unsigned long long *counts);
+
 /* ---- synthetic benchmark inputs ---------------------------------------- */
 
 /* Counter-based splitmix64 streams: element i is a function of mix(seed + first_index + i) only, so bench.py's

@@ -36,6 +36,7 @@ __all__ = [
     "quantile_axis_skipnan_mut", "quantile_mut", "quantiles_mut", "get_from_sorted_mut", "get_many_from_sorted_mut",
     "shard_lanes", "MinMaxError", "MinMaxEmptyInput", "UndefinedOrder", "argmin", "argmax", "min", "max",
     "argmin_skipnan", "argmax_skipnan", "min_skipnan", "max_skipnan", "FreedmanDiaconis", "Sqrt", "Rice", "Sturges", "Auto", "EquiSpaced", "BinsBuildError",
+    "Edges", "Bins", "Grid", "GridBuilder", "Histogram", "BinNotFound", "histogram",
 ]
 
 
@@ -346,6 +347,29 @@ class Context:
         self._raise(st)
         return out
 
+    def histogram_counts(self, a, edges):
+        """``nds_histogram``: counts of the rows of the 2-D array ``a`` (numpy or CUDA tensor) in the grid whose
+        dimension d has the sorted edges ``edges[d]``.  Returns a numpy uint64 array of shape (len(e) - 1 for e in edges)."""
+        code, ptr, shape, strides, keep, is_torch = self._describe(a)
+        if len(shape) != 2:
+            raise ValueError("histogram is defined on 2-D arrays (observations x dimensions)")
+        n_obs, n_dims = shape
+        if len(edges) != n_dims:
+            raise ValueError("the grid's dimensionality differs from the observations'")   # the reference panics (grid.rs:204-211)
+        np_dtype = keep.dtype if not is_torch else {v: k for k, v in _NP_DTYPES.items()}[code]
+        ed = [np.ascontiguousarray(e, dtype=np_dtype).reshape(-1) for e in edges]
+        out_shape = tuple(e.size - 1 if e.size else 0 for e in ed)   # (this module's `max` is QuantileExt::max)
+        counts = np.zeros(out_shape, dtype=np.uint64)
+        if counts.size == 0:
+            return counts
+        cat = np.concatenate(ed) if ed else np.zeros(0, dtype=np_dtype)
+        n_edges = (ctypes.c_size_t * n_dims)(*[e.size for e in ed])
+        st = self._lib.nds_histogram(self._h, code, ctypes.c_void_p(ptr if n_obs else 0), n_obs, n_dims,
+                                     strides[0] if n_obs else 1, strides[1] if n_obs else 1,
+                                     ctypes.c_void_p(cat.ctypes.data), n_edges, ctypes.c_void_p(counts.ctypes.data))
+        self._raise(st)
+        return counts
+
     def minmax(self, a, want_max, skipnan, want_index=True):
         """``nds_minmax`` -> (status, value or None, index tuple or None); the callers map the status.
         ``want_index=False`` asks for the value alone (max_skipnan then returns the LAST of equal maxima, as the
@@ -593,4 +617,5 @@ def max_skipnan(a, ctx=None):
 
 
 from .strategies import Auto, BinsBuildError, EquiSpaced, FreedmanDiaconis, Rice, Sqrt, Sturges  # noqa: E402,F401  
+from .histogram import BinNotFound, Bins, Edges, Grid, GridBuilder, Histogram, histogram  # noqa: E402,F401
 from . import synth  # noqa: E402,F401  (synthetic benchmark inputs)

@@ -254,3 +254,25 @@ def auto_rule(a):
     if st[0] != "ok":
         return ("fd",) + fd[1:]
     return (("sturges",) + st[1:]) if fd[1] > st[1] else (("fd",) + fd[1:])
+
+
+# ---- HistogramExt::histogram (src/histogram/histograms.rs:137-147).  TEST INFRASTRUCTURE: the reference's loop restated
+# with numpy -- per dimension the bin of Edges::indices_of (left-closed, right-open, bins.rs:217-229), rows outside skipped.
+def histogram_counts(a, edges):
+    a = np.asarray(a)
+    edges = [np.unique(np.asarray(e, dtype=a.dtype)) for e in edges]
+    shape = tuple(max(e.size - 1, 0) for e in edges)
+    counts = np.zeros(shape, dtype=np.uint64)
+    if counts.size == 0 or a.shape[0] == 0:
+        return counts
+    inside = np.ones(a.shape[0], dtype=bool)
+    idx = []
+    for d, e in enumerate(edges):
+        v = a[:, d]
+        b = np.searchsorted(e, v, side="right").astype(np.int64) - 1      # number of edges <= v, minus one
+        with np.errstate(invalid="ignore"):
+            ok = (v >= e[0]) & (v < e[-1])
+        inside &= ok
+        idx.append(np.where(ok, b, 0))
+    np.add.at(counts, tuple(i[inside] for i in idx), 1)
+    return counts

@@ -157,6 +157,18 @@ nds_status nds_get_many_from_sorted(nds_ctx *ctx, nds_dtype dtype, const void *d
                                     ptrdiff_t stride_elems, const size_t *indexes, size_t k, void *out_values);
 
 /*
+ * Sort1dExt::partition_mut               src/sort.rs:133-168 (post-conditions: tests/sort.rs:5-33)
+ * Partitions the 1-D array IN PLACE around the value at `pivot_index` and stores the pivot's new position in
+ * `*partition_index`: every element before it is < the pivot, every element after it is >= the pivot.  Index AND
+ * arrangement are those of the reference's sequential Hoare walk, bit for bit (both follow from the input alone:
+ * nds_partition.cu gives the closed form).  `data` may be a host array (staged, copied back) or device memory.
+ * pivot_index >= n -> NDS_INDEX_OUT_OF_BOUNDS (the reference panics, src/sort.rs:77-78).  n == 1 -> index 0, nothing
+ * moves (the reference's walk runs off a one-element array).  Floats stand for N32 / N64: no NaN.  Synchronous.
+ */
+nds_status nds_partition(nds_ctx *ctx, nds_dtype dtype, void *data, size_t n, ptrdiff_t stride_elems,
+                         size_t pivot_index, size_t *partition_index);
+
+/*
  * QuantileExt::{argmin, argmax, min, max}                          src/quantile/mod.rs:283-300, 320-333, 347-363, 384-397
  * QuantileExt::{argmin_skipnan, argmax_skipnan, min_skipnan, max_skipnan}   mod.rs:302-318, 335-345, 365-382, 399-409
  * over the WHOLE array (any shape / strides).  `out_value` (host, one element, optional) receives the extremum,

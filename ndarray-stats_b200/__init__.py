@@ -12,6 +12,7 @@ as the reference (paths relative to the reference checkout):
 ``Lower`` … ``Linear``             src/quantile/interpolate.rs:51-62
 ``QuantileError``                  src/errors.rs:119-143
 ``get_from_sorted_mut`` / ``get_many_from_sorted_mut``  src/sort.rs:99-131 (Sort1dExt)
+``partition_mut``                                          src/sort.rs:133-168 (Sort1dExt)
 =================================  ==========================================
 
 Arrays are numpy arrays (host; staged through the context's device arena) or torch CUDA tensors
@@ -33,7 +34,7 @@ from ._cabi import (  # noqa: F401  (re-exported status codes)
 __all__ = [
     "Axis", "Lower", "Higher", "Nearest", "Midpoint", "Linear", "QuantileError", "EmptyInput", "InvalidQuantile",
     "NanInInput", "CastOverflow", "Context", "default_context", "quantile_axis_mut", "quantiles_axis_mut",
-    "quantile_axis_skipnan_mut", "quantile_mut", "quantiles_mut", "get_from_sorted_mut", "get_many_from_sorted_mut",
+    "quantile_axis_skipnan_mut", "quantile_mut", "quantiles_mut", "get_from_sorted_mut", "get_many_from_sorted_mut", "partition_mut",
     "shard_lanes", "MinMaxError", "MinMaxEmptyInput", "UndefinedOrder", "argmin", "argmax", "min", "max",
     "argmin_skipnan", "argmax_skipnan", "min_skipnan", "max_skipnan", "FreedmanDiaconis", "Sqrt", "Rice", "Sturges", "Auto", "EquiSpaced", "BinsBuildError",
     "Edges", "Bins", "Grid", "GridBuilder", "Histogram", "BinNotFound", "histogram",
@@ -347,6 +348,20 @@ class Context:
         self._raise(st)
         return out
 
+    def partition(self, a, pivot_index):
+        """``nds_partition``: partitions the 1-D array ``a`` (writable numpy array or CUDA tensor) in place around the
+        value at ``pivot_index``; returns the pivot's new position."""
+        code, ptr, shape, strides, keep, is_torch = self._describe(a)
+        if len(shape) != 1:
+            raise ValueError("Sort1dExt is defined on 1-D arrays")
+        if not is_torch and not keep.flags.writeable:
+            raise ValueError("partition_mut needs a writable array")
+        new_index = ctypes.c_size_t(0)
+        st = self._lib.nds_partition(self._h, code, ctypes.c_void_p(ptr), shape[0], strides[0] if shape[0] else 1,
+                                     int(pivot_index), ctypes.byref(new_index))
+        self._raise(st)
+        return int(new_index.value)
+
     def histogram_counts(self, a, edges):
         """``nds_histogram``: counts of the rows of the 2-D array ``a`` (numpy or CUDA tensor) in the grid whose
         dimension d has the sorted edges ``edges[d]``.  Returns a numpy uint64 array of shape (len(e) - 1 for e in edges)."""
@@ -520,6 +535,13 @@ def get_many_from_sorted_mut(a, indexes, ctx=None):
     vals = _ctx_for(a, ctx).get_many_from_sorted(a, idx)
     vals = vals.cpu().numpy() if _is_torch(vals) else vals
     return {i: v for i, v in zip(idx, vals)}
+
+
+def partition_mut(a, pivot_index, ctx=None):
+    """Sort1dExt::partition_mut (src/sort.rs:133-168): in place; returns the new index of the pivot value.  Elements
+    before it are smaller, elements after it are greater than or equal (src/sort.rs:58-67); index and arrangement are
+    the reference's, bit for bit.  ``pivot_index >= len(a)`` raises IndexError (the reference panics)."""
+    return _ctx_for(a, ctx).partition(a, pivot_index)
 
 
 # ---- multi-GPU helper: independent lanes shard with no collective (SURVEY.md §8e) ----------------------

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "nds_quantiles_axis_enqueue": (_int, [_vp, _int, _vp, _int, _psz, _pss, _int, _pd, _sz, _int, _int, _vp, _psz]),
     "nds_quantiles_axis_masked": (_int, [_vp, _int, _vp, _vp, _int, _psz, _pss, _int, _pd, _sz, _int, _vp, _vp, _psz]),
     "nds_get_many_from_sorted": (_int, [_vp, _int, _vp, _sz, ctypes.c_ssize_t, _psz, _sz, _vp]),
+    "nds_partition": (_int, [_vp, _int, _vp, _sz, ctypes.c_ssize_t, _sz, _psz]),
     "nds_minmax": (_int, [_vp, _int, _vp, _int, _psz, _pss, _int, _int, _vp, _psz]),
     "nds_histogram": (_int, [_vp, _int, _vp, _sz, _sz, ctypes.c_ssize_t, ctypes.c_ssize_t, _vp, _psz, _vp]),
     "nds_comm_get_unique_id": (_int, [_vp]),

@@ -34,4 +34,9 @@ extern "C" {
         ctx: *mut nds_ctx, dtype: c_int, data: *const c_void, n: usize, stride_elems: isize,
         indexes: *const usize, k: usize, out_values: *mut c_void,
     ) -> c_int;
+    /// Sort1dExt::partition_mut (in place)
+    pub fn nds_partition(
+        ctx: *mut nds_ctx, dtype: c_int, data: *mut c_void, n: usize, stride_elems: isize,
+        pivot_index: usize, partition_index: *mut usize,
+    ) -> c_int;
 }

@@ -174,12 +174,23 @@ impl<A> Quantile1dExtB200<A> for ArrayRef<A, Ix1> {
 }
 
 /// `Sort1dExt::{get_from_sorted_mut, get_many_from_sorted_mut}` (`src/sort.rs:99-131`): the values at the given sorted
-/// positions; the array is left as it is.
+/// positions; the array is left as it is.  `partition_mut` (`src/sort.rs:133-168`) works in place and leaves the
+/// reference's arrangement.
 pub trait Sort1dExtB200<A>: private::SealedArray {
+    fn partition_mut(&mut self, pivot_index: usize) -> usize where A: DeviceElem;
     fn get_from_sorted_mut(&mut self, i: usize) -> A where A: DeviceElem;
     fn get_many_from_sorted_mut(&mut self, indexes: &ArrayRef<usize, Ix1>) -> IndexMap<usize, A> where A: DeviceElem;
 }
 impl<A> Sort1dExtB200<A> for ArrayRef<A, Ix1> {
+    fn partition_mut(&mut self, pivot_index: usize) -> usize where A: DeviceElem {
+        let mut new_index = 0usize;
+        let st = CTX.with(|&ctx| unsafe {
+            ffi::nds_partition(ctx, A::DTYPE, self.as_mut_ptr() as *mut _, self.len(), self.strides()[0],
+                               pivot_index, &mut new_index)
+        });
+        assert_eq!(st, ffi::NDS_OK, "pivot_index out of bounds (the reference panics, sort.rs:77-78)");
+        new_index
+    }
     fn get_from_sorted_mut(&mut self, i: usize) -> A where A: DeviceElem {
         self.get_many_from_sorted_mut(&ndarray::aview1(&[i]))[&i]
     }

@@ -287,11 +287,11 @@ nds_status run_call(nds_ctx *ctx, nds_dtype dtype, const void *data, const uint8
         c.valid = valid;
     } else {
         const char *src = (const char *)data + min_off * (long long)esize;
-        CUDA_TRY(cudaMemcpyAsync(arena + o_in, src, span_elems * esize, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(stage_h2d(ctx, arena + o_in, src, span_elems * esize));
         c.data = arena + o_in - min_off * (long long)esize;
         c.valid = nullptr;
         if (valid) {
-            CUDA_TRY(cudaMemcpyAsync(arena + o_valid, valid + min_off, span_elems, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(stage_h2d(ctx, arena + o_valid, valid + min_off, span_elems));
             c.valid = (const uint8_t *)(arena + o_valid) - min_off;
         }
     }
@@ -478,6 +478,7 @@ void nds_ctx_destroy(nds_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->nccl_comm) nds_comm_destroy(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    stage_destroy(ctx);
     if (ctx->arena) cudaFree(ctx->arena);
     delete ctx->pending;
     if (ctx->d_status) cudaFree(ctx->d_status);

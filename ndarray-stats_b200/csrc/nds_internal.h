@@ -52,6 +52,7 @@ struct nds_ctx {
     unsigned long long xseq = 0;     // sequence number of the next exchange step (identical on every rank)
     uint64_t xchg_steps = 0;         // exchange steps enqueued so far (peer-memory or NCCL)
     uint64_t host_syncs = 0;         // host round trips inside sharded calls so far
+    void *stage = nullptr;           // pinned bounce buffers + streams for pageable host inputs (nds_stage.cu)
 };
 
 namespace nds {
@@ -79,6 +80,11 @@ struct PendingCall {
 
 // Arena: returns a device pointer to at least `bytes` (256-byte aligned); contents are scratch.
 cudaError_t arena_reserve(nds_ctx *ctx, size_t bytes);
+
+// Host -> device copy of a caller's array in stream order of ctx->stream: pageable sources of a few MB and more go
+// through several host threads with pinned bounce buffers (nds_stage.cu), everything else is one cudaMemcpyAsync.
+cudaError_t stage_h2d(nds_ctx *ctx, void *dst, const void *src, size_t bytes);
+void stage_destroy(nds_ctx *ctx);
 
 // --- selection paths (each returns cudaSuccess or the first launch error) -------------------------
 // CTA-per-lane MSB radix select; any dtype / stride / lane length / mask.  The correctness workhorse.

@@ -232,7 +232,7 @@ extern "C" nds_status nds_minmax(nds_ctx *ctx, nds_dtype dtype, const void *data
     const void *dptr = data;
     if (!on_device) {
         const char *src = (const char *)data + min_off * (long long)esize;
-        if (cudaMemcpyAsync(arena + o_in, src, span * esize, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        if (stage_h2d(ctx, arena + o_in, src, span * esize) != cudaSuccess)
             return fail(NDS_CUDA_ERROR, "H2D copy");
         dptr = arena + o_in - min_off * (long long)esize;
     }

@@ -99,7 +99,7 @@ cudaError_t stage_h2d(nds_ctx *ctx, void *dst, const void *src, size_t bytes) {
         for (size_t c = (size_t)t; c < nchunks && te == cudaSuccess; c += (size_t)nt, ++turn) {
             const int b = (int)(turn % STAGE_BUFS);
             const size_t off = c * STAGE_CHUNK, len = std::min(STAGE_CHUNK, bytes - off);
-            if (turn >= (size_t)STAGE_BUFS) te = cudaEventSynchronize(p->buf_free[t][b]);
+            te = cudaEventSynchronize(p->buf_free[t][b]);   // (also the copy an earlier call left behind; a fresh event is ready)
             if (te != cudaSuccess) break;
             std::memcpy(p->bounce[t][b], (const char *)src + off, len);
             te = cudaMemcpyAsync((char *)dst + off, p->bounce[t][b], len, cudaMemcpyHostToDevice, p->stream[t]);

@@ -1726,7 +1726,7 @@ __global__ void __launch_bounds__(BRK_THREADS, 1) brk_refine_count_kernel(BrkBuf
 template <typename Key, bool COMPACT>
 __global__ void __launch_bounds__(BRK_THREADS, 2) brk_refine_round0_kernel(BrkBuf<Key> buf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char *counters = smem_raw;  // [256 digits][THREADS] private 8-bit counters (count pass only): 64 KB, 3 CTAs per SM
+    unsigned char *counters = smem_raw;  // [256 digits + 1][THREADS] private 8-bit counters (count pass only): 64 KB, 3 CTAs per SM
     __shared__ short sid[256];
     __shared__ int wanted[256];   // the digits of this bracket that some rank chose (usually one or two)
     __shared__ int n_wanted;
@@ -1937,10 +1937,14 @@ __global__ void __launch_bounds__(BRK_THREADS, 2) brk_refine_round0_kernel(BrkBu
                         }
                     }
                 }
-            } else if (valid == (KPT == 32 ? 0xffffffffu : (1u << KPT) - 1u)) {
+            } else {
+                // Partial chunks as well (the last chunk of every piece; the pieces of a lane sharded over eight ranks are
+                // shorter than one chunk): a key that is not there counts in a spare 257th row.  The key-by-key path this
+                // replaces ran at a sixth of this one's rate.
 #pragma unroll
                 for (int g = 0; g < KPT; g += 4) {  // 4 loads, equal digits merged, 4 stores (see the count kernel)
-                    const unsigned c0 = digit(k[g]), c1 = digit(k[g + 1]), c2 = digit(k[g + 2]), c3 = digit(k[g + 3]);
+                    const unsigned c0 = (valid >> g) & 1u ? digit(k[g]) : 256u, c1 = (valid >> (g + 1)) & 1u ? digit(k[g + 1]) : 256u;
+                    const unsigned c2 = (valid >> (g + 2)) & 1u ? digit(k[g + 2]) : 256u, c3 = (valid >> (g + 3)) & 1u ? digit(k[g + 3]) : 256u;
                     unsigned char *p0 = myctr + c0 * BRK_THREADS, *p1 = myctr + c1 * BRK_THREADS,
                                   *p2 = myctr + c2 * BRK_THREADS, *p3 = myctr + c3 * BRK_THREADS;
                     const unsigned x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
@@ -1951,10 +1955,6 @@ __global__ void __launch_bounds__(BRK_THREADS, 2) brk_refine_round0_kernel(BrkBu
                     *p2 = (unsigned char)(x2 + m2);
                     *p3 = (unsigned char)(x3 + m3);
                 }
-            } else {
-#pragma unroll
-                for (int e = 0; e < KPT; ++e)
-                    if (valid & (1u << e)) myctr[digit(k[e]) * BRK_THREADS] += 1;
             }
         };
         if (seek(cw, ce0)) {
@@ -2798,7 +2798,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         auto kp0 = brk_refine_round0_kernel<Key, true>;
         const size_t smem = (size_t)256 * BRK_THREADS * 2;
         if ((e = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        const size_t smem0 = (size_t)256 * BRK_THREADS;  // 8-bit counters
+        const size_t smem0 = (size_t)257 * BRK_THREADS;  // 8-bit counters, one row per digit + the spare row of absent keys
         if ((e = cudaFuncSetAttribute(kc0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0)) != cudaSuccess) return e;
         const int max_rounds = (int)sizeof(Key) + 1;
         // whole waves: as many CTAs as are resident at once (3 per SM were launched where 2 fit: a second, half-empty wave)

@@ -310,13 +310,17 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                             uint32_t inv = (round == 0) ? (TOP_INVERTED ? 0xffffffffu : 0u)
                                                         : ((IS_FLOAT && neg) ? 0xffffffffu : 0u);
                             const uint32_t *pp = pl + 15 * nrbp;
+                            uint32_t x[COLS_KMAX];   // the words of plane b; those of plane b - 1 are read while b is decided
+#pragma unroll
+                            for (int k = 0; k < COLS_KMAX; ++k) x[k] = ((unsigned)k < kw) ? pp[32 * k] : 0u;
 #pragma unroll 1
                             for (int b = 15; b >= 0; --b, pp -= nrbp) {
-                                uint32_t x[COLS_KMAX];
+                                uint32_t xn[COLS_KMAX];
+                                const uint32_t *pn = b > 0 ? pp - nrbp : pp;
                                 unsigned ones = 0;
 #pragma unroll
                                 for (int k = 0; k < COLS_KMAX; ++k) {
-                                    x[k] = ((unsigned)k < kw) ? pp[32 * k] : 0u;
+                                    xn[k] = ((unsigned)k < kw) ? pn[32 * k] : 0u;
                                     ones += __popc(m[k] & (x[k] ^ inv));
                                 }
                                 ones = __reduce_add_sync(FULLMASK, ones);
@@ -327,7 +331,10 @@ cols_bitslice_kernel(const T *__restrict__ data, LaneGeom g, QuantArgs qa, T *__
                                 const uint32_t keep = take_small ? inv : ~inv;
                                 prefix = (Raw)(prefix << 1) | (Raw)(keep & 1u);
 #pragma unroll
-                                for (int k = 0; k < COLS_KMAX; ++k) m[k] &= ~(x[k] ^ keep);
+                                for (int k = 0; k < COLS_KMAX; ++k) {
+                                    m[k] &= ~(x[k] ^ keep);
+                                    x[k] = xn[k];
+                                }
                                 if (round == 0 && b == 15) {
                                     neg = IS_FLOAT && (keep & 1u);
                                     inv = neg ? 0xffffffffu : 0u;
@@ -571,7 +578,11 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
     constexpr bool IS_FLOAT = Tr::is_float;
     constexpr bool TOP_INVERTED = IS_FLOAT || std::is_signed<T>::value;
     constexpr int EXP_LO = 7;
-    constexpr int NPL = 16;   // (no NaN planes here: 16 KB more for the ring; the walk derives the NaN masks from the exponent planes)
+    // floats: two more planes, "NaN by its top 16 bits" and "exponent all ones, top mantissa bits clear" (inf, or a NaN whose
+    // payload sits in the low bits), written by the build while the 16 plane words sit in registers.  (Deriving them at the
+    // start of the walk -- 15 plane reads per word, to free 16 KB for a longer ring -- cost 8 % of the kernel's time, and
+    // the ring is best at eight slots anyway.)
+    constexpr int NPL = IS_FLOAT ? 18 : 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const unsigned n = (unsigned)g.axis_len;
@@ -717,6 +728,15 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
                 transpose16(w);
 #pragma unroll
                 for (int b = 0; b < 16; ++b) pdst[b * nrbp + W] = w[b];
+                if constexpr (IS_FLOAT) {
+                    uint32_t e = 0xffffffffu, mhi = 0;
+#pragma unroll
+                    for (int b = EXP_LO; b <= 14; ++b) e &= w[b];
+#pragma unroll
+                    for (int b = 0; b < EXP_LO; ++b) mhi |= w[b];
+                    pdst[16 * nrbp + W] = e & mhi;
+                    pdst[17 * nrbp + W] = e & ~mhi;
+                }
                 if (!have_next && cq < q_end) have_next = fetch(true);   // still this strip's: wait for it now
             }
         }
@@ -743,13 +763,8 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
                     if (IS_FLOAT && v) {
                         // exponent all ones: a NaN for sure if one of the top mantissa bits is set, otherwise (inf, or a NaN
                         // whose payload sits in the low mantissa bits) the element itself is inspected
-                        uint32_t e = v, mhi = 0;
-#pragma unroll
-                        for (int b = EXP_LO; b <= 14; ++b) e &= pl[b * nrbp + 32 * k];
-#pragma unroll
-                        for (int b = 0; b < EXP_LO; ++b) mhi |= pl[b * nrbp + 32 * k];
-                        uint32_t nanm = e & mhi;
-                        uint32_t amb = e & ~mhi;
+                        uint32_t nanm = pl[16 * nrbp + 32 * k] & v;
+                        uint32_t amb = pl[17 * nrbp + 32 * k] & v;
                         while (amb) {
                             int p = __ffs(amb) - 1;
                             amb &= amb - 1;
@@ -821,13 +836,17 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
                             uint32_t inv = (round == 0) ? (TOP_INVERTED ? 0xffffffffu : 0u)
                                                         : ((IS_FLOAT && neg) ? 0xffffffffu : 0u);
                             const uint32_t *pp = pl + 15 * nrbp;
+                            uint32_t x[COLS_KMAX];   // the words of plane b; those of plane b - 1 are read while b is decided
+#pragma unroll
+                            for (int k = 0; k < COLS_KMAX; ++k) x[k] = ((unsigned)k < kw) ? pp[32 * k] : 0u;
 #pragma unroll 1
                             for (int b = 15; b >= 0; --b, pp -= nrbp) {
-                                uint32_t x[COLS_KMAX];
+                                uint32_t xn[COLS_KMAX];
+                                const uint32_t *pn = b > 0 ? pp - nrbp : pp;
                                 unsigned ones = 0;
 #pragma unroll
                                 for (int k = 0; k < COLS_KMAX; ++k) {
-                                    x[k] = ((unsigned)k < kw) ? pp[32 * k] : 0u;
+                                    xn[k] = ((unsigned)k < kw) ? pn[32 * k] : 0u;
                                     ones += __popc(m[k] & (x[k] ^ inv));
                                 }
                                 ones = __reduce_add_sync(FULLMASK, ones);
@@ -838,7 +857,10 @@ cols_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ 
                                 const uint32_t keep = take_small ? inv : ~inv;
                                 prefix = (Raw)(prefix << 1) | (Raw)(keep & 1u);
 #pragma unroll
-                                for (int k = 0; k < COLS_KMAX; ++k) m[k] &= ~(x[k] ^ keep);
+                                for (int k = 0; k < COLS_KMAX; ++k) {
+                                    m[k] &= ~(x[k] ^ keep);
+                                    x[k] = xn[k];
+                                }
                                 if (round == 0 && b == 15) {
                                     neg = IS_FLOAT && (keep & 1u);
                                     inv = neg ? 0xffffffffu : 0u;
@@ -1035,7 +1057,7 @@ ColsPlan plan_cols(const nds_ctx *ctx, const DeviceCall &c) {
     if (tma_knob && aligned && cwa == 8 && g.n_outer <= 2 && g.axis_stride > 0 && (g.n_outer == 1 || g.in_ostride[0] > 0) &&
         g.axis_len <= 0x7fffffffull && g.oshape[last] <= 0x7fffffffull && (g.n_outer == 1 || g.oshape[0] <= 0x7fffffffull)) {
         const unsigned sps = (unsigned)((g.axis_len + CT_SLOT_ROWS - 1) / CT_SLOT_ROWS);
-        const unsigned kw = (sps * 8 + 31) / 32, pitch_w = 16 * kw * 32 + 4;   // (16 planes: cols_tma_kernel keeps no NaN planes)
+        const unsigned kw = (sps * 8 + 31) / 32, pitch_w = npl * kw * 32 + 4;
         if (kw <= COLS_KMAX) {
             const size_t fixed = (size_t)CT_CW * pitch_w * 4 + (size_t)CT_CW * COLS_CAND * 4 + 2 * CT_MAX_SLOTS * 8 + 128;
             if ((size_t)ctx->max_smem_optin > fixed + 4 * CT_SLOT_BYTES) {

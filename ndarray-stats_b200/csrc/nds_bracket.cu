@@ -2709,7 +2709,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
             if ((e2 = allgather(buf.gsend, buf.grecv, gather_bytes<Key>(), &buf.hdr[H_GWORDS], &buf.hdr[H_GATE_SMALL])) != cudaSuccess)
                 return e2;
         }
-        brk_final_kernel<Key><<<sm, 256, 0, st>>>(buf, multi ? ctx->nranks : 0);
+        brk_final_kernel<Key><<<sm * 2, 256, 0, st>>>(buf, multi ? ctx->nranks : 0);   // up to 2 x 128 segments: one each
         return count();
     };
     // 0. threshold below which a segment is sorted by one CTA (sharded: small enough that all tasks' segments fit one

@@ -126,7 +126,7 @@ template <typename Key> struct BrkBuf {
     unsigned *fill;                  // [MAXB * nw_cap] fill of every (bracket, streaming CTA) piece
     unsigned long long *red_refine;  // [MAXSEG * 256]                               (allreduce per refine round)
     unsigned long long *loc_refine;  // [MAXSEG * 256] local copy (== red_refine on one GPU)
-    Key *s1, *s0, *blo, *bhi;
+    Key *s0, *blo, *bhi;
     Key *s0all;                      // sharded lanes: the all-gathered S0
     unsigned long long *xsend, *xrecv;  // sharded lanes, first exchange: [n_local, 0, this rank's share of the S0 keys] / of all ranks
     unsigned long long *red_refine_fail;  // sharded lanes: the fail word that travels in front of red_refine
@@ -197,61 +197,6 @@ __host__ __device__ inline unsigned pick_s1_from_need(unsigned long long n, doub
     return (unsigned)s1;
 }
 
-// `sharded`: the lane is this rank's shard of a longer one whose total length red_n[0] is only known on the device; every
-// rank samples at the same rate, so the sample size follows from the shard's share (and is published in H_S1)
-template <typename T>
-__global__ void brk_sample_kernel(const T *__restrict__ data, unsigned long long n, unsigned s1, double need, int sharded,
-                                  BrkBuf<typename Traits<T>::Key> buf) {
-    using Tr = Traits<T>;
-    using Key = typename Tr::Key;
-    if (sharded) {
-        const unsigned long long n_total = buf.red_n[0];
-        const unsigned s1_total = pick_s1_from_need(n_total, need);
-        const double share = n_total ? (double)n / (double)n_total : 0.0;
-        unsigned long long want = (unsigned long long)ceil(share * (double)s1_total);
-        if (want > n) want = n;
-        if (want > buf.s1cap) want = buf.s1cap;
-        s1 = (unsigned)want;
-        if (blockIdx.x == 0 && threadIdx.x == 0) buf.hdr[H_S1] = s1;
-    }
-    if (s1 == 0) return;
-    unsigned valid = 0;
-    // stratum i starts at floor(i n / s1) = i q + floor(i r / s1) (q = n / s1, r = n % s1): the strata must be spread EVENLY
-    // over the lane -- a sorted lane sampled at two different rates puts its quantiles in the wrong place.  The second
-    // term comes from one double multiplication (i r < 2^48 is exact; being off by one element does not matter), the
-    // offset inside the stratum from a multiply-high instead of a modulo (strata are narrower than 2^32).
-    const unsigned long long q = n / s1, r = n % s1;
-    const double inv_s1 = 1.0 / (double)s1;
-    const unsigned long long width = q + (r ? 1ull : 0ull);
-    // eight independent loads in flight per thread: the pass is bound by the latency of its scattered 32-byte reads
-    const unsigned step = gridDim.x * blockDim.x;
-    auto position = [&](unsigned i) -> unsigned long long {
-        const unsigned long long p0 = (unsigned long long)i * q + (unsigned long long)((double)((unsigned long long)i * r) * inv_s1);
-        unsigned long long pos = p0 + (((unsigned long long)mix32(i) * width) >> 32);
-        return pos >= n ? n - 1 : pos;
-    };
-    constexpr int MLP = 8;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += (unsigned long long)MLP * step) {
-        T x[MLP];
-#pragma unroll
-        for (int u = 0; u < MLP; ++u) {
-            const unsigned long long iu = i + (unsigned long long)u * step;
-            if (iu < s1) x[u] = data[position((unsigned)iu)];
-        }
-#pragma unroll
-        for (int u = 0; u < MLP; ++u) {
-            const unsigned long long iu = i + (unsigned long long)u * step;
-            if (iu < s1) {
-                Key k = Tr::to_key(x[u]);
-                const bool inv = key_is_nan<T>(k);
-                buf.s1[iu] = inv ? (Key) ~(Key)0 : k;  // NaN samples sort last and are not counted
-                valid += inv ? 0u : 1u;
-            }
-        }
-    }
-    (void)valid;  // (the number of valid samples comes out of the bucket counts; ten thousand atomics on one word cost 40 us)
-}
-
 // 0. this rank's element count (summed over ranks by the caller when the lane is sharded); final-sort threshold
 template <typename Key>
 __global__ void brk_begin_kernel(BrkBuf<Key> buf, unsigned long long n_local, unsigned final_cap, int multi, unsigned s1) {
@@ -320,7 +265,7 @@ template <typename Key> __global__ void brk_copy_counts_kernel(BrkBuf<Key> buf) 
     }
 }
 
-// 2a. S0 = every (s1 / S0)-th sample (or the gathered shares of all ranks), sorted by counting: the place of key i is
+// 2a. S0 = 8192 keys of the lane (brk_pick_local_s0_kernel; over ranks: the gathered shares), sorted by counting: the place of key i is
 // #{ j : S0[j] < S0[i], or S0[j] == S0[i] and j < i }.  8192^2 comparisons spread over 128 CTAs (64 keys each, eight
 // warps that each scan an eighth of S0 from shared memory with broadcast reads) take ~15 us; the bitonic network that
 // one CTA ran before took 100 us -- a fixed cost that a lane sharded over eight GPUs cannot amortise.
@@ -334,17 +279,7 @@ __global__ void __launch_bounds__(SORT_THREADS) brk_sort_s0_kernel(BrkBuf<Key> b
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Key *s = reinterpret_cast<Key *>(smem_raw);
     __shared__ unsigned place[SORT_KEYS_PER_CTA];
-    const unsigned s1 = (unsigned)buf.hdr[H_S1];
-    for (unsigned i = threadIdx.x; i < BRK_S0; i += blockDim.x) {
-        if (gathered) {
-            s[i] = gathered[i];
-        } else if (s1 == 0) {
-            s[i] = (Key) ~(Key)0;  // an empty lane
-        } else {
-            unsigned long long pos = (unsigned long long)i * s1 / BRK_S0;
-            s[i] = buf.s1[pos];
-        }
-    }
+    for (unsigned i = threadIdx.x; i < BRK_S0; i += blockDim.x) s[i] = gathered[i];   // (an empty lane: all ~0)
     if (threadIdx.x < SORT_KEYS_PER_CTA) place[threadIdx.x] = 0;
     __syncthreads();
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -365,13 +300,36 @@ __global__ void __launch_bounds__(SORT_THREADS) brk_sort_s0_kernel(BrkBuf<Key> b
     if (threadIdx.x < SORT_KEYS_PER_CTA) buf.s0[place[threadIdx.x]] = s[blockIdx.x * SORT_KEYS_PER_CTA + threadIdx.x];
 }
 
-// 2b. exact sample ranks of the S0 keys: hist[i] = #{ s1 keys k : S0[i-1] < k <= S0[i] }
-constexpr int BRK_BLUT = 4096;  // cells of the bucket kernel's search table
+// 2b. the sample, ranked against S0
+constexpr int BRK_BLUT = 4096;  // cells of the search table over S0
 
-template <typename Key, bool IS_FLOAT>
-__global__ void __launch_bounds__(256) brk_bucket_kernel(BrkBuf<Key> buf) {
+// Sample and bucket in ONE kernel: every sampled key is ranked against the sorted splitters S0 (picked from the lane
+// beforehand, brk_pick_local_s0_kernel) while the other scattered reads of the thread are still on their way -- the sample is
+// never written out and read back, and the histogram atomics hide behind the read latency (C4: 287 us; 256 + 184 us as two
+// kernels).  hist[i] = #{ sampled keys k : S0[i-1] < k <= S0[i] }, then #{ k == S0[i] } for the first key of every run.
+// `sharded`: the lane is this rank's shard of a longer one whose total length red_n[0] is only known on the device; every
+// rank samples at the same rate, so the sample size follows from the shard's share (and is published in H_S1).
+// The strata are spread EVENLY over the lane, one hashed position in each: stratum i starts at floor(i n / s1) = i q +
+// floor(i r / s1) (q = n / s1, r = n % s1) -- a sorted lane sampled at two different rates puts its quantiles in the wrong
+// place.  The second term comes from one double multiplication (i r < 2^48 is exact; being off by one element does not
+// matter), the offset inside the stratum from a multiply-high instead of a modulo (strata are narrower than 2^32).
+template <typename T>
+__global__ void __launch_bounds__(512) brk_sample_bucket_kernel(const T *__restrict__ data, unsigned long long n, unsigned s1,
+                                                                 double need, int sharded, BrkBuf<typename Traits<T>::Key> buf) {
+    using Tr = Traits<T>;
+    using Key = typename Tr::Key;
+    constexpr bool IS_FLOAT = Tr::is_float;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const unsigned s1 = (unsigned)buf.hdr[H_S1];
+    if (sharded) {
+        const unsigned long long n_total = buf.red_n[0];
+        const unsigned s1_total = pick_s1_from_need(n_total, need);
+        const double share = n_total ? (double)n / (double)n_total : 0.0;
+        unsigned long long want = (unsigned long long)ceil(share * (double)s1_total);
+        if (want > n) want = n;
+        if (want > buf.s1cap) want = buf.s1cap;
+        s1 = (unsigned)want;
+        if (blockIdx.x == 0 && threadIdx.x == 0) buf.hdr[H_S1] = s1;
+    }
     if (s1 == 0) return;
     Key *s = reinterpret_cast<Key *>(smem_raw);
     unsigned short *start = reinterpret_cast<unsigned short *>(s + BRK_S0);  // [BLUT + 1]: lower_bound of every cell start
@@ -385,7 +343,7 @@ __global__ void __launch_bounds__(256) brk_bucket_kernel(BrkBuf<Key> buf) {
         }
         return lo;
     };
-    // A key-linear table over [S0[0], S0[last]] narrows the 13-step binary search to the few splitters of one cell.
+    // a key-linear table over [S0[0], S0[last]] narrows the 13-step binary search to the few splitters of one cell
     const Key k0 = s[0], k1 = s[BRK_S0 - 1];
     const Key range = k1 - k0;
     int sh = key_bits_used(range) - 12;
@@ -397,18 +355,29 @@ __global__ void __launch_bounds__(256) brk_bucket_kernel(BrkBuf<Key> buf) {
         start[c] = (unsigned short)((past || off > range) ? BRK_S0 : lower_bound((Key)(k0 + off), 0, BRK_S0));
     }
     __syncthreads();
-    // four keys per thread in flight: the loop is bound by the latency of the key loads, the searches are short
-    constexpr int MLP = 4;
-    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += MLP * step) {
-        Key kk[MLP];
-#pragma unroll
-        for (int u = 0; u < MLP; ++u) kk[u] = (i + u * step < s1) ? buf.s1[i + u * step] : (Key) ~(Key)0;
+    const unsigned long long q = n / s1, r = n % s1;
+    const double inv_s1 = 1.0 / (double)s1;
+    const unsigned long long width = q + (r ? 1ull : 0ull);
+    const unsigned step = gridDim.x * blockDim.x;
+    auto position = [&](unsigned i) -> unsigned long long {
+        const unsigned long long p0 = (unsigned long long)i * q + (unsigned long long)((double)((unsigned long long)i * r) * inv_s1);
+        unsigned long long pos = p0 + (((unsigned long long)mix32(i) * width) >> 32);
+        return pos >= n ? n - 1 : pos;
+    };
+    constexpr int MLP = 8;   // independent scattered reads in flight per thread
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += (unsigned long long)MLP * step) {
+        T x[MLP];
 #pragma unroll
         for (int u = 0; u < MLP; ++u) {
-            const Key k = kk[u];
-            if (i + u * step >= s1) continue;
-            if (IS_FLOAT && k == (Key) ~(Key)0) continue;
+            const unsigned long long iu = i + (unsigned long long)u * step;
+            if (iu < s1) x[u] = data[position((unsigned)iu)];
+        }
+#pragma unroll
+        for (int u = 0; u < MLP; ++u) {
+            const unsigned long long iu = i + (unsigned long long)u * step;
+            if (iu >= s1) continue;
+            const Key k = Tr::to_key(x[u]);
+            if (IS_FLOAT && key_is_nan<T>(k)) continue;   // NaN samples are not counted
             unsigned lo;
             if (k <= k0) lo = 0;
             else if (k > k1) lo = BRK_S0;
@@ -417,7 +386,7 @@ __global__ void __launch_bounds__(256) brk_bucket_kernel(BrkBuf<Key> buf) {
                 lo = lower_bound(k, start[c], start[c + 1]);
             }
             atomicAdd(&buf.s0hist[lo], 1ull);
-            if (lo < BRK_S0 && s[lo] == k) atomicAdd(&buf.s0hist[BRK_S0 + 2 + lo], 1ull);  // #{ s1 == S0[lo] }, first of its run
+            if (lo < BRK_S0 && s[lo] == k) atomicAdd(&buf.s0hist[BRK_S0 + 2 + lo], 1ull);  // #{ sample == S0[lo] }, first of its run
         }
     }
 }
@@ -2533,7 +2502,7 @@ template <typename Key> BrkSizes brk_sizes(unsigned long long n, int nq, double 
     size_t t = 0;
     t += align256(H_WORDS * 8) + align256(2 * 8) + align256(2 * (BRK_S0 + 2) * 8) + align256((BRK_NCLS + BRK_MAXB + 2) * 8) +
          align256(BRK_MAXB * 8) + 2 * align256(((size_t)BRK_MAXSEG * 256 + 2) * 8) + align256(16) + align256((size_t)BRK_MAXB * 148 * STR_WARPS * 4);
-    t += align256((size_t)z.s1 * sizeof(Key)) + 2 * align256(BRK_S0 * sizeof(Key)) + 2 * align256(BRK_MAXB * sizeof(Key)) +
+    t += 2 * align256(BRK_S0 * sizeof(Key)) + 2 * align256(BRK_MAXB * sizeof(Key)) +
          align256(16 + BRK_S0 * sizeof(Key)) * (1 + BRK_MAX_RANKS);
     t += align256(gather_bytes<Key>()) + align256(gather_bytes<Key>() * BRK_MAX_RANKS);
     t += 2 * align256(BRK_MAXB * 8) + align256(BRK_MAXB) + align256(BRK_NC1 * 4) + align256(BRK_L2N * 2) +
@@ -2568,7 +2537,6 @@ template <typename Key> BrkBuf<Key> brk_carve(void *scratch, const BrkSizes &z, 
     b.nw_cap = 148 * STR_WARPS;
     *zero_bytes = (size_t)(p - (char *)scratch);
     // --- the rest is written before it is read ---
-    b.s1 = (Key *)take((size_t)z.s1 * sizeof(Key));
     b.s0 = (Key *)take(BRK_S0 * sizeof(Key));
     b.s0all = (Key *)take(BRK_S0 * sizeof(Key));
     b.xsend = (unsigned long long *)take(16 + BRK_S0 * sizeof(Key));
@@ -2732,25 +2700,31 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
         gathered = buf.s0all;
         timer.mark("count+S0-exchange");
     }
-    // 2. sample (every rank at the same rate: the size follows on the device from the total length), sort S0, bucket S1
+    // 2. the splitters S0 (one rank: 8192 keys at hashed, evenly spread positions of the lane; over ranks: the gathered
+    //    shares), sorted; then ONE kernel samples the lane (every rank at the same rate: the size follows on the device from
+    //    the total length) and ranks every sampled key against S0
     {
-        const unsigned bound = sharded ? z.s1 : s1_host;
-        const unsigned grid = std::max(1u, std::min<unsigned>((bound + 255) / 256, (unsigned)sm * 8));
-        brk_sample_kernel<T><<<grid, 256, 0, st>>>(lane, n, s1_host, need, sharded ? 1 : 0, buf);
-        if ((e = count()) != cudaSuccess) return e;
-        timer.mark("sample");
+        if (!multi) {
+            brk_pick_local_s0_kernel<T><<<8, 256, 0, st>>>(lane, n, buf, (unsigned)BRK_S0);
+            if ((e = count()) != cudaSuccess) return e;
+            gathered = reinterpret_cast<const Key *>(buf.xsend + 2);
+        }
         auto k = brk_sort_s0_kernel<Key>;
         const size_t smem = BRK_S0 * sizeof(Key);
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<SORT_CTAS, SORT_THREADS, smem, st>>>(buf, gathered);
         if ((e = count()) != cudaSuccess) return e;
         timer.mark("sort-S0");
-        auto kb = brk_bucket_kernel<Key, IS_FLOAT>;
-        const size_t smemb = BRK_S0 * sizeof(Key) + (BRK_BLUT + 1) * 2 + 16;
-        if ((e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemb)) != cudaSuccess) return e;
-        kb<<<std::max(1u, std::min<unsigned>((bound + 255) / 256, (unsigned)sm * 4)), 256, smemb, st>>>(buf);
+        const unsigned bound = sharded ? z.s1 : s1_host;
+        auto ks = brk_sample_bucket_kernel<T>;
+        const size_t smems = BRK_S0 * sizeof(Key) + (BRK_BLUT + 1) * 2 + 16;
+        if ((e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smems)) != cudaSuccess) return e;
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks, 512, smems);
+        const unsigned grid = std::max(1u, std::min<unsigned>((bound + 511) / 512, (unsigned)(sm * std::max(1, occ))));
+        ks<<<grid, 512, smems, st>>>(lane, n, s1_host, need, sharded ? 1 : 0, buf);
         if ((e = count()) != cudaSuccess) return e;
-        timer.mark("bucket");
+        timer.mark("sample+bucket");
     }
     if ((e = allreduce(buf.s0hist, 2 * (BRK_S0 + 2), nullptr, nullptr)) != cudaSuccess) return e;
     if (multi) timer.mark("hist-exchange");

@@ -615,7 +615,8 @@ def main():
     achieved = rec["algorithmic_bytes_per_launch"] / (rec["ms_per_step"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": dominant, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": rec["algorithmic_bytes_per_launch"]}
+                "algorithmic_bytes_per_launch": rec["algorithmic_bytes_per_launch"],
+                "frac_of_nominal_8000": achieved / 8000.0}   # against the nominal HBM3e figure as well
 
     e2e = e2e_pageable = None
     if not args.no_e2e and not one_d:

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Turn a gpurun evidence directory (tools/evidence.sh) into the tracked summaries under profiles/.
+"""Turn a gpurun evidence directory (tools/evidence_r02.sh) into the tracked summaries under profiles/.
 
 usage: tools/summarize_profile.py gpurun_out/<tag> <round-name> <workload>
 writes profiles/<round-name>_<workload>_launches.csv   (the ncu per-launch durations, kernel names shortened)

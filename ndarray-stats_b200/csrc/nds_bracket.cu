@@ -2692,7 +2692,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     const Key *gathered = nullptr;
     if (multi) {
         const unsigned share = BRK_S0 / (unsigned)ctx->nranks;
-        brk_pick_local_s0_kernel<T><<<8, 256, 0, st>>>(lane, n, buf, share);
+        brk_pick_local_s0_kernel<T><<<32, 256, 0, st>>>(lane, n, buf, share);
         if ((e = count()) != cudaSuccess) return e;
         if ((e = allgather(buf.xsend, buf.xrecv, 16 + (size_t)share * sizeof(Key), nullptr, nullptr)) != cudaSuccess) return e;
         brk_unpack_s0_kernel<Key><<<8, 256, 0, st>>>(buf, ctx->nranks, share);
@@ -2705,7 +2705,7 @@ cudaError_t launch_bracket_lane(nds_ctx *ctx, const T *lane, unsigned long long 
     //    the total length) and ranks every sampled key against S0
     {
         if (!multi) {
-            brk_pick_local_s0_kernel<T><<<8, 256, 0, st>>>(lane, n, buf, (unsigned)BRK_S0);
+            brk_pick_local_s0_kernel<T><<<32, 256, 0, st>>>(lane, n, buf, (unsigned)BRK_S0);
             if ((e = count()) != cudaSuccess) return e;
             gathered = reinterpret_cast<const Key *>(buf.xsend + 2);
         }

@@ -88,3 +88,18 @@ def test_shard_lanes_partitions_every_lane_once(nds):
         parts = [nds.shard_lanes(a, 0, r, world) for r in range(world)]
         cols = np.concatenate([p[0] for p in parts], axis=1)
         assert np.array_equal(cols, a)
+
+
+def test_cpp_mirror_selftest_host_only():
+    """include/ndstats_b200.hpp (the C++ host mirror of the trait surface): compiles against the C ABI and passes its
+    host-only checks -- validation order and error strings of the reference, and that without a device every compute call
+    fails loudly (no CPU fallback).  The device part of the self-test runs when a GPU is visible; here it is masked out."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cpp = os.path.join(root, "ndarray-stats_b200", "cpp")
+    subprocess.run(["make", "-C", cpp, "-s", "selftest"], check=True)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([os.path.join(cpp, "selftest")], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "cpp mirror self-test: ok (host-only checks" in r.stdout

@@ -110,7 +110,13 @@ cudaError_t stage_h2d(nds_ctx *ctx, void *dst, const void *src, size_t bytes) {
     };
     std::vector<std::thread> threads;
     threads.reserve((size_t)nt);
-    for (int t = 1; t < nt; ++t) threads.emplace_back(work, t);
+    for (int t = 1; t < nt; ++t) {
+        try {
+            threads.emplace_back(work, t);
+        } catch (...) {   // no more threads to be had: this one takes the chunks itself (nothing may unwind across the C ABI)
+            work(t);
+        }
+    }
     work(0);
     for (auto &th : threads) th.join();
     for (int t = 0; t < nt; ++t) {
